@@ -1,0 +1,320 @@
+/* orc_raymarch.c -- CPU ORACLE (test infrastructure): per-pixel visibility.
+ *
+ * (1) orc_ref_instanced_pixel restates what the reference's instanced draw resolves per pixel
+ *     (Samples/SimpleVoxel.cpp:146-192 VS, :220-224 FS, depth Greater/clear 0 at :322,:382, fan faces per
+ *     Runtimes/Shape/TriplePlanarCube.h:36-43 + SimpleVoxel.cpp:87-136) as "nearest of the three camera-facing
+ *     faces of every valid instance along the pixel-centre ray", in fp64.
+ * (2) orc_raymarch is the repo-DEFINED 3D-DDA ("parity unpinned by reference; bit-exact vs repo oracle").
+ *     The DDA is STATELESS: the crossing time of an integer voxel plane p on axis a is always
+ *         t_a(p) = (float(p) - o_a) * inv_a            (one fp32 sub, one fp32 mul, no fma)
+ *     and crossings are consumed in the total order key = (t, axis).  ORC_DDA_FLAT walks one voxel per step on
+ *     an unbounded grid and is the definition; ORC_DDA_HIER skips empty chunks (128^3) / empty bricks (8^3) and
+ *     re-derives the other two coordinates from the same keys, so it is bit-identical to FLAT by construction
+ *     (tests/test_oracle_raymarch.py checks it).  The CUDA kernel implements HIER.
+ */
+#include "orc_internal.h"
+
+typedef struct { float o[3], d[3], inv[3]; int step[3]; } Ray;
+typedef struct { int hit; int c[3]; int axis; float t; uint64_t steps; } Trace;
+
+typedef struct {
+  const OrcVolume* v;
+  int n[3];               /* grid size in voxels */
+  const uint8_t* chunk_any;
+  uint8_t* touched_chunk; /* may be NULL */
+  uint8_t* touched_brick; /* indexed by payload slot; may be NULL */
+} Scene;
+
+static inline void ray_init(Ray* r, const float o[3], const float d[3]) {
+  for (int i = 0; i < 3; i++) {
+    r->o[i] = o[i]; r->d[i] = d[i];
+    if (fabsf(d[i]) >= 1e-20f) { r->inv[i] = 1.0f / d[i]; r->step[i] = d[i] > 0.0f ? 1 : -1; }
+    else { r->inv[i] = 0.0f; r->step[i] = 0; }
+  }
+}
+static inline float plane_t(const Ray* r, int a, int plane) { return ((float)plane - r->o[a]) * r->inv[a]; }
+static inline int key_less(float t1, int a1, float t2, int a2) { return t1 < t2 || (t1 == t2 && a1 < a2); }
+
+/* coordinate on axis b after consuming every crossing with key < (ts, as), starting from cell coordinate cur */
+static int advance_axis(const Ray* r, int b, int cur, float ts, int as) {
+  int st = r->step[b];
+  if (st == 0) return cur;
+  float pos = r->o[b] + r->d[b] * ts;
+  float fl = floorf(pos);
+  if (fl > 1.0e9f) fl = 1.0e9f;
+  if (fl < -1.0e9f) fl = -1.0e9f;
+  int e = (int)fl;
+  if (st > 0) { if (e < cur) e = cur; } else { if (e > cur) e = cur; }
+  for (;;) {
+    int pa = st > 0 ? e + 1 : e;
+    if (key_less(plane_t(r, b, pa), b, ts, as)) e += st; else break;
+  }
+  for (;;) {
+    if (e == cur) break;
+    int pb = st > 0 ? e : e + 1;
+    if (!key_less(plane_t(r, b, pb), b, ts, as)) e -= st; else break;
+  }
+  return e;
+}
+
+static inline int inside(const Scene* s, const int c[3]) {
+  return c[0] >= 0 && c[1] >= 0 && c[2] >= 0 && c[0] < s->n[0] && c[1] < s->n[1] && c[2] < s->n[2];
+}
+/* the ray can never (re-)enter the grid from cell c */
+static inline int gone(const Scene* s, const Ray* r, const int c[3]) {
+  for (int i = 0; i < 3; i++) {
+    if (r->step[i] > 0) { if (c[i] >= s->n[i]) return 1; }
+    else if (r->step[i] < 0) { if (c[i] < 0) return 1; }
+    else if (c[i] < 0 || c[i] >= s->n[i]) return 1;
+  }
+  return 0;
+}
+
+/* level of the cell at voxel c (inside the grid): 0 = solid voxel, 1 = empty voxel in a partial brick,
+ * 8 = empty brick, 128 = empty chunk */
+static inline int cell_level(const Scene* s, const int c[3]) {
+  const OrcVolume* v = s->v;
+  int64_t ci = orc_cidx(v, c[0] >> 7, c[1] >> 7, c[2] >> 7);
+  if (!s->chunk_any[ci]) return ORC_CV;
+  if (s->touched_chunk) s->touched_chunk[ci] = 1;
+  int b = orc_bidx((c[0] >> 3) & 15, (c[1] >> 3) & 15, (c[2] >> 3) & 15);
+  if (!orc_getbit(v->occ + ci * ORC_WORDS, b)) return ORC_BR;
+  if (orc_getbit(v->full + ci * ORC_WORDS, b)) return 0;
+  uint32_t slot = v->bptr[ci][b];
+  if (s->touched_brick) s->touched_brick[slot] = 1;
+  const uint64_t* p = v->pool + (size_t)slot * 8;
+  return (int)((p[c[2] & 7] >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1u) ? 0 : 1;
+}
+
+static Trace trace(const Scene* s, const Ray* r, const int c0[3], int mode) {
+  Trace tr; tr.hit = 0; tr.axis = -1; tr.t = 0.0f; tr.steps = 0;
+  int c[3] = {c0[0], c0[1], c0[2]};
+  if (mode == ORC_DDA_FLAT) {
+    for (;;) {
+      if (inside(s, c)) { if (cell_level(s, c) == 0) { tr.hit = 1; break; } }
+      else if (gone(s, r, c)) break;
+      int a = -1; float ta = 0.0f;
+      for (int i = 0; i < 3; i++) {
+        if (!r->step[i]) continue;
+        float ti = plane_t(r, i, r->step[i] > 0 ? c[i] + 1 : c[i]);
+        if (a < 0 || key_less(ti, i, ta, a)) { a = i; ta = ti; }
+      }
+      if (a < 0) break; /* zero direction */
+      c[a] += r->step[a]; tr.axis = a; tr.t = ta; tr.steps++;
+    }
+  } else {
+    if (!inside(s, c)) {
+      if (gone(s, r, c)) goto done;
+      int a = -1; float ta = 0.0f;
+      for (int i = 0; i < 3; i++) {
+        int before = (r->step[i] > 0 && c[i] < 0) || (r->step[i] < 0 && c[i] >= s->n[i]);
+        if (!before) continue;
+        float ti = plane_t(r, i, r->step[i] > 0 ? 0 : s->n[i]);
+        if (a < 0 || key_less(ta, a, ti, i)) { a = i; ta = ti; }
+      }
+      c[a] = r->step[a] > 0 ? 0 : s->n[a] - 1;
+      for (int b = 0; b < 3; b++) if (b != a) c[b] = advance_axis(r, b, c[b], ta, a);
+      tr.axis = a; tr.t = ta; tr.steps++;
+      if (!inside(s, c)) goto done;
+    }
+    for (;;) {
+      int L = cell_level(s, c);
+      if (L == 0) { tr.hit = 1; break; }
+      int a = -1; float ta = 0.0f; int pl_a = 0;
+      for (int i = 0; i < 3; i++) {
+        if (!r->step[i]) continue;
+        int base = c[i] & ~(L - 1);
+        int pl = r->step[i] > 0 ? base + L : base;
+        float ti = plane_t(r, i, pl);
+        if (a < 0 || key_less(ti, i, ta, a)) { a = i; ta = ti; pl_a = pl; }
+      }
+      if (a < 0) break;
+      if (L == 1) c[a] += r->step[a];
+      else {
+        c[a] = r->step[a] > 0 ? pl_a : pl_a - 1;
+        for (int b = 0; b < 3; b++) if (b != a) c[b] = advance_axis(r, b, c[b], ta, a);
+      }
+      tr.axis = a; tr.t = ta; tr.steps++;
+      if (!inside(s, c)) break;
+    }
+  }
+done:
+  tr.c[0] = c[0]; tr.c[1] = c[1]; tr.c[2] = c[2];
+  return tr;
+}
+
+static inline uint32_t to_un8(float x) { return (uint32_t)(x * 255.0f + 0.5f); }
+
+typedef struct {
+  Scene sc; const OrcRaySetup* rs; int width, x0, x1, y0; uint32_t flags; int mode; OrcHitRecord* rec;
+  uint64_t primary, shadow, hits, steps; pthread_mutex_t mu;
+} RmArg;
+
+static void shade_pixel(RmArg* a, int px, int py, uint64_t cnt[4]) {
+  const OrcRaySetup* rs = a->rs;
+  float fx = ((float)px + 0.5f) * rs->two_over_w - 1.0f;
+  float fy = 1.0f - ((float)py + 0.5f) * rs->two_over_h;
+  float d[3];
+  for (int i = 0; i < 3; i++) d[i] = (fx * rs->U[i] + fy * rs->V[i]) + rs->F[i];
+  float len = sqrtf((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]);
+  for (int i = 0; i < 3; i++) d[i] = d[i] / len;
+  Ray r; ray_init(&r, rs->o, d);
+  int c0[3];
+  for (int i = 0; i < 3; i++) { float f = floorf(rs->o[i]); if (f > 1.0e9f) f = 1.0e9f; if (f < -1.0e9f) f = -1.0e9f; c0[i] = (int)f; }
+  Trace tr = trace(&a->sc, &r, c0, a->mode);
+  cnt[0]++; cnt[3] += tr.steps;
+  OrcHitRecord* out = &a->rec[(size_t)py * a->width + px];
+  if (!tr.hit) { out->w0 = 0xFFFFFFFFu; out->w1 = 0x0007FFFFu; out->t = INFINITY; out->rgba = 0xFF000000u; return; }
+  cnt[2]++;
+  int face = 6; float p[3]; int shadow = 0;
+  for (int i = 0; i < 3; i++) p[i] = r.o[i] + r.d[i] * tr.t;
+  if (tr.axis >= 0) {
+    int ax = tr.axis;
+    face = ax * 2 + (r.step[ax] > 0 ? 0 : 1);
+    p[ax] = (float)(r.step[ax] > 0 ? tr.c[ax] : tr.c[ax] + 1);
+    if (a->flags & ORC_FLAG_SHADOW) {
+      int facing = r.step[ax] > 0 ? (rs->L[ax] < 0.0f) : (rs->L[ax] > 0.0f);
+      if (!facing) shadow = 1;
+      else {
+        Ray sr; ray_init(&sr, p, rs->L);
+        int sc0[3] = {tr.c[0], tr.c[1], tr.c[2]};
+        sc0[ax] -= r.step[ax];
+        Trace st = trace(&a->sc, &sr, sc0, a->mode);
+        cnt[1]++; cnt[3] += st.steps;
+        shadow = st.hit;
+      }
+    }
+  } else { for (int i = 0; i < 3; i++) p[i] = r.o[i]; }
+  float shade = shadow ? 0.5f : 1.0f;
+  uint32_t ch[3];
+  for (int i = 0; i < 3; i++) {
+    float local = p[i] * 0.125f - (float)(tr.c[i] >> 3);
+    if (local < 0.0f) local = 0.0f;
+    if (local > 1.0f) local = 1.0f;
+    float col = (local - 0.5f) * 0.5f + 0.5f;   /* SimpleVoxel.cpp:222  Normal*0.5+0.5, Normal = local-0.5 */
+    ch[i] = to_un8(col * shade);
+  }
+  out->w0 = (uint32_t)tr.c[0] | ((uint32_t)tr.c[1] << 16);
+  out->w1 = (uint32_t)tr.c[2] | ((uint32_t)face << 16) | ((uint32_t)shadow << 19) | (1u << 20);
+  out->t = tr.t;
+  out->rgba = ch[0] | (ch[1] << 8) | (ch[2] << 16); /* alpha 0 on hits (SimpleVoxel.cpp:222), 1 on clear (:315) */
+}
+
+static void rm_range(void* ctx, int64_t b, int64_t e, int tid) {
+  (void)tid;
+  RmArg* a = (RmArg*)ctx;
+  uint64_t cnt[4] = {0, 0, 0, 0};
+  for (int64_t row = b; row < e; row++)
+    for (int px = a->x0; px < a->x1; px++) shade_pixel(a, px, a->y0 + (int)row, cnt);
+  pthread_mutex_lock(&a->mu);
+  a->primary += cnt[0]; a->shadow += cnt[1]; a->hits += cnt[2]; a->steps += cnt[3];
+  pthread_mutex_unlock(&a->mu);
+}
+
+void orc_raymarch(const OrcVolume* v, const OrcRaySetup* rs, int width, int height, int x0, int y0, int x1, int y1,
+                  uint32_t flags, int mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats) {
+  (void)height;
+  RmArg a; memset(&a, 0, sizeof(a));
+  a.sc.v = v;
+  for (int i = 0; i < 3; i++) a.sc.n[i] = v->dims[i] * ORC_CV;
+  uint8_t* any = (uint8_t*)calloc((size_t)v->nchunks, 1);
+  for (int64_t c = 0; c < v->nchunks; c++) {
+    uint64_t o = 0;
+    for (int w = 0; w < ORC_WORDS; w++) o |= v->occ[c * ORC_WORDS + w];
+    any[c] = o != 0;
+  }
+  a.sc.chunk_any = any;
+  if (stats) {
+    a.sc.touched_chunk = (uint8_t*)calloc((size_t)v->nchunks, 1);
+    a.sc.touched_brick = (uint8_t*)calloc((size_t)(v->pool_n > 0 ? v->pool_n : 1), 1);
+  }
+  a.rs = rs; a.width = width; a.x0 = x0; a.x1 = x1; a.y0 = y0; a.flags = flags; a.mode = mode; a.rec = records;
+  pthread_mutex_init(&a.mu, NULL);
+  orc_parallel_for(y1 - y0, nthreads, 4, rm_range, &a);
+  pthread_mutex_destroy(&a.mu);
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->primary = a.primary; stats->shadow = a.shadow; stats->hits = a.hits; stats->steps = a.steps;
+    for (int64_t c = 0; c < v->nchunks; c++) stats->touched_chunks += a.sc.touched_chunk[c];
+    for (int64_t i = 0; i < v->pool_n; i++) stats->touched_bricks += a.sc.touched_brick[i];
+    /* DESIGN.md "algorithmic bytes": chunk-level any/full bit grids once + 1024 B of block masks per touched
+     * chunk + (4 B pointer + 64 B payload) per touched partial brick */
+    stats->u_bytes = 2 * (uint64_t)((v->nchunks + 7) / 8) + 1024 * stats->touched_chunks + 68 * stats->touched_bricks;
+    free(a.sc.touched_chunk); free(a.sc.touched_brick);
+  }
+  free(any);
+}
+
+/* ---- reference-semantics restatement of the instanced draw ------------------------------------ */
+
+/* The fan 0,1,2,3,4,5,6,1 of table row `octant` (SimpleVoxel.cpp:87-127) covers exactly the three cube
+ * faces that meet at the row's vertex 0, whose sign on axis i is + when bit i of the octant id is set
+ * (tests/golden/triplanar_faces.json, generated from the reference table, pins this).  Face ids as in
+ * OrcHitRecord: 2*axis + (positive side). */
+void orc_triplanar_faces(int octant, int faces_out[3]) {
+  for (int i = 0; i < 3; i++) faces_out[i] = 2 * i + ((octant >> i) & 1);
+}
+
+int orc_ref_instanced_pixel(const OrcGPUUniformCamera* cam, const OrcGPUUniformSceneConfig* scene,
+                            const OrcGPUChunk* chunks, int64_t n_chunks, const OrcGPUBlock* blocks, int64_t n_blocks,
+                            int width, int height, int px, int py, int32_t out_block[3], int* out_face,
+                            double* out_t, double* out_margin, float out_rgba[4]) {
+  const float* V = cam->View; const float* P = cam->Projection;
+  double eye[3], d[3];
+  double fx = ((double)px + 0.5) * 2.0 / (double)width - 1.0;
+  double fy = 1.0 - ((double)py + 0.5) * 2.0 / (double)height;
+  double vv[3] = {fx / (double)P[0], fy / (double)P[5], -1.0};
+  for (int i = 0; i < 3; i++) {
+    eye[i] = -((double)V[i * 4 + 0] * V[12] + (double)V[i * 4 + 1] * V[13] + (double)V[i * 4 + 2] * V[14]);
+    d[i] = (double)V[i * 4 + 0] * vv[0] + (double)V[i * 4 + 1] * vv[1] + (double)V[i * 4 + 2] * vv[2];
+  }
+  double best_t = INFINITY, best_margin = 0.0; int best_face = 7; int32_t best_blk[3] = {0, 0, 0}; double best_local[3] = {0, 0, 0};
+  int found = 0;
+  for (int64_t k = 0; k < n_blocks; k++) {
+    const OrcGPUBlock* B = &blocks[k];
+    if (B->ChunkIndex == (uint32_t)INT_MAX || (int64_t)B->ChunkIndex >= n_chunks) continue;     /* SimpleVoxel.cpp:149 */
+    const OrcGPUChunk* C = &chunks[B->ChunkIndex];
+    if (C->ChunkFrameStamp != B->BlockFrameStamp) continue;                                     /* :152 */
+    int32_t off[3]; float origin[3], rel[3];
+    float inv_res = 1.0f / (float)scene->ChunkResolution;                                       /* :178 */
+    int octant = 0;
+    for (int i = 0; i < 3; i++) {
+      off[i] = (C->ChunkLocation[i] - cam->CameraChunkLocation[i]) * (int32_t)scene->ChunkResolution + (int32_t)B->BlockLocation[i]; /* :166-177 */
+      origin[i] = ((float)off[i] * inv_res) * scene->ChunkSize;                                 /* :179 */
+      rel[i] = origin[i] - cam->SubCameraLocation[i];                                           /* :181 */
+      if (rel[i] < 0.0f) octant |= 1 << i;                                                      /* :129-136 */
+    }
+    int faces[3]; orc_triplanar_faces(octant, faces);
+    for (int f = 0; f < 3; f++) {
+      int ax = faces[f] >> 1, pos = faces[f] & 1;
+      float corner = pos ? 0.5f : -0.5f;
+      float plane = (corner + 0.5f) * scene->BlockSize + origin[ax];                            /* :185 */
+      if (d[ax] == 0.0) continue;
+      double t = ((double)plane - eye[ax]) / d[ax];
+      if (!(t > 0.0)) continue;
+      double margin = INFINITY, local[3]; int ok = 1;
+      for (int b = 0; b < 3; b++) {
+        if (b == ax) { local[b] = pos ? 1.0 : 0.0; continue; }
+        double q = eye[b] + d[b] * t;
+        double lo = (double)origin[b], hi = (double)((-0.5f + 0.5f) * scene->BlockSize + origin[b]) + (double)scene->BlockSize;
+        if (q < lo || q > hi) { ok = 0; break; }
+        double m = fmin(q - lo, hi - q); if (m < margin) margin = m;
+        local[b] = (q - lo) / (double)scene->BlockSize;
+      }
+      if (!ok) continue;
+      if (t < best_t) {
+        /* margin also accounts for how close the runner-up is (depth ties at shared edges) */
+        best_margin = fmin(margin, found ? fabs(best_t - t) : INFINITY);
+        best_t = t; best_face = faces[f]; found = 1;
+        for (int b = 0; b < 3; b++) { best_blk[b] = off[b]; best_local[b] = local[b]; }
+      } else {
+        double gap = fabs(t - best_t); if (gap < best_margin) best_margin = gap;
+      }
+    }
+  }
+  if (!found) { out_rgba[0] = out_rgba[1] = out_rgba[2] = 0.0f; out_rgba[3] = 1.0f; return 0; }   /* clear: :315 */
+  for (int b = 0; b < 3; b++) { out_block[b] = best_blk[b]; out_rgba[b] = (float)((best_local[b] - 0.5) * 0.5 + 0.5); }
+  out_rgba[3] = 0.0f;
+  *out_face = best_face; *out_t = best_t; *out_margin = best_margin;
+  return 1;
+}
