@@ -1,0 +1,241 @@
+"""ctypes binding of libmeso_b200.so (include/meso_cuda.h).
+
+Plumbing only: every call goes straight through the C ABI to the hand-written CUDA kernels.  There is no Python or
+CPU implementation behind any of these methods; if the shared library is missing the import fails, and if no
+sm_100 device is present `Context()` raises with the library's own message.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libmeso_b200.so")
+
+GPUBlock = np.dtype([("ChunkIndex", "<u4"), ("BlockLocation", "u1", (4,)), ("BlockFrameStamp", "<u4")])
+GPUChunk = np.dtype([("ChunkLocation", "<i4", (3,)), ("ChunkFrameStamp", "<u4")])
+HitRecord = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("t", "<f4"), ("rgba", "<u4")])
+Quad = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("w2", "<u4"), ("w3", "<u4")])
+Camera = np.dtype([("Projection", "<f4", (16,)), ("View", "<f4", (16,)), ("CameraChunkLocation", "<i4", (4,)),
+                   ("SubCameraLocation", "<f4", (4,))])
+SceneConfig = np.dtype([("BlockSize", "<f4"), ("BlockResolution", "<u4"), ("ChunkSize", "<f4"), ("ChunkResolution", "<u4")])
+RaySetup = np.dtype([("o", "<f4", (3,)), ("two_over_w", "<f4"), ("U", "<f4", (3,)), ("two_over_h", "<f4"),
+                     ("V", "<f4", (3,)), ("pad0", "<f4"), ("F", "<f4", (3,)), ("pad1", "<f4"),
+                     ("L", "<f4", (3,)), ("pad2", "<f4")])
+RayStats = np.dtype([("primary", "<u8"), ("shadow", "<u8"), ("hits", "<u8"), ("steps", "<u8"),
+                     ("touched_chunks", "<u8"), ("touched_bricks", "<u8"), ("u_bytes", "<u8")])
+
+SDF_SPHERE, SDF_TERRAIN = 0, 1
+GRAN_BLOCK, GRAN_VOXEL = 0, 1
+FLAG_SHADOW = 1
+LAYOUT_FRAME, LAYOUT_TILES = 0, 1
+TILE_W, TILE_H = 32, 8
+
+# every symbol include/meso_cuda.h declares (tests/test_abi.py checks the header against this and the .so)
+SYMBOLS = [
+    "meso_last_error", "meso_abi_version", "meso_ctx_create", "meso_ctx_destroy", "meso_ctx_set_stream", "meso_ctx_sync",
+    "meso_ctx_set_partition", "meso_device_sm_count", "meso_scene_create", "meso_voxelize_sdf", "meso_volume_upload",
+    "meso_volume_num_partial", "meso_volume_download", "meso_build_occupancy", "meso_download_chunk_table",
+    "meso_download_mips", "meso_download_instances", "meso_ray_setup", "meso_raymarch", "meso_raymarch_device",
+    "meso_raymarch_stats", "meso_compose_tiles_device", "meso_tiles_per_rank", "meso_mesh", "meso_mesh_device",
+    "meso_carve_sphere", "meso_download_dirty", "meso_remesh_dirty", "meso_host_alloc", "meso_host_free",
+    "meso_flush_l2", "meso_launch_count",
+]
+
+
+class MesoError(RuntimeError):
+    pass
+
+
+def load():
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            "mesoengine_b200: %s is missing -- build it with `python -m mesoengine_b200.build` (nvcc, sm_100a). "
+            "There is no CPU fallback." % SO_PATH)
+    lib = C.CDLL(SO_PATH)
+    lib.meso_last_error.restype = C.c_char_p
+    lib.meso_tiles_per_rank.restype = C.c_int64
+    lib.meso_launch_count.restype = C.c_int64
+    lib.meso_launch_count.argtypes = [C.c_void_p]
+    lib.meso_device_sm_count.argtypes = [C.c_void_p]
+    return lib
+
+
+lib = load()
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+def _ck(code):
+    if code != 0:
+        raise MesoError("libmeso_b200 error %d: %s" % (code, lib.meso_last_error().decode()))
+
+
+def default_scene_config():
+    s = np.zeros(1, dtype=SceneConfig)
+    s["BlockSize"] = 1.0
+    s["BlockResolution"] = 8
+    s["ChunkSize"] = 16.0
+    s["ChunkResolution"] = 16
+    return s
+
+
+def ray_setup(cam, origin_chunk, width, height, light=(0.3, 0.5, 0.8)):
+    """Pure host function of the ABI (no device needed)."""
+    rs = np.zeros(1, dtype=RaySetup)
+    o = np.ascontiguousarray(origin_chunk, dtype=np.int32)
+    l = np.ascontiguousarray(light, dtype=np.float32)
+    _ck(lib.meso_ray_setup(_p(cam), _p(o), C.c_int(width), C.c_int(height), _p(l), _p(rs)))
+    return rs
+
+
+def tiles_per_rank(width, height, world):
+    return int(lib.meso_tiles_per_rank(C.c_int(width), C.c_int(height), C.c_int(world)))
+
+
+class Context:
+    """One GPU, one stream.  Mirrors the role of lvk::IContext for the voxel path."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _ck(lib.meso_ctx_create(C.c_int(device), C.byref(h)))
+        self.h = h
+        self.origin = None
+        self.dims = None
+        self.nchunks = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib.meso_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        _ck(lib.meso_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        _ck(lib.meso_ctx_sync(self.h))
+
+    def set_partition(self, rank, world):
+        _ck(lib.meso_ctx_set_partition(self.h, C.c_int(rank), C.c_int(world)))
+        self.rank, self.world = rank, world
+
+    def sm_count(self):
+        return int(lib.meso_device_sm_count(self.h))
+
+    def launch_count(self):
+        return int(lib.meso_launch_count(self.h))
+
+    def scene_create(self, origin_chunk, dims_chunks, max_bricks, cfg=None):
+        cfg = default_scene_config() if cfg is None else cfg
+        self.origin = np.ascontiguousarray(origin_chunk, dtype=np.int32)
+        self.dims = np.ascontiguousarray(dims_chunks, dtype=np.int32)
+        self.nchunks = int(np.prod(self.dims.astype(np.int64)))
+        _ck(lib.meso_scene_create(self.h, _p(cfg), _p(self.origin), _p(self.dims), C.c_uint32(max_bricks)))
+
+    def voxelize_sdf(self, kind, params=None, granularity=GRAN_VOXEL):
+        p = np.zeros(4, dtype=np.float64)
+        if params is not None:
+            p[: len(params)] = np.asarray(params, dtype=np.float64)
+        _ck(lib.meso_voxelize_sdf(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
+
+    def volume_upload(self, occ, full, keys, payload):
+        occ = np.ascontiguousarray(occ, dtype=np.uint64)
+        full = np.ascontiguousarray(full, dtype=np.uint64)
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        payload = np.ascontiguousarray(payload, dtype=np.uint64)
+        _ck(lib.meso_volume_upload(self.h, _p(occ), _p(full), _p(keys), _p(payload), C.c_int64(len(keys))))
+
+    def volume_download(self):
+        occ = np.zeros((self.nchunks, 64), dtype=np.uint64)
+        full = np.zeros((self.nchunks, 64), dtype=np.uint64)
+        n = C.c_int64(0)
+        _ck(lib.meso_volume_download(self.h, _p(occ), _p(full), None, None, C.c_int64(0), C.byref(n)))
+        keys = np.zeros(max(n.value, 1), dtype=np.uint64)
+        payload = np.zeros((max(n.value, 1), 8), dtype=np.uint64)
+        if n.value:
+            _ck(lib.meso_volume_download(self.h, _p(occ), _p(full), _p(keys), _p(payload), C.c_int64(n.value), C.byref(n)))
+        return occ, full, keys[: n.value], payload[: n.value]
+
+    def build_occupancy(self, stamp=1):
+        n = C.c_int64(0)
+        _ck(lib.meso_build_occupancy(self.h, C.c_uint32(stamp), C.byref(n)))
+        return n.value
+
+    def download_occupancy(self, n_inst):
+        table = np.zeros(self.nchunks, dtype=GPUChunk)
+        mips = np.zeros((self.nchunks, 3, 64), dtype=np.uint64)
+        inst = np.zeros(max(n_inst, 1), dtype=GPUBlock)
+        _ck(lib.meso_download_chunk_table(self.h, _p(table)))
+        _ck(lib.meso_download_mips(self.h, _p(mips)))
+        _ck(lib.meso_download_instances(self.h, _p(inst), C.c_int64(max(n_inst, 1))))
+        return table, mips, inst[:n_inst]
+
+    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None):
+        """End-to-end call: camera from host memory, records into host memory."""
+        rec = out if out is not None else np.zeros((height, width), dtype=HitRecord)
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(FLAG_SHADOW if shadow else 0),
+                              _p(l), _p(rec)))
+        return rec
+
+    def raymarch_device(self, cam, width, height, d_records, shadow=True, light=(0.3, 0.5, 0.8), layout=LAYOUT_FRAME):
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
+                                     C.c_uint32(FLAG_SHADOW if shadow else 0), _p(l), C.c_void_p(d_records), C.c_int(layout)))
+
+    def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8)):
+        st = np.zeros(1, dtype=RayStats)
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        _ck(lib.meso_raymarch_stats(self.h, _p(cam), C.c_int(width), C.c_int(height),
+                                    C.c_uint32(FLAG_SHADOW if shadow else 0), _p(l), _p(st)))
+        return st[0]
+
+    def compose_tiles_device(self, d_tiles, world, width, height, d_frame):
+        _ck(lib.meso_compose_tiles_device(self.h, C.c_void_p(d_tiles), C.c_int(world), C.c_int(width), C.c_int(height),
+                                          C.c_void_p(d_frame)))
+
+    def mesh(self, cap):
+        q = np.zeros(max(cap, 1), dtype=Quad)
+        n = C.c_int64(0)
+        _ck(lib.meso_mesh(self.h, _p(q), C.c_int64(cap), C.byref(n)))
+        if n.value > cap:
+            raise MesoError("mesh: %d quads exceed cap %d" % (n.value, cap))
+        return q[: n.value]
+
+    def mesh_device(self, d_quads, cap, want_count=True):
+        n = C.c_int64(0)
+        _ck(lib.meso_mesh_device(self.h, C.c_void_p(d_quads), C.c_int64(cap), C.byref(n) if want_count else None))
+        return n.value
+
+    def carve_sphere(self, center, radius):
+        c = np.ascontiguousarray(center, dtype=np.int32)
+        n = C.c_int64(0)
+        _ck(lib.meso_carve_sphere(self.h, _p(c), C.c_int32(radius), C.byref(n)))
+        return n.value
+
+    def download_dirty(self, n):
+        keys = np.zeros(max(n, 1), dtype=np.uint64)
+        _ck(lib.meso_download_dirty(self.h, _p(keys), C.c_int64(max(n, 1))))
+        return keys[:n]
+
+    def remesh_dirty(self, cap, cap_keys):
+        q = np.zeros(max(cap, 1), dtype=Quad)
+        keys = np.zeros(max(cap_keys, 1), dtype=np.uint64)
+        n = C.c_int64(0)
+        nk = C.c_int64(0)
+        _ck(lib.meso_remesh_dirty(self.h, _p(q), C.c_int64(cap), C.byref(n), _p(keys), C.c_int64(cap_keys), C.byref(nk)))
+        if n.value > cap:
+            raise MesoError("remesh: %d quads exceed cap %d" % (n.value, cap))
+        return q[: n.value], keys[: nk.value]
+
+    def flush_l2(self):
+        _ck(lib.meso_flush_l2(self.h))

@@ -1,0 +1,297 @@
+// k_raymarch.cu -- K4: per-pixel 3D-DDA through chunk (128^3) -> brick (8^3) -> voxel, primary + one hard-shadow ray.
+//
+// Replaces the reference's per-pixel visibility: the 1 M-instance triangle-fan draw + reverse-Z depth test
+// (Samples/SimpleVoxel.cpp:146-192 VS, :220-224 FS, dispatch :352-398) -- see DESIGN.md for the equivalence.
+//
+// The DDA is STATELESS (DESIGN.md "DDA"): the crossing time of integer voxel plane p on axis a is always
+//     t_a(p) = (float(p) - o_a) * inv_a          one FSUB + one FMUL, never fused (-fmad=false)
+// and crossings are consumed in the total order (t, axis).  Skipping an empty chunk or brick re-derives the two other
+// coordinates from the same keys, so the hierarchical walk visits exactly the voxels a flat one would: hit voxel,
+// face and t are bit-identical to oracle/orc_raymarch.c.
+//
+// Mapping: CTA = one 32x8 screen tile (8 warps), warp = 8x4 pixels (a 128 B-aligned 4-line store of 16 B records),
+// chunk-level any-bits staged in shared memory.  Multi-GPU: tile t belongs to rank t % world.
+#include "meso_internal.cuh"
+
+struct Ray {
+  float o[3], d[3], inv[3];
+  int step[3];
+};
+
+__device__ __forceinline__ float plane_t(const Ray& r, int a, int plane) {
+  return __fmul_rn(__fsub_rn((float)plane, r.o[a]), r.inv[a]);
+}
+__device__ __forceinline__ bool key_less(float t1, int a1, float t2, int a2) { return t1 < t2 || (t1 == t2 && a1 < a2); }
+
+__device__ __forceinline__ void ray_init(Ray& r, const float o[3], const float d[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    r.o[i] = o[i]; r.d[i] = d[i];
+    if (fabsf(d[i]) >= 1e-20f) { r.inv[i] = __fdiv_rn(1.0f, d[i]); r.step[i] = d[i] > 0.0f ? 1 : -1; }
+    else { r.inv[i] = 0.0f; r.step[i] = 0; }
+  }
+}
+
+__device__ __forceinline__ int clamp_floor_to_int(float x) {
+  float f = floorf(x);
+  f = fminf(fmaxf(f, -1.0e9f), 1.0e9f);
+  return (int)f;
+}
+
+// coordinate on axis b after consuming every crossing with key < (ts, as), starting from cell coordinate cur
+__device__ __forceinline__ int advance_axis(const Ray& r, int b, int cur, float ts, int as) {
+  const int st = r.step[b];
+  if (st == 0) return cur;
+  int e = clamp_floor_to_int(__fadd_rn(r.o[b], __fmul_rn(r.d[b], ts)));
+  if (st > 0) e = max(e, cur); else e = min(e, cur);
+  for (;;) {
+    const int pa = st > 0 ? e + 1 : e;
+    if (key_less(plane_t(r, b, pa), b, ts, as)) e += st; else break;
+  }
+  for (;;) {
+    if (e == cur) break;
+    const int pb = st > 0 ? e : e + 1;
+    if (!key_less(plane_t(r, b, pb), b, ts, as)) e -= st; else break;
+  }
+  return e;
+}
+
+struct Scene {
+  const DVolume* v;
+  const uint32_t* s_any;  // shared-memory copy of the chunk-level any-bits
+  uint8_t* touch_chunk;
+  uint8_t* touch_brick;
+};
+
+__device__ __forceinline__ bool inside(const DVolume& v, const int c[3]) {
+  return (unsigned)c[0] < (unsigned)v.nvox[0] && (unsigned)c[1] < (unsigned)v.nvox[1] && (unsigned)c[2] < (unsigned)v.nvox[2];
+}
+__device__ __forceinline__ bool gone(const DVolume& v, const Ray& r, const int c[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (r.step[i] > 0) { if (c[i] >= v.nvox[i]) return true; }
+    else if (r.step[i] < 0) { if (c[i] < 0) return true; }
+    else if (c[i] < 0 || c[i] >= v.nvox[i]) return true;
+  }
+  return false;
+}
+
+// 0 = solid voxel, 1 = empty voxel of a partial brick, 8 = empty brick, 128 = empty chunk
+template <bool STATS>
+__device__ __forceinline__ int cell_level(const Scene& s, const int c[3]) {
+  const DVolume& v = *s.v;
+  const int64_t ci = chunk_index(v, c[0] >> 7, c[1] >> 7, c[2] >> 7);
+  if (!((s.s_any[ci >> 5] >> (ci & 31)) & 1u)) return MESO_CV;
+  if (STATS) s.touch_chunk[ci] = 1;
+  const int b = block_bit((c[0] >> 3) & 15, (c[1] >> 3) & 15, (c[2] >> 3) & 15);
+  const uint64_t occ = __ldg(&v.occ[ci * 64 + (b >> 6)]);
+  if (!((occ >> (b & 63)) & 1ull)) return MESO_BR;
+  const uint64_t full = __ldg(&v.full[ci * 64 + (b >> 6)]);
+  if ((full >> (b & 63)) & 1ull) return 0;
+  const uint32_t slot = __ldg(&v.bptr[ci * MESO_BLOCKS + b]);
+  if (STATS) s.touch_brick[slot] = 1;
+  const uint64_t sl = __ldg(&v.pool[(size_t)slot * 8 + (c[2] & 7)]);
+  return ((sl >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1ull) ? 0 : 1;
+}
+
+struct Trace { bool hit; int c[3]; int axis; float t; unsigned steps; };
+
+template <bool STATS>
+__device__ __forceinline__ void trace(const Scene& s, const Ray& r, const int c0[3], Trace& tr) {
+  const DVolume& v = *s.v;
+  tr.hit = false; tr.axis = -1; tr.t = 0.0f; tr.steps = 0;
+  int c[3] = {c0[0], c0[1], c0[2]};
+  bool alive = true;
+  if (!inside(v, c)) {
+    if (gone(v, r, c)) alive = false;
+    else {
+      int a = -1; float ta = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const bool before = (r.step[i] > 0 && c[i] < 0) || (r.step[i] < 0 && c[i] >= v.nvox[i]);
+        if (before) {
+          const float ti = plane_t(r, i, r.step[i] > 0 ? 0 : v.nvox[i]);
+          if (a < 0 || key_less(ta, a, ti, i)) { a = i; ta = ti; }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        if (b == a) c[b] = r.step[b] > 0 ? 0 : v.nvox[b] - 1;
+        else c[b] = advance_axis(r, b, c[b], ta, a);
+      }
+      tr.axis = a; tr.t = ta; tr.steps++;
+      alive = inside(v, c);
+    }
+  }
+  while (alive) {
+    const int L = cell_level<STATS>(s, c);
+    if (L == 0) { tr.hit = true; break; }
+    int a = -1; float ta = 0.0f; int pl_a = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (r.step[i] != 0) {
+        const int base = c[i] & ~(L - 1);
+        const int pl = r.step[i] > 0 ? base + L : base;
+        const float ti = plane_t(r, i, pl);
+        if (a < 0 || key_less(ti, i, ta, a)) { a = i; ta = ti; pl_a = pl; }
+      }
+    }
+    if (a < 0) break;
+    if (L == 1) {
+#pragma unroll
+      for (int b = 0; b < 3; b++) if (b == a) c[b] += r.step[b];
+    } else {
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        if (b == a) c[b] = r.step[b] > 0 ? pl_a : pl_a - 1;
+        else c[b] = advance_axis(r, b, c[b], ta, a);
+      }
+    }
+    tr.axis = a; tr.t = ta; tr.steps++;
+    alive = inside(v, c);
+  }
+  tr.c[0] = c[0]; tr.c[1] = c[1]; tr.c[2] = c[2];
+}
+
+__device__ __forceinline__ uint32_t to_un8(float x) { return (uint32_t)__fadd_rn(__fmul_rn(x, 255.0f), 0.5f); }
+
+template <bool STATS>
+__global__ void __launch_bounds__(256) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
+                                                       int rank, int world, int layout, int tiles_x, int n_tiles,
+                                                       MesoHitRecord* __restrict__ out, RayStatsDev* stats,
+                                                       uint8_t* touch_chunk, uint8_t* touch_brick) {
+  extern __shared__ uint32_t s_any[];
+  for (int i = threadIdx.x; i < v.chunk_words; i += blockDim.x) s_any[i] = v.chunk_any[i];
+  __syncthreads();
+  const int local_tile = blockIdx.x;
+  const int tile = local_tile * world + rank;
+  if (tile >= n_tiles) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = (warp & 3) * 8 + (lane & 7), ty = (warp >> 2) * 4 + (lane >> 3);
+  const int px = (tile % tiles_x) * MESO_TILE_W + tx;
+  const int py = (tile / tiles_x) * MESO_TILE_H + ty;
+  if (px >= width || py >= height) return;
+
+  Scene sc; sc.v = &v; sc.s_any = s_any; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
+
+  const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)px, 0.5f), rs.two_over_w), 1.0f);
+  const float fy = __fsub_rn(1.0f, __fmul_rn(__fadd_rn((float)py, 0.5f), rs.two_over_h));
+  float d[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) d[i] = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[i]), __fmul_rn(fy, rs.V[i])), rs.F[i]);
+  const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+  for (int i = 0; i < 3; i++) d[i] = __fdiv_rn(d[i], len);
+  Ray r; ray_init(r, rs.o, d);
+  int c0[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) c0[i] = clamp_floor_to_int(rs.o[i]);
+  Trace tr;
+  trace<STATS>(sc, r, c0, tr);
+  unsigned steps = tr.steps, n_shadow = 0;
+
+  MesoHitRecord rec;
+  if (!tr.hit) {
+    rec.w0 = 0xFFFFFFFFu; rec.w1 = 0x0007FFFFu; rec.t = __int_as_float(0x7F800000); rec.rgba = 0xFF000000u;
+  } else {
+    int face = 6, shadow = 0;
+    float p[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) p[i] = __fadd_rn(r.o[i], __fmul_rn(r.d[i], tr.t));
+    if (tr.axis >= 0) {
+      const int ax = tr.axis;
+      int st_ax = 0; float l_ax = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 3; i++) if (i == ax) { st_ax = r.step[i]; l_ax = rs.L[i]; p[i] = (float)(r.step[i] > 0 ? tr.c[i] : tr.c[i] + 1); }
+      face = ax * 2 + (st_ax > 0 ? 0 : 1);
+      if (flags & MESO_FLAG_SHADOW) {
+        const bool facing = st_ax > 0 ? (l_ax < 0.0f) : (l_ax > 0.0f);
+        if (!facing) shadow = 1;
+        else {
+          Ray sr; ray_init(sr, p, rs.L);
+          int sc0[3];
+#pragma unroll
+          for (int i = 0; i < 3; i++) sc0[i] = tr.c[i] - (i == ax ? st_ax : 0);
+          Trace st;
+          trace<STATS>(sc, sr, sc0, st);
+          steps += st.steps; n_shadow = 1;
+          shadow = st.hit ? 1 : 0;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++) p[i] = r.o[i];
+    }
+    const float shade = shadow ? 0.5f : 1.0f;
+    uint32_t ch[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float local = __fsub_rn(__fmul_rn(p[i], 0.125f), (float)(tr.c[i] >> 3));
+      local = fminf(fmaxf(local, 0.0f), 1.0f);
+      const float col = __fadd_rn(__fmul_rn(__fsub_rn(local, 0.5f), 0.5f), 0.5f);  // SimpleVoxel.cpp:222
+      ch[i] = to_un8(__fmul_rn(col, shade));
+    }
+    rec.w0 = (uint32_t)tr.c[0] | ((uint32_t)tr.c[1] << 16);
+    rec.w1 = (uint32_t)tr.c[2] | ((uint32_t)face << 16) | ((uint32_t)shadow << 19) | (1u << 20);
+    rec.t = tr.t;
+    rec.rgba = ch[0] | (ch[1] << 8) | (ch[2] << 16);
+  }
+  size_t dst;
+  if (layout == MESO_LAYOUT_FRAME) dst = (size_t)py * width + px;
+  else dst = (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
+  reinterpret_cast<uint4*>(out)[dst] = make_uint4(rec.w0, rec.w1, __float_as_uint(rec.t), rec.rgba);
+
+  if (STATS) {
+    // warp-aggregate (full warps), one atomic per warp and counter
+    unsigned long long v0 = 1, v1 = n_shadow, v2 = tr.hit ? 1 : 0, v3 = steps;
+    const unsigned m = __activemask();
+    if (m == 0xffffffffu) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(m, v0, o); v1 += __shfl_xor_sync(m, v1, o);
+        v2 += __shfl_xor_sync(m, v2, o); v3 += __shfl_xor_sync(m, v3, o);
+      }
+    }
+    if (lane == 0 || m != 0xffffffffu) {
+      atomicAdd(&stats->primary, v0); atomicAdd(&stats->shadow, v1);
+      atomicAdd(&stats->hits, v2); atomicAdd(&stats->steps, v3);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) compose_tiles_kernel(const uint4* __restrict__ tiles, int world, int width, int height,
+                                                            int tiles_x, int n_tiles, int64_t tiles_per_rank, uint4* __restrict__ frame) {
+  const int tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  const int rank = tile % world; const int64_t local = tile / world;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int px = (tile % tiles_x) * MESO_TILE_W + tx, py = (tile / tiles_x) * MESO_TILE_H + ty;
+  if (px >= width || py >= height) return;
+  frame[(size_t)py * width + px] = tiles[((size_t)rank * tiles_per_rank + local) * 256 + threadIdx.x];
+}
+
+void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
+                     int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
+                     uint8_t* d_touch_brick) {
+  const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
+  const int n_tiles = tiles_x * tiles_y;
+  const int local_tiles = (n_tiles - rank + world - 1) / world;
+  if (local_tiles <= 0) return;
+  const size_t smem = sizeof(uint32_t) * (size_t)v.chunk_words;
+  if (d_stats)
+    raymarch_kernel<true><<<local_tiles, 256, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x, n_tiles,
+                                                                 d_out, d_stats, d_touch_chunk, d_touch_brick);
+  else
+    raymarch_kernel<false><<<local_tiles, 256, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x, n_tiles,
+                                                                  d_out, nullptr, nullptr, nullptr);
+  (*lc.launches)++;
+}
+
+void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame) {
+  const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
+  const int n_tiles = tiles_x * tiles_y;
+  const int64_t tpr = (n_tiles + world - 1) / world;
+  compose_tiles_kernel<<<n_tiles, 256, 0, lc.stream>>>(reinterpret_cast<const uint4*>(d_tiles), world, width, height, tiles_x,
+                                                       n_tiles, tpr, reinterpret_cast<uint4*>(d_frame));
+  (*lc.launches)++;
+}

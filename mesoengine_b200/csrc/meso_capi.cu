@@ -1,0 +1,581 @@
+// meso_capi.cu -- the C ABI of include/meso_cuda.h: context, device memory, stream plumbing, host-side ray setup.
+// No CPU fallback anywhere: every compute entry point needs a live CUDA device and fails loudly otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "meso_internal.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(MESO_ERR_RUNTIME, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+#define CK_LAST(what)                                                                                    \
+  do {                                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                                \
+    if (e__ != cudaSuccess) return fail(MESO_ERR_RUNTIME, std::string(what) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct MesoCtx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int rank = 0, world = 1;
+  int64_t launches = 0;
+  bool has_scene = false;
+  MesoGPUUniformSceneConfig cfg{};
+  DVolume v{};
+  // K2
+  MesoGPUChunk* d_table = nullptr;
+  uint32_t* d_counts = nullptr;
+  uint32_t* d_offsets = nullptr;
+  uint64_t* d_total = nullptr;
+  MesoGPUBlock* d_inst = nullptr;
+  int64_t cap_inst = 0;
+  int64_t n_inst = 0;
+  // K4
+  MesoHitRecord* d_frame = nullptr;
+  size_t frame_px = 0;
+  RayStatsDev* d_stats = nullptr;
+  uint8_t* d_touch_chunk = nullptr;
+  uint8_t* d_touch_brick = nullptr;
+  // K3
+  uint64_t* d_work = nullptr;
+  int64_t cap_work = 0;
+  uint32_t* d_work_count = nullptr;
+  unsigned long long* d_quad_count = nullptr;
+  MesoQuad* d_quads = nullptr;
+  int64_t cap_quads = 0;
+  // K5
+  uint64_t* d_dirty = nullptr;
+  uint32_t* d_dirty_count = nullptr;
+  uint32_t cap_dirty = 0;
+  uint32_t n_dirty = 0;
+  uint64_t* d_keys = nullptr;
+  uint32_t* d_keys_count = nullptr;
+  uint32_t* d_mark = nullptr;
+  int* d_overflow = nullptr;
+  // misc
+  uint32_t* d_flush = nullptr;
+  size_t flush_words = 0;
+  uint32_t* d_tmp_count = nullptr;
+
+  LaunchCtx lc() { return LaunchCtx{stream, sm_count, &launches}; }
+};
+
+extern "C" {
+
+const char* meso_last_error(void) { return g_err.c_str(); }
+int meso_abi_version(void) { return 1; }
+
+int meso_ctx_create(int device, MesoCtx** out) {
+  if (!out) return fail(MESO_ERR_ARGUMENT, "meso_ctx_create: out is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(MESO_ERR_RUNTIME, std::string("meso_ctx_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail(MESO_ERR_ARGUMENT, "meso_ctx_create: device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(MESO_ERR_RUNTIME, std::string("meso_ctx_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor) + "; libmeso_b200 carries sm_100a code only");
+  MesoCtx* c = new MesoCtx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  CK(cudaMalloc(&c->d_tmp_count, 16));
+  CK(cudaMalloc(&c->d_overflow, sizeof(int)));
+  CK(cudaMemset(c->d_overflow, 0, sizeof(int)));
+  *out = c;
+  return MESO_OK;
+}
+
+static void free_scene(MesoCtx* c) {
+  DVolume& v = c->v;
+  cudaFree(v.occ); cudaFree(v.full); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
+  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count);
+  cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
+  cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
+  cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
+  cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
+  v = DVolume{};
+  c->d_table = nullptr; c->d_counts = c->d_offsets = nullptr; c->d_total = nullptr; c->d_inst = nullptr;
+  c->d_frame = nullptr; c->frame_px = 0; c->d_stats = nullptr; c->d_touch_chunk = c->d_touch_brick = nullptr;
+  c->d_work = nullptr; c->d_work_count = nullptr; c->d_quad_count = nullptr; c->d_quads = nullptr; c->cap_quads = 0;
+  c->d_dirty = nullptr; c->d_dirty_count = nullptr; c->d_keys = nullptr; c->d_keys_count = nullptr; c->d_mark = nullptr;
+  c->has_scene = false;
+}
+
+int meso_ctx_destroy(MesoCtx* c) {
+  if (!c) return MESO_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_scene(c);
+  cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return MESO_OK;
+}
+
+int meso_ctx_set_stream(MesoCtx* c, void* s) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return MESO_OK;
+}
+
+int meso_ctx_sync(MesoCtx* c) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+
+int meso_ctx_set_partition(MesoCtx* c, int rank, int world) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  if (world < 1 || rank < 0 || rank >= world) return fail(MESO_ERR_ARGUMENT, "meso_ctx_set_partition: need 0 <= rank < world");
+  c->rank = rank; c->world = world;
+  return MESO_OK;
+}
+
+int meso_device_sm_count(MesoCtx* c) { return c ? c->sm_count : 0; }
+int64_t meso_launch_count(MesoCtx* c) { return c ? c->launches : 0; }
+
+int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const int32_t origin[3], const int32_t dims[3], uint32_t max_bricks) {
+  if (!c || !cfg || !origin || !dims) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: null argument");
+  // the kernels are specialised for the reference's constants (VoxelSceneConfig.h:22-24)
+  if (cfg->BlockResolution != 8 || cfg->ChunkResolution != 16 || cfg->BlockSize != 1.0f || cfg->ChunkSize != 16.0f)
+    return fail(MESO_ERR_ARGUMENT, "meso_scene_create: only BlockResolution 8, ChunkResolution 16, BlockSize 1, ChunkSize 16 are supported");
+  for (int i = 0; i < 3; i++)
+    if (dims[i] < 1 || dims[i] > 512) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: dims_chunks out of range [1,512]");
+  if (max_bricks == 0) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: max_bricks must be > 0");
+  CK(cudaSetDevice(c->device));
+  if (c->has_scene) { cudaStreamSynchronize(c->stream); free_scene(c); }
+  c->cfg = *cfg;
+  DVolume& v = c->v;
+  for (int i = 0; i < 3; i++) { v.dims[i] = dims[i]; v.nvox[i] = dims[i] * MESO_CV; v.origin[i] = origin[i]; }
+  v.nchunks = (int64_t)dims[0] * dims[1] * dims[2];
+  v.max_bricks = max_bricks;
+  v.chunk_words = (int)((v.nchunks + 31) / 32);
+  const size_t nc = (size_t)v.nchunks;
+  CK(cudaMalloc(&v.occ, nc * 64 * 8)); CK(cudaMalloc(&v.full, nc * 64 * 8)); CK(cudaMalloc(&v.mips, nc * 3 * 64 * 8));
+  CK(cudaMalloc(&v.bptr, nc * MESO_BLOCKS * 4));
+  CK(cudaMalloc(&v.pool, (size_t)max_bricks * 64));
+  CK(cudaMalloc(&v.chunk_any, (size_t)v.chunk_words * 4)); CK(cudaMalloc(&v.chunk_full, (size_t)v.chunk_words * 4));
+  CK(cudaMalloc(&v.pool_count, 4));
+  CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
+  CK(cudaMemsetAsync(v.mips, 0, nc * 3 * 64 * 8, c->stream));
+  CK(cudaMemsetAsync(v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
+  CK(cudaMemsetAsync(v.chunk_any, 0, (size_t)v.chunk_words * 4, c->stream));
+  CK(cudaMemsetAsync(v.chunk_full, 0, (size_t)v.chunk_words * 4, c->stream));
+  CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
+  CK(cudaMalloc(&c->d_table, nc * sizeof(MesoGPUChunk)));
+  CK(cudaMalloc(&c->d_counts, nc * 4)); CK(cudaMalloc(&c->d_offsets, nc * 4)); CK(cudaMalloc(&c->d_total, 8));
+  CK(cudaMalloc(&c->d_stats, sizeof(RayStatsDev)));
+  CK(cudaMalloc(&c->d_touch_chunk, nc)); CK(cudaMalloc(&c->d_touch_brick, max_bricks));
+  CK(cudaMalloc(&c->d_work_count, 4)); CK(cudaMalloc(&c->d_quad_count, 8));
+  c->cap_dirty = 1u << 22;
+  CK(cudaMalloc(&c->d_dirty, (size_t)c->cap_dirty * 8)); CK(cudaMalloc(&c->d_dirty_count, 4));
+  CK(cudaMalloc(&c->d_keys, (size_t)c->cap_dirty * 8)); CK(cudaMalloc(&c->d_keys_count, 4));
+  const size_t mark_words = (nc * MESO_BLOCKS + 31) / 32;
+  CK(cudaMalloc(&c->d_mark, mark_words * 4)); CK(cudaMemsetAsync(c->d_mark, 0, mark_words * 4, c->stream));
+  c->cap_inst = 0; c->n_inst = 0; c->n_dirty = 0;
+  c->has_scene = true;
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+
+#define NEED_SCENE(c)                                                               \
+  do {                                                                              \
+    if (!(c)) return fail(MESO_ERR_ARGUMENT, "null context");                       \
+    if (!(c)->has_scene) return fail(MESO_ERR_ARGUMENT, "no scene: call meso_scene_create first"); \
+    CK(cudaSetDevice((c)->device));                                                 \
+  } while (0)
+
+static int check_overflow(MesoCtx* c, const char* what) {
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (h) {
+    cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->stream);
+    return fail(MESO_ERR_RUNTIME, std::string(what) + ": brick payload pool exhausted (raise max_bricks in meso_scene_create)");
+  }
+  return MESO_OK;
+}
+
+int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granularity) {
+  NEED_SCENE(c);
+  if (kind != MESO_SDF_SPHERE && kind != MESO_SDF_TERRAIN) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown sdf kind");
+  if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown granularity");
+  if (kind == MESO_SDF_SPHERE && !params) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: sphere needs params");
+  launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
+  CK_LAST("voxelize");
+  return check_overflow(c, "meso_voxelize_sdf");
+}
+
+int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, const uint64_t* keys, const uint64_t* payload, int64_t n) {
+  NEED_SCENE(c);
+  if (!occ || !full || n < 0 || (n > 0 && (!keys || !payload))) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: null argument");
+  if ((uint64_t)n > c->v.max_bricks) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: more partial bricks than max_bricks");
+  const size_t nc = (size_t)c->v.nchunks;
+  for (int64_t i = 0; i < n; i++)
+    if (keys[i] >= (uint64_t)nc * MESO_BLOCKS) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: key out of range");
+  CK(cudaMemcpyAsync(c->v.occ, occ, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->v.full, full, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
+  const uint32_t n32 = (uint32_t)n;
+  CK(cudaMemcpyAsync(c->v.pool_count, &n32, 4, cudaMemcpyHostToDevice, c->stream));
+  uint64_t *d_k = nullptr, *d_p = nullptr;
+  if (n > 0) {
+    CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_p, (size_t)n * 64));
+    CK(cudaMemcpyAsync(d_k, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_p, payload, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream));
+    launch_scatter_payload(c->lc(), c->v, d_k, d_p, n);
+  }
+  launch_volume_finalize(c->lc(), c->v);
+  CK_LAST("volume upload");
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_k); cudaFree(d_p);
+  return MESO_OK;
+}
+
+int meso_volume_num_partial(MesoCtx* c, int64_t* out) {
+  NEED_SCENE(c);
+  if (!out) return fail(MESO_ERR_ARGUMENT, "null out");
+  // live partial bricks (payload slots retired by carving are not counted)
+  const size_t nc = (size_t)c->v.nchunks;
+  std::vector<uint64_t> occ(nc * 64), full(nc * 64);
+  CK(cudaMemcpyAsync(occ.data(), c->v.occ, nc * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(full.data(), c->v.full, nc * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t n = 0;
+  for (size_t i = 0; i < nc * 64; i++) n += __builtin_popcountll(occ[i] & ~full[i]);
+  *out = n;
+  return MESO_OK;
+}
+
+int meso_volume_download(MesoCtx* c, uint64_t* occ, uint64_t* full, uint64_t* keys, uint64_t* payload, int64_t cap, int64_t* n_partial) {
+  NEED_SCENE(c);
+  if (!occ || !full || !n_partial) return fail(MESO_ERR_ARGUMENT, "meso_volume_download: null argument");
+  const size_t nc = (size_t)c->v.nchunks;
+  CK(cudaMemcpyAsync(occ, c->v.occ, nc * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(full, c->v.full, nc * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t n = 0;
+  for (size_t i = 0; i < nc * 64; i++) n += __builtin_popcountll(occ[i] & ~full[i]);
+  *n_partial = n;
+  if (n == 0 || !keys || !payload) return MESO_OK;
+  if (cap < n) return fail(MESO_ERR_ARGUMENT, "meso_volume_download: cap_partial too small");
+  uint64_t *d_k = nullptr, *d_p = nullptr;
+  CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_p, (size_t)n * 64));
+  launch_gather_partial(c->lc(), c->v, d_k, d_p, c->d_tmp_count);
+  CK_LAST("gather partial");
+  std::vector<uint64_t> k((size_t)n), p((size_t)n * 8);
+  CK(cudaMemcpyAsync(k.data(), d_k, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(p.data(), d_p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_k); cudaFree(d_p);
+  // canonical order: ascending key (the device gathers in atomic order)
+  std::vector<int64_t> idx((size_t)n);
+  for (int64_t i = 0; i < n; i++) idx[(size_t)i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return k[(size_t)a] < k[(size_t)b]; });
+  for (int64_t i = 0; i < n; i++) {
+    keys[i] = k[(size_t)idx[(size_t)i]];
+    memcpy(payload + i * 8, p.data() + (size_t)idx[(size_t)i] * 8, 64);
+  }
+  return MESO_OK;
+}
+
+int meso_build_occupancy(MesoCtx* c, uint32_t stamp, int64_t* n_instances) {
+  NEED_SCENE(c);
+  // capacity: every block of the grid could be emitted; size to the populated block count instead
+  const size_t nc = (size_t)c->v.nchunks;
+  std::vector<uint64_t> occ(nc * 64);
+  CK(cudaMemcpyAsync(occ.data(), c->v.occ, nc * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t blocks = 0;
+  for (size_t i = 0; i < nc * 64; i++) blocks += __builtin_popcountll(occ[i]);
+  if (blocks > c->cap_inst) {
+    cudaFree(c->d_inst); c->d_inst = nullptr;
+    c->cap_inst = blocks;
+    CK(cudaMalloc(&c->d_inst, (size_t)std::max<int64_t>(blocks, 1) * sizeof(MesoGPUBlock)));
+  }
+  launch_occupancy(c->lc(), c->v, stamp, c->d_table, c->d_counts, c->d_offsets, c->d_inst, c->cap_inst, c->d_total);
+  CK_LAST("occupancy");
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&total, c->d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->n_inst = (int64_t)total;
+  if (n_instances) *n_instances = c->n_inst;
+  return MESO_OK;
+}
+
+int meso_download_chunk_table(MesoCtx* c, MesoGPUChunk* out) {
+  NEED_SCENE(c);
+  if (!out) return fail(MESO_ERR_ARGUMENT, "null out");
+  CK(cudaMemcpyAsync(out, c->d_table, (size_t)c->v.nchunks * sizeof(MesoGPUChunk), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+int meso_download_mips(MesoCtx* c, uint64_t* out) {
+  NEED_SCENE(c);
+  if (!out) return fail(MESO_ERR_ARGUMENT, "null out");
+  CK(cudaMemcpyAsync(out, c->v.mips, (size_t)c->v.nchunks * 3 * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+int meso_download_instances(MesoCtx* c, MesoGPUBlock* out, int64_t cap) {
+  NEED_SCENE(c);
+  if (!out && c->n_inst > 0) return fail(MESO_ERR_ARGUMENT, "null out");
+  if (cap < c->n_inst) return fail(MESO_ERR_ARGUMENT, "meso_download_instances: cap too small");
+  if (c->n_inst > 0) CK(cudaMemcpyAsync(out, c->d_inst, (size_t)c->n_inst * sizeof(MesoGPUBlock), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+
+// Host-side ray setup, fp32, every operation written out; identical sequence to oracle/orc_camera.c:orc_ray_setup
+// (this TU is compiled with -fmad=false / host -ffp-contract=off, see build.py).
+int meso_ray_setup(const MesoGPUUniformCamera* cam, const int32_t origin_chunk[3], int width, int height, const float light_dir[3], MesoRaySetup* rs) {
+  if (!cam || !origin_chunk || !rs || width <= 0 || height <= 0) return fail(MESO_ERR_ARGUMENT, "meso_ray_setup: bad argument");
+  const float* V = cam->View; const float* P = cam->Projection;
+  memset(rs, 0, sizeof(*rs));
+  volatile float t0 = V[12], t1 = V[13], t2 = V[14];
+  for (int i = 0; i < 3; i++) {
+    volatile float m0 = V[i * 4 + 0] * t0; volatile float m1 = V[i * 4 + 1] * t1; volatile float m2 = V[i * 4 + 2] * t2;
+    volatile float s01 = m0 + m1; volatile float s = s01 + m2;
+    volatile float e = -s;
+    volatile float off = (float)((cam->CameraChunkLocation[i] - origin_chunk[i]) * MESO_CV);
+    volatile float e8 = e * 8.0f;
+    rs->o[i] = e8 + off;
+    rs->U[i] = V[i * 4 + 0] / P[0];
+    rs->V[i] = V[i * 4 + 1] / P[5];
+    rs->F[i] = -V[i * 4 + 2];
+  }
+  rs->two_over_w = 2.0f / (float)width;
+  rs->two_over_h = 2.0f / (float)height;
+  float lx = light_dir ? light_dir[0] : 0.3f, ly = light_dir ? light_dir[1] : 0.5f, lz = light_dir ? light_dir[2] : 0.8f;
+  volatile float xx = lx * lx; volatile float yy = ly * ly; volatile float zz = lz * lz;
+  volatile float sxy = xx + yy; volatile float sl = sxy + zz;
+  volatile float inv = 1.0f / sqrtf(sl);
+  rs->L[0] = lx * inv; rs->L[1] = ly * inv; rs->L[2] = lz * inv;
+  return MESO_OK;
+}
+
+static int ensure_frame(MesoCtx* c, size_t px) {
+  if (c->frame_px >= px) return MESO_OK;
+  cudaFree(c->d_frame); c->d_frame = nullptr; c->frame_px = 0;
+  CK(cudaMalloc(&c->d_frame, px * sizeof(MesoHitRecord)));
+  c->frame_px = px;
+  return MESO_OK;
+}
+
+int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3], void* d_records, int layout) {
+  NEED_SCENE(c);
+  if (!cam || !d_records || width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad argument");
+  if (layout != MESO_LAYOUT_FRAME && layout != MESO_LAYOUT_TILES) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad layout");
+  MesoRaySetup rs;
+  int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
+  if (r != MESO_OK) return r;
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr);
+  CK_LAST("raymarch");
+  return MESO_OK;
+}
+
+int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3], MesoHitRecord* host) {
+  NEED_SCENE(c);
+  if (!host) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: null host_records");
+  if (width <= 0 || height <= 0) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad size");
+  const size_t px = (size_t)width * height;
+  int r = ensure_frame(c, px);
+  if (r != MESO_OK) return r;
+  if (c->world > 1) CK(cudaMemsetAsync(c->d_frame, 0xFF, px * sizeof(MesoHitRecord), c->stream));  // other ranks' tiles: all-ones
+  r = meso_raymarch_device(c, cam, width, height, flags, light, c->d_frame, MESO_LAYOUT_FRAME);
+  if (r != MESO_OK) return r;
+  CK(cudaMemcpyAsync(host, c->d_frame, px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+
+int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3], MesoRayStats* out) {
+  NEED_SCENE(c);
+  if (!cam || !out || width <= 0 || height <= 0) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_stats: bad argument");
+  const size_t px = (size_t)width * height;
+  int r = ensure_frame(c, px);
+  if (r != MESO_OK) return r;
+  MesoRaySetup rs;
+  r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
+  if (r != MESO_OK) return r;
+  CK(cudaMemsetAsync(c->d_stats, 0, sizeof(RayStatsDev), c->stream));
+  CK(cudaMemsetAsync(c->d_touch_chunk, 0, (size_t)c->v.nchunks, c->stream));
+  CK(cudaMemsetAsync(c->d_touch_brick, 0, c->v.max_bricks, c->stream));
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick);
+  CK_LAST("raymarch stats");
+  RayStatsDev h;
+  std::vector<uint8_t> tc((size_t)c->v.nchunks), tb(c->v.max_bricks);
+  CK(cudaMemcpyAsync(&h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(tc.data(), c->d_touch_chunk, tc.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(tb.data(), c->d_touch_brick, tb.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  memset(out, 0, sizeof(*out));
+  out->primary = h.primary; out->shadow = h.shadow; out->hits = h.hits; out->steps = h.steps;
+  for (uint8_t x : tc) out->touched_chunks += x;
+  for (uint8_t x : tb) out->touched_bricks += x;
+  // DESIGN.md "algorithmic bytes": chunk any/full bit grids once + 1024 B of block masks per touched chunk + 68 B per touched brick
+  out->u_bytes = 2 * (uint64_t)((c->v.nchunks + 7) / 8) + 1024 * out->touched_chunks + 68 * out->touched_bricks;
+  return MESO_OK;
+}
+
+int64_t meso_tiles_per_rank(int width, int height, int world) {
+  if (width <= 0 || height <= 0 || world <= 0) return 0;
+  const int64_t tx = (width + MESO_TILE_W - 1) / MESO_TILE_W, ty = (height + MESO_TILE_H - 1) / MESO_TILE_H;
+  return (tx * ty + world - 1) / world;
+}
+
+int meso_compose_tiles_device(MesoCtx* c, const void* d_tiles, int world, int width, int height, void* d_frame) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  if (!d_tiles || !d_frame || world < 1 || width <= 0 || height <= 0) return fail(MESO_ERR_ARGUMENT, "meso_compose_tiles_device: bad argument");
+  CK(cudaSetDevice(c->device));
+  launch_compose_tiles(c->lc(), (const MesoHitRecord*)d_tiles, world, width, height, (MesoHitRecord*)d_frame);
+  CK_LAST("compose tiles");
+  return MESO_OK;
+}
+
+static int ensure_mesh_buffers(MesoCtx* c) {
+  if (!c->d_work) {
+    // worst case: every block of this rank's chunks
+    c->cap_work = c->v.nchunks * MESO_BLOCKS;
+    CK(cudaMalloc(&c->d_work, (size_t)c->cap_work * 8));
+  }
+  return MESO_OK;
+}
+
+int meso_mesh_device(MesoCtx* c, void* d_quads, int64_t cap, int64_t* n_quads) {
+  NEED_SCENE(c);
+  if (cap < 0 || (cap > 0 && !d_quads)) return fail(MESO_ERR_ARGUMENT, "meso_mesh_device: bad argument");
+  int r = ensure_mesh_buffers(c);
+  if (r != MESO_OK) return r;
+  launch_mesh(c->lc(), c->v, c->rank, c->world, c->d_work, c->d_work_count, (MesoQuad*)d_quads, cap, c->d_quad_count);
+  CK_LAST("mesh");
+  if (n_quads) {
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *n_quads = (int64_t)n;
+  }
+  return MESO_OK;
+}
+
+int meso_mesh(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads) {
+  NEED_SCENE(c);
+  if (!n_quads) return fail(MESO_ERR_ARGUMENT, "meso_mesh: n_quads is null");
+  if (cap > c->cap_quads) {
+    cudaFree(c->d_quads); c->d_quads = nullptr; c->cap_quads = 0;
+    CK(cudaMalloc(&c->d_quads, (size_t)cap * sizeof(MesoQuad)));
+    c->cap_quads = cap;
+  }
+  int r = meso_mesh_device(c, c->d_quads, cap, n_quads);
+  if (r != MESO_OK) return r;
+  const int64_t n = std::min<int64_t>(*n_quads, cap);
+  if (n > 0 && host) {
+    CK(cudaMemcpyAsync(host, c->d_quads, (size_t)n * sizeof(MesoQuad), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return MESO_OK;
+}
+
+int meso_carve_sphere(MesoCtx* c, const int32_t center[3], int32_t radius, int64_t* n_dirty) {
+  NEED_SCENE(c);
+  if (!center || radius < 0 || radius > 30000) return fail(MESO_ERR_ARGUMENT, "meso_carve_sphere: bad argument");
+  launch_carve(c->lc(), c->v, center, radius, c->d_dirty, c->cap_dirty, c->d_dirty_count, c->d_overflow);
+  CK_LAST("carve");
+  uint32_t n = 0;
+  CK(cudaMemcpyAsync(&n, c->d_dirty_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  int r = check_overflow(c, "meso_carve_sphere");
+  if (r != MESO_OK) return r;
+  if (n > c->cap_dirty) return fail(MESO_ERR_RUNTIME, "meso_carve_sphere: dirty list overflow");
+  c->n_dirty = n;
+  if (n_dirty) *n_dirty = n;
+  return MESO_OK;
+}
+
+int meso_download_dirty(MesoCtx* c, uint64_t* keys, int64_t cap) {
+  NEED_SCENE(c);
+  if (cap < (int64_t)c->n_dirty || (!keys && c->n_dirty)) return fail(MESO_ERR_ARGUMENT, "meso_download_dirty: cap too small");
+  if (c->n_dirty) CK(cudaMemcpyAsync(keys, c->d_dirty, (size_t)c->n_dirty * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  std::sort(keys, keys + c->n_dirty);
+  return MESO_OK;
+}
+
+int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads, uint64_t* host_keys, int64_t cap_keys, int64_t* n_keys) {
+  NEED_SCENE(c);
+  if (!n_quads) return fail(MESO_ERR_ARGUMENT, "meso_remesh_dirty: n_quads is null");
+  launch_expand_dirty(c->lc(), c->v, c->d_dirty, c->n_dirty, c->d_keys, c->cap_dirty, c->d_keys_count, c->d_mark);
+  CK_LAST("expand dirty");
+  uint32_t nk = 0;
+  CK(cudaMemcpyAsync(&nk, c->d_keys_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (nk > c->cap_dirty) {
+    cudaMemsetAsync(c->d_mark, 0, (((size_t)c->v.nchunks * MESO_BLOCKS + 31) / 32) * 4, c->stream);
+    return fail(MESO_ERR_RUNTIME, "meso_remesh_dirty: key list overflow");
+  }
+  if (n_keys) *n_keys = nk;
+  if (host_keys) {
+    if (cap_keys < (int64_t)nk) return fail(MESO_ERR_ARGUMENT, "meso_remesh_dirty: cap_keys too small");
+    if (nk) CK(cudaMemcpyAsync(host_keys, c->d_keys, (size_t)nk * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (cap > c->cap_quads) {
+    cudaFree(c->d_quads); c->d_quads = nullptr; c->cap_quads = 0;
+    CK(cudaMalloc(&c->d_quads, (size_t)cap * sizeof(MesoQuad)));
+    c->cap_quads = cap;
+  }
+  launch_mesh_list(c->lc(), c->v, c->d_keys, nk, c->d_quads, cap, c->d_quad_count);
+  CK_LAST("remesh");
+  unsigned long long n = 0;
+  CK(cudaMemcpyAsync(&n, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n_quads = (int64_t)n;
+  const int64_t m = std::min<int64_t>((int64_t)n, cap);
+  if (m > 0 && host) {
+    CK(cudaMemcpyAsync(host, c->d_quads, (size_t)m * sizeof(MesoQuad), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return MESO_OK;
+}
+
+int meso_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(MESO_ERR_ARGUMENT, "null out");
+  CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return MESO_OK;
+}
+int meso_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
+  return MESO_OK;
+}
+
+int meso_flush_l2(MesoCtx* c) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  CK(cudaSetDevice(c->device));
+  if (!c->d_flush) {
+    c->flush_words = (size_t)64 << 20;  // 256 MiB > 126 MB L2
+    CK(cudaMalloc(&c->d_flush, c->flush_words * 4));
+  }
+  launch_flush(c->lc(), c->d_flush, c->flush_words);
+  CK_LAST("flush");
+  return MESO_OK;
+}
+
+}  // extern "C"

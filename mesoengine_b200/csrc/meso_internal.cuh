@@ -1,0 +1,73 @@
+// meso_internal.cuh -- private declarations shared by the kernels and the C ABI (libmeso_b200.so).
+// Whole library is compiled with -fmad=false: every fp32/fp64 operation rounds exactly as written, which is what
+// makes hit voxels / faces / quads bit-identical to the CPU oracle (DESIGN.md "determinism").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/meso_cuda.h"
+
+#define MESO_CR 16
+#define MESO_BR 8
+#define MESO_CV 128
+#define MESO_WORDS 64
+#define MESO_BLOCKS 4096
+
+// Device view of the resident volume.  Chunk slot == linear grid index cx + dx*(cy + dy*cz); everything dense per
+// chunk except brick payloads (pool, 64 B each, allocated for partial bricks only).
+struct DVolume {
+  int dims[3];          // chunks
+  int nvox[3];          // voxels
+  int origin[3];        // chunk coordinates of the grid minimum
+  int64_t nchunks;
+  uint64_t* occ;        // nchunks*64   block present (Mip0)
+  uint64_t* full;       // nchunks*64   brick all-solid
+  uint64_t* mips;       // nchunks*3*64 erode Mip1..3
+  uint32_t* bptr;       // nchunks*4096 payload slot of partial bricks (0xFFFFFFFF otherwise)
+  uint64_t* pool;       // max_bricks*8 words
+  uint32_t* chunk_any;  // bit per chunk: has >=1 block
+  uint32_t* chunk_full; // bit per chunk: all 4096 bricks full
+  uint32_t* pool_count; // device counter: payload slots in use
+  uint32_t max_bricks;
+  int chunk_words;      // number of u32 words in chunk_any / chunk_full
+};
+
+struct RayStatsDev {
+  unsigned long long primary, shadow, hits, steps;
+};
+
+// ---- launch wrappers (one per .cu) -------------------------------------------------------------------------
+struct LaunchCtx {
+  cudaStream_t stream;
+  int sm_count;
+  int64_t* launches;
+};
+
+void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* d_overflow);
+void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v);  // chunk_any / chunk_full bit grids
+void launch_scatter_payload(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, const uint64_t* d_payload, int64_t n);
+void launch_gather_partial(const LaunchCtx& lc, const DVolume& v, uint64_t* d_keys, uint64_t* d_payload, uint32_t* d_count);
+
+void launch_occupancy(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, MesoGPUChunk* d_table, uint32_t* d_counts,
+                      uint32_t* d_offsets, MesoGPUBlock* d_inst, int64_t cap_inst, uint64_t* d_total);
+
+void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
+                     int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
+                     uint8_t* d_touch_brick);
+void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
+
+void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
+                 MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count);
+void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
+                      int64_t cap, unsigned long long* d_quad_count);
+
+void launch_carve(const LaunchCtx& lc, const DVolume& v, const int32_t center[3], int32_t radius, uint64_t* d_dirty,
+                  uint32_t cap_dirty, uint32_t* d_dirty_count, int* d_overflow);
+void launch_expand_dirty(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_dirty, uint32_t n_dirty, uint64_t* d_keys,
+                         uint32_t cap, uint32_t* d_count, uint32_t* d_mark);
+void launch_flush(const LaunchCtx& lc, uint32_t* d_scratch, size_t n_words);
+
+// ---- small device helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t chunk_index(const DVolume& v, int cx, int cy, int cz) {
+  return (int64_t)cx + (int64_t)v.dims[0] * ((int64_t)cy + (int64_t)v.dims[1] * (int64_t)cz);
+}
+__device__ __forceinline__ int block_bit(int x, int y, int z) { return x + 16 * y + 256 * z; }

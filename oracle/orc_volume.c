@@ -78,16 +78,16 @@ static void set_brick(OrcVolume* v, int64_t c, int b, const uint64_t s[8]) {
   uint64_t any = 0, all = ~0ull;
   for (int z = 0; z < 8; z++) { any |= s[z]; all &= s[z]; }
   uint64_t* occ = v->occ + c * ORC_WORDS; uint64_t* full = v->full + c * ORC_WORDS;
+  pthread_mutex_lock(&v->lock); /* X slabs of one chunk share occupancy words */
   orc_setbit(occ, b, any != 0);
   orc_setbit(full, b, all == ~0ull);
   if (any != 0 && all != ~0ull) {
-    pthread_mutex_lock(&v->lock);
     if (!v->bptr[c]) { v->bptr[c] = (uint32_t*)malloc(sizeof(uint32_t) * ORC_BLOCKS); memset(v->bptr[c], 0xFF, sizeof(uint32_t) * ORC_BLOCKS); }
     uint32_t idx = v->bptr[c][b];
     if (idx == 0xFFFFFFFFu) { idx = orc_alloc_payload(v); v->bptr[c][b] = idx; }
     memcpy(v->pool + (size_t)idx * 8, s, sizeof(uint64_t) * 8);
-    pthread_mutex_unlock(&v->lock);
   }
+  pthread_mutex_unlock(&v->lock);
 }
 
 typedef struct { OrcVolume* v; int kind; const double* params; int gran; int sin_mode; } VoxArg;
@@ -97,7 +97,9 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
   (void)tid;
   VoxArg* a = (VoxArg*)ctx; OrcVolume* v = a->v;
   const double BlockSize = 1.0;
-  for (int64_t c = b; c < e; c++) {
+  for (int64_t item = b; item < e; item++) {
+    /* work item = (chunk, X slab) for voxel granularity, whole chunk for block granularity */
+    int64_t c = a->gran == ORC_GRAN_BLOCK ? item : item / ORC_CR;
     int cx = (int)(c % v->dims[0]), cy = (int)((c / v->dims[0]) % v->dims[1]), cz = (int)(c / ((int64_t)v->dims[0] * v->dims[1]));
     int32_t loc[3] = {v->origin[0] + cx, v->origin[1] + cy, v->origin[2] + cz};
     if (a->gran == ORC_GRAN_BLOCK) {
@@ -107,7 +109,8 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
       for (int i = 0; i < n; i++) set_brick(v, c, orc_bidx(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), ones);
     } else {
       double cs[3]; for (int k = 0; k < 3; k++) cs[k] = (double)loc[k] * BlockSize * (double)ORC_CR;
-      for (int X = 0; X < ORC_CR; X++) for (int Y = 0; Y < ORC_CR; Y++) for (int Z = 0; Z < ORC_CR; Z++) {
+      int X = (int)(item % ORC_CR);
+      for (int Y = 0; Y < ORC_CR; Y++) for (int Z = 0; Z < ORC_CR; Z++) {
         double bc[3] = {cs[0] + (double)X * BlockSize, cs[1] + (double)Y * BlockSize, cs[2] + (double)Z * BlockSize};
         uint64_t s[8];
         for (int vz = 0; vz < 8; vz++) {
@@ -126,7 +129,7 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
 void orc_volume_voxelize(OrcVolume* v, int kind, const double params[4], int gran, int sin_mode, int nthreads) {
   clear_volume(v);
   VoxArg a = {v, kind, params, gran, sin_mode};
-  orc_parallel_for(v->nchunks, nthreads, 1, vox_range, &a);
+  orc_parallel_for(gran == ORC_GRAN_BLOCK ? v->nchunks : v->nchunks * ORC_CR, nthreads, 1, vox_range, &a);
 }
 
 int64_t orc_volume_num_chunks(const OrcVolume* v) { return v->nchunks; }

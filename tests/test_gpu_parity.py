@@ -1,0 +1,280 @@
+"""GPU parity tests: every kernel, called through the C ABI (libmeso_b200.so), against the CPU oracle on the same
+inputs.  Bar: bit-exact (integer/bit outputs and, because both sides avoid fma, also t and rgba)."""
+import numpy as np
+import pytest
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mesoengine_b200 import capi as _capi
+    return _capi
+
+
+@pytest.fixture(scope="module")
+def ctx(capi):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _make(ctx, orc, origin, dims, kind, params, gran, max_bricks=1 << 18):
+    ctx.scene_create(origin, dims, max_bricks)
+    ctx.voxelize_sdf(kind, params, gran)
+    vol = orc.Volume(origin, dims).voxelize(kind, params, granularity=gran, sin_mode=orc.SIN_PORTABLE)
+    return vol
+
+
+def _assert_volume_equal(ctx, vol):
+    occ, full, keys, payload = ctx.volume_download()
+    assert np.array_equal(occ, vol.occ())
+    assert np.array_equal(full, vol.full())
+    k2, p2 = vol.export_partial()
+    assert np.array_equal(keys, k2)
+    assert np.array_equal(payload, p2)
+
+
+# ---- K1 -------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_voxelize_sphere_voxel(ctx, orc, n):
+    origin, dims, params = scenes.sphere_scene(n)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    assert vol.num_partial() > 0
+    _assert_volume_equal(ctx, vol)
+
+
+def test_voxelize_reference_sphere_blocks(ctx, orc):
+    """The reference configuration itself: GenerateSphere over the 8^3 chunks that contain it, one sample per block."""
+    origin, dims, params = scenes.sphere_scene(1024)
+    assert params == scenes.REF_SPHERE
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_BLOCK)
+    assert vol.num_partial() == 0
+    _assert_volume_equal(ctx, vol)
+    assert vol.count_voxels() == 523155 * 512  # block count of the reference sphere (tests/test_oracle_kat.py)
+
+
+def test_voxelize_terrain_voxel(ctx, orc):
+    origin, dims = (0, -1, 0), (1, 2, 1)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_TERRAIN, None, orc.GRAN_VOXEL)
+    assert 0 < vol.num_partial()
+    _assert_volume_equal(ctx, vol)
+
+
+def test_voxelize_terrain_blocks_with_cull_band(ctx, orc):
+    """Tall grid: bricks above/below the +-20.58 band are decided by the exact cull, the rest sampled."""
+    origin, dims = (3, -3, -2), (2, 6, 2)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_TERRAIN, None, orc.GRAN_BLOCK)
+    _assert_volume_equal(ctx, vol)
+
+
+def test_voxelize_terrain_voxel_cull_band(ctx, orc):
+    """Voxel granularity across the upper cull boundary (y = 20.58 world units lies in chunk y=1)."""
+    origin, dims = (5, 1, 7), (1, 1, 1)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_TERRAIN, None, orc.GRAN_VOXEL)
+    _assert_volume_equal(ctx, vol)
+
+
+def test_volume_upload_roundtrip(ctx, orc):
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL)
+    ctx.scene_create(origin, dims, 1 << 16)
+    k, p = vol.export_partial()
+    ctx.volume_upload(vol.occ(), vol.full(), k, p)
+    _assert_volume_equal(ctx, vol)
+
+
+def test_empty_volume(ctx, orc):
+    """Edge case: nothing solid anywhere (sphere far outside the grid)."""
+    origin, dims = (0, 0, 0), (2, 1, 1)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, (1000.0, 0, 0, 5.0), orc.GRAN_VOXEL)
+    _assert_volume_equal(ctx, vol)
+    assert ctx.build_occupancy(7) == 0
+    cam = orc.camera_uniform((5, 2, 2), (16, 8, 8), width=64, height=32)
+    rec = ctx.raymarch(cam, 64, 32)
+    assert np.all(rec["w1"] == 0x0007FFFF) and np.all(rec["rgba"] == 0xFF000000)
+    assert len(ctx.mesh(16)) == 0
+
+
+# ---- K2 -------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["ref_sphere_blocks", "sphere_voxel_256", "terrain_blocks"])
+def test_occupancy_mips_instances(ctx, orc, case):
+    if case == "ref_sphere_blocks":
+        origin, dims, params = scenes.sphere_scene(1024)
+        vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_BLOCK)
+    elif case == "sphere_voxel_256":
+        origin, dims, params = scenes.sphere_scene(256)
+        vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    else:
+        origin, dims = (0, -2, 0), (3, 4, 3)
+        vol = _make(ctx, orc, origin, dims, orc.SDF_TERRAIN, None, orc.GRAN_BLOCK)
+    n = ctx.build_occupancy(stamp=42)
+    table, mips, inst = ctx.download_occupancy(n)
+    t2, m2, i2 = vol.build_occupancy(stamp=42)
+    assert np.array_equal(mips, m2)
+    assert table.tobytes() == t2.tobytes()
+    assert n == len(i2)
+    assert inst.tobytes() == i2.tobytes()  # same records in the same (generator) order
+    if case == "ref_sphere_blocks":
+        assert n == 201936
+
+
+# ---- K4 -------------------------------------------------------------------------------------------------------
+
+def _cams(orc, origin, dims, w, h, extra=()):
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cams = [orc.camera_uniform(e, ctr, width=w, height=h) for e in eyes]
+    for e, c in extra:
+        cams.append(orc.camera_uniform(e, c, width=w, height=h))
+    return cams
+
+
+def _compare_frames(ctx, orc, vol, cams, w, h, shadow=True):
+    for i, cam in enumerate(cams):
+        rec = ctx.raymarch(cam, w, h, shadow=shadow)
+        rs = orc.ray_setup(cam, vol.origin, w, h)
+        ref = vol.raymarch(rs, w, h, shadow=shadow, mode=orc.DDA_HIER)
+        if rec.tobytes() != ref.tobytes():
+            a, b = orc.unpack_records(rec), orc.unpack_records(ref)
+            bad = {k: int((a[k] != b[k]).sum()) for k in a if k != "t"}
+            bad["t"] = int((rec["t"].view(np.uint32) != ref["t"].view(np.uint32)).sum())
+            raise AssertionError("camera %d: mismatching fields %s" % (i, bad))
+
+
+def test_raymarch_sphere_voxel_256(ctx, orc):
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 320, 184
+    ctr = scenes.grid_center_world(origin, dims)
+    extra = [((ctr[0] + 1.3, ctr[1] + 0.2, ctr[2] - 0.7), (ctr[0] + 30, ctr[1] + 5, ctr[2] + 3)),   # eye inside the solid
+             ((ctr[0] - 13.1, ctr[1] + 0.3, ctr[2] + 0.2), ctr),                                    # skimming just outside
+             ((5.0, 2.0, 2.0), (0.0, 0.0, 0.0))]                                                     # reference start pose (VoxelCamera.h:23)
+    _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, w, h, extra), w, h)
+
+
+def test_raymarch_no_shadow(ctx, orc):
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, 160, 96)[:3], 160, 96, shadow=False)
+
+
+def test_raymarch_reference_blocks(ctx, orc):
+    """Reference semantics: block-granular reference sphere (every brick all-ones)."""
+    origin, dims, params = scenes.sphere_scene(1024)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_BLOCK)
+    _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, 256, 144)[:4], 256, 144)
+
+
+def test_raymarch_terrain(ctx, orc):
+    origin, dims = (0, -1, 0), (2, 2, 2)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_TERRAIN, None, orc.GRAN_BLOCK)
+    w, h = 256, 144
+    ctr = scenes.grid_center_world(origin, dims)
+    extra = [((ctr[0] - 14.0, 9.0, ctr[2] - 13.0), (ctr[0] + 10, -3.0, ctr[2] + 12))]  # skim over the surface from inside the grid
+    _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, w, h, extra), w, h)
+
+
+def test_raymarch_ragged_frame(ctx, orc):
+    """Frame size not a multiple of the 32x8 tile."""
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, 101, 37)[:3], 101, 37)
+
+
+def test_raymarch_stats_and_u(ctx, orc):
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 320, 184
+    cam = _cams(orc, origin, dims, w, h)[2]
+    st = ctx.raymarch_stats(cam, w, h)
+    _, ref = vol.raymarch(orc.ray_setup(cam, vol.origin, w, h), w, h, stats=True)
+    for k in ("primary", "shadow", "hits", "steps", "touched_chunks", "touched_bricks", "u_bytes"):
+        assert int(st[k]) == int(ref[k]), k
+
+
+def test_raymarch_tile_partition_composes(ctx, capi, orc):
+    """Multi-GPU data path on one device: every rank's packed tiles, gathered and composed, equal the 1-GPU frame."""
+    import torch
+    origin, dims, params = scenes.sphere_scene(256)
+    _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 320, 184
+    cam = _cams(orc, origin, dims, w, h)[1]
+    ctx.set_partition(0, 1)
+    full = ctx.raymarch(cam, w, h).copy()
+    for world in (2, 3, 8):
+        tpr = capi.tiles_per_rank(w, h, world)
+        gathered = torch.zeros((world, tpr, 256, 4), dtype=torch.int32, device="cuda")
+        for rank in range(world):
+            ctx.set_partition(rank, world)
+            ctx.raymarch_device(cam, w, h, gathered[rank].data_ptr(), layout=capi.LAYOUT_TILES)
+        ctx.set_partition(0, 1)
+        frame = torch.zeros((h, w, 4), dtype=torch.int32, device="cuda")
+        ctx.compose_tiles_device(gathered.data_ptr(), world, w, h, frame.data_ptr())
+        ctx.sync()
+        torch.cuda.synchronize()
+        got = frame.cpu().numpy().view(np.uint32).reshape(h, w, 4)
+        exp = full.view(np.uint32).reshape(h, w, 4)
+        assert np.array_equal(got, exp), world
+
+
+# ---- K3 -------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case", ["sphere_voxel_256", "sphere_blocks", "terrain_voxel"])
+def test_mesh_quads(ctx, orc, case):
+    if case == "sphere_voxel_256":
+        origin, dims, params = scenes.sphere_scene(256)
+        vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    elif case == "sphere_blocks":
+        origin, dims, params = scenes.sphere_scene(512)
+        vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_BLOCK)
+    else:
+        origin, dims = (0, -1, 0), (1, 2, 1)
+        vol = _make(ctx, orc, origin, dims, orc.SDF_TERRAIN, None, orc.GRAN_VOXEL)
+    ref = vol.mesh()
+    got = ctx.mesh(len(ref) + 1024)
+    assert len(got) == len(ref)
+    assert orc.sort_quads(got).tobytes() == orc.sort_quads(ref).tobytes()
+    area = int((((got["w1"] >> 24) & 0xFF).astype(np.int64) * got["w2"].astype(np.int64)).sum())
+    assert area == vol.count_exposed_faces()
+
+
+def test_mesh_partition_union(ctx, orc):
+    """Brick ranges over 'ranks' (chunk % world): the union of the per-rank quad lists is the 1-GPU list."""
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    ref = orc.sort_quads(vol.mesh())
+    parts = []
+    for rank in range(3):
+        ctx.set_partition(rank, 3)
+        parts.append(ctx.mesh(len(ref) + 16))
+    ctx.set_partition(0, 1)
+    got = orc.sort_quads(np.concatenate(parts))
+    assert got.tobytes() == ref.tobytes()
+
+
+# ---- K5 -------------------------------------------------------------------------------------------------------
+
+def test_carve_and_remesh(ctx, orc):
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    n = 256
+    carves = [((n // 2 - 90, n // 2, n // 2), 24), ((n // 2, n // 2 + 100, n // 2 + 10), 40), ((3, 5, 250), 9), ((n // 2, n // 2, n // 2), 30)]
+    for center, radius in carves:
+        nd = ctx.carve_sphere(center, radius)
+        dirty = ctx.download_dirty(nd)
+        ref_dirty = vol.carve_sphere(center, radius)
+        assert np.array_equal(dirty, ref_dirty)
+        _assert_volume_equal(ctx, vol)
+        quads, keys = ctx.remesh_dirty(1 << 20, 1 << 20)
+        keys = np.sort(keys)
+        ref_q = vol.mesh_bricks(keys)
+        assert orc.sort_quads(quads).tobytes() == orc.sort_quads(ref_q).tobytes()
+    # after the edits a full re-mesh and a frame still agree with the oracle
+    ref = vol.mesh()
+    got = ctx.mesh(len(ref) + 16)
+    assert orc.sort_quads(got).tobytes() == orc.sort_quads(ref).tobytes()
+    _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, 160, 96)[:2], 160, 96)
