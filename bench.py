@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native voxel hot path.
+
+Metric (BASELINE.json): Mrays/s of the primary + hard-shadow voxel raymarch, whole job over N GPUs.
+Workload (default, every N): BASELINE.json configs[3] -- 4096^3 sparse-brick scene (V-sphere, voxel-granular),
+3840x2160 primary rays + one shadow ray per lit-facing hit, eight orbit cameras cycled per step, screen tiles
+(32x8) interleaved over the ranks, tile records gathered with NCCL and composed into the row-major frame.
+`--workload cfg1` runs configs[1] (1024^3, 1920x1080).  A "step" is one frame.
+
+    python bench.py --gpus 1 --steps 100 --warmup 10
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8
+    python bench.py --impl reference        # the CPU restatement of the reference path (oracle/), all host threads
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB
+write) between steps outside the timed spans, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LIGHT = (0.3, 0.5, 0.8)
+WORKLOADS = {
+    # name: (N voxels, width, height, description)
+    "cfg3": (4096, 3840, 2160, "BASELINE.json configs[3]: 4096^3 sparse-brick V-sphere, 3840x2160 primary + shadow rays, 8 orbit cameras"),
+    "cfg1": (1024, 1920, 1080, "BASELINE.json configs[1]: 1024^3 sparse-brick V-sphere, 1920x1080 primary + shadow rays, 8 orbit cameras"),
+    "cfg0": (256, 1280, 720, "BASELINE.json configs[0]: 256^3 V-sphere, 1280x720 primary + shadow rays, 8 orbit cameras"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(workload):
+    """dram bytes per launch of the raymarch kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "raymarch_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_cameras(scene, width, height):
+    from mesoengine_b200 import camera, scenes
+    origin, dims, _ = scene
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    return [camera.camera_uniform(e, ctr, width, height) for e in eyes]
+
+
+def sample_bands(height, n_bands=8, rows=8):
+    """The bounded CPU sample: n_bands bands of `rows` scanlines spread evenly over the frame."""
+    out = []
+    for b in range(n_bands):
+        y0 = int((b + 0.5) * height / n_bands) - rows // 2
+        y0 = max(0, min(height - rows, y0))
+        out.append((y0, y0 + rows))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU restatement (oracle/), all host threads, bounded sample per step
+# ------------------------------------------------------------------------------------------------------------------
+
+def cpu_build_volume(orc, scene):
+    origin, dims, params = scene
+    return orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL, fast=True)
+
+
+def cpu_step(orc, vol, cam, width, height, bands, nthreads):
+    rs = orc.ray_setup(cam, vol.origin, width, height, LIGHT)
+    rays = 0
+    recs = []
+    for (y0, y1) in bands:
+        rec, st = vol.raymarch(rs, width, height, rect=(0, y0, width, y1), shadow=True, mode=orc.DDA_HIER, nthreads=nthreads, stats=True)
+        rays += int(st["primary"]) + int(st["shadow"])
+        recs.append(rec[y0:y1])
+    return rays, recs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    from mesoengine_b200 import scenes
+    n, width, height, desc = WORKLOADS[args.workload]
+    scene = scenes.sphere_scene(n)
+    nthreads = orc.hw_threads()
+    vol = cpu_build_volume(orc, scene)
+    cams = make_cameras(scene, width, height)
+    bands = sample_bands(height)
+    for k in range(max(1, min(args.warmup, 2))):
+        cpu_step(orc, vol, cams[k % 8], width, height, bands, nthreads)
+    t0 = time.perf_counter()
+    rays = 0
+    for k in range(args.steps):
+        r, _ = cpu_step(orc, vol, cams[k % 8], width, height, bands, nthreads)
+        rays += r
+    dt = time.perf_counter() - t0
+    value = rays / dt / 1e6
+    sample = "%d bands x %d rows x %d px per step (%.1f%% of the frame), cameras cycled" % (len(bands), bands[0][1] - bands[0][0], width,
+                                                                                           100.0 * sum(b[1] - b[0] for b in bands) / height)
+    line = {
+        "impl": "reference", "metric": "Mrays/s voxel raymarch (primary + shadow)", "value": value, "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "scene": "V-sphere %d^3 voxel-granular" % n, "resolution": [width, height],
+                   "note": "reference cannot be built here (SURVEY.md 8c); this is the CPU restatement (oracle/) of the same path"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mesoengine_b200 import capi, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the voxel path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n, width, height, desc = WORKLOADS[args.workload]
+    scene = scenes.sphere_scene(n)
+    origin, dims, params = scene
+    ctx = capi.Context(local_rank)
+    # one side stream carries everything: our kernels (through the C ABI), NCCL, the timing events
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.scene_create(origin, dims, max_bricks=(1 << 20) if n >= 4096 else (1 << 18))
+    t_build = time.perf_counter()
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)  # replicated on every rank
+    ctx.sync()
+    t_build = time.perf_counter() - t_build
+    cams = make_cameras(scene, width, height)
+
+    # per-camera ray counts and algorithmic bytes (full frame, instrumented launch outside the timed region)
+    ctx.set_partition(0, 1)
+    stats = [ctx.raymarch_stats(c, width, height, shadow=True, light=LIGHT) for c in cams]
+    rays_cam = [int(s["primary"]) + int(s["shadow"]) for s in stats]
+    u_cam = [int(s["u_bytes"]) for s in stats]
+    ctx.set_partition(rank, world)
+
+    px = width * height
+    frame = torch.empty((height, width, 4), dtype=torch.int32, device=dev)
+    tpr = capi.tiles_per_rank(width, height, world)
+    if world > 1:
+        tiles = torch.empty((tpr, 256, 4), dtype=torch.int32, device=dev)
+        gathered = torch.empty((world, tpr, 256, 4), dtype=torch.int32, device=dev)
+
+    def step(k):
+        cam = cams[k % 8]
+        if world == 1:
+            ctx.raymarch_device(cam, width, height, frame.data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+        else:
+            ctx.raymarch_device(cam, width, height, tiles.data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_TILES)
+            dist.all_gather_into_tensor(gathered, tiles)
+            ctx.compose_tiles_device(gathered.data_ptr(), world, width, height, frame.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+    if sampler:
+        sampler.start()
+
+    # ---- timed region: K steps, CUDA events per step on the launching stream, L2 flushed between steps ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = ctx.launch_count()
+    barrier()
+    for k in range(args.steps):
+        ctx.flush_l2()
+        ev[k][0].record(stream)
+        step(k)
+        ev[k][1].record(stream)
+    barrier()
+    launches = ctx.launch_count() - launches0 - args.steps  # minus the flush launches
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    total_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms = float(total_ms.item())
+    rays_total = sum(rays_cam[k % 8] for k in range(args.steps))
+    value = rays_total / (ms * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (this rank's tiles), for the roofline ----
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kbuf = frame if world == 1 else tiles
+    klayout = capi.LAYOUT_FRAME if world == 1 else capi.LAYOUT_TILES
+    for k in range(args.steps):
+        ctx.flush_l2()
+        kev[k][0].record(stream)
+        ctx.raymarch_device(cams[k % 8], width, height, kbuf.data_ptr(), shadow=True, light=LIGHT, layout=klayout)
+        kev[k][1].record(stream)
+    barrier()
+    kms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    hbm_peak, peak_src = load_peaks()
+    # algorithmic bytes per launch: 16 B per pixel of this rank + scene bytes touched (U, counted once)
+    alg_bytes = float(np.mean([16.0 * px / world + u_cam[k % 8] for k in range(args.steps)]))
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer API: camera in host memory -> records in pinned host memory ----
+    host = torch.empty((height, width, 4), dtype=torch.int32).pin_memory()
+    host_np = host.numpy().view(capi.HitRecord).reshape(height, width)
+    e2e_steps = max(3, min(args.steps, 30))
+
+    def e2e_step(k):
+        if world == 1:
+            ctx.raymarch(cams[k % 8], width, height, shadow=True, light=LIGHT, out=host_np)  # H2D camera, kernel, D2H, sync
+        else:
+            step(k)
+            if rank == 0:
+                host.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_rays = sum(rays_cam[k % 8] for k in range(e2e_steps))
+    e2e_value = e2e_rays / float(e2e_dt.item()) / 1e6
+    clocks = sampler.stop() if sampler else None
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s voxel raymarch (primary + shadow)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "scene": "V-sphere %d^3 voxel-granular, %d chunks, replicated per GPU" % (n, int(np.prod(dims))),
+                       "resolution": [width, height], "rays_per_frame_mean": rays_total / args.steps,
+                       "partition": "32x8 screen tiles, tile %% %d == rank; NCCL all_gather of tile records + compose" % world if world > 1 else "single GPU, row-major frame",
+                       "cache": "L2 flushed (256 MiB write) between timed steps, outside the timed spans",
+                       "scene_build_s": t_build},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
+                    "steps": e2e_steps, "note": "meso_raymarch(): FGPUUniformCamera from host memory (passed as kernel parameters), records copied to pinned host memory"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "raymarch_kernel<false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
+                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "latency/divergence-bound traversal; working set is L2-resident (SURVEY.md 8d)"},
+        }
+
+    # ---- secondary metric of BASELINE.json: meshed voxels/s (configs[2]-style, 1 GPU leg only) ----
+    if world == 1 and not args.no_mesh and rank == 0:
+        line["mesh"] = bench_mesh(ctx, capi, scenes, torch, stream, args, dev)
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample, outputs byte-compared ----
+    if world == 1 and not args.no_cpu and rank == 0:
+        line["cpu_baseline"] = cpu_baseline(ctx, capi, scene, cams, width, height, args)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    return 0
+
+
+def bench_mesh(ctx, capi, scenes, torch, stream, args, dev):
+    """Face-cull + greedy meshing throughput on a 1024^3 grid (meshed voxels/s = N^3 / time)."""
+    out = {}
+    n = 1024
+    for name, kind, gran, scene in (("terrain_1024_blocks", capi.SDF_TERRAIN, capi.GRAN_BLOCK, scenes.terrain_scene(n)),
+                                    ("sphere_1024_voxels", capi.SDF_SPHERE, capi.GRAN_VOXEL, scenes.sphere_scene(n))):
+        origin, dims, params = scene
+        ctx.scene_create(origin, dims, 1 << 18)
+        ctx.voxelize_sdf(kind, params, gran)
+        cap = 1 << 24
+        quads = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+        nq = ctx.mesh_device(quads.data_ptr(), cap)
+        steps = max(5, min(args.steps, 30))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            ctx.flush_l2()
+            evs[k][0].record(stream)
+            ctx.mesh_device(quads.data_ptr(), cap, want_count=False)
+            evs[k][1].record(stream)
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        occ, full, keys, _ = ctx.volume_download()
+        populated = int(sum(bin(int(x)).count("1") for x in occ.ravel()[occ.ravel() != 0]))
+        alg = 64.0 * len(keys) + 1024.0 * int(np.prod(dims)) + 16.0 * nq + 4
+        out[name] = {"meshed_voxels_per_s": n ** 3 / (ms * 1e-3), "ms": ms, "quads": int(nq), "populated_bricks": populated,
+                     "partial_bricks": int(len(keys)), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9}
+        del quads
+    return out
+
+
+def cpu_baseline(ctx, capi, scene, cams, width, height, args):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    origin, dims, params = scene
+    # re-create the raymarch scene (the mesh leg replaced it) and hand the oracle the very same volume
+    ctx.scene_create(origin, dims, max_bricks=(1 << 20) if dims[0] >= 32 else (1 << 18))
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
+    occ, full, keys, payload = ctx.volume_download()
+    vol = orc.Volume(origin, dims).import_(occ, full, keys, payload)
+    nthreads = orc.hw_threads()
+    bands = sample_bands(height, 32, 8)
+    cpu_step(orc, vol, cams[0], width, height, bands, nthreads)
+    rays = 0
+    mism = 0
+    n_steps = 16
+    dt = 0.0
+    for k in range(n_steps):
+        t1 = time.perf_counter()
+        r, recs = cpu_step(orc, vol, cams[k % 8], width, height, bands, nthreads)
+        dt += time.perf_counter() - t1
+        rays += r
+        # byte-compare the same scanlines of the GPU frame (outside the CPU timing)
+        gpu = ctx.raymarch(cams[k % 8], width, height, shadow=True, light=LIGHT)
+        for (y0, y1), rec in zip(bands, recs):
+            mism += int((gpu[y0:y1].view(np.uint32).reshape(-1, 4) != rec.view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
+    return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": nthreads, "kind": "port",
+            "sample": "%d steps x %d bands x %d rows x %d px (cameras cycled); records byte-compared with the GPU frame: %d mismatching pixels"
+                      % (n_steps, len(bands), bands[0][1] - bands[0][0], width, mism),
+            "parity_mismatches": mism}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-mesh", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if args.gpus == 1 and world == 1:
+            pass
+        elif world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+            return subprocess.call(cmd)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

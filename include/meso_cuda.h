@@ -93,8 +93,10 @@ MESO_API int meso_abi_version(void);
  * Runtimes/Instance/VoxelWindowsInstance.cpp:104-111) for the voxel path.  One context = one GPU = one stream. */
 MESO_API int meso_ctx_create(int device, MesoCtx** out);
 MESO_API int meso_ctx_destroy(MesoCtx* ctx);
-/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the context's own stream. */
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream; NULL = the CUDA default stream). */
 MESO_API int meso_ctx_set_stream(MesoCtx* ctx, void* cuda_stream);
+/* Back to the context's own non-blocking stream (the default after meso_ctx_create). */
+MESO_API int meso_ctx_use_own_stream(MesoCtx* ctx);
 /* lvk::IContext::wait(SubmitHandle) (LVK.h:801) */
 MESO_API int meso_ctx_sync(MesoCtx* ctx);
 /* Multi-GPU split: this context renders screen tiles t with t % world == rank and meshes

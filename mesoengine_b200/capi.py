@@ -33,7 +33,7 @@ TILE_W, TILE_H = 32, 8
 
 # every symbol include/meso_cuda.h declares (tests/test_abi.py checks the header against this and the .so)
 SYMBOLS = [
-    "meso_last_error", "meso_abi_version", "meso_ctx_create", "meso_ctx_destroy", "meso_ctx_set_stream", "meso_ctx_sync",
+    "meso_last_error", "meso_abi_version", "meso_ctx_create", "meso_ctx_destroy", "meso_ctx_set_stream", "meso_ctx_use_own_stream", "meso_ctx_sync",
     "meso_ctx_set_partition", "meso_device_sm_count", "meso_scene_create", "meso_voxelize_sdf", "meso_volume_upload",
     "meso_volume_num_partial", "meso_volume_download", "meso_build_occupancy", "meso_download_chunk_table",
     "meso_download_mips", "meso_download_instances", "meso_ray_setup", "meso_raymarch", "meso_raymarch_device",
@@ -119,7 +119,11 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream):
-        _ck(lib.meso_ctx_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+        """cuda_stream: integer cudaStream_t handle (0 = CUDA default stream)."""
+        _ck(lib.meso_ctx_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def use_own_stream(self):
+        _ck(lib.meso_ctx_use_own_stream(self.h))
 
     def sync(self):
         _ck(lib.meso_ctx_sync(self.h))

@@ -42,7 +42,16 @@ __device__ __forceinline__ int clamp_floor_to_int(float x) {
 __device__ __forceinline__ int advance_axis(const Ray& r, int b, int cur, float ts, int as) {
   const int st = r.step[b];
   if (st == 0) return cur;
-  int e = clamp_floor_to_int(__fadd_rn(r.o[b], __fmul_rn(r.d[b], ts)));
+  const float pos = __fadd_rn(r.o[b], __fmul_rn(r.d[b], ts));
+  const float fl = floorf(pos);
+  int e = (int)fminf(fmaxf(fl, -1.0e9f), 1.0e9f);
+  // Fast path (DESIGN.md "advance_axis shortcut"): when the estimated position is farther than eps from every voxel
+  // plane, every plane behind it has a computed crossing time < ts and every plane ahead > ts (fp32 error of
+  // t_b(p) <= 1.8e-7 |t|, of pos <= 6e-8 (|ts| + |pos|)), so the exact answer is floor(pos).  Otherwise decide with
+  // the keys themselves.  Same result either way; the oracle only has the slow path.
+  const float fr = __fsub_rn(pos, fl);
+  const float eps = __fadd_rn(__fmul_rn(__fadd_rn(fabsf(ts), fabsf(pos)), 5e-7f), 1e-5f);
+  if (fr > eps && fr < __fsub_rn(1.0f, eps)) return e;
   if (st > 0) e = max(e, cur); else e = min(e, cur);
   for (;;) {
     const int pa = st > 0 ? e + 1 : e;
@@ -76,32 +85,27 @@ __device__ __forceinline__ bool gone(const DVolume& v, const Ray& r, const int c
   return false;
 }
 
-// 0 = solid voxel, 1 = empty voxel of a partial brick, 8 = empty brick, 128 = empty chunk
-template <bool STATS>
-__device__ __forceinline__ int cell_level(const Scene& s, const int c[3]) {
-  const DVolume& v = *s.v;
-  const int64_t ci = chunk_index(v, c[0] >> 7, c[1] >> 7, c[2] >> 7);
-  if (!((s.s_any[ci >> 5] >> (ci & 31)) & 1u)) return MESO_CV;
-  if (STATS) s.touch_chunk[ci] = 1;
-  const int b = block_bit((c[0] >> 3) & 15, (c[1] >> 3) & 15, (c[2] >> 3) & 15);
-  const uint64_t occ = __ldg(&v.occ[ci * 64 + (b >> 6)]);
-  if (!((occ >> (b & 63)) & 1ull)) return MESO_BR;
-  const uint64_t full = __ldg(&v.full[ci * 64 + (b >> 6)]);
-  if ((full >> (b & 63)) & 1ull) return 0;
-  const uint32_t slot = __ldg(&v.bptr[ci * MESO_BLOCKS + b]);
-  if (STATS) s.touch_brick[slot] = 1;
-  const uint64_t sl = __ldg(&v.pool[(size_t)slot * 8 + (c[2] & 7)]);
-  return ((sl >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1ull) ? 0 : 1;
-}
-
 struct Trace { bool hit; int c[3]; int axis; float t; unsigned steps; };
 
+// crossing time of the next level-`sh` plane ahead of coordinate ci on axis i (+inf on inactive axes)
+__device__ __forceinline__ float next_plane_t(const Ray& r, int i, int ci, int sh) {
+  if (r.step[i] == 0) return __int_as_float(0x7F800000);
+  const int base = (ci >> sh) << sh;
+  return plane_t(r, i, r.step[i] > 0 ? base + (1 << sh) : base);
+}
+
+// One loop, three levels (2 = chunk 128^3, 1 = brick 8^3, 0 = voxel), identical step sequence to the oracle's
+// hierarchical walk.  Per level the three pending crossing times are cached (tn) and only the stepped axis is
+// recomputed; the parents' pending times are parked in sp1/sp2 while a finer level runs (a finer step never moves the
+// parent's pending planes on the other two axes).  Above voxel level only the stepped coordinate is kept exact; the
+// other two hold an older true coordinate inside the same cell and are made exact (advance_axis) when the walk
+// descends or hits.
 template <bool STATS>
 __device__ __forceinline__ void trace(const Scene& s, const Ray& r, const int c0[3], Trace& tr) {
   const DVolume& v = *s.v;
-  tr.hit = false; tr.axis = -1; tr.t = 0.0f; tr.steps = 0;
   int c[3] = {c0[0], c0[1], c0[2]};
-  bool alive = true;
+  int la = -1; float lt = 0.0f; unsigned steps = 0;
+  bool hit = false, alive = true, exact = true;
   if (!inside(v, c)) {
     if (gone(v, r, c)) alive = false;
     else {
@@ -119,39 +123,102 @@ __device__ __forceinline__ void trace(const Scene& s, const Ray& r, const int c0
         if (b == a) c[b] = r.step[b] > 0 ? 0 : v.nvox[b] - 1;
         else c[b] = advance_axis(r, b, c[b], ta, a);
       }
-      tr.axis = a; tr.t = ta; tr.steps++;
+      la = a; lt = ta; steps = 1;
       alive = inside(v, c);
     }
   }
+  float tn[3], sp1[3] = {0.f, 0.f, 0.f}, sp2[3] = {0.f, 0.f, 0.f};
+  int lvl = 2;
+#pragma unroll
+  for (int i = 0; i < 3; i++) tn[i] = next_plane_t(r, i, c[i], 7);
+  int ci = 0, wtag = -1, ztag = -1;
+  uint32_t slot = 0;
+  unsigned long long wocc = 0, wfull = 0, slice = 0;
+
   while (alive) {
-    const int L = cell_level<STATS>(s, c);
-    if (L == 0) { tr.hit = true; break; }
-    int a = -1; float ta = 0.0f; int pl_a = 0;
+    if (lvl == 2) {
+      ci = (c[0] >> 7) + v.dims[0] * ((c[1] >> 7) + v.dims[1] * (c[2] >> 7));
+      if ((s.s_any[ci >> 5] >> (ci & 31)) & 1u) {
+        if (STATS) s.touch_chunk[ci] = 1;
+        if (!exact) {
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      if (r.step[i] != 0) {
-        const int base = c[i] & ~(L - 1);
-        const int pl = r.step[i] > 0 ? base + L : base;
-        const float ti = plane_t(r, i, pl);
-        if (a < 0 || key_less(ti, i, ta, a)) { a = i; ta = ti; pl_a = pl; }
+          for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);
+          exact = true;
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) { sp2[i] = tn[i]; tn[i] = next_plane_t(r, i, c[i], 3); }
+        lvl = 1; wtag = -1;
+        continue;
       }
-    }
-    if (a < 0) break;
-    if (L == 1) {
+    } else if (lvl == 1) {
+      const int bx = (c[0] >> 3) & 15, by = (c[1] >> 3) & 15, bz = (c[2] >> 3) & 15;
+      const int w = bz * 4 + (by >> 2);
+      if (w != wtag) {
+        const ulonglong2 p = __ldg(&v.of[(size_t)ci * 64 + w]);
+        wocc = p.x; wfull = p.y; wtag = w;
+      }
+      const int bit = bx + 16 * (by & 3);
+      if ((wocc >> bit) & 1ull) {
+        if (!exact) {
 #pragma unroll
-      for (int b = 0; b < 3; b++) if (b == a) c[b] += r.step[b];
+          for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);
+          exact = true;
+        }
+        if ((wfull >> bit) & 1ull) { hit = true; break; }
+        slot = __ldg(&v.bptr[(size_t)ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
+        if (STATS) s.touch_brick[slot] = 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { sp1[i] = tn[i]; tn[i] = next_plane_t(r, i, c[i], 0); }
+        lvl = 0; ztag = -1;
+        continue;
+      }
     } else {
+      const int z = c[2] & 7;
+      if (z != ztag) { slice = __ldg(&v.pool[(size_t)slot * 8 + z]); ztag = z; }
+      if ((slice >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1ull) { hit = true; break; }
+    }
+    // ---- one step at the current level: consume the smallest pending key (ties: lower axis first) ----
+    int a = 0; float ta = tn[0];
+    if (tn[1] < ta) { a = 1; ta = tn[1]; }
+    if (tn[2] < ta) { a = 2; ta = tn[2]; }
+    if (!(ta < __int_as_float(0x7F800000))) break;  // zero direction
+    const int sh = lvl == 0 ? 0 : (lvl == 1 ? 3 : 7);
+    int cross = 0, ca = 0;
 #pragma unroll
-      for (int b = 0; b < 3; b++) {
-        if (b == a) c[b] = r.step[b] > 0 ? pl_a : pl_a - 1;
-        else c[b] = advance_axis(r, b, c[b], ta, a);
+    for (int b = 0; b < 3; b++) {
+      if (b == a) {
+        const int old = c[b];
+        const int base = (old >> sh) << sh;
+        const int nc = r.step[b] > 0 ? base + (1 << sh) : base - 1;
+        c[b] = nc; ca = nc; cross = old ^ nc;
       }
     }
-    tr.axis = a; tr.t = ta; tr.steps++;
-    alive = inside(v, c);
+    la = a; lt = ta; steps++;
+    exact = (lvl == 0);
+    if (lvl == 0 && (cross >> 3)) {
+      lvl = 1;
+#pragma unroll
+      for (int i = 0; i < 3; i++) tn[i] = sp1[i];
+    }
+    if (lvl == 1 && (cross >> 7)) {
+      lvl = 2;
+#pragma unroll
+      for (int i = 0; i < 3; i++) tn[i] = sp2[i];
+    }
+    if (lvl == 2) {
+      int na = 0;
+#pragma unroll
+      for (int b = 0; b < 3; b++) if (b == a) na = v.nvox[b];
+      alive = (unsigned)ca < (unsigned)na;
+    }
+    const int sh2 = lvl == 0 ? 0 : (lvl == 1 ? 3 : 7);
+#pragma unroll
+    for (int b = 0; b < 3; b++) if (b == a) tn[b] = next_plane_t(r, b, ca, sh2);
   }
+  tr.hit = hit; tr.axis = la; tr.t = lt; tr.steps = steps;
   tr.c[0] = c[0]; tr.c[1] = c[1]; tr.c[2] = c[2];
 }
+
 
 __device__ __forceinline__ uint32_t to_un8(float x) { return (uint32_t)__fadd_rn(__fmul_rn(x, 255.0f), 0.5f); }
 

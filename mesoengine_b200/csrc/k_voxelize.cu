@@ -123,6 +123,30 @@ __device__ __forceinline__ bool sdf_solid(const SdfParams& sp, double x, double 
 // fixed once |y * 0.5| > 10.3 * 0.9981 = 10.2805; 10.29 leaves a 1e-2 margin.  Exact cull, never approximate.
 #define TERRAIN_Y_HALF_BOUND 10.29
 
+// Exact brick classification for the sphere.  sqrt((dx*dx + dy*dy) + dz*dz) - r is monotone non-decreasing in each of
+// |dx|, |dy|, |dz| separately (every rounding step is monotone), so over the 8^3 sample lattice of a brick the maximum
+// is at the per-axis farthest sample and the minimum at the per-axis nearest: all-solid <=> farthest sample solid,
+// all-empty <=> nearest sample not solid.  No tolerance involved (same argument as oracle/orc_volume.c).
+__device__ __forceinline__ int sphere_brick_class(const SdfParams& sp, double b0, double b1, double b2) {
+  double nr[3], fr[3];
+  const double lo[3] = {b0, b1, b2};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double dn = 1.0e300, df = -1.0, pn = lo[k], pf = lo[k];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const double p = lo[k] + (double)i * 0.125;
+      const double d = fabs(p - sp.p[k]);
+      if (d < dn) { dn = d; pn = p; }
+      if (d > df) { df = d; pf = p; }
+    }
+    nr[k] = pn; fr[k] = pf;
+  }
+  if (sdf_solid<MESO_SDF_SPHERE>(sp, fr[0], fr[1], fr[2])) return 1;
+  if (!sdf_solid<MESO_SDF_SPHERE>(sp, nr[0], nr[1], nr[2])) return 0;
+  return -1;
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParams sp, int* overflow) {
   const int64_t word_global = blockIdx.x;  // chunk*64 + word
@@ -145,6 +169,10 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
     if (KIND == MESO_SDF_TERRAIN) {
       if (b1 * .5 > TERRAIN_Y_HALF_BOUND) { s = 0ull; decided = true; }
       else if ((b1 + 0.875) * .5 < -TERRAIN_Y_HALF_BOUND) { s = ~0ull; decided = true; }
+    } else {
+      const int cls = sphere_brick_class(sp, b0, b1, b2);
+      if (cls == 0) { s = 0ull; decided = true; }
+      else if (cls == 1) { s = ~0ull; decided = true; }
     }
     if (!decided) {
       uint32_t bits = 0;
@@ -221,6 +249,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(DVolume v) {
   if (c >= v.nchunks) return;
   uint64_t o0 = v.occ[c * 64 + lane], o1 = v.occ[c * 64 + 32 + lane];
   uint64_t f0 = v.full[c * 64 + lane], f1 = v.full[c * 64 + 32 + lane];
+  v.of[c * 64 + lane] = make_ulonglong2(o0, f0);
+  v.of[c * 64 + 32 + lane] = make_ulonglong2(o1, f1);
   const bool any = __any_sync(0xffffffffu, (o0 | o1) != 0ull);
   const bool all = __all_sync(0xffffffffu, (f0 & f1) == ~0ull);
   if (lane == 0) {

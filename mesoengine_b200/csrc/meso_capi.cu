@@ -106,7 +106,7 @@ int meso_ctx_create(int device, MesoCtx** out) {
 
 static void free_scene(MesoCtx* c) {
   DVolume& v = c->v;
-  cudaFree(v.occ); cudaFree(v.full); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
+  cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
   cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count);
   cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
@@ -133,7 +133,12 @@ int meso_ctx_destroy(MesoCtx* c) {
 
 int meso_ctx_set_stream(MesoCtx* c, void* s) {
   if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->stream = (cudaStream_t)s;  // NULL is the CUDA (legacy) default stream, a perfectly valid choice
+  return MESO_OK;
+}
+int meso_ctx_use_own_stream(MesoCtx* c) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  c->stream = c->own_stream;
   return MESO_OK;
 }
 
@@ -172,6 +177,7 @@ int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const in
   v.chunk_words = (int)((v.nchunks + 31) / 32);
   const size_t nc = (size_t)v.nchunks;
   CK(cudaMalloc(&v.occ, nc * 64 * 8)); CK(cudaMalloc(&v.full, nc * 64 * 8)); CK(cudaMalloc(&v.mips, nc * 3 * 64 * 8));
+  CK(cudaMalloc(&v.of, nc * 64 * 16)); CK(cudaMemsetAsync(v.of, 0, nc * 64 * 16, c->stream));
   CK(cudaMalloc(&v.bptr, nc * MESO_BLOCKS * 4));
   CK(cudaMalloc(&v.pool, (size_t)max_bricks * 64));
   CK(cudaMalloc(&v.chunk_any, (size_t)v.chunk_words * 4)); CK(cudaMalloc(&v.chunk_full, (size_t)v.chunk_words * 4));

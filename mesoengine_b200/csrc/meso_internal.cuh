@@ -21,6 +21,7 @@ struct DVolume {
   int64_t nchunks;
   uint64_t* occ;        // nchunks*64   block present (Mip0)
   uint64_t* full;       // nchunks*64   brick all-solid
+  ulonglong2* of;       // nchunks*64   {occ, full} interleaved: one 16 B load per 64 bricks in the raymarch (derived)
   uint64_t* mips;       // nchunks*3*64 erode Mip1..3
   uint32_t* bptr;       // nchunks*4096 payload slot of partial bricks (0xFFFFFFFF otherwise)
   uint64_t* pool;       // max_bricks*8 words

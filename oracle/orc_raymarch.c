@@ -14,6 +14,10 @@
  */
 #include "orc_internal.h"
 
+/* optional instrumentation: steps taken at voxel / brick / chunk level (DESIGN.md "where the steps go") */
+static uint64_t* orc_debug_level_hist = NULL;
+void orc_debug_set_level_hist(uint64_t* hist3) { orc_debug_level_hist = hist3; }
+
 typedef struct { float o[3], d[3], inv[3]; int step[3]; } Ray;
 typedef struct { int hit; int c[3]; int axis; float t; uint64_t steps; } Trace;
 
@@ -135,6 +139,7 @@ static Trace trace(const Scene* s, const Ray* r, const int c0[3], int mode) {
         for (int b = 0; b < 3; b++) if (b != a) c[b] = advance_axis(r, b, c[b], ta, a);
       }
       tr.axis = a; tr.t = ta; tr.steps++;
+      if (orc_debug_level_hist) __atomic_fetch_add(&orc_debug_level_hist[L == 1 ? 0 : (L == ORC_BR ? 1 : 2)], 1, __ATOMIC_RELAXED);
       if (!inside(s, c)) break;
     }
   }

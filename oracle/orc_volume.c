@@ -90,7 +90,31 @@ static void set_brick(OrcVolume* v, int64_t c, int b, const uint64_t s[8]) {
   pthread_mutex_unlock(&v->lock);
 }
 
-typedef struct { OrcVolume* v; int kind; const double* params; int gran; int sin_mode; } VoxArg;
+typedef struct { OrcVolume* v; int kind; const double* params; int gran; int sin_mode; int fast; } VoxArg;
+
+/* Sphere fast path (ORC_FAST=1 in orc_volume_voxelize_ex).  The fp64 sphere SDF sqrt((dx*dx + dy*dy) + dz*dz) - r is
+ * monotone non-decreasing in each of |dx|, |dy|, |dz| separately (every rounding step is monotone), so over an
+ * axis-aligned lattice of sample points its maximum is taken at the per-axis farthest sample and its minimum at the
+ * per-axis nearest one.  A box of samples is therefore all-solid iff the farthest sample is solid and all-empty iff
+ * the nearest sample is not: exact, no tolerance.  tests/test_oracle_kat.py checks it against the brute-force walk. */
+static void axis_extremes(double lo, double step, int n, double c, double* nearest, double* farthest) {
+  double best_n = 0, best_f = 0, dn = INFINITY, df = -1.0;
+  for (int i = 0; i < n; i++) {
+    double p = lo + (double)i * step;
+    double d = fabs(p - c);
+    if (d < dn) { dn = d; best_n = p; }
+    if (d > df) { df = d; best_f = p; }
+  }
+  *nearest = best_n; *farthest = best_f;
+}
+/* returns 1 = all solid, 0 = all empty, -1 = mixed, for the n^3 samples lo + i*step */
+static int sphere_box_class(const double* params, const double lo[3], double step, int n) {
+  double nr[3], fr[3];
+  for (int k = 0; k < 3; k++) axis_extremes(lo[k], step, n, params[k], &nr[k], &fr[k]);
+  if (orc_sdf(ORC_SDF_SPHERE, params, 0, fr[0], fr[1], fr[2]) < 0.0) return 1;
+  if (!(orc_sdf(ORC_SDF_SPHERE, params, 0, nr[0], nr[1], nr[2]) < 0.0)) return 0;
+  return -1;
+}
 /* One chunk: block-granular = GeneratorHelper.h:120-150 verbatim (block solid <=> sdf(min corner) < 0, brick
  * all-ones); voxel-granular (extension) samples every voxel min corner p = blockCorner + (vx,vy,vz)*BlockSize/8. */
 static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
@@ -110,9 +134,17 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
     } else {
       double cs[3]; for (int k = 0; k < 3; k++) cs[k] = (double)loc[k] * BlockSize * (double)ORC_CR;
       int X = (int)(item % ORC_CR);
+      int chunk_class = -1;
+      if (a->fast && a->kind == ORC_SDF_SPHERE) chunk_class = sphere_box_class(a->params, cs, BlockSize / 8.0, ORC_CV);
+      if (chunk_class == 0) continue;
       for (int Y = 0; Y < ORC_CR; Y++) for (int Z = 0; Z < ORC_CR; Z++) {
         double bc[3] = {cs[0] + (double)X * BlockSize, cs[1] + (double)Y * BlockSize, cs[2] + (double)Z * BlockSize};
         uint64_t s[8];
+        if (a->fast && a->kind == ORC_SDF_SPHERE) {
+          int cls = chunk_class == 1 ? 1 : sphere_box_class(a->params, bc, BlockSize / 8.0, ORC_BR);
+          if (cls == 0) continue;
+          if (cls == 1) { for (int z = 0; z < 8; z++) s[z] = ~0ull; set_brick(v, c, orc_bidx(X, Y, Z), s); continue; }
+        }
         for (int vz = 0; vz < 8; vz++) {
           uint64_t m = 0;
           for (int vy = 0; vy < 8; vy++) for (int vx = 0; vx < 8; vx++) {
@@ -126,10 +158,13 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
     }
   }
 }
-void orc_volume_voxelize(OrcVolume* v, int kind, const double params[4], int gran, int sin_mode, int nthreads) {
+void orc_volume_voxelize_ex(OrcVolume* v, int kind, const double params[4], int gran, int sin_mode, int nthreads, int fast) {
   clear_volume(v);
-  VoxArg a = {v, kind, params, gran, sin_mode};
+  VoxArg a = {v, kind, params, gran, sin_mode, fast};
   orc_parallel_for(gran == ORC_GRAN_BLOCK ? v->nchunks : v->nchunks * ORC_CR, nthreads, 1, vox_range, &a);
+}
+void orc_volume_voxelize(OrcVolume* v, int kind, const double params[4], int gran, int sin_mode, int nthreads) {
+  orc_volume_voxelize_ex(v, kind, params, gran, sin_mode, nthreads, 0);
 }
 
 int64_t orc_volume_num_chunks(const OrcVolume* v) { return v->nchunks; }

@@ -177,10 +177,10 @@ class Volume:
             lib.orc_volume_destroy(self.h)
             self.h = None
 
-    def voxelize(self, kind, params=None, granularity=GRAN_VOXEL, sin_mode=SIN_PORTABLE, nthreads=None):
+    def voxelize(self, kind, params=None, granularity=GRAN_VOXEL, sin_mode=SIN_PORTABLE, nthreads=None, fast=False):
         self._params = _d4(params)
-        lib.orc_volume_voxelize(self.h, C.c_int(kind), _p(self._params), C.c_int(granularity), C.c_int(sin_mode),
-                                C.c_int(nthreads or hw_threads()))
+        lib.orc_volume_voxelize_ex(self.h, C.c_int(kind), _p(self._params), C.c_int(granularity), C.c_int(sin_mode),
+                                   C.c_int(nthreads or hw_threads()), C.c_int(1 if fast else 0))
         return self
 
     def occ(self):
