@@ -1,21 +1,28 @@
-// k_raymarch.cu -- K4: per-pixel 3D-DDA through chunk (128^3) -> brick (8^3) -> voxel, primary + one hard-shadow ray.
+// k_raymarch.cu -- K4: per-pixel 3D-DDA, primary + one hard-shadow ray.
 //
 // Replaces the reference's per-pixel visibility: the 1 M-instance triangle-fan draw + reverse-Z depth test
 // (Samples/SimpleVoxel.cpp:146-192 VS, :220-224 FS, dispatch :352-398) -- see DESIGN.md for the equivalence.
 //
 // The DDA is STATELESS (DESIGN.md "DDA"): the crossing time of integer voxel plane p on axis a is always
 //     t_a(p) = (float(p) - o_a) * inv_a          one FSUB + one FMUL, never fused (-fmad=false)
-// and crossings are consumed in the total order (t, axis).  Skipping an empty chunk or brick re-derives the two other
-// coordinates from the same keys, so the hierarchical walk visits exactly the voxels a flat one would: hit voxel,
-// face and t are bit-identical to oracle/orc_raymarch.c.
+// and crossings are consumed in the total order (t, axis).  Skipping an empty aligned cell (512^3 region, 128^3 chunk,
+// 32^3 cell, 8^3 brick) consumes the smallest of the cell's three exit keys and re-derives the other two coordinates
+// from the same keys only when the walk has to look finer (advance_axis), so the hierarchical walk visits exactly the
+// voxels the oracle's flat walk would: hit voxel, face and t are bit-identical to oracle/orc_raymarch.c.
 //
-// Mapping: CTA = one 32x8 screen tile (8 warps), warp = 8x4 pixels (a 128 B-aligned 4-line store of 16 B records),
-// chunk-level any-bits staged in shared memory.  Multi-GPU: tile t belongs to rank t % world.
+// Mapping: CTA = one 32x8 screen tile (8 warps), warp = 8x4 pixels (a 128 B-aligned 4-line store of 16 B records).
+// Region / chunk any-bits are staged in shared memory; 32^3-cell masks, {occ,full} word pairs (16 B loads) and brick
+// slices are cached in registers behind tags.  Shadow rays are compacted across the CTA (ballot + prefix sum through
+// shared memory) so the second trace runs in dense warps.  Multi-GPU: tile t belongs to rank t % world.
 #include "meso_internal.cuh"
+
+#define F_INF __int_as_float(0x7F800000)
 
 struct Ray {
   float o[3], d[3], inv[3];
-  int step[3];
+  int step[3];  // +1 / -1 / 0 (inactive: |d| < 1e-20, never crosses a plane)
+  int sgn[3];   // 0 or -1: coordinates are kept mirrored (c ^ sgn) so every step is "+"
+  int lim[3];   // mirrored coordinate at which the ray has left the grid on that axis
 };
 
 __device__ __forceinline__ float plane_t(const Ray& r, int a, int plane) {
@@ -23,12 +30,14 @@ __device__ __forceinline__ float plane_t(const Ray& r, int a, int plane) {
 }
 __device__ __forceinline__ bool key_less(float t1, int a1, float t2, int a2) { return t1 < t2 || (t1 == t2 && a1 < a2); }
 
-__device__ __forceinline__ void ray_init(Ray& r, const float o[3], const float d[3]) {
+__device__ __forceinline__ void ray_init(Ray& r, const float o[3], const float d[3], const DVolume& v) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     r.o[i] = o[i]; r.d[i] = d[i];
     if (fabsf(d[i]) >= 1e-20f) { r.inv[i] = __fdiv_rn(1.0f, d[i]); r.step[i] = d[i] > 0.0f ? 1 : -1; }
     else { r.inv[i] = 0.0f; r.step[i] = 0; }
+    r.sgn[i] = r.step[i] < 0 ? -1 : 0;
+    r.lim[i] = r.step[i] > 0 ? v.nvox[i] : (r.step[i] < 0 ? 0 : 0x7FFFFFFF);
   }
 }
 
@@ -38,7 +47,8 @@ __device__ __forceinline__ int clamp_floor_to_int(float x) {
   return (int)f;
 }
 
-// coordinate on axis b after consuming every crossing with key < (ts, as), starting from cell coordinate cur
+// True coordinate on axis b after consuming every crossing with key < (ts, as), starting from the (older) true cell
+// coordinate cur.
 __device__ __forceinline__ int advance_axis(const Ray& r, int b, int cur, float ts, int as) {
   const int st = r.step[b];
   if (st == 0) return cur;
@@ -67,7 +77,8 @@ __device__ __forceinline__ int advance_axis(const Ray& r, int b, int cur, float 
 
 struct Scene {
   const DVolume* v;
-  const uint32_t* s_any;  // shared-memory copy of the chunk-level any-bits
+  const uint32_t* s_any;     // shared: bit per chunk
+  const uint32_t* s_region;  // shared: bit per 512^3 region
   uint8_t* touch_chunk;
   uint8_t* touch_brick;
 };
@@ -87,25 +98,13 @@ __device__ __forceinline__ bool gone(const DVolume& v, const Ray& r, const int c
 
 struct Trace { bool hit; int c[3]; int axis; float t; unsigned steps; };
 
-// crossing time of the next level-`sh` plane ahead of coordinate ci on axis i (+inf on inactive axes)
-__device__ __forceinline__ float next_plane_t(const Ray& r, int i, int ci, int sh) {
-  if (r.step[i] == 0) return __int_as_float(0x7F800000);
-  const int base = (ci >> sh) << sh;
-  return plane_t(r, i, r.step[i] > 0 ? base + (1 << sh) : base);
-}
-
-// One loop, three levels (2 = chunk 128^3, 1 = brick 8^3, 0 = voxel), identical step sequence to the oracle's
-// hierarchical walk.  Per level the three pending crossing times are cached (tn) and only the stepped axis is
-// recomputed; the parents' pending times are parked in sp1/sp2 while a finer level runs (a finer step never moves the
-// parent's pending planes on the other two axes).  Above voxel level only the stepped coordinate is kept exact; the
-// other two hold an older true coordinate inside the same cell and are made exact (advance_axis) when the walk
-// descends or hits.
+// levels: 4 = region (512^3), 3 = chunk (128^3), 2 = cell (32^3), 1 = brick (8^3), 0 = voxel
 template <bool STATS>
 __device__ __forceinline__ void trace(const Scene& s, const Ray& r, const int c0[3], Trace& tr) {
   const DVolume& v = *s.v;
   int c[3] = {c0[0], c0[1], c0[2]};
   int la = -1; float lt = 0.0f; unsigned steps = 0;
-  bool hit = false, alive = true, exact = true;
+  bool hit = false, alive = true;
   if (!inside(v, c)) {
     if (gone(v, r, c)) alive = false;
     else {
@@ -127,199 +126,240 @@ __device__ __forceinline__ void trace(const Scene& s, const Ray& r, const int c0
       alive = inside(v, c);
     }
   }
-  float tn[3], sp1[3] = {0.f, 0.f, 0.f}, sp2[3] = {0.f, 0.f, 0.f};
-  int lvl = 2;
+  // mirrored coordinates: cs = c ^ sgn.  Above voxel level only the last stepped axis is exact; the other two hold an
+  // older true coordinate inside the same cell of the level that was stepped, and are made exact before looking finer.
+  int cs[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) tn[i] = next_plane_t(r, i, c[i], 7);
+  for (int i = 0; i < 3; i++) cs[i] = c[i] ^ r.sgn[i];
+  int gran = 0;  // shift of the level last stepped: non-stepped axes are only valid at this granularity
+  int need = 4;
   int ci = 0, wtag = -1, ztag = -1;
   uint32_t slot = 0;
-  unsigned long long wocc = 0, wfull = 0, slice = 0;
+  unsigned long long cellmask = 0, wocc = 0, wfull = 0, slice = 0;
 
   while (alive) {
-    if (lvl == 2) {
-      ci = (c[0] >> 7) + v.dims[0] * ((c[1] >> 7) + v.dims[1] * (c[2] >> 7));
-      if ((s.s_any[ci >> 5] >> (ci & 31)) & 1u) {
-        if (STATS) s.touch_chunk[ci] = 1;
-        if (!exact) {
+    int sh;
+    {
 #pragma unroll
-          for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);
-          exact = true;
+      for (int i = 0; i < 3; i++) c[i] = cs[i] ^ r.sgn[i];
+      bool go = true;  // keep looking finer
+      sh = 0;
+      if (need >= 4) {
+        const int ri = (c[0] >> 9) + v.rdims[0] * ((c[1] >> 9) + v.rdims[1] * (c[2] >> 9));
+        if (!((s.s_region[ri >> 5] >> (ri & 31)) & 1u)) { sh = 9; go = false; }
+      }
+#define MESO_SYNC_IF_COARSER(S)                                                            \
+      if (go && gran > (S)) { /* looking finer than the level that was stepped: make the other two axes exact */ \
+        _Pragma("unroll") for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);   \
+        _Pragma("unroll") for (int i = 0; i < 3; i++) cs[i] = c[i] ^ r.sgn[i];                                 \
+        gran = 0;                                                                            \
+      }
+      MESO_SYNC_IF_COARSER(7)
+      if (go && need >= 3) {
+        ci = (c[0] >> 7) + v.dims[0] * ((c[1] >> 7) + v.dims[1] * (c[2] >> 7));
+        if (!((s.s_any[ci >> 5] >> (ci & 31)) & 1u)) { sh = 7; go = false; }
+        else {
+          if (STATS) s.touch_chunk[ci] = 1;
+          cellmask = __ldg(&v.cells[ci]);
+          wtag = -1;
         }
-#pragma unroll
-        for (int i = 0; i < 3; i++) { sp2[i] = tn[i]; tn[i] = next_plane_t(r, i, c[i], 3); }
-        lvl = 1; wtag = -1;
-        continue;
       }
-    } else if (lvl == 1) {
-      const int bx = (c[0] >> 3) & 15, by = (c[1] >> 3) & 15, bz = (c[2] >> 3) & 15;
-      const int w = bz * 4 + (by >> 2);
-      if (w != wtag) {
-        const ulonglong2 p = __ldg(&v.of[(size_t)ci * 64 + w]);
-        wocc = p.x; wfull = p.y; wtag = w;
+      MESO_SYNC_IF_COARSER(5)
+      if (go && need >= 2) {
+        const int e = ((c[0] >> 5) & 3) + 4 * ((c[1] >> 5) & 3) + 16 * ((c[2] >> 5) & 3);
+        if (!((cellmask >> e) & 1ull)) { sh = 5; go = false; }
       }
-      const int bit = bx + 16 * (by & 3);
-      if ((wocc >> bit) & 1ull) {
-        if (!exact) {
-#pragma unroll
-          for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);
-          exact = true;
+      MESO_SYNC_IF_COARSER(3)
+      if (go && need >= 1) {
+        const int bx = (c[0] >> 3) & 15, by = (c[1] >> 3) & 15, bz = (c[2] >> 3) & 15;
+        const int w = bz * 4 + (by >> 2);
+        if (w != wtag) {
+          const ulonglong2 p = __ldg(&v.of[(size_t)ci * 64 + w]);
+          wocc = p.x; wfull = p.y; wtag = w;
         }
-        if ((wfull >> bit) & 1ull) { hit = true; break; }
-        slot = __ldg(&v.bptr[(size_t)ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
-        if (STATS) s.touch_brick[slot] = 1;
+        const int bit = bx + 16 * (by & 3);
+        if (!((wocc >> bit) & 1ull)) { sh = 3; go = false; }
+        else {
+          if ((wfull >> bit) & 1ull) {
+            if (gran > 0) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) { sp1[i] = tn[i]; tn[i] = next_plane_t(r, i, c[i], 0); }
-        lvl = 0; ztag = -1;
-        continue;
+              for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);
+            }
+            hit = true; break;
+          }
+          slot = __ldg(&v.bptr[(size_t)ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
+          if (STATS) s.touch_brick[slot] = 1;
+          ztag = -1;
+        }
       }
-    } else {
-      const int z = c[2] & 7;
-      if (z != ztag) { slice = __ldg(&v.pool[(size_t)slot * 8 + z]); ztag = z; }
-      if ((slice >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1ull) { hit = true; break; }
+      MESO_SYNC_IF_COARSER(0)
+      if (go) {
+        const int z = c[2] & 7;
+        if (z != ztag) { slice = __ldg(&v.pool[(size_t)slot * 8 + z]); ztag = z; }
+        if ((slice >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1ull) { hit = true; break; }
+      }
     }
-    // ---- one step at the current level: consume the smallest pending key (ties: lower axis first) ----
+    // ---- one step at level sh: consume the smallest of the three pending keys (ties: lower axis first) ----
+    const int mask = (1 << sh) - 1;
+    int nx[3]; float tn[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      nx[i] = (cs[i] | mask) + 1;                         // mirrored coordinate after crossing
+      const int pl = (nx[i] ^ r.sgn[i]) - r.sgn[i];       // true plane index
+      const float t = __fmul_rn(__fsub_rn((float)pl, r.o[i]), r.inv[i]);
+      tn[i] = r.step[i] != 0 ? t : F_INF;
+    }
     int a = 0; float ta = tn[0];
     if (tn[1] < ta) { a = 1; ta = tn[1]; }
     if (tn[2] < ta) { a = 2; ta = tn[2]; }
-    if (!(ta < __int_as_float(0x7F800000))) break;  // zero direction
-    const int sh = lvl == 0 ? 0 : (lvl == 1 ? 3 : 7);
-    int cross = 0, ca = 0;
+    if (!(ta < F_INF)) break;  // zero direction
+    int cross = 0, lim = 0, ca = 0;
 #pragma unroll
-    for (int b = 0; b < 3; b++) {
-      if (b == a) {
-        const int old = c[b];
-        const int base = (old >> sh) << sh;
-        const int nc = r.step[b] > 0 ? base + (1 << sh) : base - 1;
-        c[b] = nc; ca = nc; cross = old ^ nc;
-      }
-    }
+    for (int b = 0; b < 3; b++) if (b == a) { cross = cs[b] ^ nx[b]; cs[b] = nx[b]; ca = nx[b]; lim = r.lim[b]; }
     la = a; lt = ta; steps++;
-    exact = (lvl == 0);
-    if (lvl == 0 && (cross >> 3)) {
-      lvl = 1;
-#pragma unroll
-      for (int i = 0; i < 3; i++) tn[i] = sp1[i];
-    }
-    if (lvl == 1 && (cross >> 7)) {
-      lvl = 2;
-#pragma unroll
-      for (int i = 0; i < 3; i++) tn[i] = sp2[i];
-    }
-    if (lvl == 2) {
-      int na = 0;
-#pragma unroll
-      for (int b = 0; b < 3; b++) if (b == a) na = v.nvox[b];
-      alive = (unsigned)ca < (unsigned)na;
-    }
-    const int sh2 = lvl == 0 ? 0 : (lvl == 1 ? 3 : 7);
-#pragma unroll
-    for (int b = 0; b < 3; b++) if (b == a) tn[b] = next_plane_t(r, b, ca, sh2);
+    gran = sh;
+    const unsigned ucross = (unsigned)cross;
+    need = (ucross >> 9) ? 4 : ((ucross >> 7) ? 3 : ((ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0)));
+    if (need >= 3) alive = ca < lim;
   }
+#pragma unroll
+  for (int i = 0; i < 3; i++) tr.c[i] = hit ? c[i] : (cs[i] ^ r.sgn[i]);
   tr.hit = hit; tr.axis = la; tr.t = lt; tr.steps = steps;
-  tr.c[0] = c[0]; tr.c[1] = c[1]; tr.c[2] = c[2];
 }
 
-
 __device__ __forceinline__ uint32_t to_un8(float x) { return (uint32_t)__fadd_rn(__fmul_rn(x, 255.0f), 0.5f); }
+
+struct ShadowJob { float p[3]; int c[3]; int owner; };
 
 template <bool STATS>
 __global__ void __launch_bounds__(256) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
                                                        int rank, int world, int layout, int tiles_x, int n_tiles,
                                                        MesoHitRecord* __restrict__ out, RayStatsDev* stats,
                                                        uint8_t* touch_chunk, uint8_t* touch_brick) {
-  extern __shared__ uint32_t s_any[];
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_any = s_dyn;
+  uint32_t* s_region = s_dyn + v.chunk_words;
+  __shared__ ShadowJob s_jobs[256];
+  __shared__ uint8_t s_shadow[256];
+  __shared__ int s_warp_cnt[8];
   for (int i = threadIdx.x; i < v.chunk_words; i += blockDim.x) s_any[i] = v.chunk_any[i];
+  for (int i = threadIdx.x; i < v.region_words; i += blockDim.x) s_region[i] = v.region_any[i];
   __syncthreads();
   const int local_tile = blockIdx.x;
   const int tile = local_tile * world + rank;
-  if (tile >= n_tiles) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tx = (warp & 3) * 8 + (lane & 7), ty = (warp >> 2) * 4 + (lane >> 3);
   const int px = (tile % tiles_x) * MESO_TILE_W + tx;
   const int py = (tile / tiles_x) * MESO_TILE_H + ty;
-  if (px >= width || py >= height) return;
+  const bool valid = tile < n_tiles && px < width && py < height;
 
-  Scene sc; sc.v = &v; sc.s_any = s_any; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
+  Scene sc; sc.v = &v; sc.s_any = s_any; sc.s_region = s_region; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
 
-  const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)px, 0.5f), rs.two_over_w), 1.0f);
-  const float fy = __fsub_rn(1.0f, __fmul_rn(__fadd_rn((float)py, 0.5f), rs.two_over_h));
-  float d[3];
+  // ---- phase 1: primary ray ----
+  Trace tr; tr.hit = false; tr.axis = -1; tr.t = 0.0f; tr.steps = 0; tr.c[0] = tr.c[1] = tr.c[2] = 0;
+  float p[3] = {0.f, 0.f, 0.f};
+  int face = 7, shadow = 0;
+  bool want_shadow = false;
+  unsigned steps = 0, n_shadow = 0;
+  if (valid) {
+    const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)px, 0.5f), rs.two_over_w), 1.0f);
+    const float fy = __fsub_rn(1.0f, __fmul_rn(__fadd_rn((float)py, 0.5f), rs.two_over_h));
+    float d[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) d[i] = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[i]), __fmul_rn(fy, rs.V[i])), rs.F[i]);
-  const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    for (int i = 0; i < 3; i++) d[i] = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[i]), __fmul_rn(fy, rs.V[i])), rs.F[i]);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
 #pragma unroll
-  for (int i = 0; i < 3; i++) d[i] = __fdiv_rn(d[i], len);
-  Ray r; ray_init(r, rs.o, d);
-  int c0[3];
+    for (int i = 0; i < 3; i++) d[i] = __fdiv_rn(d[i], len);
+    Ray r; ray_init(r, rs.o, d, v);
+    int c0[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) c0[i] = clamp_floor_to_int(rs.o[i]);
-  Trace tr;
-  trace<STATS>(sc, r, c0, tr);
-  unsigned steps = tr.steps, n_shadow = 0;
-
-  MesoHitRecord rec;
-  if (!tr.hit) {
-    rec.w0 = 0xFFFFFFFFu; rec.w1 = 0x0007FFFFu; rec.t = __int_as_float(0x7F800000); rec.rgba = 0xFF000000u;
-  } else {
-    int face = 6, shadow = 0;
-    float p[3];
+    for (int i = 0; i < 3; i++) c0[i] = clamp_floor_to_int(rs.o[i]);
+    trace<STATS>(sc, r, c0, tr);
+    steps = tr.steps;
+    if (tr.hit) {
+      face = 6;
 #pragma unroll
-    for (int i = 0; i < 3; i++) p[i] = __fadd_rn(r.o[i], __fmul_rn(r.d[i], tr.t));
-    if (tr.axis >= 0) {
-      const int ax = tr.axis;
-      int st_ax = 0; float l_ax = 0.0f;
+      for (int i = 0; i < 3; i++) p[i] = __fadd_rn(r.o[i], __fmul_rn(r.d[i], tr.t));
+      if (tr.axis >= 0) {
+        const int ax = tr.axis;
+        int st_ax = 0; float l_ax = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 3; i++) if (i == ax) { st_ax = r.step[i]; l_ax = rs.L[i]; p[i] = (float)(r.step[i] > 0 ? tr.c[i] : tr.c[i] + 1); }
-      face = ax * 2 + (st_ax > 0 ? 0 : 1);
-      if (flags & MESO_FLAG_SHADOW) {
-        const bool facing = st_ax > 0 ? (l_ax < 0.0f) : (l_ax > 0.0f);
-        if (!facing) shadow = 1;
-        else {
-          Ray sr; ray_init(sr, p, rs.L);
-          int sc0[3];
-#pragma unroll
-          for (int i = 0; i < 3; i++) sc0[i] = tr.c[i] - (i == ax ? st_ax : 0);
-          Trace st;
-          trace<STATS>(sc, sr, sc0, st);
-          steps += st.steps; n_shadow = 1;
-          shadow = st.hit ? 1 : 0;
+        for (int i = 0; i < 3; i++) if (i == ax) { st_ax = r.step[i]; l_ax = rs.L[i]; p[i] = (float)(r.step[i] > 0 ? tr.c[i] : tr.c[i] + 1); }
+        face = ax * 2 + (st_ax > 0 ? 0 : 1);
+        if (flags & MESO_FLAG_SHADOW) {
+          const bool facing = st_ax > 0 ? (l_ax < 0.0f) : (l_ax > 0.0f);
+          if (!facing) shadow = 1; else want_shadow = true;
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) p[i] = r.o[i];
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 3; i++) p[i] = r.o[i];
     }
-    const float shade = shadow ? 0.5f : 1.0f;
-    uint32_t ch[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      float local = __fsub_rn(__fmul_rn(p[i], 0.125f), (float)(tr.c[i] >> 3));
-      local = fminf(fmaxf(local, 0.0f), 1.0f);
-      const float col = __fadd_rn(__fmul_rn(__fsub_rn(local, 0.5f), 0.5f), 0.5f);  // SimpleVoxel.cpp:222
-      ch[i] = to_un8(__fmul_rn(col, shade));
-    }
-    rec.w0 = (uint32_t)tr.c[0] | ((uint32_t)tr.c[1] << 16);
-    rec.w1 = (uint32_t)tr.c[2] | ((uint32_t)face << 16) | ((uint32_t)shadow << 19) | (1u << 20);
-    rec.t = tr.t;
-    rec.rgba = ch[0] | (ch[1] << 8) | (ch[2] << 16);
   }
-  size_t dst;
-  if (layout == MESO_LAYOUT_FRAME) dst = (size_t)py * width + px;
-  else dst = (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
-  reinterpret_cast<uint4*>(out)[dst] = make_uint4(rec.w0, rec.w1, __float_as_uint(rec.t), rec.rgba);
+
+  // ---- phase 2: shadow rays, compacted across the CTA ----
+  if (flags & MESO_FLAG_SHADOW) {
+    const unsigned bal = __ballot_sync(0xffffffffu, want_shadow);
+    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const int n = s_warp_cnt[w]; if (w < warp) base += n; total += n; }
+    if (want_shadow) {
+      const int idx = base + __popc(bal & ((1u << lane) - 1u));
+      ShadowJob& j = s_jobs[idx];
+      const int ax = tr.axis;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { j.p[i] = p[i]; j.c[i] = tr.c[i] - ((i == ax) ? ((face & 1) ? -1 : 1) : 0); }
+      j.owner = threadIdx.x;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < total) {
+      const ShadowJob j = s_jobs[threadIdx.x];
+      Ray sr; ray_init(sr, j.p, rs.L, v);
+      Trace st;
+      trace<STATS>(sc, sr, j.c, st);
+      s_shadow[j.owner] = st.hit ? 1 : 0;
+      steps += st.steps; n_shadow = 1;
+    }
+    __syncthreads();
+    if (want_shadow) shadow = s_shadow[threadIdx.x];
+  }
+
+  // ---- phase 3: shade + store ----
+  if (valid) {
+    MesoHitRecord rec;
+    if (!tr.hit) {
+      rec.w0 = 0xFFFFFFFFu; rec.w1 = 0x0007FFFFu; rec.t = F_INF; rec.rgba = 0xFF000000u;
+    } else {
+      const float shade = shadow ? 0.5f : 1.0f;
+      uint32_t ch[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float local = __fsub_rn(__fmul_rn(p[i], 0.125f), (float)(tr.c[i] >> 3));
+        local = fminf(fmaxf(local, 0.0f), 1.0f);
+        const float col = __fadd_rn(__fmul_rn(__fsub_rn(local, 0.5f), 0.5f), 0.5f);  // SimpleVoxel.cpp:222
+        ch[i] = to_un8(__fmul_rn(col, shade));
+      }
+      rec.w0 = (uint32_t)tr.c[0] | ((uint32_t)tr.c[1] << 16);
+      rec.w1 = (uint32_t)tr.c[2] | ((uint32_t)face << 16) | ((uint32_t)shadow << 19) | (1u << 20);
+      rec.t = tr.t;
+      rec.rgba = ch[0] | (ch[1] << 8) | (ch[2] << 16);
+    }
+    size_t dst;
+    if (layout == MESO_LAYOUT_FRAME) dst = (size_t)py * width + px;
+    else dst = (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
+    reinterpret_cast<uint4*>(out)[dst] = make_uint4(rec.w0, rec.w1, __float_as_uint(rec.t), rec.rgba);
+  }
 
   if (STATS) {
-    // warp-aggregate (full warps), one atomic per warp and counter
-    unsigned long long v0 = 1, v1 = n_shadow, v2 = tr.hit ? 1 : 0, v3 = steps;
-    const unsigned m = __activemask();
-    if (m == 0xffffffffu) {
+    unsigned long long v0 = valid ? 1 : 0, v1 = n_shadow, v2 = tr.hit ? 1 : 0, v3 = steps;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        v0 += __shfl_xor_sync(m, v0, o); v1 += __shfl_xor_sync(m, v1, o);
-        v2 += __shfl_xor_sync(m, v2, o); v3 += __shfl_xor_sync(m, v3, o);
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
     }
-    if (lane == 0 || m != 0xffffffffu) {
+    if (lane == 0) {
       atomicAdd(&stats->primary, v0); atomicAdd(&stats->shadow, v1);
       atomicAdd(&stats->hits, v2); atomicAdd(&stats->steps, v3);
     }
@@ -344,7 +384,7 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
   const int n_tiles = tiles_x * tiles_y;
   const int local_tiles = (n_tiles - rank + world - 1) / world;
   if (local_tiles <= 0) return;
-  const size_t smem = sizeof(uint32_t) * (size_t)v.chunk_words;
+  const size_t smem = sizeof(uint32_t) * ((size_t)v.chunk_words + (size_t)v.region_words);
   if (d_stats)
     raymarch_kernel<true><<<local_tiles, 256, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x, n_tiles,
                                                                  d_out, d_stats, d_touch_chunk, d_touch_brick);

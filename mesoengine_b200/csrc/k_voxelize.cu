@@ -253,10 +253,40 @@ __global__ void __launch_bounds__(256) finalize_kernel(DVolume v) {
   v.of[c * 64 + 32 + lane] = make_ulonglong2(o1, f1);
   const bool any = __any_sync(0xffffffffu, (o0 | o1) != 0ull);
   const bool all = __all_sync(0xffffffffu, (f0 & f1) == ~0ull);
+  // 32^3-voxel cells (4x4x4 bricks): word w = bz*4 + by/4 feeds cells (x/4 = nibble, y/4 = w & 3, z/4 = w >> 4)
+  uint32_t lo = 0, hi = 0;
+  {
+    const uint32_t r0 = (uint32_t)((o0 | (o0 >> 16) | (o0 >> 32) | (o0 >> 48)) & 0xFFFFull);
+    const uint32_t r1 = (uint32_t)((o1 | (o1 >> 16) | (o1 >> 32) | (o1 >> 48)) & 0xFFFFull);
+    uint32_t n0 = 0, n1 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { n0 |= ((r0 >> (4 * i)) & 0xFu) ? (1u << i) : 0u; n1 |= ((r1 >> (4 * i)) & 0xFu) ? (1u << i) : 0u; }
+    lo = n0 << (4 * (lane & 3) + 16 * (lane >> 4));          // words 0..31  -> z/4 in {0,1}
+    hi = n1 << (4 * (lane & 3) + 16 * (lane >> 4));          // words 32..63 -> z/4 in {2,3}
+  }
+  lo = __reduce_or_sync(0xffffffffu, lo);
+  hi = __reduce_or_sync(0xffffffffu, hi);
   if (lane == 0) {
+    v.cells[c] = (uint64_t)lo | ((uint64_t)hi << 32);
     if (any) atomicOr(&v.chunk_any[c >> 5], 1u << (c & 31));
     if (all) atomicOr(&v.chunk_full[c >> 5], 1u << (c & 31));
   }
+}
+
+// bit per 512^3-voxel region (4x4x4 chunks): one thread per region
+__global__ void region_kernel(DVolume v) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nr = v.rdims[0] * v.rdims[1] * v.rdims[2];
+  if (r >= nr) return;
+  const int rx = r % v.rdims[0], ry = (r / v.rdims[0]) % v.rdims[1], rz = r / (v.rdims[0] * v.rdims[1]);
+  bool any = false;
+  for (int z = rz * 4; z < min(rz * 4 + 4, v.dims[2]); z++)
+    for (int y = ry * 4; y < min(ry * 4 + 4, v.dims[1]); y++)
+      for (int x = rx * 4; x < min(rx * 4 + 4, v.dims[0]); x++) {
+        const int ci = x + v.dims[0] * (y + v.dims[1] * z);
+        any |= (v.chunk_any[ci >> 5] >> (ci & 31)) & 1u;
+      }
+  if (any) atomicOr(&v.region_any[r >> 5], 1u << (r & 31));
 }
 
 __global__ void scatter_payload_kernel(DVolume v, const uint64_t* __restrict__ keys, const uint64_t* __restrict__ payload, int64_t n) {
@@ -300,8 +330,11 @@ void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const doub
 void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v) {
   cudaMemsetAsync(v.chunk_any, 0, sizeof(uint32_t) * v.chunk_words, lc.stream);
   cudaMemsetAsync(v.chunk_full, 0, sizeof(uint32_t) * v.chunk_words, lc.stream);
+  cudaMemsetAsync(v.region_any, 0, sizeof(uint32_t) * v.region_words, lc.stream);
   finalize_kernel<<<(unsigned)((v.nchunks + 7) / 8), 256, 0, lc.stream>>>(v);
-  (*lc.launches)++;
+  const int nr = v.rdims[0] * v.rdims[1] * v.rdims[2];
+  region_kernel<<<(nr + 127) / 128, 128, 0, lc.stream>>>(v);
+  (*lc.launches) += 2;
 }
 
 void launch_scatter_payload(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, const uint64_t* d_payload, int64_t n) {

@@ -106,7 +106,7 @@ int meso_ctx_create(int device, MesoCtx** out) {
 
 static void free_scene(MesoCtx* c) {
   DVolume& v = c->v;
-  cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
+  cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.cells); cudaFree(v.region_any); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
   cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count);
   cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
@@ -178,6 +178,10 @@ int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const in
   const size_t nc = (size_t)v.nchunks;
   CK(cudaMalloc(&v.occ, nc * 64 * 8)); CK(cudaMalloc(&v.full, nc * 64 * 8)); CK(cudaMalloc(&v.mips, nc * 3 * 64 * 8));
   CK(cudaMalloc(&v.of, nc * 64 * 16)); CK(cudaMemsetAsync(v.of, 0, nc * 64 * 16, c->stream));
+  for (int i = 0; i < 3; i++) v.rdims[i] = (dims[i] + 3) / 4;
+  v.region_words = (v.rdims[0] * v.rdims[1] * v.rdims[2] + 31) / 32;
+  CK(cudaMalloc(&v.cells, nc * 8)); CK(cudaMemsetAsync(v.cells, 0, nc * 8, c->stream));
+  CK(cudaMalloc(&v.region_any, (size_t)v.region_words * 4)); CK(cudaMemsetAsync(v.region_any, 0, (size_t)v.region_words * 4, c->stream));
   CK(cudaMalloc(&v.bptr, nc * MESO_BLOCKS * 4));
   CK(cudaMalloc(&v.pool, (size_t)max_bricks * 64));
   CK(cudaMalloc(&v.chunk_any, (size_t)v.chunk_words * 4)); CK(cudaMalloc(&v.chunk_full, (size_t)v.chunk_words * 4));

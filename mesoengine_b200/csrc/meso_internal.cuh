@@ -27,6 +27,10 @@ struct DVolume {
   uint64_t* pool;       // max_bricks*8 words
   uint32_t* chunk_any;  // bit per chunk: has >=1 block
   uint32_t* chunk_full; // bit per chunk: all 4096 bricks full
+  uint64_t* cells;      // per chunk: bit per 32^3-voxel cell (4x4x4 bricks), index x + 4y + 16z (derived)
+  uint32_t* region_any; // bit per 512^3-voxel region (4x4x4 chunks) (derived)
+  int rdims[3];         // regions per axis = ceil(dims / 4)
+  int region_words;
   uint32_t* pool_count; // device counter: payload slots in use
   uint32_t max_bricks;
   int chunk_words;      // number of u32 words in chunk_any / chunk_full

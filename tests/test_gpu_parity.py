@@ -192,8 +192,10 @@ def test_raymarch_stats_and_u(ctx, orc):
     cam = _cams(orc, origin, dims, w, h)[2]
     st = ctx.raymarch_stats(cam, w, h)
     _, ref = vol.raymarch(orc.ray_setup(cam, vol.origin, w, h), w, h, stats=True)
-    for k in ("primary", "shadow", "hits", "steps", "touched_chunks", "touched_bricks", "u_bytes"):
+    # `steps` is not a parity quantity: the kernel also skips 512^3 regions and 32^3 cells, the oracle walks 128/8/1
+    for k in ("primary", "shadow", "hits", "touched_chunks", "touched_bricks", "u_bytes"):
         assert int(st[k]) == int(ref[k]), k
+    assert 0 < int(st["steps"]) <= int(ref["steps"])
 
 
 def test_raymarch_tile_partition_composes(ctx, capi, orc):
