@@ -111,9 +111,9 @@ class Context:
         self.nchunks = 0
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:  # `lib` is already None during interpreter shutdown
             lib.meso_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         self.close()

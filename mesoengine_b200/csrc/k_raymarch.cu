@@ -10,35 +10,38 @@
 // from the same keys only when the walk has to look finer (advance_axis), so the hierarchical walk visits exactly the
 // voxels the oracle's flat walk would: hit voxel, face and t are bit-identical to oracle/orc_raymarch.c.
 //
-// Mapping: CTA = one 32x8 screen tile (8 warps), warp = 8x4 pixels (a 128 B-aligned 4-line store of 16 B records).
+// Execution model: CTA = one 32x8 screen tile (tile t belongs to rank t % world), warp = 8x4 pixels.  All primary rays
+// of a warp start together at the eye and stay at similar levels of the hierarchy; the shadow rays of the tile are
+// compacted across the CTA (ballot + prefix sum through shared memory) and traced together in dense warps.
 // Region / chunk any-bits are staged in shared memory; 32^3-cell masks, {occ,full} word pairs (16 B loads) and brick
-// slices are cached in registers behind tags.  Shadow rays are compacted across the CTA (ballot + prefix sum through
-// shared memory) so the second trace runs in dense warps.  Multi-GPU: tile t belongs to rank t % world.
+// slices are cached in registers behind tags.
+// (A persistent "idle lanes pull the next pixel" variant was measured and dropped: mixing rays of different phases in
+// one warp cut SIMT efficiency from 20/32 to 8/32 active threads -- profiles/README.md.)
+//
+// All per-ray state is kept in named scalars (x/y/z members, SEL3 selects), never in indexable arrays: the compiler
+// turns "if (i == a) v = arr[i]" chains into a dynamically indexed load, which would push the whole state to local memory.
 #include "meso_internal.cuh"
 
 #define F_INF __int_as_float(0x7F800000)
+#define RM_THREADS 256
+#define RM_REFILL_MIN 8   // retire/refill when at least this many lanes are idle
+#define SEL3(a, X, Y, Z) ((a) == 0 ? (X) : ((a) == 1 ? (Y) : (Z)))
 
 struct Ray {
-  float o[3], d[3], inv[3];
-  int step[3];  // +1 / -1 / 0 (inactive: |d| < 1e-20, never crosses a plane)
-  int sgn[3];   // 0 or -1: coordinates are kept mirrored (c ^ sgn) so every step is "+"
-  int lim[3];   // mirrored coordinate at which the ray has left the grid on that axis
+  float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+  int sx, sy, sz;  // step: +1 / -1 / 0 (inactive: |d| < 1e-20, never crosses a plane); mirror sign = step >> 31
 };
 
-__device__ __forceinline__ float plane_t(const Ray& r, int a, int plane) {
-  return __fmul_rn(__fsub_rn((float)plane, r.o[a]), r.inv[a]);
-}
+__device__ __forceinline__ float plane_t1(float o, float inv, int plane) { return __fmul_rn(__fsub_rn((float)plane, o), inv); }
 __device__ __forceinline__ bool key_less(float t1, int a1, float t2, int a2) { return t1 < t2 || (t1 == t2 && a1 < a2); }
 
-__device__ __forceinline__ void ray_init(Ray& r, const float o[3], const float d[3], const DVolume& v) {
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    r.o[i] = o[i]; r.d[i] = d[i];
-    if (fabsf(d[i]) >= 1e-20f) { r.inv[i] = __fdiv_rn(1.0f, d[i]); r.step[i] = d[i] > 0.0f ? 1 : -1; }
-    else { r.inv[i] = 0.0f; r.step[i] = 0; }
-    r.sgn[i] = r.step[i] < 0 ? -1 : 0;
-    r.lim[i] = r.step[i] > 0 ? v.nvox[i] : (r.step[i] < 0 ? 0 : 0x7FFFFFFF);
-  }
+__device__ __forceinline__ void dir1(float d, float& inv, int& step) {
+  if (fabsf(d) >= 1e-20f) { inv = __fdiv_rn(1.0f, d); step = d > 0.0f ? 1 : -1; }
+  else { inv = 0.0f; step = 0; }
+}
+__device__ __forceinline__ void ray_dir(Ray& r, float dx, float dy, float dz) {
+  r.dx = dx; r.dy = dy; r.dz = dz;
+  dir1(dx, r.ix, r.sx); dir1(dy, r.iy, r.sy); dir1(dz, r.iz, r.sz);
 }
 
 __device__ __forceinline__ int clamp_floor_to_int(float x) {
@@ -48,11 +51,10 @@ __device__ __forceinline__ int clamp_floor_to_int(float x) {
 }
 
 // True coordinate on axis b after consuming every crossing with key < (ts, as), starting from the (older) true cell
-// coordinate cur.
-__device__ __forceinline__ int advance_axis(const Ray& r, int b, int cur, float ts, int as) {
-  const int st = r.step[b];
+// coordinate cur.  (o, d, inv, st) are the ray's components on axis b.
+__device__ __forceinline__ int advance_axis(float o, float d, float inv, int st, int b, int cur, float ts, int as) {
   if (st == 0) return cur;
-  const float pos = __fadd_rn(r.o[b], __fmul_rn(r.d[b], ts));
+  const float pos = __fadd_rn(o, __fmul_rn(d, ts));
   const float fl = floorf(pos);
   int e = (int)fminf(fmaxf(fl, -1.0e9f), 1.0e9f);
   // Fast path (DESIGN.md "advance_axis shortcut"): when the estimated position is farther than eps from every voxel
@@ -65,12 +67,12 @@ __device__ __forceinline__ int advance_axis(const Ray& r, int b, int cur, float 
   if (st > 0) e = max(e, cur); else e = min(e, cur);
   for (;;) {
     const int pa = st > 0 ? e + 1 : e;
-    if (key_less(plane_t(r, b, pa), b, ts, as)) e += st; else break;
+    if (key_less(plane_t1(o, inv, pa), b, ts, as)) e += st; else break;
   }
   for (;;) {
     if (e == cur) break;
     const int pb = st > 0 ? e : e + 1;
-    if (!key_less(plane_t(r, b, pb), b, ts, as)) e -= st; else break;
+    if (!key_less(plane_t1(o, inv, pb), b, ts, as)) e -= st; else break;
   }
   return e;
 }
@@ -83,216 +85,239 @@ struct Scene {
   uint8_t* touch_brick;
 };
 
-__device__ __forceinline__ bool inside(const DVolume& v, const int c[3]) {
-  return (unsigned)c[0] < (unsigned)v.nvox[0] && (unsigned)c[1] < (unsigned)v.nvox[1] && (unsigned)c[2] < (unsigned)v.nvox[2];
-}
-__device__ __forceinline__ bool gone(const DVolume& v, const Ray& r, const int c[3]) {
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    if (r.step[i] > 0) { if (c[i] >= v.nvox[i]) return true; }
-    else if (r.step[i] < 0) { if (c[i] < 0) return true; }
-    else if (c[i] < 0 || c[i] >= v.nvox[i]) return true;
-  }
-  return false;
+// Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every step is "(cs | mask) + 1".
+// Above voxel level only the last stepped axis is exact; the other two hold an older true coordinate inside the same
+// cell of the level that was stepped (`gran`), and are made exact before the walk looks finer.
+struct Walk {
+  int csx, csy, csz;
+  int la; float lt;
+  int gran, need;
+  int ci, wtag, ztag;
+  uint32_t slot;
+  unsigned long long cellmask, wocc, wfull, slice;
+};
+
+enum { W_CONTINUE = 0, W_HIT = 1, W_EXIT = 2 };
+
+// make the two axes other than w.la exact (true coordinates cx,cy,cz in/out)
+__device__ __forceinline__ void sync_axes(const Ray& r, const Walk& w, int& cx, int& cy, int& cz) {
+  if (w.la != 0) cx = advance_axis(r.ox, r.dx, r.ix, r.sx, 0, cx, w.lt, w.la);
+  if (w.la != 1) cy = advance_axis(r.oy, r.dy, r.iy, r.sy, 1, cy, w.lt, w.la);
+  if (w.la != 2) cz = advance_axis(r.oz, r.dz, r.iz, r.sz, 2, cz, w.lt, w.la);
 }
 
-struct Trace { bool hit; int c[3]; int axis; float t; unsigned steps; };
-
-// levels: 4 = region (512^3), 3 = chunk (128^3), 2 = cell (32^3), 1 = brick (8^3), 0 = voxel
-template <bool STATS>
-__device__ __forceinline__ void trace(const Scene& s, const Ray& r, const int c0[3], Trace& tr) {
-  const DVolume& v = *s.v;
-  int c[3] = {c0[0], c0[1], c0[2]};
-  int la = -1; float lt = 0.0f; unsigned steps = 0;
-  bool hit = false, alive = true;
-  if (!inside(v, c)) {
-    if (gone(v, r, c)) alive = false;
+// Places the ray at its first cell inside the grid (entry from outside included).  Returns false if it never enters.
+__device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int cx, int cy, int cz, Walk& w, unsigned& steps) {
+  const int nx = v.nvox[0], ny = v.nvox[1], nz = v.nvox[2];
+  w.la = -1; w.lt = 0.0f;
+  bool alive = true;
+  const bool in = (unsigned)cx < (unsigned)nx && (unsigned)cy < (unsigned)ny && (unsigned)cz < (unsigned)nz;
+  if (!in) {
+    bool gone = false;
+    gone |= r.sx > 0 ? cx >= nx : (r.sx < 0 ? cx < 0 : (cx < 0 || cx >= nx));
+    gone |= r.sy > 0 ? cy >= ny : (r.sy < 0 ? cy < 0 : (cy < 0 || cy >= ny));
+    gone |= r.sz > 0 ? cz >= nz : (r.sz < 0 ? cz < 0 : (cz < 0 || cz >= nz));
+    if (gone) alive = false;
     else {
       int a = -1; float ta = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const bool before = (r.step[i] > 0 && c[i] < 0) || (r.step[i] < 0 && c[i] >= v.nvox[i]);
-        if (before) {
-          const float ti = plane_t(r, i, r.step[i] > 0 ? 0 : v.nvox[i]);
-          if (a < 0 || key_less(ta, a, ti, i)) { a = i; ta = ti; }
-        }
-      }
-#pragma unroll
-      for (int b = 0; b < 3; b++) {
-        if (b == a) c[b] = r.step[b] > 0 ? 0 : v.nvox[b] - 1;
-        else c[b] = advance_axis(r, b, c[b], ta, a);
-      }
-      la = a; lt = ta; steps = 1;
-      alive = inside(v, c);
+      if ((r.sx > 0 && cx < 0) || (r.sx < 0 && cx >= nx)) { const float ti = plane_t1(r.ox, r.ix, r.sx > 0 ? 0 : nx); if (a < 0 || key_less(ta, a, ti, 0)) { a = 0; ta = ti; } }
+      if ((r.sy > 0 && cy < 0) || (r.sy < 0 && cy >= ny)) { const float ti = plane_t1(r.oy, r.iy, r.sy > 0 ? 0 : ny); if (a < 0 || key_less(ta, a, ti, 1)) { a = 1; ta = ti; } }
+      if ((r.sz > 0 && cz < 0) || (r.sz < 0 && cz >= nz)) { const float ti = plane_t1(r.oz, r.iz, r.sz > 0 ? 0 : nz); if (a < 0 || key_less(ta, a, ti, 2)) { a = 2; ta = ti; } }
+      cx = a == 0 ? (r.sx > 0 ? 0 : nx - 1) : advance_axis(r.ox, r.dx, r.ix, r.sx, 0, cx, ta, a);
+      cy = a == 1 ? (r.sy > 0 ? 0 : ny - 1) : advance_axis(r.oy, r.dy, r.iy, r.sy, 1, cy, ta, a);
+      cz = a == 2 ? (r.sz > 0 ? 0 : nz - 1) : advance_axis(r.oz, r.dz, r.iz, r.sz, 2, cz, ta, a);
+      w.la = a; w.lt = ta; steps++;
+      alive = (unsigned)cx < (unsigned)nx && (unsigned)cy < (unsigned)ny && (unsigned)cz < (unsigned)nz;
     }
   }
-  // mirrored coordinates: cs = c ^ sgn.  Above voxel level only the last stepped axis is exact; the other two hold an
-  // older true coordinate inside the same cell of the level that was stepped, and are made exact before looking finer.
-  int cs[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) cs[i] = c[i] ^ r.sgn[i];
-  int gran = 0;  // shift of the level last stepped: non-stepped axes are only valid at this granularity
-  int need = 4;
-  int ci = 0, wtag = -1, ztag = -1;
-  uint32_t slot = 0;
-  unsigned long long cellmask = 0, wocc = 0, wfull = 0, slice = 0;
+  w.csx = cx ^ (r.sx >> 31); w.csy = cy ^ (r.sy >> 31); w.csz = cz ^ (r.sz >> 31);
+  w.gran = 0; w.need = 4; w.ci = 0; w.wtag = -1; w.ztag = -1; w.slot = 0;
+  w.cellmask = 0; w.wocc = 0; w.wfull = 0; w.slice = 0;
+  return alive;
+}
 
-  while (alive) {
-    int sh;
-    {
-#pragma unroll
-      for (int i = 0; i < 3; i++) c[i] = cs[i] ^ r.sgn[i];
-      bool go = true;  // keep looking finer
-      sh = 0;
-      if (need >= 4) {
-        const int ri = (c[0] >> 9) + v.rdims[0] * ((c[1] >> 9) + v.rdims[1] * (c[2] >> 9));
-        if (!((s.s_region[ri >> 5] >> (ri & 31)) & 1u)) { sh = 9; go = false; }
-      }
-#define MESO_SYNC_IF_COARSER(S)                                                            \
-      if (go && gran > (S)) { /* looking finer than the level that was stepped: make the other two axes exact */ \
-        _Pragma("unroll") for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);   \
-        _Pragma("unroll") for (int i = 0; i < 3; i++) cs[i] = c[i] ^ r.sgn[i];                                 \
-        gran = 0;                                                                            \
-      }
-      MESO_SYNC_IF_COARSER(7)
-      if (go && need >= 3) {
-        ci = (c[0] >> 7) + v.dims[0] * ((c[1] >> 7) + v.dims[1] * (c[2] >> 7));
-        if (!((s.s_any[ci >> 5] >> (ci & 31)) & 1u)) { sh = 7; go = false; }
-        else {
-          if (STATS) s.touch_chunk[ci] = 1;
-          cellmask = __ldg(&v.cells[ci]);
-          wtag = -1;
-        }
-      }
-      MESO_SYNC_IF_COARSER(5)
-      if (go && need >= 2) {
-        const int e = ((c[0] >> 5) & 3) + 4 * ((c[1] >> 5) & 3) + 16 * ((c[2] >> 5) & 3);
-        if (!((cellmask >> e) & 1ull)) { sh = 5; go = false; }
-      }
-      MESO_SYNC_IF_COARSER(3)
-      if (go && need >= 1) {
-        const int bx = (c[0] >> 3) & 15, by = (c[1] >> 3) & 15, bz = (c[2] >> 3) & 15;
-        const int w = bz * 4 + (by >> 2);
-        if (w != wtag) {
-          const ulonglong2 p = __ldg(&v.of[(size_t)ci * 64 + w]);
-          wocc = p.x; wfull = p.y; wtag = w;
-        }
-        const int bit = bx + 16 * (by & 3);
-        if (!((wocc >> bit) & 1ull)) { sh = 3; go = false; }
-        else {
-          if ((wfull >> bit) & 1ull) {
-            if (gran > 0) {
-#pragma unroll
-              for (int b = 0; b < 3; b++) if (b != la) c[b] = advance_axis(r, b, c[b], lt, la);
-            }
-            hit = true; break;
-          }
-          slot = __ldg(&v.bptr[(size_t)ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
-          if (STATS) s.touch_brick[slot] = 1;
-          ztag = -1;
-        }
-      }
-      MESO_SYNC_IF_COARSER(0)
-      if (go) {
-        const int z = c[2] & 7;
-        if (z != ztag) { slice = __ldg(&v.pool[(size_t)slot * 8 + z]); ztag = z; }
-        if ((slice >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1ull) { hit = true; break; }
-      }
-    }
-    // ---- one step at level sh: consume the smallest of the three pending keys (ties: lower axis first) ----
-    const int mask = (1 << sh) - 1;
-    int nx[3]; float tn[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      nx[i] = (cs[i] | mask) + 1;                         // mirrored coordinate after crossing
-      const int pl = (nx[i] ^ r.sgn[i]) - r.sgn[i];       // true plane index
-      const float t = __fmul_rn(__fsub_rn((float)pl, r.o[i]), r.inv[i]);
-      tn[i] = r.step[i] != 0 ? t : F_INF;
-    }
-    int a = 0; float ta = tn[0];
-    if (tn[1] < ta) { a = 1; ta = tn[1]; }
-    if (tn[2] < ta) { a = 2; ta = tn[2]; }
-    if (!(ta < F_INF)) break;  // zero direction
-    int cross = 0, lim = 0, ca = 0;
-#pragma unroll
-    for (int b = 0; b < 3; b++) if (b == a) { cross = cs[b] ^ nx[b]; cs[b] = nx[b]; ca = nx[b]; lim = r.lim[b]; }
-    la = a; lt = ta; steps++;
-    gran = sh;
-    const unsigned ucross = (unsigned)cross;
-    need = (ucross >> 9) ? 4 : ((ucross >> 7) ? 3 : ((ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0)));
-    if (need >= 3) alive = ca < lim;
+// One iteration: classify the current cell from the coarsest level that changed down to the first empty level (or a
+// solid voxel), then take one step at that level.  levels: 4 region (512^3), 3 chunk (128^3), 2 cell (32^3), 1 brick, 0 voxel.
+// On W_HIT (cx,cy,cz) is the exact hit voxel.
+template <bool STATS>
+__device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, int& cx, int& cy, int& cz, unsigned& steps) {
+  const DVolume& v = *s.v;
+  const int gx = r.sx >> 31, gy = r.sy >> 31, gz = r.sz >> 31;
+  cx = w.csx ^ gx; cy = w.csy ^ gy; cz = w.csz ^ gz;
+  bool go = true;  // keep looking finer
+  int sh = 0;
+#define MESO_SYNC_IF_COARSER(S)                                                                                 \
+  if (go && w.gran > (S)) { /* looking finer than the level that was stepped: make the other two axes exact */  \
+    sync_axes(r, w, cx, cy, cz);                                                                                \
+    w.csx = cx ^ gx; w.csy = cy ^ gy; w.csz = cz ^ gz;                                                          \
+    w.gran = 0;                                                                                                 \
   }
-#pragma unroll
-  for (int i = 0; i < 3; i++) tr.c[i] = hit ? c[i] : (cs[i] ^ r.sgn[i]);
-  tr.hit = hit; tr.axis = la; tr.t = lt; tr.steps = steps;
+  if (w.need >= 4) {
+    const int ri = (cx >> 9) + v.rdims[0] * ((cy >> 9) + v.rdims[1] * (cz >> 9));
+    if (!((s.s_region[ri >> 5] >> (ri & 31)) & 1u)) { sh = 9; go = false; }
+  }
+  MESO_SYNC_IF_COARSER(7)
+  if (go && w.need >= 3) {
+    w.ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
+    if (!((s.s_any[w.ci >> 5] >> (w.ci & 31)) & 1u)) { sh = 7; go = false; }
+    else {
+      if (STATS) s.touch_chunk[w.ci] = 1;
+      w.cellmask = __ldg(&v.cells[w.ci]);
+      w.wtag = -1;
+    }
+  }
+  MESO_SYNC_IF_COARSER(5)
+  if (go && w.need >= 2) {
+    const int e = ((cx >> 5) & 3) + 4 * ((cy >> 5) & 3) + 16 * ((cz >> 5) & 3);
+    if (!((w.cellmask >> e) & 1ull)) { sh = 5; go = false; }
+  }
+  MESO_SYNC_IF_COARSER(3)
+  if (go && w.need >= 1) {
+    const int bx = (cx >> 3) & 15, by = (cy >> 3) & 15, bz = (cz >> 3) & 15;
+    const int wi = bz * 4 + (by >> 2);
+    if (wi != w.wtag) {
+      const ulonglong2 p = __ldg(&v.of[(size_t)w.ci * 64 + wi]);
+      w.wocc = p.x; w.wfull = p.y; w.wtag = wi;
+    }
+    const int bit = bx + 16 * (by & 3);
+    if (!((w.wocc >> bit) & 1ull)) { sh = 3; go = false; }
+    else {
+      if ((w.wfull >> bit) & 1ull) {
+        if (w.gran > 0) sync_axes(r, w, cx, cy, cz);
+        return W_HIT;
+      }
+      w.slot = __ldg(&v.bptr[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
+      if (STATS) s.touch_brick[w.slot] = 1;
+      w.ztag = -1;
+    }
+  }
+  MESO_SYNC_IF_COARSER(0)
+  if (go) {
+    const int z = cz & 7;
+    if (z != w.ztag) { w.slice = __ldg(&v.pool[(size_t)w.slot * 8 + z]); w.ztag = z; }
+    if ((w.slice >> ((cx & 7) + 8 * (cy & 7))) & 1ull) return W_HIT;
+  }
+#undef MESO_SYNC_IF_COARSER
+  // ---- one step at level sh: consume the smallest of the three pending keys (ties: lower axis first) ----
+  const int mask = (1 << sh) - 1;
+  const int nxx = (w.csx | mask) + 1, nxy = (w.csy | mask) + 1, nxz = (w.csz | mask) + 1;   // mirrored coordinate after crossing
+  const float tx = r.sx != 0 ? plane_t1(r.ox, r.ix, (nxx ^ gx) - gx) : F_INF;               // (n ^ g) - g = true plane index
+  const float ty = r.sy != 0 ? plane_t1(r.oy, r.iy, (nxy ^ gy) - gy) : F_INF;
+  const float tz = r.sz != 0 ? plane_t1(r.oz, r.iz, (nxz ^ gz) - gz) : F_INF;
+  int a = 0; float ta = tx;
+  if (ty < ta) { a = 1; ta = ty; }
+  if (tz < ta) { a = 2; ta = tz; }
+  if (!(ta < F_INF)) return W_EXIT;  // zero direction
+  const int olds = SEL3(a, w.csx, w.csy, w.csz);
+  const int news = SEL3(a, nxx, nxy, nxz);
+  if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
+  w.la = a; w.lt = ta; steps++;
+  w.gran = sh;
+  const unsigned ucross = (unsigned)(olds ^ news);
+  w.need = (ucross >> 9) ? 4 : ((ucross >> 7) ? 3 : ((ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0)));
+  if (w.need >= 3) {
+    const int st = SEL3(a, r.sx, r.sy, r.sz);
+    const int nv = SEL3(a, v.nvox[0], v.nvox[1], v.nvox[2]);
+    if (news >= (st > 0 ? nv : 0)) return W_EXIT;   // mirrored coordinate at which the ray has left the grid
+  }
+  return W_CONTINUE;
 }
 
 __device__ __forceinline__ uint32_t to_un8(float x) { return (uint32_t)__fadd_rn(__fmul_rn(x, 255.0f), 0.5f); }
 
-struct ShadowJob { float p[3]; int c[3]; int owner; };
+// per-lane result of a finished pixel, kept until the next batched retire
+struct Done {
+  int cx, cy, cz;   // hit voxel
+  int face;         // 0..5, 6 inside, 7 miss
+  int shadow;
+  float t;
+  float px, py, pz; // hit point
+};
 
+__device__ __forceinline__ uint32_t shade1(float p, int c, float shade) {
+  float local = __fsub_rn(__fmul_rn(p, 0.125f), (float)(c >> 3));
+  local = fminf(fmaxf(local, 0.0f), 1.0f);
+  const float col = __fadd_rn(__fmul_rn(__fsub_rn(local, 0.5f), 0.5f), 0.5f);  // SimpleVoxel.cpp:222
+  return to_un8(__fmul_rn(col, shade));
+}
+__device__ __forceinline__ uint4 shade_record(const Done& dn) {
+  if (dn.face == 7) return make_uint4(0xFFFFFFFFu, 0x0007FFFFu, 0x7F800000u, 0xFF000000u);
+  const float shade = dn.shadow ? 0.5f : 1.0f;
+  const uint32_t r = shade1(dn.px, dn.cx, shade), g = shade1(dn.py, dn.cy, shade), b = shade1(dn.pz, dn.cz, shade);
+  return make_uint4((uint32_t)dn.cx | ((uint32_t)dn.cy << 16),
+                    (uint32_t)dn.cz | ((uint32_t)dn.face << 16) | ((uint32_t)dn.shadow << 19) | (1u << 20),
+                    __float_as_uint(dn.t), r | (g << 8) | (b << 16));
+}
+
+struct ShadowJob { float px, py, pz; int cx, cy, cz; int owner; };
+
+// CTA = one 32x8 screen tile; warp = 8x4 pixels (four full 128 B lines per record store).  All primary rays of a warp
+// start together from the same eye, so the lanes stay at similar levels of the hierarchy (measured: mixing rays of
+// different phases in one warp -- a persistent "refill idle lanes" loop -- dropped SIMT efficiency from 20/32 to 8/32).
+// Shadow rays are compacted across the CTA (ballot + prefix through shared memory) and start together as well.
 template <bool STATS>
-__global__ void __launch_bounds__(256) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
-                                                       int rank, int world, int layout, int tiles_x, int n_tiles,
-                                                       MesoHitRecord* __restrict__ out, RayStatsDev* stats,
-                                                       uint8_t* touch_chunk, uint8_t* touch_brick) {
+__global__ void __launch_bounds__(RM_THREADS) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
+                                                              int rank, int world, int layout, int tiles_x, int n_tiles,
+                                                              int local_tile0,
+                                                              MesoHitRecord* __restrict__ out, RayStatsDev* stats,
+                                                              uint8_t* touch_chunk, uint8_t* touch_brick) {
   extern __shared__ uint32_t s_dyn[];
   uint32_t* s_any = s_dyn;
   uint32_t* s_region = s_dyn + v.chunk_words;
-  __shared__ ShadowJob s_jobs[256];
-  __shared__ uint8_t s_shadow[256];
-  __shared__ int s_warp_cnt[8];
+  __shared__ ShadowJob s_jobs[RM_THREADS];
+  __shared__ uint8_t s_shadow[RM_THREADS];
+  __shared__ int s_warp_cnt[RM_THREADS / 32];
   for (int i = threadIdx.x; i < v.chunk_words; i += blockDim.x) s_any[i] = v.chunk_any[i];
   for (int i = threadIdx.x; i < v.region_words; i += blockDim.x) s_region[i] = v.region_any[i];
   __syncthreads();
-  const int local_tile = blockIdx.x;
-  const int tile = local_tile * world + rank;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int local_tile = local_tile0 + blockIdx.x;
+  const int tile = local_tile * world + rank;
   const int tx = (warp & 3) * 8 + (lane & 7), ty = (warp >> 2) * 4 + (lane >> 3);
   const int px = (tile % tiles_x) * MESO_TILE_W + tx;
   const int py = (tile / tiles_x) * MESO_TILE_H + ty;
   const bool valid = tile < n_tiles && px < width && py < height;
-
   Scene sc; sc.v = &v; sc.s_any = s_any; sc.s_region = s_region; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
+  const float Lx = rs.L[0], Ly = rs.L[1], Lz = rs.L[2];
 
   // ---- phase 1: primary ray ----
-  Trace tr; tr.hit = false; tr.axis = -1; tr.t = 0.0f; tr.steps = 0; tr.c[0] = tr.c[1] = tr.c[2] = 0;
-  float p[3] = {0.f, 0.f, 0.f};
-  int face = 7, shadow = 0;
+  Done dn; dn.cx = dn.cy = dn.cz = 0; dn.face = 7; dn.shadow = 0; dn.t = 0.f; dn.px = dn.py = dn.pz = 0.f;
   bool want_shadow = false;
+  int hit_axis = -1;
   unsigned steps = 0, n_shadow = 0;
   if (valid) {
     const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)px, 0.5f), rs.two_over_w), 1.0f);
     const float fy = __fsub_rn(1.0f, __fmul_rn(__fadd_rn((float)py, 0.5f), rs.two_over_h));
-    float d[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) d[i] = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[i]), __fmul_rn(fy, rs.V[i])), rs.F[i]);
-    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
-#pragma unroll
-    for (int i = 0; i < 3; i++) d[i] = __fdiv_rn(d[i], len);
-    Ray r; ray_init(r, rs.o, d, v);
-    int c0[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) c0[i] = clamp_floor_to_int(rs.o[i]);
-    trace<STATS>(sc, r, c0, tr);
-    steps = tr.steps;
-    if (tr.hit) {
-      face = 6;
-#pragma unroll
-      for (int i = 0; i < 3; i++) p[i] = __fadd_rn(r.o[i], __fmul_rn(r.d[i], tr.t));
-      if (tr.axis >= 0) {
-        const int ax = tr.axis;
-        int st_ax = 0; float l_ax = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 3; i++) if (i == ax) { st_ax = r.step[i]; l_ax = rs.L[i]; p[i] = (float)(r.step[i] > 0 ? tr.c[i] : tr.c[i] + 1); }
-        face = ax * 2 + (st_ax > 0 ? 0 : 1);
+    float dx = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[0]), __fmul_rn(fy, rs.V[0])), rs.F[0]);
+    float dy = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[1]), __fmul_rn(fy, rs.V[1])), rs.F[1]);
+    float dz = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[2]), __fmul_rn(fy, rs.V[2])), rs.F[2]);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
+    Ray r; r.ox = rs.o[0]; r.oy = rs.o[1]; r.oz = rs.o[2];
+    ray_dir(r, dx, dy, dz);
+    Walk w;
+    int cx = 0, cy = 0, cz = 0, res = W_EXIT;
+    if (walk_begin(v, r, clamp_floor_to_int(r.ox), clamp_floor_to_int(r.oy), clamp_floor_to_int(r.oz), w, steps)) {
+      do { res = walk_iter<STATS>(sc, r, w, cx, cy, cz, steps); } while (res == W_CONTINUE);
+    }
+    if (res == W_HIT) {
+      dn.t = w.lt; dn.cx = cx; dn.cy = cy; dn.cz = cz;
+      dn.px = __fadd_rn(r.ox, __fmul_rn(r.dx, w.lt)); dn.py = __fadd_rn(r.oy, __fmul_rn(r.dy, w.lt)); dn.pz = __fadd_rn(r.oz, __fmul_rn(r.dz, w.lt));
+      if (w.la >= 0) {
+        const int st_ax = SEL3(w.la, r.sx, r.sy, r.sz);
+        const float l_ax = SEL3(w.la, Lx, Ly, Lz);
+        const int c_ax = SEL3(w.la, cx, cy, cz);
+        const float pl = (float)(st_ax > 0 ? c_ax : c_ax + 1);
+        if (w.la == 0) dn.px = pl; else if (w.la == 1) dn.py = pl; else dn.pz = pl;
+        dn.face = w.la * 2 + (st_ax > 0 ? 0 : 1);
+        hit_axis = w.la;
         if (flags & MESO_FLAG_SHADOW) {
           const bool facing = st_ax > 0 ? (l_ax < 0.0f) : (l_ax > 0.0f);
-          if (!facing) shadow = 1; else want_shadow = true;
+          if (!facing) dn.shadow = 1; else want_shadow = true;
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < 3; i++) p[i] = r.o[i];
+        dn.face = 6;
+        dn.px = r.ox; dn.py = r.oy; dn.pz = r.oz;
       }
     }
   }
@@ -304,56 +329,42 @@ __global__ void __launch_bounds__(256) raymarch_kernel(DVolume v, MesoRaySetup r
     __syncthreads();
     int base = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) { const int n = s_warp_cnt[w]; if (w < warp) base += n; total += n; }
+    for (int k = 0; k < RM_THREADS / 32; k++) { const int n = s_warp_cnt[k]; if (k < warp) base += n; total += n; }
     if (want_shadow) {
-      const int idx = base + __popc(bal & ((1u << lane) - 1u));
-      ShadowJob& j = s_jobs[idx];
-      const int ax = tr.axis;
-#pragma unroll
-      for (int i = 0; i < 3; i++) { j.p[i] = p[i]; j.c[i] = tr.c[i] - ((i == ax) ? ((face & 1) ? -1 : 1) : 0); }
+      // origin = hit point, start cell = the empty cell in front of the hit face
+      const int nrm = (dn.face & 1) ? 1 : -1;
+      ShadowJob j;
+      j.px = dn.px; j.py = dn.py; j.pz = dn.pz;
+      j.cx = dn.cx + (hit_axis == 0 ? nrm : 0); j.cy = dn.cy + (hit_axis == 1 ? nrm : 0); j.cz = dn.cz + (hit_axis == 2 ? nrm : 0);
       j.owner = threadIdx.x;
+      s_jobs[base + __popc(bal & ((1u << lane) - 1u))] = j;
     }
     __syncthreads();
     if ((int)threadIdx.x < total) {
       const ShadowJob j = s_jobs[threadIdx.x];
-      Ray sr; ray_init(sr, j.p, rs.L, v);
-      Trace st;
-      trace<STATS>(sc, sr, j.c, st);
-      s_shadow[j.owner] = st.hit ? 1 : 0;
-      steps += st.steps; n_shadow = 1;
+      Ray r; r.ox = j.px; r.oy = j.py; r.oz = j.pz;
+      ray_dir(r, Lx, Ly, Lz);
+      Walk w;
+      int cx = 0, cy = 0, cz = 0, res = W_EXIT;
+      if (walk_begin(v, r, j.cx, j.cy, j.cz, w, steps)) {
+        do { res = walk_iter<STATS>(sc, r, w, cx, cy, cz, steps); } while (res == W_CONTINUE);
+      }
+      s_shadow[j.owner] = res == W_HIT ? 1 : 0;
+      n_shadow = 1;
     }
     __syncthreads();
-    if (want_shadow) shadow = s_shadow[threadIdx.x];
+    if (want_shadow) dn.shadow = s_shadow[threadIdx.x];
   }
 
   // ---- phase 3: shade + store ----
   if (valid) {
-    MesoHitRecord rec;
-    if (!tr.hit) {
-      rec.w0 = 0xFFFFFFFFu; rec.w1 = 0x0007FFFFu; rec.t = F_INF; rec.rgba = 0xFF000000u;
-    } else {
-      const float shade = shadow ? 0.5f : 1.0f;
-      uint32_t ch[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        float local = __fsub_rn(__fmul_rn(p[i], 0.125f), (float)(tr.c[i] >> 3));
-        local = fminf(fmaxf(local, 0.0f), 1.0f);
-        const float col = __fadd_rn(__fmul_rn(__fsub_rn(local, 0.5f), 0.5f), 0.5f);  // SimpleVoxel.cpp:222
-        ch[i] = to_un8(__fmul_rn(col, shade));
-      }
-      rec.w0 = (uint32_t)tr.c[0] | ((uint32_t)tr.c[1] << 16);
-      rec.w1 = (uint32_t)tr.c[2] | ((uint32_t)face << 16) | ((uint32_t)shadow << 19) | (1u << 20);
-      rec.t = tr.t;
-      rec.rgba = ch[0] | (ch[1] << 8) | (ch[2] << 16);
-    }
-    size_t dst;
-    if (layout == MESO_LAYOUT_FRAME) dst = (size_t)py * width + px;
-    else dst = (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
-    reinterpret_cast<uint4*>(out)[dst] = make_uint4(rec.w0, rec.w1, __float_as_uint(rec.t), rec.rgba);
+    const size_t dst = layout == MESO_LAYOUT_FRAME ? (size_t)py * width + px
+                                                   : (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
+    reinterpret_cast<uint4*>(out)[dst] = shade_record(dn);
   }
 
   if (STATS) {
-    unsigned long long v0 = valid ? 1 : 0, v1 = n_shadow, v2 = tr.hit ? 1 : 0, v3 = steps;
+    unsigned long long v0 = valid ? 1 : 0, v1 = n_shadow, v2 = dn.face != 7 ? 1 : 0, v3 = steps;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
@@ -379,18 +390,19 @@ __global__ void __launch_bounds__(256) compose_tiles_kernel(const uint4* __restr
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick) {
+                     uint8_t* d_touch_brick, unsigned int* /*d_tile_counter*/, int local_tile0, int local_tile_count) {
   const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
   const int n_tiles = tiles_x * tiles_y;
-  const int local_tiles = (n_tiles - rank + world - 1) / world;
-  if (local_tiles <= 0) return;
+  const int all_local = (n_tiles - rank + world - 1) / world;
+  if (local_tile_count < 0) local_tile_count = all_local - local_tile0;
+  if (local_tile_count <= 0) return;
   const size_t smem = sizeof(uint32_t) * ((size_t)v.chunk_words + (size_t)v.region_words);
   if (d_stats)
-    raymarch_kernel<true><<<local_tiles, 256, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x, n_tiles,
-                                                                 d_out, d_stats, d_touch_chunk, d_touch_brick);
+    raymarch_kernel<true><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
+                                                                             n_tiles, local_tile0, d_out, d_stats, d_touch_chunk, d_touch_brick);
   else
-    raymarch_kernel<false><<<local_tiles, 256, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x, n_tiles,
-                                                                  d_out, nullptr, nullptr, nullptr);
+    raymarch_kernel<false><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
+                                                                              n_tiles, local_tile0, d_out, nullptr, nullptr, nullptr);
   (*lc.launches)++;
 }
 

@@ -69,6 +69,11 @@ struct MesoCtx {
   uint32_t* d_flush = nullptr;
   size_t flush_words = 0;
   uint32_t* d_tmp_count = nullptr;
+  unsigned int* d_tile_counter = nullptr;
+  cudaStream_t copy_stream = nullptr;       // D2H of finished bands overlaps the next band's kernel (meso_raymarch)
+  cudaEvent_t band_done[16] = {nullptr};
+  cudaStream_t band_stream[2] = {nullptr, nullptr};
+  cudaEvent_t band_fork = nullptr;
 
   LaunchCtx lc() { return LaunchCtx{stream, sm_count, &launches}; }
 };
@@ -98,6 +103,11 @@ int meso_ctx_create(int device, MesoCtx** out) {
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CK(cudaMalloc(&c->d_tmp_count, 16));
+  CK(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&c->band_done[i], cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->band_stream[i], cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->band_fork, cudaEventDisableTiming));
   CK(cudaMalloc(&c->d_overflow, sizeof(int)));
   CK(cudaMemset(c->d_overflow, 0, sizeof(int)));
   *out = c;
@@ -125,7 +135,11 @@ int meso_ctx_destroy(MesoCtx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_scene(c);
-  cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow);
+  cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow); cudaFree(c->d_tile_counter);
+  for (int i = 0; i < 16; i++) if (c->band_done[i]) cudaEventDestroy(c->band_done[i]);
+  cudaStreamDestroy(c->copy_stream);
+  for (int i = 0; i < 2; i++) if (c->band_stream[i]) cudaStreamDestroy(c->band_stream[i]);
+  if (c->band_fork) cudaEventDestroy(c->band_fork);
   cudaStreamDestroy(c->own_stream);
   delete c;
   return MESO_OK;
@@ -399,23 +413,55 @@ int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width,
   MesoRaySetup rs;
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr);
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr, c->d_tile_counter);
   CK_LAST("raymarch");
   return MESO_OK;
 }
 
 int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3], MesoHitRecord* host) {
   NEED_SCENE(c);
-  if (!host) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: null host_records");
-  if (width <= 0 || height <= 0) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad size");
+  if (!host || !cam) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: null argument");
+  if (width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad size");
   const size_t px = (size_t)width * height;
   int r = ensure_frame(c, px);
   if (r != MESO_OK) return r;
-  if (c->world > 1) CK(cudaMemsetAsync(c->d_frame, 0xFF, px * sizeof(MesoHitRecord), c->stream));  // other ranks' tiles: all-ones
-  r = meso_raymarch_device(c, cam, width, height, flags, light, c->d_frame, MESO_LAYOUT_FRAME);
+  if (c->world > 1) {
+    // other ranks' tiles stay all-ones; single launch + one copy
+    CK(cudaMemsetAsync(c->d_frame, 0xFF, px * sizeof(MesoHitRecord), c->stream));
+    r = meso_raymarch_device(c, cam, width, height, flags, light, c->d_frame, MESO_LAYOUT_FRAME);
+    if (r != MESO_OK) return r;
+    CK(cudaMemcpyAsync(host, c->d_frame, px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MESO_OK;
+  }
+  // Single GPU: the frame is rendered in bands of whole tile rows; the device-to-host copy of a finished band runs on
+  // the copy stream while the next band is being traced, so the PCIe transfer hides behind the kernel (or vice versa).
+  MesoRaySetup rs;
+  r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
-  CK(cudaMemcpyAsync(host, c->d_frame, px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
+  int bands = tiles_y >= 64 ? 4 : (tiles_y >= 16 ? 2 : 1);   // measured on B200 at 4K: 1 -> 5.6 ms, 4 -> 4.0 ms, 16 -> 5.7 ms
+  if (const char* e = getenv("MESO_E2E_BANDS")) bands = std::max(1, std::min(16, atoi(e)));  // tuning knob
+  const int rows_per_band = (tiles_y + bands - 1) / bands;
+  // Band kernels alternate between two compute streams so the long tail of one band (a few slow silhouette tiles)
+  // overlaps the body of the next; both are ordered after whatever the caller enqueued on the context's stream.
+  CK(cudaEventRecord(c->band_fork, c->stream));
+  CK(cudaStreamWaitEvent(c->band_stream[0], c->band_fork, 0));
+  CK(cudaStreamWaitEvent(c->band_stream[1], c->band_fork, 0));
+  for (int b = 0; b < bands; b++) {
+    const int ty0 = b * rows_per_band, ty1 = std::min(tiles_y, ty0 + rows_per_band);
+    if (ty0 >= ty1) break;
+    LaunchCtx lc = c->lc();
+    lc.stream = c->band_stream[b & 1];
+    launch_raymarch(lc, c->v, rs, width, height, flags, 0, 1, MESO_LAYOUT_FRAME, c->d_frame, nullptr, nullptr, nullptr,
+                    c->d_tile_counter, ty0 * tiles_x, (ty1 - ty0) * tiles_x);
+    CK_LAST("raymarch band");
+    CK(cudaEventRecord(c->band_done[b], lc.stream));
+    CK(cudaStreamWaitEvent(c->copy_stream, c->band_done[b], 0));
+    const size_t y0 = (size_t)ty0 * MESO_TILE_H, y1 = std::min((size_t)height, (size_t)ty1 * MESO_TILE_H);
+    CK(cudaMemcpyAsync(host + y0 * width, c->d_frame + y0 * width, (y1 - y0) * width * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  CK(cudaStreamSynchronize(c->copy_stream));   // every band kernel precedes its copy, so this covers both band streams
   return MESO_OK;
 }
 
@@ -431,7 +477,7 @@ int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaMemsetAsync(c->d_stats, 0, sizeof(RayStatsDev), c->stream));
   CK(cudaMemsetAsync(c->d_touch_chunk, 0, (size_t)c->v.nchunks, c->stream));
   CK(cudaMemsetAsync(c->d_touch_brick, 0, c->v.max_bricks, c->stream));
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick);
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick, c->d_tile_counter);
   CK_LAST("raymarch stats");
   RayStatsDev h;
   std::vector<uint8_t> tc((size_t)c->v.nchunks), tb(c->v.max_bricks);

@@ -57,7 +57,7 @@ void launch_occupancy(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, Mes
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick);
+                     uint8_t* d_touch_brick, unsigned int* d_tile_counter, int local_tile0 = 0, int local_tile_count = -1);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
