@@ -219,16 +219,44 @@ def run_ours(args):
     ctx.set_partition(rank, world)
 
     px = width * height
-    frame = torch.empty((height, width, 4), dtype=torch.int32, device=dev)
     tpr = capi.tiles_per_rank(width, height, world)
-    if world > 1:
+    gather = "single GPU"
+    frame_ptr = None          # device pointer every rank stores its tile records to (fused gather)
+    frame_owner_ptr = None
+    if world > 1 and args.gather == "p2p":
+        # Fused gather: rank 0 owns the frame (cudaMalloc through the C ABI, exported over CUDA IPC); every rank's
+        # raymarch kernel stores its tile records straight into it over NVLink.  No gather pass, no compose pass.
+        try:
+            handle = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                frame_owner_ptr = ctx.device_alloc(px * 16)
+                handle.copy_(torch.from_numpy(ctx.ipc_export(frame_owner_ptr)))
+            dist.broadcast(handle, src=0)
+            frame_ptr = frame_owner_ptr if rank == 0 else ctx.ipc_open(handle.cpu().numpy())
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as e:  # e.g. IPC not permitted in this container
+            sys.stderr.write("bench: p2p gather unavailable on rank %d (%s); falling back to NCCL all_gather\n" % (rank, e))
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            gather = "p2p"
+        else:
+            frame_ptr = None
+    if world == 1 or gather != "p2p":
+        frame = torch.empty((height, width, 4), dtype=torch.int32, device=dev)
+    if world > 1 and gather != "p2p":
+        gather = "nccl"
         tiles = torch.empty((tpr, 256, 4), dtype=torch.int32, device=dev)
         gathered = torch.empty((world, tpr, 256, 4), dtype=torch.int32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def step(k):
         cam = cams[k % 8]
         if world == 1:
             ctx.raymarch_device(cam, width, height, frame.data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+        elif gather == "p2p":
+            ctx.raymarch_device(cam, width, height, frame_ptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+            dist.all_reduce(flag)   # stream-ordered 4-byte rendezvous: when it completes on rank 0 every tile has landed
         else:
             ctx.raymarch_device(cam, width, height, tiles.data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_TILES)
             dist.all_gather_into_tensor(gathered, tiles)
@@ -265,14 +293,35 @@ def run_ours(args):
     rays_total = sum(rays_cam[k % 8] for k in range(args.steps))
     value = rays_total / (ms * 1e-3) / 1e6
 
+    # ---- 1 == N check (outside the timed region): the gathered frame equals the frame one GPU renders on its own ----
+    gather_verified = None
+    if world > 1:
+        step(0)
+        barrier()
+        if rank == 0:
+            got = np.empty((height, width), dtype=capi.HitRecord)
+            if gather == "p2p":
+                ctx.download(got, frame_owner_ptr)
+            else:
+                got = frame.cpu().numpy().view(capi.HitRecord).reshape(height, width)
+            ctx.set_partition(0, 1)
+            ref = ctx.raymarch(cams[0], width, height, shadow=True, light=LIGHT)
+            ctx.set_partition(rank, world)
+            gather_verified = bool(got.tobytes() == ref.tobytes())
+        barrier()
+
     # ---- dominant kernel alone (this rank's tiles), for the roofline ----
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kbuf = frame if world == 1 else tiles
-    klayout = capi.LAYOUT_FRAME if world == 1 else capi.LAYOUT_TILES
+    if world == 1:
+        kptr, klayout = frame.data_ptr(), capi.LAYOUT_FRAME
+    elif gather == "p2p":
+        kptr, klayout = frame_ptr, capi.LAYOUT_FRAME
+    else:
+        kptr, klayout = tiles.data_ptr(), capi.LAYOUT_TILES
     for k in range(args.steps):
         ctx.flush_l2()
         kev[k][0].record(stream)
-        ctx.raymarch_device(cams[k % 8], width, height, kbuf.data_ptr(), shadow=True, light=LIGHT, layout=klayout)
+        ctx.raymarch_device(cams[k % 8], width, height, kptr, shadow=True, light=LIGHT, layout=klayout)
         kev[k][1].record(stream)
     barrier()
     kms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
@@ -292,7 +341,10 @@ def run_ours(args):
         else:
             step(k)
             if rank == 0:
-                host.copy_(frame, non_blocking=True)
+                if gather == "p2p":
+                    ctx.download(host_np, frame_owner_ptr)
+                else:
+                    host.copy_(frame, non_blocking=True)
             torch.cuda.synchronize()
 
     e2e_step(0)
@@ -316,8 +368,12 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": "V-sphere %d^3 voxel-granular, %d chunks, replicated per GPU" % (n, int(np.prod(dims))),
                        "resolution": [width, height], "rays_per_frame_mean": rays_total / args.steps,
-                       "partition": "32x8 screen tiles, tile %% %d == rank; NCCL all_gather of tile records + compose" % world if world > 1 else "single GPU, row-major frame",
+                       "partition": ("single GPU, row-major frame" if world == 1 else
+                                     ("32x8 screen tiles, tile %% %d == rank; " % world) +
+                                     ("fused gather: every rank's kernel stores its records into rank 0's frame over NVLink peer memory, 4-byte NCCL all-reduce as the rendezvous"
+                                      if gather == "p2p" else "NCCL all_gather of packed tile records + compose kernel")),
                        "cache": "L2 flushed (256 MiB write) between timed steps, outside the timed spans",
+                       "gather": gather, "gather_verified_equal_to_1gpu_frame": gather_verified,
                        "scene_build_s": t_build},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
                     "steps": e2e_steps, "note": "meso_raymarch(): FGPUUniformCamera from host memory (passed as kernel parameters), records copied to pinned host memory"},
@@ -416,6 +472,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-mesh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame gather (p2p falls back to nccl if IPC is unavailable)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

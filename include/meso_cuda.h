@@ -174,6 +174,21 @@ MESO_API int meso_download_dirty(MesoCtx* ctx, uint64_t* keys, int64_t cap);
 MESO_API int meso_remesh_dirty(MesoCtx* ctx, MesoQuad* host_quads, int64_t cap, int64_t* n_quads, uint64_t* host_keys,
                                int64_t cap_keys, int64_t* n_keys);
 
+/* ---- peer memory (one process per GPU) -------------------------------------------------------------------------
+ * Fused gather: every rank's raymarch kernel stores its tile records straight into the frame buffer of the gathering
+ * rank over NVLink (16 B stores to a peer mapping), so the transfer overlaps the traversal and no separate gather or
+ * compose pass runs.  The gathering rank allocates the frame with meso_device_alloc and exports it; the others open the
+ * handle and pass the returned pointer as d_records to meso_raymarch_device(..., MESO_LAYOUT_FRAME).  A stream-ordered
+ * barrier between the ranks (e.g. a 4-byte NCCL all-reduce) tells the owner that all tiles have landed. */
+#define MESO_IPC_HANDLE_BYTES 64
+MESO_API int meso_device_alloc(MesoCtx* ctx, size_t bytes, void** dptr);
+MESO_API int meso_device_free(MesoCtx* ctx, void* dptr);
+MESO_API int meso_ipc_export(MesoCtx* ctx, void* dptr, unsigned char handle[MESO_IPC_HANDLE_BYTES]);
+MESO_API int meso_ipc_open(MesoCtx* ctx, const unsigned char handle[MESO_IPC_HANDLE_BYTES], void** peer_dptr);
+MESO_API int meso_ipc_close(MesoCtx* ctx, void* peer_dptr);
+/* lvk::IContext::download (LVK.h:831): device -> host on the context's stream, returns when the bytes are in host memory. */
+MESO_API int meso_download(MesoCtx* ctx, void* host_dst, const void* dptr, size_t bytes);
+
 /* ---- utilities -------------------------------------------------------------------------------------------- */
 MESO_API int meso_host_alloc(size_t bytes, void** out); /* pinned */
 MESO_API int meso_host_free(void* p);

@@ -40,7 +40,9 @@ SYMBOLS = [
     "meso_raymarch_stats", "meso_compose_tiles_device", "meso_tiles_per_rank", "meso_mesh", "meso_mesh_device",
     "meso_carve_sphere", "meso_download_dirty", "meso_remesh_dirty", "meso_host_alloc", "meso_host_free",
     "meso_flush_l2", "meso_launch_count",
+    "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download",
 ]
+IPC_HANDLE_BYTES = 64
 
 
 class MesoError(RuntimeError):
@@ -243,3 +245,31 @@ class Context:
 
     def flush_l2(self):
         _ck(lib.meso_flush_l2(self.h))
+
+    # ---- peer memory (fused gather) ----
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        _ck(lib.meso_device_alloc(self.h, C.c_size_t(nbytes), C.byref(p)))
+        return p.value
+
+    def device_free(self, dptr):
+        _ck(lib.meso_device_free(self.h, C.c_void_p(dptr)))
+
+    def ipc_export(self, dptr):
+        h = np.zeros(IPC_HANDLE_BYTES, dtype=np.uint8)
+        _ck(lib.meso_ipc_export(self.h, C.c_void_p(dptr), _p(h)))
+        return h
+
+    def ipc_open(self, handle):
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        p = C.c_void_p()
+        _ck(lib.meso_ipc_open(self.h, _p(h), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, peer_dptr):
+        _ck(lib.meso_ipc_close(self.h, C.c_void_p(peer_dptr)))
+
+    def download(self, host_array, dptr, nbytes=None):
+        """device -> host (numpy array or raw host address), synchronous on the context's stream."""
+        n = host_array.nbytes if nbytes is None else nbytes
+        _ck(lib.meso_download(self.h, _p(host_array), C.c_void_p(dptr), C.c_size_t(n)))

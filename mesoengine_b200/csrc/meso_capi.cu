@@ -612,6 +612,50 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
   return MESO_OK;
 }
 
+int meso_device_alloc(MesoCtx* c, size_t bytes, void** dptr) {
+  if (!c || !dptr || bytes == 0) return fail(MESO_ERR_ARGUMENT, "meso_device_alloc: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMalloc(dptr, bytes));   // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+  return MESO_OK;
+}
+int meso_device_free(MesoCtx* c, void* dptr) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  CK(cudaSetDevice(c->device));
+  if (dptr) CK(cudaFree(dptr));
+  return MESO_OK;
+}
+int meso_ipc_export(MesoCtx* c, void* dptr, unsigned char handle[MESO_IPC_HANDLE_BYTES]) {
+  if (!c || !dptr || !handle) return fail(MESO_ERR_ARGUMENT, "meso_ipc_export: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MESO_IPC_HANDLE_BYTES, "ipc handle size");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, dptr));
+  memcpy(handle, &h, sizeof(h));
+  return MESO_OK;
+}
+int meso_ipc_open(MesoCtx* c, const unsigned char handle[MESO_IPC_HANDLE_BYTES], void** peer) {
+  if (!c || !handle || !peer) return fail(MESO_ERR_ARGUMENT, "meso_ipc_open: bad argument");
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  CK(cudaIpcOpenMemHandle(peer, h, cudaIpcMemLazyEnablePeerAccess));
+  return MESO_OK;
+}
+int meso_ipc_close(MesoCtx* c, void* peer) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  CK(cudaSetDevice(c->device));
+  if (peer) CK(cudaIpcCloseMemHandle(peer));
+  return MESO_OK;
+}
+
+int meso_download(MesoCtx* c, void* host_dst, const void* dptr, size_t bytes) {
+  if (!c || !host_dst || !dptr) return fail(MESO_ERR_ARGUMENT, "meso_download: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(host_dst, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+
 int meso_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(MESO_ERR_ARGUMENT, "null out");
   CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
