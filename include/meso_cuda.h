@@ -149,6 +149,15 @@ MESO_API int meso_ray_setup(const MesoGPUUniformCamera* cam, const int32_t origi
 /* End-to-end: camera in host memory -> records in host memory (row-major width x height). */
 MESO_API int meso_raymarch(MesoCtx* ctx, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags,
                            const float light_dir[3], MesoHitRecord* host_records);
+/* Frame ring, the reference's kNumBufferedFrames (Samples/SimpleVoxel.cpp:15; per-frame buffers indexed by
+ * RenderFrameIndex, VoxelWindowsInstance.cpp:404-408): meso_raymarch_async renders into ring slot `slot` (0..3) and
+ * starts the copy of the records into host_records (pinned memory recommended) on a copy stream; it returns as soon as
+ * the work is enqueued.  meso_frame_wait(slot) returns when that slot's records are in host memory.  Re-using a slot
+ * waits for its previous frame first.  The copy of frame k overlaps the traversal of frame k+1. */
+#define MESO_FRAME_RING 4
+MESO_API int meso_raymarch_async(MesoCtx* ctx, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags,
+                                 const float light_dir[3], MesoHitRecord* host_records, int slot);
+MESO_API int meso_frame_wait(MesoCtx* ctx, int slot);
 /* Enqueue only; d_records is device memory.  MESO_LAYOUT_FRAME: row-major frame, only this rank's tiles are written.
  * MESO_LAYOUT_TILES: this rank's tiles packed as [local_tile][MESO_TILE_H][MESO_TILE_W]. */
 MESO_API int meso_raymarch_device(MesoCtx* ctx, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags,

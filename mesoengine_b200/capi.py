@@ -40,7 +40,7 @@ SYMBOLS = [
     "meso_raymarch_stats", "meso_compose_tiles_device", "meso_tiles_per_rank", "meso_mesh", "meso_mesh_device",
     "meso_carve_sphere", "meso_download_dirty", "meso_remesh_dirty", "meso_host_alloc", "meso_host_free",
     "meso_flush_l2", "meso_launch_count",
-    "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download",
+    "meso_raymarch_async", "meso_frame_wait", "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -192,6 +192,15 @@ class Context:
         _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(FLAG_SHADOW if shadow else 0),
                               _p(l), _p(rec)))
         return rec
+
+    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8)):
+        """Frame-ring call: enqueue frame + copy into `out` (pinned numpy array); pair with frame_wait(slot)."""
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        _ck(lib.meso_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(FLAG_SHADOW if shadow else 0),
+                                    _p(l), _p(out), C.c_int(slot)))
+
+    def frame_wait(self, slot):
+        _ck(lib.meso_frame_wait(self.h, C.c_int(slot)))
 
     def raymarch_device(self, cam, width, height, d_records, shadow=True, light=(0.3, 0.5, 0.8), layout=LAYOUT_FRAME):
         l = np.ascontiguousarray(light, dtype=np.float32)

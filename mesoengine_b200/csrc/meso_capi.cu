@@ -74,6 +74,12 @@ struct MesoCtx {
   cudaEvent_t band_done[16] = {nullptr};
   cudaStream_t band_stream[2] = {nullptr, nullptr};
   cudaEvent_t band_fork = nullptr;
+  // frame ring (meso_raymarch_async): the reference's kNumBufferedFrames
+  MesoHitRecord* d_ring[MESO_FRAME_RING] = {nullptr};
+  size_t ring_px = 0;
+  bool ring_busy[MESO_FRAME_RING] = {false};
+  cudaEvent_t ring_traced[MESO_FRAME_RING] = {nullptr};
+  cudaEvent_t ring_copied[MESO_FRAME_RING] = {nullptr};
 
   LaunchCtx lc() { return LaunchCtx{stream, sm_count, &launches}; }
 };
@@ -108,6 +114,10 @@ int meso_ctx_create(int device, MesoCtx** out) {
   for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&c->band_done[i], cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->band_stream[i], cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->band_fork, cudaEventDisableTiming));
+  for (int i = 0; i < MESO_FRAME_RING; i++) {
+    CK(cudaEventCreateWithFlags(&c->ring_traced[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ring_copied[i], cudaEventDisableTiming));
+  }
   CK(cudaMalloc(&c->d_overflow, sizeof(int)));
   CK(cudaMemset(c->d_overflow, 0, sizeof(int)));
   *out = c;
@@ -140,6 +150,11 @@ int meso_ctx_destroy(MesoCtx* c) {
   cudaStreamDestroy(c->copy_stream);
   for (int i = 0; i < 2; i++) if (c->band_stream[i]) cudaStreamDestroy(c->band_stream[i]);
   if (c->band_fork) cudaEventDestroy(c->band_fork);
+  for (int i = 0; i < MESO_FRAME_RING; i++) {
+    cudaFree(c->d_ring[i]);
+    if (c->ring_traced[i]) cudaEventDestroy(c->ring_traced[i]);
+    if (c->ring_copied[i]) cudaEventDestroy(c->ring_copied[i]);
+  }
   cudaStreamDestroy(c->own_stream);
   delete c;
   return MESO_OK;
@@ -462,6 +477,42 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
     CK(cudaMemcpyAsync(host + y0 * width, c->d_frame + y0 * width, (y1 - y0) * width * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->copy_stream));
   }
   CK(cudaStreamSynchronize(c->copy_stream));   // every band kernel precedes its copy, so this covers both band streams
+  return MESO_OK;
+}
+
+int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3], MesoHitRecord* host, int slot) {
+  NEED_SCENE(c);
+  if (!host || !cam) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_async: null argument");
+  if (width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_async: bad size");
+  if (slot < 0 || slot >= MESO_FRAME_RING) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_async: slot out of range");
+  const size_t px = (size_t)width * height;
+  if (c->ring_px < px) {   // (re)allocate the ring
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < MESO_FRAME_RING; i++) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
+    for (int i = 0; i < MESO_FRAME_RING; i++) CK(cudaMalloc(&c->d_ring[i], px * sizeof(MesoHitRecord)));
+    c->ring_px = px;
+  }
+  if (c->ring_busy[slot]) { CK(cudaEventSynchronize(c->ring_copied[slot])); c->ring_busy[slot] = false; }
+  MesoRaySetup rs;
+  int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
+  if (r != MESO_OK) return r;
+  if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * sizeof(MesoHitRecord), c->stream));
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr,
+                  c->d_tile_counter);
+  CK_LAST("raymarch async");
+  CK(cudaEventRecord(c->ring_traced[slot], c->stream));
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ring_traced[slot], 0));
+  CK(cudaMemcpyAsync(host, c->d_ring[slot], px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->copy_stream));
+  CK(cudaEventRecord(c->ring_copied[slot], c->copy_stream));
+  c->ring_busy[slot] = true;
+  return MESO_OK;
+}
+
+int meso_frame_wait(MesoCtx* c, int slot) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  if (slot < 0 || slot >= MESO_FRAME_RING) return fail(MESO_ERR_ARGUMENT, "meso_frame_wait: slot out of range");
+  CK(cudaSetDevice(c->device));
+  if (c->ring_busy[slot]) { CK(cudaEventSynchronize(c->ring_copied[slot])); c->ring_busy[slot] = false; }
   return MESO_OK;
 }
 
