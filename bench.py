@@ -4,15 +4,18 @@
 Metric (BASELINE.json): Mrays/s of the primary + hard-shadow voxel raymarch, whole job over N GPUs.
 Workload (default, every N): BASELINE.json configs[3] -- 4096^3 sparse-brick scene (V-sphere, voxel-granular),
 3840x2160 primary rays + one shadow ray per lit-facing hit, eight orbit cameras cycled per step, screen tiles
-(32x8) interleaved over the ranks, tile records gathered with NCCL and composed into the row-major frame.
-`--workload cfg1` runs configs[1] (1024^3, 1920x1080).  A "step" is one frame.
+(32x8) interleaved over the ranks; every rank's kernel stores its tile records straight into rank 0's frame over
+NVLink peer memory (fused gather; `--gather nccl` = all_gather + compose).  Four frames in flight on alternating
+streams, like the reference's kNumBufferedFrames = 4.  `--workload cfg1` runs configs[1] (1024^3, 1920x1080).
+A "step" is one frame.
 
     python bench.py --gpus 1 --steps 100 --warmup 10
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8
     python bench.py --impl reference        # the CPU restatement of the reference path (oracle/), all host threads
 
-Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB
-write) between steps outside the timed spans, barrier + synchronize on both sides, max over ranks.
+Prints ONE JSON line (rank 0).  Timing: exactly K steps between two barrier + synchronize points, CUDA events on the
+launching streams, max over ranks.  Every step writes its own 132.7 MB frame buffer and re-reads the scene (footprint
+above the 126 MB L2); the separate kernel-alone loop behind `roofline` flushes L2 between launches.
 """
 import argparse
 import json
@@ -351,7 +354,7 @@ def run_ours(args):
     # 132.7 MB device-to-host copy of frame k overlaps the traversal of frame k+1; every frame's records are consumed
     # (first and last record read on the host) before its slot is reused.  N > 1: frame gathered on rank 0, then copied.
     RING = 4
-    hosts = [torch.empty((height, width, 4), dtype=torch.int32).pin_memory() for _ in range(RING if world == 1 else 1)]
+    hosts = [torch.empty((height, width, 4), dtype=torch.int32).pin_memory() for _ in range(RING if world == 1 else (R if rank == 0 else 1))]
     hosts_np = [h.numpy().view(capi.HitRecord).reshape(height, width) for h in hosts]
     host, host_np = hosts[0], hosts_np[0]
     e2e_steps = max(8, min(args.steps, 40))
@@ -370,14 +373,30 @@ def run_ours(args):
                 ctx.frame_wait(slot)
                 consumed += int(hosts_np[slot]["w1"][0, 0]) + int(hosts_np[slot]["w1"][-1, -1])
         else:
+            # ring over the R frames in flight: rank 0 enqueues the copy of the gathered frame right behind the frame's
+            # rendezvous on that frame's stream, so it overlaps the next frame; a slot is consumed before it is reused
+            pend = [None] * R
             for k in range(nsteps):
-                step(k, 0)
-                if rank == 0:
-                    if gather == "p2p":
-                        ctx.download(host_np, frame_owner_ptrs[0])
-                    else:
-                        host.copy_(frames[0], non_blocking=True)
-                torch.cuda.synchronize()
+                slot = k % R
+                if pend[slot] is not None:
+                    pend[slot].synchronize()
+                    if rank == 0:
+                        consumed += int(hosts_np[slot]["w1"][0, 0]) + int(hosts_np[slot]["w1"][-1, -1])
+                step(k, slot)
+                with torch.cuda.stream(streams[slot]):
+                    if rank == 0:
+                        if gather == "p2p":
+                            ctx.set_stream(streams[slot].cuda_stream)
+                            ctx.download_async(hosts_np[slot], frame_owner_ptrs[slot])
+                            ctx.set_stream(stream.cuda_stream)
+                        else:
+                            hosts[slot].copy_(frames[slot], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(streams[slot])
+                    pend[slot] = e
+            for slot in range(R):
+                if pend[slot] is not None:
+                    pend[slot].synchronize()
 
     e2e_run(RING)
     barrier()
@@ -410,7 +429,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
                     "steps": e2e_steps,
                     "note": ("meso_raymarch_async()/meso_frame_wait() frame ring of 4: FGPUUniformCamera from host memory (kernel parameters), records copied to pinned host memory, copy of frame k overlapping frame k+1"
-                             if world == 1 else "frame gathered on rank 0, then copied to pinned host memory (serial)")},
+                             if world == 1 else "frame gathered on rank 0 (fused p2p stores or NCCL), then copied to pinned host memory on that frame's stream, overlapping the next frame in flight")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "raymarch_kernel<false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -506,7 +525,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-mesh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--frames-in-flight", type=int, default=2, help="frame ring depth of the timed loop (reference: kNumBufferedFrames = 4)")
+    ap.add_argument("--frames-in-flight", type=int, default=4, help="frame ring depth of the timed loop (reference: kNumBufferedFrames = 4)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame gather (p2p falls back to nccl if IPC is unavailable)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -197,6 +197,8 @@ MESO_API int meso_ipc_open(MesoCtx* ctx, const unsigned char handle[MESO_IPC_HAN
 MESO_API int meso_ipc_close(MesoCtx* ctx, void* peer_dptr);
 /* lvk::IContext::download (LVK.h:831): device -> host on the context's stream, returns when the bytes are in host memory. */
 MESO_API int meso_download(MesoCtx* ctx, void* host_dst, const void* dptr, size_t bytes);
+/* Same, enqueue only (host_dst should be pinned); meso_ctx_sync or an event on the stream tells when the bytes are there. */
+MESO_API int meso_download_async(MesoCtx* ctx, void* host_dst, const void* dptr, size_t bytes);
 
 /* ---- utilities -------------------------------------------------------------------------------------------- */
 MESO_API int meso_host_alloc(size_t bytes, void** out); /* pinned */

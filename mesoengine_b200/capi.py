@@ -40,7 +40,7 @@ SYMBOLS = [
     "meso_raymarch_stats", "meso_compose_tiles_device", "meso_tiles_per_rank", "meso_mesh", "meso_mesh_device",
     "meso_carve_sphere", "meso_download_dirty", "meso_remesh_dirty", "meso_host_alloc", "meso_host_free",
     "meso_flush_l2", "meso_launch_count",
-    "meso_raymarch_async", "meso_frame_wait", "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download",
+    "meso_raymarch_async", "meso_frame_wait", "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download", "meso_download_async",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -277,6 +277,11 @@ class Context:
 
     def ipc_close(self, peer_dptr):
         _ck(lib.meso_ipc_close(self.h, C.c_void_p(peer_dptr)))
+
+    def download_async(self, host_array, dptr, nbytes=None):
+        """device -> pinned host, enqueued on the context's stream (no wait)."""
+        n = host_array.nbytes if nbytes is None else nbytes
+        _ck(lib.meso_download_async(self.h, _p(host_array), C.c_void_p(dptr), C.c_size_t(n)))
 
     def download(self, host_array, dptr, nbytes=None):
         """device -> host (numpy array or raw host address), synchronous on the context's stream."""

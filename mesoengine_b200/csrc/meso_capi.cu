@@ -707,6 +707,13 @@ int meso_download(MesoCtx* c, void* host_dst, const void* dptr, size_t bytes) {
   return MESO_OK;
 }
 
+int meso_download_async(MesoCtx* c, void* host_dst, const void* dptr, size_t bytes) {
+  if (!c || !host_dst || !dptr) return fail(MESO_ERR_ARGUMENT, "meso_download_async: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(host_dst, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return MESO_OK;
+}
+
 int meso_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(MESO_ERR_ARGUMENT, "null out");
   CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));

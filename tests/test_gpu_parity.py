@@ -223,6 +223,46 @@ def test_raymarch_tile_partition_composes(ctx, capi, orc):
         assert np.array_equal(got, exp), world
 
 
+def test_frame_ring_async_equals_sync(ctx, capi, orc):
+    """meso_raymarch_async / meso_frame_wait (4-slot ring, copy of frame k overlapping frame k+1) returns exactly the
+    frames meso_raymarch does, slot reuse included."""
+    import torch
+    origin, dims, params = scenes.sphere_scene(256)
+    _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 320, 184
+    cams = _cams(orc, origin, dims, w, h)
+    expect = [ctx.raymarch(c, w, h).copy() for c in cams]
+    hosts = [torch.empty((h, w, 4), dtype=torch.int32).pin_memory() for _ in range(4)]
+    views = [t.numpy().view(capi.HitRecord).reshape(h, w) for t in hosts]
+    for k in range(8):
+        slot = k % 4
+        if k >= 4:
+            ctx.frame_wait(slot)
+            assert views[slot].tobytes() == expect[k - 4].tobytes()
+        ctx.raymarch_async(cams[k], w, h, views[slot], slot)
+    for k in range(4, 8):
+        ctx.frame_wait(k % 4)
+        assert views[k % 4].tobytes() == expect[k].tobytes()
+    with pytest.raises(capi.MesoError):
+        ctx.raymarch_async(cams[0], w, h, views[0], 7)   # slot out of range -> ArgumentOutOfRange-class error
+
+
+def test_device_alloc_download(ctx, capi, orc):
+    """The buffer path of the fused multi-GPU gather on one device: library-owned frame, kernel stores, download."""
+    origin, dims, params = scenes.sphere_scene(256)
+    _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 320, 184
+    cam = _cams(orc, origin, dims, w, h)[5]
+    ptr = ctx.device_alloc(w * h * 16)
+    handle = ctx.ipc_export(ptr)
+    assert handle.shape == (capi.IPC_HANDLE_BYTES,) and handle.any()
+    ctx.raymarch_device(cam, w, h, ptr)
+    got = np.zeros((h, w), dtype=capi.HitRecord)
+    ctx.download(got, ptr)
+    ctx.device_free(ptr)
+    assert got.tobytes() == ctx.raymarch(cam, w, h).tobytes()
+
+
 # ---- K3 -------------------------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("case", ["sphere_voxel_256", "sphere_blocks", "terrain_voxel"])

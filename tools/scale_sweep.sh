@@ -3,9 +3,9 @@
 mkdir -p gpurun_out
 for N in 1 2 4 8; do
   if [ "$N" = "1" ]; then
-    python bench.py --gpus 1 --steps 50 --warmup 5 --no-mesh --no-cpu 2>gpurun_out/scale_$N.err | tail -1 > gpurun_out/scale_$N.json
+    python bench.py --gpus 1 --steps 80 --warmup 8 --no-mesh --no-cpu 2>gpurun_out/scale_$N.err | tail -1 > gpurun_out/scale_$N.json
   else
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --steps 50 --warmup 5 2>gpurun_out/scale_$N.err | tail -1 > gpurun_out/scale_$N.json
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --steps 80 --warmup 8 2>gpurun_out/scale_$N.err | tail -1 > gpurun_out/scale_$N.json
   fi
   python - <<PY
 import json
