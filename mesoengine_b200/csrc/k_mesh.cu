@@ -5,56 +5,67 @@
 // Neither quads nor a face-neighbour test exist in the reference: the definition is oracle/orc_mesh.c
 // ("parity unpinned by reference; bit-exact vs repo oracle" after the canonical sort).
 //
-// Pass A (worklist): one thread per potential brick; occupied bricks that are not buried (full with six full
-// neighbours) are compacted with a warp ballot + one atomic per warp.
-// Pass B (mesh): one warp per brick.  Lanes 0..7 own one z-slice each (64 voxels as a u64) and build the six
-// exposed-face slice masks with shifts against the neighbour slices; the 48 (direction, layer) 8x8 images are then
-// merged greedily by 48 lane-tasks, counted, prefix-summed across the warp, and written behind one atomicAdd.
+// Pass A (worklist): one thread per 64-brick occupancy word; occupied bricks that are not buried (full with six full
+// neighbours, decided with word-wide shifts) are compacted with a warp prefix sum + one atomic per warp.
+// Pass B (mesh): one warp per brick.  Lanes 0..6 resolve the seven bricks involved, then lanes 0..7 own one z-slice
+// each (64 voxels as a u64, every slice an independent 8 B load) and build the six exposed-face slice masks with
+// shifts against the neighbour slices; the 48 (direction, layer) 8x8 images are then merged greedily by 48
+// lane-tasks, counted, prefix-summed across the warp, and written behind one atomicAdd.
 // HBM-bound integer work: 64 B per populated brick + 16 B per quad (+ neighbour slices, mostly L2 hits).
 #include "meso_internal.cuh"
 
-// slice z of the brick at global block coordinates (zeros outside the grid / absent, ones for full bricks)
-__device__ __forceinline__ uint64_t fetch_slice(const DVolume& v, int bx, int by, int bz, int z) {
-  if ((unsigned)bx >= (unsigned)(v.dims[0] * 16) || (unsigned)by >= (unsigned)(v.dims[1] * 16) || (unsigned)bz >= (unsigned)(v.dims[2] * 16)) return 0ull;
-  const int64_t c = chunk_index(v, bx >> 4, by >> 4, bz >> 4);
-  const int b = block_bit(bx & 15, by & 15, bz & 15);
-  if (!((__ldg(&v.occ[c * 64 + (b >> 6)]) >> (b & 63)) & 1ull)) return 0ull;
-  if ((__ldg(&v.full[c * 64 + (b >> 6)]) >> (b & 63)) & 1ull) return ~0ull;
-  return __ldg(&v.pool[(size_t)__ldg(&v.bptr[c * MESO_BLOCKS + b]) * 8 + z]);
-}
-__device__ __forceinline__ bool brick_full(const DVolume& v, int bx, int by, int bz) {
-  if ((unsigned)bx >= (unsigned)(v.dims[0] * 16) || (unsigned)by >= (unsigned)(v.dims[1] * 16) || (unsigned)bz >= (unsigned)(v.dims[2] * 16)) return false;
-  const int64_t c = chunk_index(v, bx >> 4, by >> 4, bz >> 4);
-  const int b = block_bit(bx & 15, by & 15, bz & 15);
-  return (__ldg(&v.full[c * 64 + (b >> 6)]) >> (b & 63)) & 1ull;
+// full word w of chunk (cx,cy,cz), zeros outside the grid
+__device__ __forceinline__ uint64_t full_word(const DVolume& v, int cx, int cy, int cz, int w) {
+  if ((unsigned)cx >= (unsigned)v.dims[0] || (unsigned)cy >= (unsigned)v.dims[1] || (unsigned)cz >= (unsigned)v.dims[2]) return 0ull;
+  return __ldg(&v.full[chunk_index(v, cx, cy, cz) * 64 + w]);
 }
 
+// Pass A, one thread per 64-brick occupancy word (word = z*4 + y/4, four 16-bit x-rows): bricks that are full and
+// have six full neighbours are buried (no exposed face); the six neighbour masks come from shifted full-words of this
+// and the adjacent words / chunks.  Survivors are appended to the work list (warp prefix + one atomic per warp).
 __global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank, int world, uint64_t* work, uint32_t* work_count) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
-  if (t < v.nchunks * MESO_BLOCKS) {
-    const int64_t c = t >> 12; const int b = (int)(t & 4095);
+  uint64_t todo = 0;
+  int64_t c = 0; int w = 0;
+  if (t < v.nchunks * MESO_WORDS) {
+    c = t >> 6; w = (int)(t & 63);
     if ((c % world) == rank) {
-      const uint64_t o = __ldg(&v.occ[c * 64 + (b >> 6)]);
-      if ((o >> (b & 63)) & 1ull) {
-        keep = true;
-        if ((__ldg(&v.full[c * 64 + (b >> 6)]) >> (b & 63)) & 1ull) {
+      const uint64_t O = __ldg(&v.occ[t]);
+      if (O) {
+        const uint64_t F = __ldg(&v.full[t]);
+        uint64_t buried = 0;
+        if (F) {
           const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
-          const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
-          if (brick_full(v, bx - 1, by, bz) && brick_full(v, bx + 1, by, bz) && brick_full(v, bx, by - 1, bz) &&
-              brick_full(v, bx, by + 1, bz) && brick_full(v, bx, by, bz - 1) && brick_full(v, bx, by, bz + 1))
-            keep = false;  // buried: no exposed face
+          const int z = w >> 2, yq = w & 3;
+          const uint64_t X0 = 0x0001000100010001ull, X15 = 0x8000800080008000ull;
+          const uint64_t fxm = ((F << 1) & ~X0) | ((full_word(v, cx - 1, cy, cz, w) >> 15) & X0);
+          const uint64_t fxp = ((F >> 1) & ~X15) | ((full_word(v, cx + 1, cy, cz, w) << 15) & X15);
+          const uint64_t ym_src = yq > 0 ? __ldg(&v.full[t - 1]) : full_word(v, cx, cy - 1, cz, z * 4 + 3);
+          const uint64_t yp_src = yq < 3 ? __ldg(&v.full[t + 1]) : full_word(v, cx, cy + 1, cz, z * 4 + 0);
+          const uint64_t fym = (F << 16) | (ym_src >> 48);
+          const uint64_t fyp = (F >> 16) | (yp_src << 48);
+          const uint64_t fzm = z > 0 ? __ldg(&v.full[t - 4]) : full_word(v, cx, cy, cz - 1, 15 * 4 + yq);
+          const uint64_t fzp = z < 15 ? __ldg(&v.full[t + 4]) : full_word(v, cx, cy, cz + 1, 0 * 4 + yq);
+          buried = F & fxm & fxp & fym & fyp & fzm & fzp;
         }
+        todo = O & ~buried;
       }
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, keep);
-  if (m) {
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(work_count, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (keep) work[base + __popc(m & ((1u << lane) - 1u))] = (uint64_t)t;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = (uint32_t)__popcll(todo);
+  uint32_t incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(work_count, total);
+  base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+  while (todo) {
+    const int bit = __ffsll((long long)todo) - 1;
+    todo &= todo - 1;
+    work[base++] = (uint64_t)c * MESO_BLOCKS + (uint64_t)(w * 64 + bit);
   }
 }
 
@@ -94,10 +105,37 @@ __device__ __forceinline__ int greedy_image(uint64_t img, int dir, int layer, in
   return n;
 }
 
+#define MQ_CAP 128   // quads staged per brick in shared memory (a smooth surface brick yields ~20)
+
+// Same greedy merge, staging the quads in shared memory; slots come from a shared-memory atomic counter.
+__device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count) {
+  const int ax = dir >> 1;
+#pragma unroll 1
+  for (int vv = 0; vv < 8; vv++) {
+    uint32_t row = (uint32_t)(img >> (8 * vv)) & 0xFFu;
+    while (row) {
+      const int u0 = __ffs(row) - 1;
+      const int w = __ffs(~(row >> u0)) - 1;
+      const uint32_t m = ((1u << w) - 1u) << u0;
+      int h = 1;
+      while (vv + h < 8 && (((uint32_t)(img >> (8 * (vv + h))) & m) == m)) { img &= ~((uint64_t)m << (8 * (vv + h))); h++; }
+      row &= ~m;
+      int x, y, z;
+      if (ax == 0) { x = layer; y = u0; z = vv; } else if (ax == 1) { x = u0; y = layer; z = vv; } else { x = u0; y = vv; z = layer; }
+      const int idx = atomicAdd(count, 1);
+      if (idx < MQ_CAP)
+        stage[idx] = make_uint4((uint32_t)(ox + x) | ((uint32_t)(oy + y) << 16), (uint32_t)(oz + z) | ((uint32_t)dir << 16) | ((uint32_t)w << 24),
+                                (uint32_t)h, 0u);
+    }
+  }
+}
+
 // Persistent, grid-stride over the work list (count read from device memory: no host round trip between the passes).
 __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
                                                           uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
   __shared__ uint64_t s_e[8][6][8];
+  __shared__ uint4 s_q[8][MQ_CAP];
+  __shared__ int s_n[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_work = work_count_ptr ? *work_count_ptr : work_count_imm;
   for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < n_work; item += (int64_t)gridDim.x * 8) {
@@ -108,15 +146,38 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
   const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
 
   const int z = lane & 7;
-  uint64_t s = 0, nzm = 0, nzp = 0;
-  if (lane < 8) s = fetch_slice(v, bx, by, bz, z);
-  if (lane == 0) nzm = fetch_slice(v, bx, by, bz - 1, 7);
-  if (lane == 7) nzp = fetch_slice(v, bx, by, bz + 1, 0);
+  // Step 1: lanes 0..6 resolve the seven bricks involved (self, -x, +x, -y, +y, -z, +z) in parallel: one 16 B
+  // {occ,full} load each, then the payload slot of the partial ones.  state: 0 empty / outside, 1 full, 2 partial.
+  int st = 0; uint32_t slot = 0;
+  if (lane < 7) {
+    const int nx = bx + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
+    const int ny = by + (lane == 3 ? -1 : (lane == 4 ? 1 : 0));
+    const int nz = bz + (lane == 5 ? -1 : (lane == 6 ? 1 : 0));
+    if ((unsigned)nx < (unsigned)(v.dims[0] * 16) && (unsigned)ny < (unsigned)(v.dims[1] * 16) && (unsigned)nz < (unsigned)(v.dims[2] * 16)) {
+      const int64_t nc = chunk_index(v, nx >> 4, ny >> 4, nz >> 4);
+      const int nb = block_bit(nx & 15, ny & 15, nz & 15);
+      const ulonglong2 p = __ldg(&v.of[nc * 64 + (nb >> 6)]);
+      if ((p.x >> (nb & 63)) & 1ull) {
+        if ((p.y >> (nb & 63)) & 1ull) st = 1;
+        else { st = 2; slot = __ldg(&v.bptr[nc * MESO_BLOCKS + nb]); }
+      }
+    }
+  }
+  // Step 2: every slice needed is one independent 8 B load (lanes 0..7: slice z of self and of the four lateral
+  // neighbours; lane 0 / 7: the facing slice of the -z / +z neighbour).
+  auto slice_of = [&](int which, int zz) -> uint64_t {
+    const int s_st = __shfl_sync(0xffffffffu, st, which);
+    const uint32_t s_slot = __shfl_sync(0xffffffffu, slot, which);
+    if (s_st == 2 && lane < 8) return __ldg(&v.pool[(size_t)s_slot * 8 + zz]);
+    return s_st == 1 ? ~0ull : 0ull;
+  };
+  uint64_t s = slice_of(0, z);   // every lane takes part in the shuffles
+  if (lane >= 8) s = 0ull;
+  const uint64_t xm = slice_of(1, z), xp = slice_of(2, z), ym = slice_of(3, z), yp = slice_of(4, z);
+  const uint64_t nzm = slice_of(5, 7), nzp = slice_of(6, 0);
   const uint64_t s_dn = __shfl_up_sync(0xffffffffu, s, 1), s_up = __shfl_down_sync(0xffffffffu, s, 1);
   if (lane < 8) {
     const uint64_t C0 = 0x0101010101010101ull;
-    const uint64_t xm = fetch_slice(v, bx - 1, by, bz, z), xp = fetch_slice(v, bx + 1, by, bz, z);
-    const uint64_t ym = fetch_slice(v, bx, by - 1, bz, z), yp = fetch_slice(v, bx, by + 1, bz, z);
     const uint64_t n_xm = ((s << 1) & ~C0) | ((xm >> 7) & C0);
     const uint64_t n_xp = ((s >> 1) & ~(C0 << 7)) | ((xp & C0) << 7);
     const uint64_t n_ym = (s << 8) | (ym >> 56);
@@ -147,9 +208,30 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
         }
         img[k] = im;
       }
-      if (img[k]) cnt += greedy_image<false>(img[k], dir, l, 0, 0, 0, nullptr, 0, 0);
     }
   }
+  // Fast path: one greedy pass that stages the quads of the brick in shared memory (slot = shared atomic, order
+  // inside a brick is irrelevant), then one global atomicAdd and a coalesced copy of 16 B records.
+  if (lane == 0) s_n[warp] = 0;
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+    if (lane + 32 * k < 48 && img[k]) greedy_stage(img[k], tdir[k], tlay[k], bx * 8, by * 8, bz * 8, s_q[warp], &s_n[warp]);
+  __syncwarp();
+  const int staged = s_n[warp];
+  if (staged == 0) continue;
+  if (staged <= MQ_CAP) {
+    unsigned long long sbase = 0;
+    if (lane == 0) sbase = atomicAdd(quad_count, (unsigned long long)staged);
+    sbase = __shfl_sync(0xffffffffu, sbase, 0);
+    for (int i = lane; i < staged; i += 32)
+      if ((int64_t)sbase + i < cap) reinterpret_cast<uint4*>(quads)[sbase + i] = s_q[warp][i];
+    continue;
+  }
+  // Rare: more quads than the staging area holds -> count, prefix, emit straight to global memory.
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+    if (lane + 32 * k < 48 && img[k]) cnt += greedy_image<false>(img[k], tdir[k], tlay[k], 0, 0, 0, nullptr, 0, 0);
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
@@ -170,7 +252,7 @@ void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uin
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count) {
   cudaMemsetAsync(d_work_count, 0, sizeof(uint32_t), lc.stream);
   cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
-  const int64_t n = v.nchunks * MESO_BLOCKS;
+  const int64_t n = v.nchunks * MESO_WORDS;
   mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, d_work, d_work_count);
   mesh_bricks_kernel<<<lc.sm_count * 8, 256, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count);
   (*lc.launches) += 2;

@@ -156,10 +156,16 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(DVolume v, uint32_t
   }
 }
 
-void launch_occupancy(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, MesoGPUChunk* d_table, uint32_t* d_counts,
-                      uint32_t* d_offsets, MesoGPUBlock* d_inst, int64_t cap_inst, uint64_t* d_total) {
+// pass 1: mips + per-chunk instance counts + exclusive scan (d_total = number of instances)
+void launch_occupancy_count(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, MesoGPUChunk* d_table, uint32_t* d_counts,
+                            uint32_t* d_offsets, uint64_t* d_total) {
   occupancy_mips_kernel<<<(unsigned)v.nchunks, 64, 0, lc.stream>>>(v, stamp, d_table, d_counts);
   scan_counts_kernel<<<1, 1024, 0, lc.stream>>>(d_counts, d_offsets, v.nchunks, d_total);
+  (*lc.launches) += 2;
+}
+// pass 2: compacted FGPUBlock list in generator order
+void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, const uint32_t* d_counts, const uint32_t* d_offsets,
+                           MesoGPUBlock* d_inst, int64_t cap_inst) {
   emit_instances_kernel<<<(unsigned)v.nchunks, 256, 0, lc.stream>>>(v, stamp, d_counts, d_offsets, d_inst, cap_inst);
-  (*lc.launches) += 3;
+  (*lc.launches) += 1;
 }

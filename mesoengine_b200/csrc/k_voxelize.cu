@@ -155,46 +155,64 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
   const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int vz = lane >> 2, q = lane & 3;
-  __shared__ uint64_t s_occ[8], s_full[8];
-  uint64_t occ_bits = 0, full_bits = 0;
+  __shared__ unsigned long long s_occ, s_full;
+  __shared__ int s_list[64];
+  __shared__ int s_mixed;
   const double cs0 = (double)(v.origin[0] + cx) * 1.0 * 16.0, cs1 = (double)(v.origin[1] + cy) * 1.0 * 16.0,
                cs2 = (double)(v.origin[2] + cz) * 1.0 * 16.0;
-  for (int k = 0; k < 8; k++) {
-    const int i = warp * 8 + k;            // bit in word
-    const int bi = W * 64 + i;             // block index in chunk
+  if (threadIdx.x == 0) { s_occ = 0ull; s_full = 0ull; s_mixed = 0; }
+  __syncthreads();
+  // ---- pass A: one thread per brick classifies it exactly (all-solid / all-empty / mixed) ----
+  if (threadIdx.x < 64) {
+    const int i = threadIdx.x;
+    const int bi = W * 64 + i;
     const int X = bi & 15, Y = (bi >> 4) & 15, Z = bi >> 8;
     const double b0 = cs0 + (double)X * 1.0, b1 = cs1 + (double)Y * 1.0, b2 = cs2 + (double)Z * 1.0;
-    uint64_t s;
-    bool decided = false;
+    int cls = -1;
     if (KIND == MESO_SDF_TERRAIN) {
-      if (b1 * .5 > TERRAIN_Y_HALF_BOUND) { s = 0ull; decided = true; }
-      else if ((b1 + 0.875) * .5 < -TERRAIN_Y_HALF_BOUND) { s = ~0ull; decided = true; }
+      if (b1 * .5 > TERRAIN_Y_HALF_BOUND) cls = 0;
+      else if ((b1 + 0.875) * .5 < -TERRAIN_Y_HALF_BOUND) cls = 1;
     } else {
-      const int cls = sphere_brick_class(sp, b0, b1, b2);
-      if (cls == 0) { s = 0ull; decided = true; }
-      else if (cls == 1) { s = ~0ull; decided = true; }
+      cls = sphere_brick_class(sp, b0, b1, b2);
     }
-    if (!decided) {
-      uint32_t bits = 0;
-      const double pz = b2 + (double)vz * 0.125;
+    const unsigned solid = __ballot_sync(0xffffffffu, cls == 1);
+    const unsigned mixed = __ballot_sync(0xffffffffu, cls < 0);
+    if (lane == 0) {
+      atomicOr(&s_occ, (unsigned long long)solid << (32 * warp));
+      atomicOr(&s_full, (unsigned long long)solid << (32 * warp));
+    }
+    if (cls < 0) s_list[atomicAdd(&s_mixed, 1)] = i;   // order is irrelevant: every mixed brick is evaluated in full
+    (void)mixed;
+  }
+  __syncthreads();
+  // ---- pass B: a warp evaluates all 512 samples of a mixed brick, 16 per lane ----
+  const int n_mixed = s_mixed;
+  for (int k = warp; k < n_mixed; k += 8) {
+    const int i = s_list[k];
+    const int bi = W * 64 + i;
+    const int X = bi & 15, Y = (bi >> 4) & 15, Z = bi >> 8;
+    const double b0 = cs0 + (double)X * 1.0, b1 = cs1 + (double)Y * 1.0, b2 = cs2 + (double)Z * 1.0;
+    uint32_t bits = 0;
+    const double pz = b2 + (double)vz * 0.125;
 #pragma unroll 1
-      for (int r = 0; r < 2; r++) {
-        const int vy = 2 * q + r;
-        const double py = b1 + (double)vy * 0.125;
+    for (int r = 0; r < 2; r++) {
+      const int vy = 2 * q + r;
+      const double py = b1 + (double)vy * 0.125;
 #pragma unroll 1
-        for (int vx = 0; vx < 8; vx++) {
-          const double px = b0 + (double)vx * 0.125;
-          if (sdf_solid<KIND>(sp, px, py, pz)) bits |= 1u << (vx + 8 * r);
-        }
+      for (int vx = 0; vx < 8; vx++) {
+        const double px = b0 + (double)vx * 0.125;
+        if (sdf_solid<KIND>(sp, px, py, pz)) bits |= 1u << (vx + 8 * r);
       }
-      s = (uint64_t)bits << (16 * q);
-      s |= __shfl_xor_sync(0xffffffffu, s, 1);
-      s |= __shfl_xor_sync(0xffffffffu, s, 2);
     }
+    uint64_t s = (uint64_t)bits << (16 * q);
+    s |= __shfl_xor_sync(0xffffffffu, s, 1);
+    s |= __shfl_xor_sync(0xffffffffu, s, 2);
     const bool any = __any_sync(0xffffffffu, s != 0ull);
     const bool all = __all_sync(0xffffffffu, s == ~0ull);
-    if (any) occ_bits |= 1ull << i;
-    if (all) full_bits |= 1ull << i;
+    if (lane == 0) {
+      if (any) atomicOr(&s_occ, 1ull << i);
+      if (all) atomicOr(&s_full, 1ull << i);
+    }
     if (any && !all) {
       uint32_t slot = 0;
       if (lane == 0) slot = atomicAdd(v.pool_count, 1u);
@@ -207,14 +225,10 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
       }
     }
   }
-  if (lane == 0) { s_occ[warp] = occ_bits; s_full[warp] = full_bits; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint64_t o = 0, f = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) { o |= s_occ[w]; f |= s_full[w]; }
-    v.occ[word_global] = o;
-    v.full[word_global] = f;
+    v.occ[word_global] = s_occ;
+    v.full[word_global] = s_full;
   }
 }
 

@@ -340,23 +340,19 @@ int meso_volume_download(MesoCtx* c, uint64_t* occ, uint64_t* full, uint64_t* ke
 
 int meso_build_occupancy(MesoCtx* c, uint32_t stamp, int64_t* n_instances) {
   NEED_SCENE(c);
-  // capacity: every block of the grid could be emitted; size to the populated block count instead
-  const size_t nc = (size_t)c->v.nchunks;
-  std::vector<uint64_t> occ(nc * 64);
-  CK(cudaMemcpyAsync(occ.data(), c->v.occ, nc * 64 * 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  int64_t blocks = 0;
-  for (size_t i = 0; i < nc * 64; i++) blocks += __builtin_popcountll(occ[i]);
-  if (blocks > c->cap_inst) {
-    cudaFree(c->d_inst); c->d_inst = nullptr;
-    c->cap_inst = blocks;
-    CK(cudaMalloc(&c->d_inst, (size_t)std::max<int64_t>(blocks, 1) * sizeof(MesoGPUBlock)));
-  }
-  launch_occupancy(c->lc(), c->v, stamp, c->d_table, c->d_counts, c->d_offsets, c->d_inst, c->cap_inst, c->d_total);
-  CK_LAST("occupancy");
+  // pass 1 on the device (mips, per-chunk counts, scan); the 8-byte total sizes the instance buffer, then pass 2 emits
+  launch_occupancy_count(c->lc(), c->v, stamp, c->d_table, c->d_counts, c->d_offsets, c->d_total);
+  CK_LAST("occupancy count");
   uint64_t total = 0;
   CK(cudaMemcpyAsync(&total, c->d_total, 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  if ((int64_t)total > c->cap_inst) {
+    cudaFree(c->d_inst); c->d_inst = nullptr;
+    c->cap_inst = (int64_t)total + (int64_t)total / 8;   // a little headroom for edits
+    CK(cudaMalloc(&c->d_inst, (size_t)c->cap_inst * sizeof(MesoGPUBlock)));
+  }
+  launch_occupancy_emit(c->lc(), c->v, stamp, c->d_counts, c->d_offsets, c->d_inst, c->cap_inst);
+  CK_LAST("occupancy emit");
   c->n_inst = (int64_t)total;
   if (n_instances) *n_instances = c->n_inst;
   return MESO_OK;
