@@ -87,16 +87,20 @@ __global__ void __launch_bounds__(64) occupancy_mips_kernel(DVolume v, uint32_t 
   }
 }
 
-// exclusive scan of per-chunk counts (single CTA; nchunks <= a few 10^5)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* counts, uint32_t* offsets, int64_t n, uint64_t* total) {
+// exclusive scan of per-chunk counts: a single CTA, 32 consecutive counts per thread (one pass covers 32 768 chunks)
+#define SCAN_PER_THREAD 32
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* __restrict__ counts, uint32_t* offsets, int64_t n, uint64_t* total) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < n; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    uint32_t x = i < n ? counts[i] : 0u;
+  for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    uint32_t loc[SCAN_PER_THREAD];
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) { loc[k] = (i0 + k < n) ? counts[i0 + k] : 0u; x += loc[k]; }
     uint32_t incl = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
@@ -110,7 +114,9 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* count
     }
     __syncthreads();
     const uint32_t carry = s_carry;
-    if (i < n) offsets[i] = carry + s_warp[warp] + incl - x;
+    uint32_t run = carry + s_warp[warp] + incl - x;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) { if (i0 + k < n) offsets[i0 + k] = run; run += loc[k]; }
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
     __syncthreads();
@@ -120,11 +126,14 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* count
 
 // One CTA (256 threads) per chunk.  Thread t <-> column (X = t>>4, Y = t&15), i.e. thread order is the reference's
 // generator order (X outer, Y, Z inner; GeneratorHelper.h:125-129): a block-wide exclusive scan of the per-column
-// popcounts gives every emitted block its rank in exactly the order PushToBlockPool walks Chunk.Blocks.
+// popcounts gives every emitted block its rank in exactly the order PushToBlockPool walks Chunk.Blocks.  Records are
+// staged in shared memory at their rank and copied out as one contiguous, coalesced run of 32-bit words.
 __global__ void __launch_bounds__(256) emit_instances_kernel(DVolume v, uint32_t stamp, const uint32_t* __restrict__ counts,
                                                              const uint32_t* __restrict__ offsets, MesoGPUBlock* inst, int64_t cap) {
   const int64_t c = blockIdx.x;
-  if (counts[c] == 0) return;
+  const uint32_t total = counts[c];
+  if (total == 0) return;
+  extern __shared__ uint32_t s_rec[];   // 3 words per record, up to 4096 records
   __shared__ uint64_t cull[64];
   __shared__ uint32_t s_warp[8];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -142,18 +151,21 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(DVolume v, uint32_t
   __syncthreads();
   uint32_t wbase = 0;
   for (int k = 0; k < warp; k++) wbase += s_warp[k];
-  int64_t dst = (int64_t)offsets[c] + wbase + incl - n;
-  uint32_t* out = reinterpret_cast<uint32_t*>(inst);
+  uint32_t r = wbase + incl - n;
   while (col) {
     const int Z = __ffs(col) - 1;
     col &= col - 1;
-    if (dst < cap) {
-      out[dst * 3 + 0] = (uint32_t)c;                                                   // ChunkIndex (+ thread offset 0)
-      out[dst * 3 + 1] = (uint32_t)X | ((uint32_t)Y << 8) | ((uint32_t)Z << 16) | (255u << 24);  // u8vec4(x,y,z,255)
-      out[dst * 3 + 2] = stamp;
-    }
-    dst++;
+    s_rec[r * 3 + 0] = (uint32_t)c;                                                           // ChunkIndex (+ thread offset 0)
+    s_rec[r * 3 + 1] = (uint32_t)X | ((uint32_t)Y << 8) | ((uint32_t)Z << 16) | (255u << 24);  // u8vec4(x,y,z,255)
+    s_rec[r * 3 + 2] = stamp;
+    r++;
   }
+  __syncthreads();
+  const int64_t first = (int64_t)offsets[c];
+  const int64_t room = cap - first;
+  const uint32_t words = (uint32_t)(room <= 0 ? 0 : (room < (int64_t)total ? room : (int64_t)total)) * 3u;
+  uint32_t* out = reinterpret_cast<uint32_t*>(inst) + first * 3;
+  for (uint32_t i = t; i < words; i += 256) out[i] = s_rec[i];
 }
 
 // pass 1: mips + per-chunk instance counts + exclusive scan (d_total = number of instances)
@@ -166,6 +178,9 @@ void launch_occupancy_count(const LaunchCtx& lc, const DVolume& v, uint32_t stam
 // pass 2: compacted FGPUBlock list in generator order
 void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, const uint32_t* d_counts, const uint32_t* d_offsets,
                            MesoGPUBlock* d_inst, int64_t cap_inst) {
-  emit_instances_kernel<<<(unsigned)v.nchunks, 256, 0, lc.stream>>>(v, stamp, d_counts, d_offsets, d_inst, cap_inst);
+  static bool attr_set = false;
+  const int smem = MESO_BLOCKS * 12;
+  if (!attr_set) { cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  emit_instances_kernel<<<(unsigned)v.nchunks, 256, smem, lc.stream>>>(v, stamp, d_counts, d_offsets, d_inst, cap_inst);
   (*lc.launches) += 1;
 }
