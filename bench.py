@@ -438,6 +438,10 @@ def run_ours(args):
                          "note": "latency/divergence-bound traversal; working set is L2-resident (SURVEY.md 8d)"},
         }
 
+    # ---- BASELINE.json configs[4]: interactive edit loop (1 GPU leg; carve is replicated compute on N GPUs) ----
+    if world == 1 and not args.no_mesh and rank == 0:
+        line["edit_loop"] = bench_edit_loop(ctx, capi, cams, width, height)
+
     # ---- secondary metric of BASELINE.json: meshed voxels/s (configs[2]-style, 1 GPU leg only) ----
     if world == 1 and not args.no_mesh and rank == 0:
         line["mesh"] = bench_mesh(ctx, capi, scenes, torch, stream, args, dev)
@@ -453,6 +457,37 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     ctx.close()
     return 0
+
+
+def bench_edit_loop(ctx, capi, cams, width, height, frames=48):
+    """SURVEY.md 8d edit loop: frame k carves a sphere (r = 24 voxels) at the hit point of the centre pixel of camera
+    C_{k mod 8}, re-meshes the dirty bricks (+ their six neighbours) and re-renders 4K.  Host-API calls, wall clock."""
+    import torch
+    t_carve = t_mesh = t_render = 0.0
+    dirty_total = quads_total = 0
+    pinned = torch.empty((height, width, 4), dtype=torch.int32).pin_memory()
+    out = pinned.numpy().view(capi.HitRecord).reshape(height, width)
+    rec = ctx.raymarch(cams[0], width, height, shadow=True, light=LIGHT, out=out)
+    t_all = time.perf_counter()
+    for k in range(frames):
+        r = rec[height // 2, width // 2]
+        if (int(r["w1"]) >> 20) & 1:
+            center = [int(r["w0"]) & 0xFFFF, int(r["w0"]) >> 16, int(r["w1"]) & 0xFFFF]
+            t0 = time.perf_counter()
+            nd = ctx.carve_sphere(center, 24)
+            t1 = time.perf_counter()
+            quads, keys = ctx.remesh_dirty(1 << 16, 1 << 13)
+            t2 = time.perf_counter()
+            t_carve += t1 - t0; t_mesh += t2 - t1
+            dirty_total += nd; quads_total += len(quads)
+        t0 = time.perf_counter()
+        rec = ctx.raymarch(cams[(k + 1) % 8], width, height, shadow=True, light=LIGHT, out=out)
+        t_render += time.perf_counter() - t0
+    t_all = time.perf_counter() - t_all
+    return {"frames": frames, "fps": frames / t_all, "ms_per_frame": t_all / frames * 1e3, "ms_carve": t_carve / frames * 1e3,
+            "ms_remesh_dirty": t_mesh / frames * 1e3, "ms_render_to_host": t_render / frames * 1e3,
+            "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": quads_total / frames,
+            "note": "carve r=24 voxels at the centre-pixel hit, re-mesh dirty bricks + neighbours, re-render 3840x2160 to host memory (synchronous API)"}
 
 
 def bench_mesh(ctx, capi, scenes, torch, stream, args, dev):

@@ -256,7 +256,7 @@ struct ShadowJob { float px, py, pz; int cx, cy, cz; int owner; };
 // different phases in one warp -- a persistent "refill idle lanes" loop -- dropped SIMT efficiency from 20/32 to 8/32).
 // Shadow rays are compacted across the CTA (ballot + prefix through shared memory) and start together as well.
 template <bool STATS>
-__global__ void __launch_bounds__(RM_THREADS) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
+__global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
                                                               int rank, int world, int layout, int tiles_x, int n_tiles,
                                                               int local_tile0,
                                                               MesoHitRecord* __restrict__ out, RayStatsDev* stats,

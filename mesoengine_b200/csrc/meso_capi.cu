@@ -492,11 +492,17 @@ int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   MesoRaySetup rs;
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
-  if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * sizeof(MesoHitRecord), c->stream));
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr,
+  // Frames of the ring alternate between the two band streams so that the tail of frame k (a few tiles with grazing
+  // rays) overlaps the body of frame k+1; each is ordered after whatever the caller enqueued on the context's stream.
+  LaunchCtx lc = c->lc();
+  lc.stream = c->band_stream[slot & 1];
+  CK(cudaEventRecord(c->band_fork, c->stream));
+  CK(cudaStreamWaitEvent(lc.stream, c->band_fork, 0));
+  if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * sizeof(MesoHitRecord), lc.stream));
+  launch_raymarch(lc, c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr,
                   c->d_tile_counter);
   CK_LAST("raymarch async");
-  CK(cudaEventRecord(c->ring_traced[slot], c->stream));
+  CK(cudaEventRecord(c->ring_traced[slot], lc.stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ring_traced[slot], 0));
   CK(cudaMemcpyAsync(host, c->d_ring[slot], px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->copy_stream));
   CK(cudaEventRecord(c->ring_copied[slot], c->copy_stream));
