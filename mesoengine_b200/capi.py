@@ -24,6 +24,10 @@ RaySetup = np.dtype([("o", "<f4", (3,)), ("two_over_w", "<f4"), ("U", "<f4", (3,
                      ("L", "<f4", (3,)), ("pad2", "<f4")])
 RayStats = np.dtype([("primary", "<u8"), ("shadow", "<u8"), ("hits", "<u8"), ("steps", "<u8"),
                      ("touched_chunks", "<u8"), ("touched_bricks", "<u8"), ("u_bytes", "<u8")])
+ChunkCandidate = np.dtype([("Importance", "<f4"), ("Offset", "<i4", (3,))])          # FTempChunkDataType
+ViewConfig = np.dtype([("ViewForwardLoadChunkSize", "<u4"), ("ViewBackwardLoadChunkSize", "<u4"), ("ViewChunkAngle", "<f4"),
+                       ("Mode", "<u4")])
+StreamStats = np.dtype([("generated", "<u4"), ("missing", "<u4"), ("candidates", "<u4"), ("in_window", "<u4")])
 
 SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
@@ -41,6 +45,8 @@ SYMBOLS = [
     "meso_carve_sphere", "meso_download_dirty", "meso_remesh_dirty", "meso_host_alloc", "meso_host_free",
     "meso_flush_l2", "meso_launch_count",
     "meso_raymarch_async", "meso_frame_wait", "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download", "meso_download_async",
+    "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
+    "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -99,6 +105,25 @@ def ray_setup(cam, origin_chunk, width, height, light=(0.3, 0.5, 0.8)):
 
 def tiles_per_rank(width, height, world):
     return int(lib.meso_tiles_per_rank(C.c_int(width), C.c_int(height), C.c_int(world)))
+
+
+def view_config(forward_load=24, backward_load=6, view_angle=120.0, mode=0):
+    """The view fields of FVoxelSceneConfig (VoxelSceneConfig.h:34-35,40) with the reference's defaults."""
+    v = np.zeros(1, dtype=ViewConfig)
+    v["ViewForwardLoadChunkSize"] = forward_load
+    v["ViewBackwardLoadChunkSize"] = backward_load
+    v["ViewChunkAngle"] = view_angle
+    v["Mode"] = mode
+    return v
+
+
+def baked_direction(samples, forward):
+    """Pure host function: the baked Fibonacci direction the reference's TNearestMap returns for `forward`."""
+    f = np.ascontiguousarray(forward, dtype=np.float32)
+    out = np.zeros(3, dtype=np.float32)
+    idx = C.c_uint32(0)
+    _ck(lib.meso_baked_direction(C.c_uint32(samples), _p(f), _p(out), C.byref(idx)))
+    return out, idx.value
 
 
 class Context:
@@ -254,6 +279,52 @@ class Context:
 
     def flush_l2(self):
         _ck(lib.meso_flush_l2(self.h))
+
+    # ---- K6: resident-set selection / streaming generation ----
+    def select_view_chunks(self, forward, view=None):
+        """FChunkManageHelper::GetDesiredShowChunkLocationByView in priority-queue pop order."""
+        view = view_config() if view is None else view
+        f = np.ascontiguousarray(forward, dtype=np.float32)
+        side = 2 * int(view["ViewForwardLoadChunkSize"][0]) + 1
+        out = np.zeros(side ** 3, dtype=ChunkCandidate)
+        n = C.c_int64(0)
+        _ck(lib.meso_select_view_chunks(self.h, _p(f), _p(view), _p(out), C.c_int64(out.shape[0]), C.byref(n)))
+        return out[: n.value]
+
+    def chunk_importance(self, camera_chunk, forward, locations):
+        loc = np.ascontiguousarray(locations, dtype=np.int32).reshape(-1, 3)
+        out = np.zeros(loc.shape[0], dtype=np.float32)
+        cc = np.ascontiguousarray(camera_chunk, dtype=np.int32)
+        f = np.ascontiguousarray(forward, dtype=np.float32)
+        _ck(lib.meso_chunk_importance(self.h, _p(cc), _p(f), _p(loc), C.c_int64(loc.shape[0]), _p(out)))
+        return out
+
+    def stream_begin(self, kind, params=None, granularity=GRAN_VOXEL):
+        p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        _ck(lib.meso_stream_begin(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
+
+    def stream_update(self, camera_chunk, forward, max_new, view=None, wait=True):
+        """FChunkManage::UpdateChunks + UpdateLoadingQueue; returns StreamStats (wait=True) or None (enqueue only)."""
+        view = view_config() if view is None else view
+        cc = np.ascontiguousarray(camera_chunk, dtype=np.int32)
+        f = np.ascontiguousarray(forward, dtype=np.float32)
+        if not wait:
+            _ck(lib.meso_stream_update_async(self.h, _p(cc), _p(f), _p(view), C.c_uint32(max_new)))
+            return None
+        st = np.zeros(1, dtype=StreamStats)
+        _ck(lib.meso_stream_update(self.h, _p(cc), _p(f), _p(view), C.c_uint32(max_new), _p(st)))
+        return st[0]
+
+    def stream_stats(self):
+        st = np.zeros(1, dtype=StreamStats)
+        _ck(lib.meso_stream_stats(self.h, _p(st)))
+        return st[0]
+
+    def stream_loaded(self, nchunks):
+        """bool per chunk slot of the window: generated."""
+        words = np.zeros((nchunks + 31) // 32, dtype=np.uint32)
+        _ck(lib.meso_stream_loaded(self.h, _p(words), C.c_int64(words.shape[0])))
+        return np.unpackbits(words.view(np.uint8), bitorder="little")[:nchunks].astype(bool)
 
     # ---- peer memory (fused gather) ----
     def device_alloc(self, nbytes):

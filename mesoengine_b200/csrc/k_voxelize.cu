@@ -148,10 +148,16 @@ __device__ __forceinline__ int sphere_brick_class(const SdfParams& sp, double b0
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParams sp, int* overflow) {
-  const int64_t word_global = blockIdx.x;  // chunk*64 + word
-  const int64_t c = word_global >> 6;
-  const int W = (int)(word_global & 63);
+__global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParams sp, int* overflow, const uint32_t* __restrict__ list,
+                                                             const uint32_t* __restrict__ list_n) {
+  // whole grid: blockIdx = chunk*64 + word; streaming (K6): blockIdx = list position*64 + word, chunk = list[position]
+  int64_t c = blockIdx.x >> 6;
+  if (list) {
+    if (c >= (int64_t)*list_n) return;
+    c = list[c];
+  }
+  const int W = (int)(blockIdx.x & 63);
+  const int64_t word_global = c * 64 + W;
   const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int vz = lane >> 2, q = lane & 3;
@@ -234,10 +240,15 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
 
 // Block-granular (reference semantics, GeneratorHelper.h:120-150): one sample at the block min corner; brick all-ones.
 template <int KIND>
-__global__ void __launch_bounds__(64) voxelize_block_kernel(DVolume v, SdfParams sp) {
-  const int64_t word_global = blockIdx.x;
-  const int64_t c = word_global >> 6;
-  const int W = (int)(word_global & 63);
+__global__ void __launch_bounds__(64) voxelize_block_kernel(DVolume v, SdfParams sp, const uint32_t* __restrict__ list,
+                                                            const uint32_t* __restrict__ list_n) {
+  int64_t c = blockIdx.x >> 6;
+  if (list) {
+    if (c >= (int64_t)*list_n) return;
+    c = list[c];
+  }
+  const int W = (int)(blockIdx.x & 63);
+  const int64_t word_global = c * 64 + W;
   const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
   const int bi = W * 64 + threadIdx.x;
   const int X = bi & 15, Y = (bi >> 4) & 15, Z = bi >> 8;
@@ -257,10 +268,8 @@ __global__ void __launch_bounds__(64) voxelize_block_kernel(DVolume v, SdfParams
 }
 
 // chunk-level any/full bit grids: one warp per chunk
-__global__ void __launch_bounds__(256) finalize_kernel(DVolume v) {
-  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= v.nchunks) return;
+template <bool SET_REGION>
+__device__ __forceinline__ void finalize_chunk(const DVolume& v, int64_t c, int lane) {
   uint64_t o0 = v.occ[c * 64 + lane], o1 = v.occ[c * 64 + 32 + lane];
   uint64_t f0 = v.full[c * 64 + lane], f1 = v.full[c * 64 + 32 + lane];
   v.of[c * 64 + lane] = make_ulonglong2(o0, f0);
@@ -284,7 +293,25 @@ __global__ void __launch_bounds__(256) finalize_kernel(DVolume v) {
     v.cells[c] = (uint64_t)lo | ((uint64_t)hi << 32);
     if (any) atomicOr(&v.chunk_any[c >> 5], 1u << (c & 31));
     if (all) atomicOr(&v.chunk_full[c >> 5], 1u << (c & 31));
+    if (SET_REGION && any) {
+      const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
+      const int r = (cx >> 2) + v.rdims[0] * ((cy >> 2) + v.rdims[1] * (cz >> 2));
+      atomicOr(&v.region_any[r >> 5], 1u << (r & 31));
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(DVolume v) {
+  const int64_t c = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= v.nchunks) return;
+  finalize_chunk<false>(v, c, threadIdx.x & 31);
+}
+
+// streaming (K6): derived data of the listed, newly generated chunks only; bits are only ever added
+__global__ void __launch_bounds__(256) finalize_list_kernel(DVolume v, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_n) {
+  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= (int64_t)*list_n) return;
+  finalize_chunk<true>(v, (int64_t)list[k], threadIdx.x & 31);
 }
 
 // bit per 512^3-voxel region (4x4x4 chunks): one thread per region
@@ -331,14 +358,33 @@ void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const doub
   cudaMemsetAsync(v.pool_count, 0, sizeof(uint32_t), lc.stream);
   const unsigned grid = (unsigned)(v.nchunks * 64);
   if (granularity == MESO_GRAN_VOXEL) {
-    if (kind == MESO_SDF_SPHERE) voxelize_voxel_kernel<MESO_SDF_SPHERE><<<grid, 256, 0, lc.stream>>>(v, sp, g_overflow);
-    else voxelize_voxel_kernel<MESO_SDF_TERRAIN><<<grid, 256, 0, lc.stream>>>(v, sp, g_overflow);
+    if (kind == MESO_SDF_SPHERE) voxelize_voxel_kernel<MESO_SDF_SPHERE><<<grid, 256, 0, lc.stream>>>(v, sp, g_overflow, nullptr, nullptr);
+    else voxelize_voxel_kernel<MESO_SDF_TERRAIN><<<grid, 256, 0, lc.stream>>>(v, sp, g_overflow, nullptr, nullptr);
   } else {
-    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp);
-    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp);
+    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp, nullptr, nullptr);
+    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp, nullptr, nullptr);
   }
   (*lc.launches)++;
   launch_volume_finalize(lc, v);
+}
+
+// K6 streaming: generate only the chunks d_list[0 .. *d_n) (grid slots), at most max_n of them; the rest of the volume is
+// untouched.  The launch is sized for max_n; CTAs beyond *d_n exit (no host readback between selection and generation).
+void launch_voxelize_list(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* g_overflow,
+                          const uint32_t* d_list, const uint32_t* d_n, uint32_t max_n) {
+  if (max_n == 0) return;
+  SdfParams sp;
+  for (int i = 0; i < 4; i++) sp.p[i] = params ? params[i] : 0.0;
+  const unsigned grid = max_n * 64u;
+  if (granularity == MESO_GRAN_VOXEL) {
+    if (kind == MESO_SDF_SPHERE) voxelize_voxel_kernel<MESO_SDF_SPHERE><<<grid, 256, 0, lc.stream>>>(v, sp, g_overflow, d_list, d_n);
+    else voxelize_voxel_kernel<MESO_SDF_TERRAIN><<<grid, 256, 0, lc.stream>>>(v, sp, g_overflow, d_list, d_n);
+  } else {
+    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp, d_list, d_n);
+    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp, d_list, d_n);
+  }
+  finalize_list_kernel<<<(max_n + 7) / 8, 256, 0, lc.stream>>>(v, d_list, d_n);
+  (*lc.launches) += 2;
 }
 
 void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v) {

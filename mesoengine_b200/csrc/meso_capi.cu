@@ -65,6 +65,18 @@ struct MesoCtx {
   uint32_t* d_keys_count = nullptr;
   uint32_t* d_mark = nullptr;
   int* d_overflow = nullptr;
+  // K6
+  uint64_t* d_sel_keys = nullptr;         // candidate keys (scratch), sel_cap entries
+  MesoChunkCandidate* d_sel_out = nullptr;  // sorted candidates, sel_cap entries
+  int64_t sel_cap = 0;
+  uint32_t* d_sel_count = nullptr;
+  uint32_t* d_loaded = nullptr;           // bit per chunk slot (scene-sized)
+  uint32_t* d_stream_list = nullptr;      // generation list of the current update
+  uint32_t stream_list_cap = 0;
+  uint32_t* d_stream_stats = nullptr;     // 4 words
+  bool streaming = false;
+  int stream_kind = 0, stream_gran = 0;
+  double stream_params[4] = {0, 0, 0, 0};
   // misc
   uint32_t* d_flush = nullptr;
   size_t flush_words = 0;
@@ -132,6 +144,8 @@ static void free_scene(MesoCtx* c) {
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
   cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
+  cudaFree(c->d_loaded); cudaFree(c->d_stream_list); cudaFree(c->d_stream_stats);
+  c->d_loaded = nullptr; c->d_stream_list = nullptr; c->stream_list_cap = 0; c->d_stream_stats = nullptr; c->streaming = false;
   v = DVolume{};
   c->d_table = nullptr; c->d_counts = c->d_offsets = nullptr; c->d_total = nullptr; c->d_inst = nullptr;
   c->d_frame = nullptr; c->frame_px = 0; c->d_stats = nullptr; c->d_touch_chunk = c->d_touch_brick = nullptr;
@@ -146,6 +160,7 @@ int meso_ctx_destroy(MesoCtx* c) {
   cudaStreamSynchronize(c->stream);
   free_scene(c);
   cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow); cudaFree(c->d_tile_counter);
+  cudaFree(c->d_sel_keys); cudaFree(c->d_sel_out); cudaFree(c->d_sel_count);
   for (int i = 0; i < 16; i++) if (c->band_done[i]) cudaEventDestroy(c->band_done[i]);
   cudaStreamDestroy(c->copy_stream);
   for (int i = 0; i < 2; i++) if (c->band_stream[i]) cudaStreamDestroy(c->band_stream[i]);
@@ -260,6 +275,7 @@ int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granular
   if (kind != MESO_SDF_SPHERE && kind != MESO_SDF_TERRAIN) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown sdf kind");
   if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown granularity");
   if (kind == MESO_SDF_SPHERE && !params) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: sphere needs params");
+  c->streaming = false;  // the whole grid is regenerated: a stream in progress ends (meso_stream_begin starts a new one)
   launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
   CK_LAST("voxelize");
   return check_overflow(c, "meso_voxelize_sdf");
@@ -662,6 +678,171 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
     CK(cudaMemcpyAsync(host, c->d_quads, (size_t)m * sizeof(MesoQuad), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
+  return MESO_OK;
+}
+
+// ---- K6 ---------------------------------------------------------------------------------------------------------
+static int check_view(const float* fwd, const MesoViewConfig* vc, const char* who) {
+  if (!fwd || !vc) return fail(MESO_ERR_ARGUMENT, std::string(who) + ": null argument");
+  if (vc->ViewForwardLoadChunkSize < 1 || vc->ViewForwardLoadChunkSize > 200)
+    return fail(MESO_ERR_ARGUMENT, std::string(who) + ": ViewForwardLoadChunkSize out of range [1,200]");
+  if (vc->Mode > 1) return fail(MESO_ERR_ARGUMENT, std::string(who) + ": unknown Mode");
+  return MESO_OK;
+}
+static int ensure_select_buffers(MesoCtx* c, const MesoViewConfig& vc) {
+  const int64_t need = resident_max_candidates(vc);
+  if (!c->d_sel_count) CK(cudaMalloc(&c->d_sel_count, 4));
+  if (need > c->sel_cap) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_sel_keys); cudaFree(c->d_sel_out); c->d_sel_keys = nullptr; c->d_sel_out = nullptr; c->sel_cap = 0;
+    CK(cudaMalloc(&c->d_sel_keys, (size_t)need * 8));
+    CK(cudaMalloc(&c->d_sel_out, (size_t)need * sizeof(MesoChunkCandidate)));
+    c->sel_cap = need;
+  }
+  return MESO_OK;
+}
+
+int meso_select_view_chunks(MesoCtx* c, const float forward[3], const MesoViewConfig* view, MesoChunkCandidate* host, int64_t cap, int64_t* count) {
+  if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
+  int r = check_view(forward, view, "meso_select_view_chunks");
+  if (r != MESO_OK) return r;
+  if (!count || cap < 0 || (cap > 0 && !host)) return fail(MESO_ERR_ARGUMENT, "meso_select_view_chunks: bad output arguments");
+  CK(cudaSetDevice(c->device));
+  r = ensure_select_buffers(c, *view);
+  if (r != MESO_OK) return r;
+  launch_select_view(c->lc(), forward, *view, c->d_sel_keys, c->d_sel_count, c->d_sel_out, c->sel_cap);
+  CK_LAST("select view chunks");
+  uint32_t n = 0;
+  CK(cudaMemcpyAsync(&n, c->d_sel_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *count = n;
+  const int64_t m = std::min<int64_t>(n, cap);
+  if (m > 0) {
+    CK(cudaMemcpyAsync(host, c->d_sel_out, (size_t)m * sizeof(MesoChunkCandidate), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return MESO_OK;
+}
+
+int meso_chunk_importance(MesoCtx* c, const int32_t cam[3], const float forward[3], const int32_t* locations, int64_t n, float* host_out) {
+  if (!c || !cam || !forward || n < 0 || (n > 0 && (!locations || !host_out))) return fail(MESO_ERR_ARGUMENT, "meso_chunk_importance: bad argument");
+  if (n == 0) return MESO_OK;
+  CK(cudaSetDevice(c->device));
+  int32_t* d_loc = nullptr; float* d_out = nullptr;
+  CK(cudaMalloc(&d_loc, (size_t)n * 12));
+  if (cudaMalloc(&d_out, (size_t)n * 4) != cudaSuccess) { cudaFree(d_loc); return fail(MESO_ERR_RUNTIME, "meso_chunk_importance: out of device memory"); }
+  cudaMemcpyAsync(d_loc, locations, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream);
+  launch_chunk_importance(c->lc(), d_loc, n, cam, forward, d_out);
+  cudaMemcpyAsync(host_out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream);
+  const cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_loc); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(MESO_ERR_RUNTIME, std::string("meso_chunk_importance: ") + cudaGetErrorString(e));
+  return MESO_OK;
+}
+
+int meso_baked_direction(uint32_t samples, const float forward[3], float out_direction[3], uint32_t* out_index) {
+  if (samples < 2 || !forward || !out_direction) return fail(MESO_ERR_ARGUMENT, "meso_baked_direction: bad argument");
+  // GetFibonacciSphere<float> (VoxelMathHelper.h:49-71); volatile temporaries keep the host compiler from contracting
+  const float phi = (float)(3.14159265358979323846 * (std::sqrt(5.0) - 1.0));
+  uint32_t best = 0;
+  float bd = INFINITY, bx = 0, by = 0, bz = 0;
+  for (uint32_t i = 0; i < samples; i++) {
+    volatile float frac = (float)(int32_t)i / (float)(samples - 1);
+    volatile float y2 = frac * 2.0f;
+    const float y = 1.0f - y2;
+    volatile float yy = y * y;
+    const float radius = sqrtf(1.0f - yy);
+    volatile float theta = phi * (float)(int32_t)i;
+    volatile float x = cosf(theta) * radius;
+    volatile float z = sinf(theta) * radius;
+    volatile float xx = x * x, zz = z * z, y_sq = y * y;
+    volatile float s1 = xx + y_sq;
+    const float inv = 1.0f / sqrtf(s1 + zz);
+    volatile float nx = x * inv, ny = y * inv, nz = z * inv;
+    volatile float dx = nx - forward[0], dy = ny - forward[1], dz = nz - forward[2];
+    volatile float dxx = dx * dx, dyy = dy * dy, dzz = dz * dz;
+    volatile float s2 = dxx + dyy;
+    const float dd = s2 + dzz;
+    if (dd < bd) { bd = dd; best = i; bx = nx; by = ny; bz = nz; }
+  }
+  out_direction[0] = bx; out_direction[1] = by; out_direction[2] = bz;
+  if (out_index) *out_index = best;
+  return MESO_OK;
+}
+
+int meso_stream_begin(MesoCtx* c, int kind, const double params[4], int granularity) {
+  NEED_SCENE(c);
+  if (kind != MESO_SDF_SPHERE && kind != MESO_SDF_TERRAIN) return fail(MESO_ERR_ARGUMENT, "meso_stream_begin: unknown sdf kind");
+  if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_stream_begin: unknown granularity");
+  if (kind == MESO_SDF_SPHERE && !params) return fail(MESO_ERR_ARGUMENT, "meso_stream_begin: sphere needs params");
+  DVolume& v = c->v;
+  const size_t nc = (size_t)v.nchunks;
+  if (!c->d_loaded) CK(cudaMalloc(&c->d_loaded, (size_t)v.chunk_words * 4));
+  if (!c->d_stream_stats) CK(cudaMalloc(&c->d_stream_stats, 16));
+  // empty volume: nothing is generated yet (FChunkPool::Initialize, ChunkPool.h:283-345)
+  CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
+  CK(cudaMemsetAsync(v.of, 0, nc * 64 * 16, c->stream)); CK(cudaMemsetAsync(v.cells, 0, nc * 8, c->stream));
+  CK(cudaMemsetAsync(v.mips, 0, nc * 3 * 64 * 8, c->stream));
+  CK(cudaMemsetAsync(v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
+  CK(cudaMemsetAsync(v.chunk_any, 0, (size_t)v.chunk_words * 4, c->stream));
+  CK(cudaMemsetAsync(v.chunk_full, 0, (size_t)v.chunk_words * 4, c->stream));
+  CK(cudaMemsetAsync(v.region_any, 0, (size_t)v.region_words * 4, c->stream));
+  CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
+  CK(cudaMemsetAsync(c->d_loaded, 0, (size_t)v.chunk_words * 4, c->stream));
+  CK(cudaMemsetAsync(c->d_stream_stats, 0, 16, c->stream));
+  c->stream_kind = kind; c->stream_gran = granularity;
+  for (int i = 0; i < 4; i++) c->stream_params[i] = params ? params[i] : 0.0;
+  c->streaming = true;
+  return MESO_OK;
+}
+
+int meso_stream_update_async(MesoCtx* c, const int32_t cam[3], const float forward[3], const MesoViewConfig* view, uint32_t max_new) {
+  NEED_SCENE(c);
+  if (!c->streaming) return fail(MESO_ERR_ARGUMENT, "meso_stream_update: call meso_stream_begin first");
+  if (!cam) return fail(MESO_ERR_ARGUMENT, "meso_stream_update: camera_chunk is null");
+  int r = check_view(forward, view, "meso_stream_update");
+  if (r != MESO_OK) return r;
+  if (max_new > (1u << 20)) return fail(MESO_ERR_ARGUMENT, "meso_stream_update: max_new out of range");
+  r = ensure_select_buffers(c, *view);
+  if (r != MESO_OK) return r;
+  if (max_new > c->stream_list_cap) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_stream_list); c->d_stream_list = nullptr; c->stream_list_cap = 0;
+    CK(cudaMalloc(&c->d_stream_list, (size_t)max_new * 4));
+    c->stream_list_cap = max_new;
+  }
+  launch_select_view(c->lc(), forward, *view, c->d_sel_keys, c->d_sel_count, c->d_sel_out, c->sel_cap);
+  launch_stream_worklist(c->lc(), c->v, c->d_sel_out, c->d_sel_count, c->sel_cap, cam, c->d_loaded, max_new, c->d_stream_list, c->d_stream_stats);
+  launch_voxelize_list(c->lc(), c->v, c->stream_kind, c->stream_params, c->stream_gran, c->d_overflow, c->d_stream_list, c->d_stream_stats, max_new);
+  CK_LAST("stream update");
+  return MESO_OK;
+}
+
+int meso_stream_stats(MesoCtx* c, MesoStreamStats* stats) {
+  NEED_SCENE(c);
+  if (!c->streaming || !stats) return fail(MESO_ERR_ARGUMENT, "meso_stream_stats: no stream or null argument");
+  uint32_t h[4];
+  CK(cudaMemcpyAsync(h, c->d_stream_stats, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  stats->generated = h[0]; stats->missing = h[1]; stats->candidates = h[2]; stats->in_window = h[3];
+  return MESO_OK;
+}
+
+int meso_stream_update(MesoCtx* c, const int32_t cam[3], const float forward[3], const MesoViewConfig* view, uint32_t max_new, MesoStreamStats* stats) {
+  int r = meso_stream_update_async(c, cam, forward, view, max_new);
+  if (r != MESO_OK) return r;
+  MesoStreamStats s;
+  r = meso_stream_stats(c, &s);
+  if (r != MESO_OK) return r;
+  if (stats) *stats = s;
+  return check_overflow(c, "meso_stream_update");
+}
+
+int meso_stream_loaded(MesoCtx* c, uint32_t* host_words, int64_t n_words) {
+  NEED_SCENE(c);
+  if (!c->streaming || !host_words || n_words < c->v.chunk_words) return fail(MESO_ERR_ARGUMENT, "meso_stream_loaded: no stream or buffer too small");
+  CK(cudaMemcpyAsync(host_words, c->d_loaded, (size_t)c->v.chunk_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return MESO_OK;
 }
 

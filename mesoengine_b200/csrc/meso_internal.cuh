@@ -73,6 +73,16 @@ void launch_expand_dirty(const LaunchCtx& lc, const DVolume& v, const uint64_t* 
                          uint32_t cap, uint32_t* d_count, uint32_t* d_mark);
 void launch_flush(const LaunchCtx& lc, uint32_t* d_scratch, size_t n_words);
 
+// K6 (k_resident.cu, k_voxelize.cu)
+int64_t resident_max_candidates(const MesoViewConfig& vc);
+void launch_select_view(const LaunchCtx& lc, const float fwd[3], const MesoViewConfig& vc, uint64_t* d_keys, uint32_t* d_count,
+                        MesoChunkCandidate* d_out, int64_t cap);
+void launch_chunk_importance(const LaunchCtx& lc, const int32_t* d_loc, int64_t n, const int32_t cam[3], const float fwd[3], float* d_out);
+void launch_stream_worklist(const LaunchCtx& lc, const DVolume& v, const MesoChunkCandidate* d_cand, const uint32_t* d_count, int64_t cap,
+                            const int32_t cam[3], uint32_t* d_loaded, uint32_t max_new, uint32_t* d_list, uint32_t* d_stats);
+void launch_voxelize_list(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* d_overflow,
+                          const uint32_t* d_list, const uint32_t* d_n, uint32_t max_n);
+
 // ---- small device helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t chunk_index(const DVolume& v, int cx, int cy, int cz) {
   return (int64_t)cx + (int64_t)v.dims[0] * ((int64_t)cy + (int64_t)v.dims[1] * (int64_t)cz);

@@ -48,10 +48,18 @@ struct FVoxelSceneConfig {
   uint32_t MaxVolumeCount = 65536 * 16;   // brick payload pool (meso_scene_create max_bricks)
   uint32_t MaxChunkCount = 8192 * 2;
   uint32_t MaxEmptyChunkCount = 8192 * 4;
+  uint32_t BakeVisibilityViewNum = 256;   // > 0: snap the forward vector to the nearest of this many baked directions
+  uint32_t ViewForwardLoadChunkSize = 24;
+  uint32_t ViewBackwardLoadChunkSize = 6;
+  uint32_t MaxSyncedLoadChunkCount = 0;
+  uint32_t MaxUnsyncedLoadChunkCount = 256;  // chunks generated per UpdateLoadingQueue (one device launch, no CPU workers)
+  uint32_t ChunkTaskPerCore = 8;             // unused: batching is the launch itself
+  EChunkOverrideMode ChunkOverrideMode = EChunkOverrideMode::FindMin;  // unused: everything in the window is resident
+  float ViewChunkAngle = 120.0f;
   uint32_t ChunkOccupancyDepth = 4;
   uint32_t ChunkInnerVoxelCullDepthThreshold = 1;
-  EChunkOverrideMode ChunkOverrideMode = EChunkOverrideMode::FindMin;  // unused: everything in the window is resident
   float GetChunkSize() const { return ChunkResolution * BlockSize; }
+  MesoViewConfig GetViewConfig() const { return MesoViewConfig{ViewForwardLoadChunkSize, ViewBackwardLoadChunkSize, ViewChunkAngle, 0u}; }
 };
 
 struct FBlock { uint32_t ChunkIndex = INT_MAX; uint8_t BlockLocation[3] = {255u, 255u, 255u}; uint32_t VolumeIndex = INT_MAX; };
@@ -144,8 +152,42 @@ struct FGeneratorDesc {
   int Granularity = MESO_GRAN_BLOCK;                // reference: one sample per block
 };
 
-// Facade with FChunkManage's shape.  The resident set is a fixed window of chunks [WindowOrigin, WindowOrigin+WindowDims)
-// ("everything resident"); UpdateLoadingQueue regenerates it on the device when dirty instead of dispatching CPU workers.
+// FImportanceComputeInfo / FChunkManageHelper (ChunkManagerHelper.h:22-198) over the C ABI (K6 runs on the device).
+struct FImportanceComputeInfo {
+  ivec3 CameraChunk{0, 0, 0};
+  vec3 CameraForwardVector{};
+  // CalculateChunkImportance for a batch of absolute chunk locations (ChunkManagerHelper.h:26-48)
+  std::vector<float> CalculateChunkImportance(MesoCtx* Ctx, const std::vector<ivec3>& ChunkLocations) const {
+    static_assert(sizeof(ivec3) == 12, "ivec3 is three packed int32");
+    std::vector<float> out(ChunkLocations.size());
+    const int32_t cc[3] = {CameraChunk.x, CameraChunk.y, CameraChunk.z};
+    const float f[3] = {CameraForwardVector.x, CameraForwardVector.y, CameraForwardVector.z};
+    Check(meso_chunk_importance(Ctx, cc, f, reinterpret_cast<const int32_t*>(ChunkLocations.data()), (int64_t)ChunkLocations.size(), out.data()),
+          "meso_chunk_importance");
+    return out;
+  }
+};
+struct FChunkManageHelper {
+  using FTempChunkDataType = MesoChunkCandidate;  // <Importance, ChunkLocation offset>
+  // The reference's priority queue, already in pop order (ChunkManagerHelper.h:89-150)
+  static std::vector<FTempChunkDataType> GetDesiredShowChunkLocationByView(MesoCtx* Ctx, vec3 ForwardVector, const FVoxelSceneConfig& VoxelSceneConfig) {
+    const MesoViewConfig vc = VoxelSceneConfig.GetViewConfig();
+    const int64_t side = 2 * (int64_t)vc.ViewForwardLoadChunkSize + 1;
+    std::vector<FTempChunkDataType> out((size_t)(side * side * side));
+    const float f[3] = {ForwardVector.x, ForwardVector.y, ForwardVector.z};
+    int64_t n = 0;
+    Check(meso_select_view_chunks(Ctx, f, &vc, out.data(), (int64_t)out.size(), &n), "meso_select_view_chunks");
+    out.resize((size_t)n);
+    return out;
+  }
+};
+
+// Facade with FChunkManage's shape over a window of chunks [WindowOrigin, WindowOrigin+WindowDims) that stands where the
+// chunk pool stood.  Two modes:
+//   bStreaming = false: everything in the window is generated at the first UpdateLoadingQueue ("everything resident");
+//   bStreaming = true : the reference's loop -- UpdateChunks records the view, UpdateLoadingQueue generates the most
+//                       important missing chunks of the desired set, at most MaxSynced+MaxUnsyncedLoadChunkCount per
+//                       call, on the device (meso_stream_update) instead of dispatching CPU workers.
 class FChunkManage {
  public:
   struct FChunkPoolView {             // the public buffers of FChunkPool (ChunkPool.h:222-223), now device-side counts
@@ -154,20 +196,50 @@ class FChunkManage {
   ivec3 WindowOrigin{0, 0, 0}, WindowDims{1, 1, 1};
   uint32_t FrameStamp = 1;
   bool bDirty = true;
+  bool bStreaming = false;
+  bool bDebugDisableUpdateChunk = false;                                   // ChunkManager.h:76
+  uint32_t DebugVisibleChunkNum = 0, DebugLoadedChunkNum = 0, DebugMissingChunkNum = 0;  // ChunkManager.h:66-75 counters
 
-  void Initialize(MesoCtx* Ctx_, const FVoxelSceneConfig& VoxelSceneConfig, FGeneratorDesc Generator_, ivec3 WindowOrigin_, ivec3 WindowDims_) {
-    Ctx = Ctx_; Generator = Generator_; WindowOrigin = WindowOrigin_; WindowDims = WindowDims_;
+  void Initialize(MesoCtx* Ctx_, const FVoxelSceneConfig& VoxelSceneConfig, FGeneratorDesc Generator_, ivec3 WindowOrigin_, ivec3 WindowDims_,
+                  bool bStreaming_ = false) {
+    Ctx = Ctx_; Generator = Generator_; WindowOrigin = WindowOrigin_; WindowDims = WindowDims_; bStreaming = bStreaming_;
     const FGPUUniformSceneConfig cfg{VoxelSceneConfig.BlockSize, (uint32_t)VoxelSceneConfig.BlockResolution, VoxelSceneConfig.GetChunkSize(), (uint32_t)VoxelSceneConfig.ChunkResolution};
     const int32_t o[3] = {WindowOrigin.x, WindowOrigin.y, WindowOrigin.z}, d[3] = {WindowDims.x, WindowDims.y, WindowDims.z};
     Check(meso_scene_create(Ctx, &cfg, o, d, VoxelSceneConfig.MaxVolumeCount), "meso_scene_create");
     ChunkPool.MaxBlockCount = VoxelSceneConfig.MaxBlockCount;
     ChunkPool.ChunkCount = (int64_t)d[0] * d[1] * d[2];
+    if (bStreaming) Check(meso_stream_begin(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_stream_begin");
     bDirty = true;
   }
-  // camera moved to another chunk / turned: the window is static here, so only the stamp advances (ChunkManager.h:134-159)
-  void UpdateChunks(ivec3, vec3, const FVoxelSceneConfig&) { FrameStamp++; }
+  // View direction or camera chunk changed (ChunkManager.h:134-159).  With BakeVisibilityViewNum > 0 the reference answers
+  // from the table baked for the nearest Fibonacci direction (ChunkManager.h:106-124): the same direction is used here.
+  void UpdateChunks(ivec3 NewChunkLocation, vec3 NewForwardVector, const FVoxelSceneConfig& VoxelSceneConfig) {
+    if (bDebugDisableUpdateChunk) return;
+    CameraChunk = NewChunkLocation;
+    ViewDirection = NewForwardVector;
+    if (VoxelSceneConfig.BakeVisibilityViewNum > 1) {
+      const float f[3] = {NewForwardVector.x, NewForwardVector.y, NewForwardVector.z};
+      float d[3];
+      Check(meso_baked_direction(VoxelSceneConfig.BakeVisibilityViewNum, f, d, nullptr), "meso_baked_direction");
+      ViewDirection = {d[0], d[1], d[2]};
+    }
+    bHasView = true;
+    FrameStamp++;
+  }
   // ChunkManager.h:211-400: generate what is missing, then publish chunk table + block instances (K1 + K2 on the device)
-  void UpdateLoadingQueue(const FVoxelSceneConfig&, uint32_t /*RenderFrameIndex*/) {
+  void UpdateLoadingQueue(const FVoxelSceneConfig& VoxelSceneConfig, uint32_t /*RenderFrameIndex*/) {
+    if (bStreaming) {
+      if (!bHasView) return;
+      const int32_t cc[3] = {CameraChunk.x, CameraChunk.y, CameraChunk.z};
+      const float f[3] = {ViewDirection.x, ViewDirection.y, ViewDirection.z};
+      const MesoViewConfig vc = VoxelSceneConfig.GetViewConfig();
+      MesoStreamStats st{};
+      Check(meso_stream_update(Ctx, cc, f, &vc, VoxelSceneConfig.MaxSyncedLoadChunkCount + VoxelSceneConfig.MaxUnsyncedLoadChunkCount, &st), "meso_stream_update");
+      DebugVisibleChunkNum = st.candidates; DebugMissingChunkNum = st.missing; DebugLoadedChunkNum += st.generated;
+      if (st.generated > 0 || bDirty) Check(meso_build_occupancy(Ctx, FrameStamp, &ChunkPool.CurrentBlockCount), "meso_build_occupancy");
+      bDirty = false;
+      return;
+    }
     if (!bDirty) return;
     Check(meso_voxelize_sdf(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_voxelize_sdf");
     Check(meso_build_occupancy(Ctx, FrameStamp, &ChunkPool.CurrentBlockCount), "meso_build_occupancy");
@@ -176,6 +248,9 @@ class FChunkManage {
  private:
   MesoCtx* Ctx = nullptr;
   FGeneratorDesc Generator;
+  ivec3 CameraChunk{0, 0, 0};
+  vec3 ViewDirection{};
+  bool bHasView = false;
 };
 
 struct VoxelInstanceInitialConfig {

@@ -3,7 +3,9 @@
 // instanced draw of Render() (cmdBindVertexBuffer / cmdPushConstants / cmdDrawIndexed(8, MaxBlockCount),
 // SimpleVoxel.cpp:352-398) is one call: meso_raymarch().
 //
-//   SimpleVoxel [frames] [width height] [eye x y z] [target x y z] [out.bin]
+//   SimpleVoxel [--stream] [frames] [width height] [eye x y z] [target x y z] [out.bin]
+// --stream: the reference's loading loop -- chunks are generated as the view asks for them (FChunkManage::UpdateChunks +
+// UpdateLoadingQueue, at most MaxUnsyncedLoadChunkCount per frame), not all at once.
 // Prints an FNV-1a checksum of the last frame's records (tests/test_gpu_host_sample.py compares it with the Python path).
 #include <chrono>
 #include <cstdlib>
@@ -16,6 +18,7 @@ using namespace meso;
 class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
  public:
   FChunkManage ChunkManager;
+  bool bStream = false;
   uint32_t CameraUpdates = 0, ChunkUpdates = 0;
   double RenderMs = 0.0;
 
@@ -23,7 +26,7 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
     VoxelWindowsInstance::InitializeBegin();
     FGeneratorDesc Generator;   // FGeneratorHelper::GenerateSphere, the generator SimpleVoxel.cpp:263-267 wires in
     // the 8^3 chunks around the reference sphere (centre (100,0,0), radius 50 blocks)
-    ChunkManager.Initialize(Context, VoxelSceneConfig, Generator, ivec3{2, -4, -4}, ivec3{8, 8, 8});
+    ChunkManager.Initialize(Context, VoxelSceneConfig, Generator, ivec3{2, -4, -4}, ivec3{8, 8, 8}, bStream);
   }
   void WhenCameraChunkUpdate() override { ChunkUpdates++; }
   void WhenCameraUpdate() override {
@@ -41,6 +44,8 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
 };
 
 int main(int argc, char* argv[]) {
+  bool stream = false;
+  if (argc > 1 && std::strcmp(argv[1], "--stream") == 0) { stream = true; argc--; argv++; }
   const uint32_t frames = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 4;
   VoxelInstanceInitialConfig cfg;
   if (argc > 3) { cfg.WindowsWidth = std::atoi(argv[2]); cfg.WindowsHeight = std::atoi(argv[3]); }
@@ -51,6 +56,7 @@ int main(int argc, char* argv[]) {
   }
   try {
     SimpleVoxelWindowsInstance Instance;
+    Instance.bStream = stream;
     Instance.WindowsCamera.SetPose(eye, target, {0.0f, 0.0f, 1.0f});
     Instance.Initialize(cfg);
     Instance.RunInstance(frames);
@@ -60,9 +66,9 @@ int main(int argc, char* argv[]) {
     for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
     size_t hits = 0;
     for (const auto& r : Instance.OffscreenRecords) hits += (r.w1 >> 20) & 1u;
-    std::printf("frames=%u size=%dx%d blocks=%lld hits=%zu checksum=%016llx ms_per_frame=%.3f camera_updates=%u\n", frames, cfg.WindowsWidth,
+    std::printf("frames=%u size=%dx%d blocks=%lld hits=%zu checksum=%016llx ms_per_frame=%.3f camera_updates=%u loaded=%u missing=%u\n", frames, cfg.WindowsWidth,
                 cfg.WindowsHeight, (long long)Instance.ChunkManager.ChunkPool.CurrentBlockCount, hits, (unsigned long long)h,
-                Instance.RenderMs / frames, Instance.CameraUpdates);
+                Instance.RenderMs / frames, Instance.CameraUpdates, Instance.ChunkManager.DebugLoadedChunkNum, Instance.ChunkManager.DebugMissingChunkNum);
     if (argc > 10) {
       FILE* f = std::fopen(argv[10], "wb");
       if (f) { std::fwrite(p, 1, n, f); std::fclose(f); }

@@ -152,6 +152,19 @@ void orc_sort_quads(OrcQuad* q, int64_t n);
  * dirty receives keys (chunk*4096+block) of bricks whose contents changed, ascending. Returns count. */
 int64_t orc_carve_sphere(OrcVolume*, const int32_t center[3], int32_t radius, uint64_t* dirty, int64_t cap);
 
+/* ---- K6: resident-set selection (orc_resident.c) ------------------------ */
+/* FChunkManageHelper::FTempChunkDataType = std::pair<float, ivec3> (ChunkManagerHelper.h:76), 16 B */
+typedef struct { float Importance; int32_t Offset[3]; } OrcChunkCandidate;
+float orc_chunk_importance(const int32_t cam_chunk[3], const float fwd[3], const int32_t loc[3]);
+float orc_block_importance(const int32_t cam_chunk[3], const float fwd[3], const int32_t chunk[3], const uint8_t block[3],
+                           uint32_t chunk_resolution);
+/* mode 0 = GetDesiredShowChunkLocationByView, 1 = ...Simple.  Writes min(count, cap) candidates, importance descending,
+ * ties in loop order; returns the full count (-1: out of memory). */
+int64_t orc_select_view_chunks(const float fwd[3], uint32_t forward_load, uint32_t backward_load, float view_angle_deg,
+                               int mode, OrcChunkCandidate* out, int64_t cap);
+void orc_fibonacci_sphere_f32(uint32_t samples, float* out_xyz);
+uint32_t orc_nearest_direction(const float* dirs, uint32_t n, const float q[3]);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

@@ -165,6 +165,44 @@ def hw_threads():
     return int(lib.orc_hardware_threads())
 
 
+# ---- K6: resident-set selection -------------------------------------------------------------
+ChunkCandidate = np.dtype([("Importance", "<f4"), ("Offset", "<i4", (3,))])
+assert ChunkCandidate.itemsize == 16
+lib.orc_chunk_importance.restype = C.c_float
+lib.orc_block_importance.restype = C.c_float
+lib.orc_select_view_chunks.restype = C.c_int64
+lib.orc_nearest_direction.restype = C.c_uint32
+
+
+def chunk_importance(cam_chunk, fwd, loc):
+    return float(lib.orc_chunk_importance(_p(_i3(cam_chunk)), _p(_f3(fwd)), _p(_i3(loc))))
+
+
+def block_importance(cam_chunk, fwd, chunk, block, chunk_resolution=16):
+    b = np.asarray(block, dtype=np.uint8)
+    return float(lib.orc_block_importance(_p(_i3(cam_chunk)), _p(_f3(fwd)), _p(_i3(chunk)), _p(b), C.c_uint32(chunk_resolution)))
+
+
+def select_view_chunks(fwd, forward_load=24, backward_load=6, view_angle=120.0, mode=0):
+    side = 2 * forward_load + 1
+    out = np.zeros(side ** 3, dtype=ChunkCandidate)
+    n = lib.orc_select_view_chunks(_p(_f3(fwd)), C.c_uint32(forward_load), C.c_uint32(backward_load), C.c_float(view_angle),
+                                   C.c_int(mode), _p(out), C.c_int64(out.shape[0]))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def fibonacci_sphere_f32(samples):
+    out = np.zeros((samples, 3), dtype=np.float32)
+    lib.orc_fibonacci_sphere_f32(C.c_uint32(samples), _p(out))
+    return out
+
+
+def nearest_direction(dirs, q):
+    d = np.ascontiguousarray(dirs, dtype=np.float32)
+    return int(lib.orc_nearest_direction(_p(d), C.c_uint32(d.shape[0]), _p(_f3(q))))
+
+
 class Volume:
     def __init__(self, origin_chunk, dims_chunks):
         self.origin = _i3(origin_chunk)

@@ -88,6 +88,23 @@ def constants():
     b6 = occ[occ.index("Get6Offsets"):occ.index("ErodeSingleVoxel")]
     out["offsets6"] = [[int(a), int(b), int(c)] for a, b, c in re.findall(r"\{(-?\d), (-?\d), (-?\d)\}", b6)]
     assert len(out["offsets26"]) == 26 and len(out["offsets6"]) == 6
+    # K6: resident-set selection constants (VoxelSceneConfig.h:33-41, ChunkManagerHelper.h:26-44)
+    sc = {}
+    for name in ("BakeVisibilityViewNum", "ViewForwardLoadChunkSize", "ViewBackwardLoadChunkSize", "MaxChunkCheckTimes",
+                 "MaxUnsyncedLoadChunkCount", "ChunkTaskPerCore"):
+        sc[name] = int(re.search(name + r"\s*=\s*(\d+)", cfg).group(1))
+    sc["ViewChunkAngle"] = float(re.search(r"ViewChunkAngle\s*=\s*([\d.]+)f", cfg).group(1))
+    sc["ChunkOverrideMode"] = re.search(r"ChunkOverrideMode\s*=\s*EChunkOverrideMode::(\w+)", cfg).group(1)
+    out["scene_config"] = sc
+    mh2 = read("Runtimes/Voxel/Chunk/ChunkManagerHelper.h")
+    imp = mh2[mh2.index("CalculateChunkImportance"):mh2.index("CalculateBlockImportance")]
+    out["importance"] = {
+        "Far": float(re.search(r"Far = ([\d.]+)f", imp).group(1)),
+        "Near": float(re.search(r"Importance = ([\d.]+e\d+)f", imp).group(1)),
+        "near_cube": int(re.search(r"CurrentOffset\.x >= -(\d)", imp).group(1)),
+        "angle_term": [float(x) for x in re.search(r"CameraForwardVector\)\) - ([\d.]+)f\) \* ([\d.]+)f, ([\d.]+)f\)", imp).groups()],
+        "distance_floor": float(re.search(r"std::max\(([\d.]+)f, Far - Distance\)", imp).group(1)),
+    }
     return out
 
 
