@@ -446,6 +446,10 @@ def run_ours(args):
     if world == 1 and not args.no_mesh and rank == 0:
         line["mesh"] = bench_mesh(ctx, capi, scenes, torch, stream, args, dev)
 
+    # ---- the reference's own streaming loop on its own scene (1 GPU leg) ----
+    if world == 1 and not args.no_mesh and rank == 0:
+        line["stream"] = bench_stream(ctx, capi, torch, stream)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample, outputs byte-compared ----
     if world == 1 and not args.no_cpu and rank == 0:
         line["cpu_baseline"] = cpu_baseline(ctx, capi, scene, cams, width, height, args)
@@ -488,6 +492,42 @@ def bench_edit_loop(ctx, capi, cams, width, height, frames=48):
             "ms_remesh_dirty": t_mesh / frames * 1e3, "ms_render_to_host": t_render / frames * 1e3,
             "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": quads_total / frames,
             "note": "carve r=24 voxels at the centre-pixel hit, re-mesh dirty bricks + neighbours, re-render 3840x2160 to host memory (synchronous API)"}
+
+
+def bench_stream(ctx, capi, torch, stream):
+    """K6: FChunkManage::UpdateChunks + UpdateLoadingQueue on the reference's defaults (TestGenerator terrain, one sample
+    per block, view radius 24 / 6 chunks, 120 degrees, 256 chunks per update) in a 49 x 6 x 49-chunk window around the
+    camera chunk: updates until the desired set is resident, then a 90-degree turn.  CUDA events on the launching stream."""
+    origin, dims = (-24, -3, -24), (49, 6, 49)
+    ctx.scene_create(origin, dims, 1 << 16)
+    ctx.stream_begin(capi.SDF_TERRAIN, None, capi.GRAN_BLOCK)
+    view = capi.view_config()
+
+    def until_resident(fwd):
+        ms, gen, n = 0.0, 0, 0
+        while n < 400:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); ctx.stream_update((0, 0, 0), fwd, 256, view, wait=False); b.record(stream)
+            torch.cuda.synchronize()
+            st = ctx.stream_stats()
+            ms += a.elapsed_time(b); gen += int(st["generated"]); n += 1
+            if int(st["missing"]) == 0:
+                break
+        return ms, gen, n, st
+
+    ms0, gen0, n0, st0 = until_resident((0.2, 0.1, 0.97))
+    ms1, gen1, n1, _ = until_resident((0.97, 0.1, -0.2))
+    idle = []
+    for _ in range(10):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); ctx.stream_update((0, 0, 0), (0.97, 0.1, -0.2), 256, view, wait=False); b.record(stream)
+        torch.cuda.synchronize()
+        idle.append(a.elapsed_time(b))
+    return {"window_chunks": int(np.prod(dims)), "desired_set": int(st0["candidates"]), "desired_in_window": int(st0["in_window"]),
+            "fill": {"updates": n0, "chunks": gen0, "ms": ms0, "chunks_per_s": gen0 / (ms0 * 1e-3)},
+            "turn_90deg": {"updates": n1, "chunks": gen1, "ms": ms1},
+            "ms_update_nothing_missing": float(np.median(idle)),
+            "note": "select (117 649 offsets -> desired set, rank-sorted) + dispatch list + generation of <= 256 chunks + derived data per update, no host round trip inside an update"}
 
 
 def bench_mesh(ctx, capi, scenes, torch, stream, args, dev):
