@@ -23,7 +23,9 @@ RaySetup = np.dtype([("o", "<f4", (3,)), ("two_over_w", "<f4"), ("U", "<f4", (3,
                      ("V", "<f4", (3,)), ("pad0", "<f4"), ("F", "<f4", (3,)), ("pad1", "<f4"),
                      ("L", "<f4", (3,)), ("pad2", "<f4")])
 RayStats = np.dtype([("primary", "<u8"), ("shadow", "<u8"), ("hits", "<u8"), ("steps", "<u8"),
-                     ("touched_chunks", "<u8"), ("touched_bricks", "<u8"), ("u_bytes", "<u8")])
+                     ("touched_chunks", "<u8"), ("touched_bricks", "<u8"), ("u_bytes", "<u8"),
+                     ("steps_primary", "<u8"), ("warp_slots_primary", "<u8"), ("warp_slots_shadow", "<u8"),
+                     ("level_steps", "<u8", (5,))])
 ChunkCandidate = np.dtype([("Importance", "<f4"), ("Offset", "<i4", (3,))])          # FTempChunkDataType
 ViewConfig = np.dtype([("ViewForwardLoadChunkSize", "<u4"), ("ViewBackwardLoadChunkSize", "<u4"), ("ViewChunkAngle", "<f4"),
                        ("Mode", "<u4")])

@@ -83,6 +83,7 @@ struct Scene {
   const uint32_t* s_region;  // shared: bit per 512^3 region
   uint8_t* touch_chunk;
   uint8_t* touch_brick;
+  unsigned* lv;              // STATS only: per-thread steps per level
 };
 
 // Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every step is "(cs | mask) + 1".
@@ -212,6 +213,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   const int news = SEL3(a, nxx, nxy, nxz);
   if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
   w.la = a; w.lt = ta; steps++;
+  if (STATS) s.lv[sh == 9 ? 4 : (sh == 7 ? 3 : (sh == 5 ? 2 : (sh == 3 ? 1 : 0)))]++;
   w.gran = sh;
   const unsigned ucross = (unsigned)(olds ^ news);
   w.need = (ucross >> 9) ? 4 : ((ucross >> 7) ? 3 : ((ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0)));
@@ -278,6 +280,8 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
   const int py = (tile / tiles_x) * MESO_TILE_H + ty;
   const bool valid = tile < n_tiles && px < width && py < height;
   Scene sc; sc.v = &v; sc.s_any = s_any; sc.s_region = s_region; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
+  unsigned lv[5] = {0, 0, 0, 0, 0};
+  sc.lv = lv;
   const float Lx = rs.L[0], Ly = rs.L[1], Lz = rs.L[2];
 
   // ---- phase 1: primary ray ----
@@ -322,6 +326,7 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
     }
   }
 
+  const unsigned steps_p = steps;
   // ---- phase 2: shadow rays, compacted across the CTA ----
   if (flags & MESO_FLAG_SHADOW) {
     const unsigned bal = __ballot_sync(0xffffffffu, want_shadow);
@@ -370,9 +375,23 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
       v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
       v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
     }
+    unsigned long long v4 = steps_p;
+    unsigned mp = steps_p, ms = steps - steps_p;
+    unsigned long long l0 = lv[0], l1 = lv[1], l2 = lv[2], l3 = lv[3], l4 = lv[4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+      mp = max(mp, __shfl_xor_sync(0xffffffffu, mp, o)); ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+      l0 += __shfl_xor_sync(0xffffffffu, l0, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o); l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+      l3 += __shfl_xor_sync(0xffffffffu, l3, o); l4 += __shfl_xor_sync(0xffffffffu, l4, o);
+    }
     if (lane == 0) {
       atomicAdd(&stats->primary, v0); atomicAdd(&stats->shadow, v1);
       atomicAdd(&stats->hits, v2); atomicAdd(&stats->steps, v3);
+      atomicAdd(&stats->steps_primary, v4);
+      atomicAdd(&stats->warp_slots_primary, 32ull * mp); atomicAdd(&stats->warp_slots_shadow, 32ull * ms);
+      atomicAdd(&stats->level_steps[0], l0); atomicAdd(&stats->level_steps[1], l1); atomicAdd(&stats->level_steps[2], l2);
+      atomicAdd(&stats->level_steps[3], l3); atomicAdd(&stats->level_steps[4], l4);
     }
   }
 }

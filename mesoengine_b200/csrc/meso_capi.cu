@@ -556,6 +556,8 @@ int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaStreamSynchronize(c->stream));
   memset(out, 0, sizeof(*out));
   out->primary = h.primary; out->shadow = h.shadow; out->hits = h.hits; out->steps = h.steps;
+  out->steps_primary = h.steps_primary; out->warp_slots_primary = h.warp_slots_primary; out->warp_slots_shadow = h.warp_slots_shadow;
+  for (int i = 0; i < 5; i++) out->level_steps[i] = h.level_steps[i];
   for (uint8_t x : tc) out->touched_chunks += x;
   for (uint8_t x : tb) out->touched_bricks += x;
   // DESIGN.md "algorithmic bytes": chunk any/full bit grids once + 1024 B of block masks per touched chunk + 68 B per touched brick

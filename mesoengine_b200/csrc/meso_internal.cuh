@@ -38,6 +38,8 @@ struct DVolume {
 
 struct RayStatsDev {
   unsigned long long primary, shadow, hits, steps;
+  unsigned long long steps_primary, warp_slots_primary, warp_slots_shadow;
+  unsigned long long level_steps[5];
 };
 
 // ---- launch wrappers (one per .cu) -------------------------------------------------------------------------

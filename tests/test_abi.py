@@ -38,7 +38,7 @@ def test_struct_sizes_match_reference_layouts(tmp_path):
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [12, 16, 160, 16, 16, 16, 80, 56]   # FGPUBlock 12 B, FGPUChunk 16 B, FGPUUniformCamera 160 B, scene 16 B
+    assert sizes == [12, 16, 160, 16, 16, 16, 80, 120]  # FGPUBlock 12 B, FGPUChunk 16 B, FGPUUniformCamera 160 B, scene 16 B
     assert [capi.GPUBlock.itemsize, capi.GPUChunk.itemsize, capi.Camera.itemsize, capi.SceneConfig.itemsize,
             capi.HitRecord.itemsize, capi.Quad.itemsize, capi.RaySetup.itemsize, capi.RayStats.itemsize] == sizes
 
