@@ -109,7 +109,7 @@ void launch_carve(const LaunchCtx& lc, const DVolume& v, const int32_t center[3]
   if (n <= 0) return;
   carve_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, lc.stream>>>(v, box, d_dirty, cap_dirty, d_dirty_count, d_overflow);
   (*lc.launches)++;
-  launch_volume_finalize(lc, v);
+  launch_volume_finalize(lc, v, /*rebuild_df=*/false);   // voxels were only removed: the distance field stays conservative
 }
 
 // d_mark: zero-initialised bit grid over all blocks of the scene (left all-zero again on return)

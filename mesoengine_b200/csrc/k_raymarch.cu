@@ -5,16 +5,17 @@
 //
 // The DDA is STATELESS (DESIGN.md "DDA"): the crossing time of integer voxel plane p on axis a is always
 //     t_a(p) = (float(p) - o_a) * inv_a          one FSUB + one FMUL, never fused (-fmad=false)
-// and crossings are consumed in the total order (t, axis).  Skipping an empty aligned cell (512^3 region, 128^3 chunk,
-// 32^3 cell, 8^3 brick) consumes the smallest of the cell's three exit keys and re-derives the other two coordinates
-// from the same keys only when the walk has to look finer (advance_axis), so the hierarchical walk visits exactly the
-// voxels the oracle's flat walk would: hit voxel, face and t are bit-identical to oracle/orc_raymarch.c.
+// and crossings are consumed in the total order (t, axis).  Skipping an empty box -- an aligned 8^3 brick, or the cube
+// of 32^3 cells the distance field DVolume.df certifies empty around the current cell -- consumes the smallest of the
+// box's three exit keys and re-derives the other two coordinates from the same keys (advance_axis), so the walk visits
+// exactly the voxels the oracle's flat walk would: hit voxel, face and t are bit-identical to oracle/orc_raymarch.c.
+// Any empty box is a legal skip; how big the boxes are only changes the number of steps, never the result.
 //
 // Execution model: CTA = one 32x8 screen tile (tile t belongs to rank t % world), warp = 8x4 pixels.  All primary rays
 // of a warp start together at the eye and stay at similar levels of the hierarchy; the shadow rays of the tile are
 // compacted across the CTA (ballot + prefix sum through shared memory) and traced together in dense warps.
-// Region / chunk any-bits are staged in shared memory; 32^3-cell masks, {occ,full} word pairs (16 B loads) and brick
-// slices are cached in registers behind tags.
+// Distance-field bytes come through L1/L2 (2 MB at 4096^3); {occ,full} word pairs (16 B loads) and brick slices are
+// cached in registers behind tags.
 // (A persistent "idle lanes pull the next pixel" variant was measured and dropped: mixing rays of different phases in
 // one warp cut SIMT efficiency from 20/32 to 8/32 active threads -- profiles/README.md.)
 //
@@ -79,23 +80,22 @@ __device__ __forceinline__ int advance_axis(float o, float d, float inv, int st,
 
 struct Scene {
   const DVolume* v;
-  const uint32_t* s_any;     // shared: bit per chunk
-  const uint32_t* s_region;  // shared: bit per 512^3 region
   uint8_t* touch_chunk;
   uint8_t* touch_brick;
   unsigned* lv;              // STATS only: per-thread steps per level
 };
 
-// Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every step is "(cs | mask) + 1".
-// Above voxel level only the last stepped axis is exact; the other two hold an older true coordinate inside the same
-// cell of the level that was stepped (`gran`), and are made exact before the walk looks finer.
+// Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every aligned step is "(cs | mask) + 1".
+// After a brick step only the stepped axis is exact; the other two hold an older true coordinate inside the same brick
+// (`gran` = 3) and are made exact before the walk looks at voxels.  Distance-field steps make all three exact at once.
+// need: 2 = the 32^3 cell may have changed (look the distance field up), 1 = the brick changed, 0 = same brick.
 struct Walk {
   int csx, csy, csz;
   int la; float lt;
   int gran, need;
   int ci, wtag, ztag;
   uint32_t slot;
-  unsigned long long cellmask, wocc, wfull, slice;
+  unsigned long long wocc, wfull, slice;
 };
 
 enum { W_CONTINUE = 0, W_HIT = 1, W_EXIT = 2 };
@@ -132,13 +132,14 @@ __device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int c
     }
   }
   w.csx = cx ^ (r.sx >> 31); w.csy = cy ^ (r.sy >> 31); w.csz = cz ^ (r.sz >> 31);
-  w.gran = 0; w.need = 4; w.ci = 0; w.wtag = -1; w.ztag = -1; w.slot = 0;
-  w.cellmask = 0; w.wocc = 0; w.wfull = 0; w.slice = 0;
+  w.gran = 0; w.need = 2; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0;
+  w.wocc = 0; w.wfull = 0; w.slice = 0;
   return alive;
 }
 
 // One iteration: classify the current cell from the coarsest level that changed down to the first empty level (or a
-// solid voxel), then take one step at that level.  levels: 4 region (512^3), 3 chunk (128^3), 2 cell (32^3), 1 brick, 0 voxel.
+// solid voxel), then take one step at that level.  Levels: the distance field over 32^3 cells (a step leaves the whole
+// empty cube of half-width df - 1 cells around the current cell, clamped to the grid), bricks (8^3), voxels.
 // On W_HIT (cx,cy,cz) is the exact hit voxel.
 template <bool STATS>
 __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, int& cx, int& cy, int& cz, unsigned& steps) {
@@ -146,33 +147,29 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   const int gx = r.sx >> 31, gy = r.sy >> 31, gz = r.sz >> 31;
   cx = w.csx ^ gx; cy = w.csy ^ gy; cz = w.csz ^ gz;
   bool go = true;  // keep looking finer
-  int sh = 0;
+  int sh = 0;      // level of the step: 0 voxel, 3 brick, 5 distance-field cube
+  int kdf = 1;     // cells to advance at that level (> 1 only for distance-field steps)
 #define MESO_SYNC_IF_COARSER(S)                                                                                 \
-  if (go && w.gran > (S)) { /* looking finer than the level that was stepped: make the other two axes exact */  \
+  if (go && w.gran > (S)) { /* looking finer than the box that was stepped: make the other two axes exact */    \
     sync_axes(r, w, cx, cy, cz);                                                                                \
     w.csx = cx ^ gx; w.csy = cy ^ gy; w.csz = cz ^ gz;                                                          \
     w.gran = 0;                                                                                                 \
   }
-  if (w.need >= 4) {
-    const int ri = (cx >> 9) + v.rdims[0] * ((cy >> 9) + v.rdims[1] * (cz >> 9));
-    if (!((s.s_region[ri >> 5] >> (ri & 31)) & 1u)) { sh = 9; go = false; }
-  }
-  MESO_SYNC_IF_COARSER(7)
-  if (go && w.need >= 3) {
-    w.ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
-    if (!((s.s_any[w.ci >> 5] >> (w.ci & 31)) & 1u)) { sh = 7; go = false; }
+  if (w.need >= 2) {
+    // After a brick step (gran 3) the other two axes are still inside their brick, so the cell is known; after a
+    // distance-field step (gran 5) they can be anywhere in the cube that was left: make them exact first.
+    MESO_SYNC_IF_COARSER(3)
+    const int df = (int)__ldg(&v.df[(cx >> 5) + v.ddims[0] * ((cy >> 5) + v.ddims[1] * (cz >> 5))]);
+    if (df > 0) { sh = 5; kdf = df; go = false; }   // the cube of half-width df - 1 cells around this cell is empty
     else {
-      if (STATS) s.touch_chunk[w.ci] = 1;
-      w.cellmask = __ldg(&v.cells[w.ci]);
-      w.wtag = -1;
+      const int ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
+      if (ci != w.ci) { w.ci = ci; w.wtag = -1; }
+      if (STATS) {
+        const int e = ((cx >> 5) & 3) + 4 * ((cy >> 5) & 3) + 16 * ((cz >> 5) & 3);
+        if ((v.cells[ci] >> e) & 1ull) s.touch_chunk[ci] = 1;   // exact cell occupancy (df may be stale-conservative after a carve)
+      }
     }
   }
-  MESO_SYNC_IF_COARSER(5)
-  if (go && w.need >= 2) {
-    const int e = ((cx >> 5) & 3) + 4 * ((cy >> 5) & 3) + 16 * ((cz >> 5) & 3);
-    if (!((w.cellmask >> e) & 1ull)) { sh = 5; go = false; }
-  }
-  MESO_SYNC_IF_COARSER(3)
   if (go && w.need >= 1) {
     const int bx = (cx >> 3) & 15, by = (cy >> 3) & 15, bz = (cz >> 3) & 15;
     const int wi = bz * 4 + (by >> 2);
@@ -200,8 +197,11 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   }
 #undef MESO_SYNC_IF_COARSER
   // ---- one step at level sh: consume the smallest of the three pending keys (ties: lower axis first) ----
-  const int mask = (1 << sh) - 1;
-  const int nxx = (w.csx | mask) + 1, nxy = (w.csy | mask) + 1, nxz = (w.csz | mask) + 1;   // mirrored coordinate after crossing
+  // mirrored coordinate after crossing: kdf cells of size 2^sh ahead, never beyond the grid end (nvox if step > 0, else 0);
+  // for the aligned levels (kdf = 1) this is (cs | mask) + 1 and the clamp never binds
+  const int nxx = min(((w.csx >> sh) + kdf) << sh, v.nvox[0] & ~gx);
+  const int nxy = min(((w.csy >> sh) + kdf) << sh, v.nvox[1] & ~gy);
+  const int nxz = min(((w.csz >> sh) + kdf) << sh, v.nvox[2] & ~gz);
   const float tx = r.sx != 0 ? plane_t1(r.ox, r.ix, (nxx ^ gx) - gx) : F_INF;               // (n ^ g) - g = true plane index
   const float ty = r.sy != 0 ? plane_t1(r.oy, r.iy, (nxy ^ gy) - gy) : F_INF;
   const float tz = r.sz != 0 ? plane_t1(r.oz, r.iz, (nxz ^ gz) - gz) : F_INF;
@@ -213,11 +213,11 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   const int news = SEL3(a, nxx, nxy, nxz);
   if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
   w.la = a; w.lt = ta; steps++;
-  if (STATS) s.lv[sh == 9 ? 4 : (sh == 7 ? 3 : (sh == 5 ? 2 : (sh == 3 ? 1 : 0)))]++;
+  if (STATS) s.lv[sh == 0 ? 0 : (sh == 3 ? 1 : (kdf == 1 ? 2 : (kdf <= 4 ? 3 : 4)))]++;
   w.gran = sh;
   const unsigned ucross = (unsigned)(olds ^ news);
-  w.need = (ucross >> 9) ? 4 : ((ucross >> 7) ? 3 : ((ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0)));
-  if (w.need >= 3) {
+  w.need = (ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0);
+  if (w.need >= 2) {
     const int st = SEL3(a, r.sx, r.sy, r.sz);
     const int nv = SEL3(a, v.nvox[0], v.nvox[1], v.nvox[2]);
     if (news >= (st > 0 ? nv : 0)) return W_EXIT;   // mirrored coordinate at which the ray has left the grid
@@ -263,15 +263,9 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
                                                               int local_tile0,
                                                               MesoHitRecord* __restrict__ out, RayStatsDev* stats,
                                                               uint8_t* touch_chunk, uint8_t* touch_brick) {
-  extern __shared__ uint32_t s_dyn[];
-  uint32_t* s_any = s_dyn;
-  uint32_t* s_region = s_dyn + v.chunk_words;
   __shared__ ShadowJob s_jobs[RM_THREADS];
   __shared__ uint8_t s_shadow[RM_THREADS];
   __shared__ int s_warp_cnt[RM_THREADS / 32];
-  for (int i = threadIdx.x; i < v.chunk_words; i += blockDim.x) s_any[i] = v.chunk_any[i];
-  for (int i = threadIdx.x; i < v.region_words; i += blockDim.x) s_region[i] = v.region_any[i];
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int local_tile = local_tile0 + blockIdx.x;
   const int tile = local_tile * world + rank;
@@ -279,7 +273,7 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
   const int px = (tile % tiles_x) * MESO_TILE_W + tx;
   const int py = (tile / tiles_x) * MESO_TILE_H + ty;
   const bool valid = tile < n_tiles && px < width && py < height;
-  Scene sc; sc.v = &v; sc.s_any = s_any; sc.s_region = s_region; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
+  Scene sc; sc.v = &v; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
   unsigned lv[5] = {0, 0, 0, 0, 0};
   sc.lv = lv;
   const float Lx = rs.L[0], Ly = rs.L[1], Lz = rs.L[2];
@@ -415,7 +409,7 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
   const int all_local = (n_tiles - rank + world - 1) / world;
   if (local_tile_count < 0) local_tile_count = all_local - local_tile0;
   if (local_tile_count <= 0) return;
-  const size_t smem = sizeof(uint32_t) * ((size_t)v.chunk_words + (size_t)v.region_words);
+  const size_t smem = 0;
   if (d_stats)
     raymarch_kernel<true><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
                                                                              n_tiles, local_tile0, d_out, d_stats, d_touch_chunk, d_touch_brick);

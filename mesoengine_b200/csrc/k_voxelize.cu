@@ -330,6 +330,48 @@ __global__ void region_kernel(DVolume v) {
   if (any) atomicOr(&v.region_any[r >> 5], 1u << (r & 31));
 }
 
+// ---- cell distance field (raymarch empty-space skipping) -------------------------------------------------------
+// df(c) = min over non-empty 32^3 cells e of max(|cx-ex|, |cy-ey|, |cz-ez|), capped at K + 1: the cube of half-width
+// df - 1 cells around c is empty.  The L-infinity transform is separable: three identical passes
+//     out(i) = min over |k| <= K of max(in(i + k), |k|)
+// along x, y, z, starting from 0 / cap (outside the grid counts as empty).  One thread per cell, 63 byte loads from L1.
+__global__ void __launch_bounds__(256) df_seed_kernel(DVolume v) {
+  const int64_t n = (int64_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int ex = (int)(i % v.ddims[0]), ey = (int)((i / v.ddims[0]) % v.ddims[1]), ez = (int)(i / ((int64_t)v.ddims[0] * v.ddims[1]));
+  const int64_t c = (ex >> 2) + (int64_t)v.dims[0] * ((ey >> 2) + (int64_t)v.dims[1] * (ez >> 2));
+  const int e = (ex & 3) + 4 * (ey & 3) + 16 * (ez & 3);
+  v.df[i] = ((v.cells[c] >> e) & 1ull) ? 0 : (MESO_DF_K + 1);
+}
+template <int AXIS>
+__global__ void __launch_bounds__(256) df_pass_kernel(DVolume v, const uint8_t* __restrict__ in, uint8_t* __restrict__ out) {
+  const int64_t n = (int64_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int ex = (int)(i % v.ddims[0]), ey = (int)((i / v.ddims[0]) % v.ddims[1]), ez = (int)(i / ((int64_t)v.ddims[0] * v.ddims[1]));
+  const int p = AXIS == 0 ? ex : (AXIS == 1 ? ey : ez);
+  const int len = v.ddims[AXIS];
+  const int64_t stride = AXIS == 0 ? 1 : (AXIS == 1 ? v.ddims[0] : (int64_t)v.ddims[0] * v.ddims[1]);
+  int best = in[i];
+  for (int a = 1; a <= MESO_DF_K && a < best; a++) {  // outwards: a tap at distance a cannot give less than a
+    if (p - a >= 0) best = min(best, max((int)in[i - a * stride], a));
+    if (p + a < len) best = min(best, max((int)in[i + a * stride], a));
+  }
+  out[i] = (uint8_t)best;
+}
+
+void launch_df_build(const LaunchCtx& lc, const DVolume& v) {
+  const int64_t n = (int64_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  df_seed_kernel<<<grid, 256, 0, lc.stream>>>(v);
+  df_pass_kernel<0><<<grid, 256, 0, lc.stream>>>(v, v.df, v.df_tmp);
+  df_pass_kernel<1><<<grid, 256, 0, lc.stream>>>(v, v.df_tmp, v.df);
+  df_pass_kernel<2><<<grid, 256, 0, lc.stream>>>(v, v.df, v.df_tmp);
+  cudaMemcpyAsync(v.df, v.df_tmp, (size_t)n, cudaMemcpyDeviceToDevice, lc.stream);
+  (*lc.launches) += 4;
+}
+
 __global__ void scatter_payload_kernel(DVolume v, const uint64_t* __restrict__ keys, const uint64_t* __restrict__ payload, int64_t n) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = t >> 3; const int j = (int)(t & 7);
@@ -385,9 +427,10 @@ void launch_voxelize_list(const LaunchCtx& lc, const DVolume& v, int kind, const
   }
   finalize_list_kernel<<<(max_n + 7) / 8, 256, 0, lc.stream>>>(v, d_list, d_n);
   (*lc.launches) += 2;
+  launch_df_build(lc, v);   // voxels were added: the distance field must not overestimate
 }
 
-void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v) {
+void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v, bool rebuild_df) {
   cudaMemsetAsync(v.chunk_any, 0, sizeof(uint32_t) * v.chunk_words, lc.stream);
   cudaMemsetAsync(v.chunk_full, 0, sizeof(uint32_t) * v.chunk_words, lc.stream);
   cudaMemsetAsync(v.region_any, 0, sizeof(uint32_t) * v.region_words, lc.stream);
@@ -395,6 +438,7 @@ void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v) {
   const int nr = v.rdims[0] * v.rdims[1] * v.rdims[2];
   region_kernel<<<(nr + 127) / 128, 128, 0, lc.stream>>>(v);
   (*lc.launches) += 2;
+  if (rebuild_df) launch_df_build(lc, v);
 }
 
 void launch_scatter_payload(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, const uint64_t* d_payload, int64_t n) {

@@ -139,7 +139,7 @@ int meso_ctx_create(int device, MesoCtx** out) {
 static void free_scene(MesoCtx* c) {
   DVolume& v = c->v;
   cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.cells); cudaFree(v.region_any); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
-  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count);
+  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count); cudaFree(v.df); cudaFree(v.df_tmp);
   cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
@@ -225,6 +225,9 @@ int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const in
   for (int i = 0; i < 3; i++) v.rdims[i] = (dims[i] + 3) / 4;
   v.region_words = (v.rdims[0] * v.rdims[1] * v.rdims[2] + 31) / 32;
   CK(cudaMalloc(&v.cells, nc * 8)); CK(cudaMemsetAsync(v.cells, 0, nc * 8, c->stream));
+  for (int i = 0; i < 3; i++) v.ddims[i] = dims[i] * 4;
+  CK(cudaMalloc(&v.df, nc * 64)); CK(cudaMalloc(&v.df_tmp, nc * 64));
+  CK(cudaMemsetAsync(v.df, MESO_DF_K + 1, nc * 64, c->stream));   // empty volume: nothing within reach anywhere
   CK(cudaMalloc(&v.region_any, (size_t)v.region_words * 4)); CK(cudaMemsetAsync(v.region_any, 0, (size_t)v.region_words * 4, c->stream));
   CK(cudaMalloc(&v.bptr, nc * MESO_BLOCKS * 4));
   CK(cudaMalloc(&v.pool, (size_t)max_bricks * 64));
@@ -790,6 +793,7 @@ int meso_stream_begin(MesoCtx* c, int kind, const double params[4], int granular
   CK(cudaMemsetAsync(v.chunk_full, 0, (size_t)v.chunk_words * 4, c->stream));
   CK(cudaMemsetAsync(v.region_any, 0, (size_t)v.region_words * 4, c->stream));
   CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
+  CK(cudaMemsetAsync(v.df, MESO_DF_K + 1, nc * 64, c->stream));
   CK(cudaMemsetAsync(c->d_loaded, 0, (size_t)v.chunk_words * 4, c->stream));
   CK(cudaMemsetAsync(c->d_stream_stats, 0, 16, c->stream));
   c->stream_kind = kind; c->stream_gran = granularity;

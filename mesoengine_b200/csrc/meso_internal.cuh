@@ -11,6 +11,7 @@
 #define MESO_CV 128
 #define MESO_WORDS 64
 #define MESO_BLOCKS 4096
+#define MESO_DF_K 31          // window half-width of the distance-field passes; stored values are 0 .. MESO_DF_K + 1
 
 // Device view of the resident volume.  Chunk slot == linear grid index cx + dx*(cy + dy*cz); everything dense per
 // chunk except brick payloads (pool, 64 B each, allocated for partial bricks only).
@@ -29,6 +30,11 @@ struct DVolume {
   uint32_t* chunk_full; // bit per chunk: all 4096 bricks full
   uint64_t* cells;      // per chunk: bit per 32^3-voxel cell (4x4x4 bricks), index x + 4y + 16z (derived)
   uint32_t* region_any; // bit per 512^3-voxel region (4x4x4 chunks) (derived)
+  uint8_t* df;          // per 32^3 cell: Chebyshev distance (in cells, capped at MESO_DF_CAP) to the nearest non-empty cell;
+                        // 0 = non-empty.  Conservative: never larger than the true distance (derived; rebuilt whenever
+                        // voxels may have been ADDED, left alone by the carve, which only removes)
+  uint8_t* df_tmp;      // scratch of the separable passes
+  int ddims[3];         // cells per axis = dims * 4
   int rdims[3];         // regions per axis = ceil(dims / 4)
   int region_words;
   uint32_t* pool_count; // device counter: payload slots in use
@@ -50,7 +56,8 @@ struct LaunchCtx {
 };
 
 void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* d_overflow);
-void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v);  // chunk_any / chunk_full bit grids
+void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v, bool rebuild_df = true);  // derived data: of, cells, chunk/region bits, df
+void launch_df_build(const LaunchCtx& lc, const DVolume& v);
 void launch_scatter_payload(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, const uint64_t* d_payload, int64_t n);
 void launch_gather_partial(const LaunchCtx& lc, const DVolume& v, uint64_t* d_keys, uint64_t* d_payload, uint32_t* d_count);
 

@@ -80,7 +80,14 @@ static inline int cell_level(const Scene* s, const int c[3]) {
   const OrcVolume* v = s->v;
   int64_t ci = orc_cidx(v, c[0] >> 7, c[1] >> 7, c[2] >> 7);
   if (!s->chunk_any[ci]) return ORC_CV;
-  if (s->touched_chunk) s->touched_chunk[ci] = 1;
+  if (s->touched_chunk && !s->touched_chunk[ci]) {
+    /* A chunk's block masks count as needed once a ray stands in one of its non-empty 32^3 cells (4x4x4 bricks): the
+     * unit the GPU walk resolves before it reads them.  occ word w = bz*4 + by/4 holds four 16-bit x-rows. */
+    int ex = (c[0] >> 5) & 3, ey = (c[1] >> 5) & 3, ez = (c[2] >> 5) & 3;
+    uint64_t m = 0;
+    for (int bz = 4 * ez; bz < 4 * ez + 4; bz++) m |= v->occ[ci * ORC_WORDS + bz * 4 + ey] & (0x000F000F000F000Full << (4 * ex));
+    if (m) s->touched_chunk[ci] = 1;
+  }
   int b = orc_bidx((c[0] >> 3) & 15, (c[1] >> 3) & 15, (c[2] >> 3) & 15);
   if (!orc_getbit(v->occ + ci * ORC_WORDS, b)) return ORC_BR;
   if (orc_getbit(v->full + ci * ORC_WORDS, b)) return 0;
