@@ -25,7 +25,9 @@
 
 #define F_INF __int_as_float(0x7F800000)
 #define RM_THREADS 256
-#define RM_REFILL_MIN 8   // retire/refill when at least this many lanes are idle
+#ifndef RM_WARP_SHADOW
+#define RM_WARP_SHADOW 1  // experiment: shadow rays traced by the lane that found the hit (no CTA-wide compaction, no barriers)
+#endif
 #define SEL3(a, X, Y, Z) ((a) == 0 ? (X) : ((a) == 1 ? (Y) : (Z)))
 
 struct Ray {
@@ -323,6 +325,22 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
   const unsigned steps_p = steps;
   // ---- phase 2: shadow rays, compacted across the CTA ----
   if (flags & MESO_FLAG_SHADOW) {
+#if RM_WARP_SHADOW
+    if (want_shadow) {
+      const int nrm = (dn.face & 1) ? 1 : -1;
+      Ray r; r.ox = dn.px; r.oy = dn.py; r.oz = dn.pz;
+      ray_dir(r, Lx, Ly, Lz);
+      Walk w;
+      int cx = 0, cy = 0, cz = 0, res = W_EXIT;
+      if (walk_begin(v, r, dn.cx + (hit_axis == 0 ? nrm : 0), dn.cy + (hit_axis == 1 ? nrm : 0), dn.cz + (hit_axis == 2 ? nrm : 0), w, steps)) {
+        do { res = walk_iter<STATS>(sc, r, w, cx, cy, cz, steps); } while (res == W_CONTINUE);
+      }
+      dn.shadow = res == W_HIT ? 1 : 0;
+      n_shadow = 1;
+    }
+  }
+  if (false) {
+#endif
     const unsigned bal = __ballot_sync(0xffffffffu, want_shadow);
     if (lane == 0) s_warp_cnt[warp] = __popc(bal);
     __syncthreads();
