@@ -12,8 +12,9 @@
 // Any empty box is a legal skip; how big the boxes are only changes the number of steps, never the result.
 //
 // Execution model: CTA = one 32x8 screen tile (tile t belongs to rank t % world), warp = 8x4 pixels.  All primary rays
-// of a warp start together at the eye and stay at similar levels of the hierarchy; the shadow rays of the tile are
-// compacted across the CTA (ballot + prefix sum through shared memory) and traced together in dense warps.
+// of a warp start together at the eye and stay at similar levels of the walk; afterwards the lanes that hit a lit-facing
+// face trace their shadow rays, starting together again.  Every level of the walk shares ONE step section per
+// iteration: separate step code for the distance-field level was measured twice and costs 12 % more warp instructions.
 // Distance-field bytes come through L1/L2 (2 MB at 4096^3); {occ,full} word pairs (16 B loads) and brick slices are
 // cached in registers behind tags.
 // (A persistent "idle lanes pull the next pixel" variant was measured and dropped: mixing rays of different phases in
@@ -25,9 +26,6 @@
 
 #define F_INF __int_as_float(0x7F800000)
 #define RM_THREADS 256
-#ifndef RM_WARP_SHADOW
-#define RM_WARP_SHADOW 1  // experiment: shadow rays traced by the lane that found the hit (no CTA-wide compaction, no barriers)
-#endif
 #define SEL3(a, X, Y, Z) ((a) == 0 ? (X) : ((a) == 1 ? (Y) : (Z)))
 
 struct Ray {
@@ -161,9 +159,19 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
     // After a brick step (gran 3) the other two axes are still inside their brick, so the cell is known; after a
     // distance-field step (gran 5) they can be anywhere in the cube that was left: make them exact first.
     MESO_SYNC_IF_COARSER(3)
-    const int df = (int)__ldg(&v.df[(cx >> 5) + v.ddims[0] * ((cy >> 5) + v.ddims[1] * (cz >> 5))]);
-    if (df > 0) { sh = 5; kdf = df; go = false; }   // the cube of half-width df - 1 cells around this cell is empty
-    else {
+    const int ex = cx >> 5, ey = cy >> 5, ez = cz >> 5;
+    const int df = (int)__ldg(&v.df[ex + v.ddims[0] * (ey + v.ddims[1] * ez)]);
+    if (df > 0) {   // the cube of half-width df - 1 cells around this cell is empty
+      sh = 5; kdf = df; go = false;
+      // Probe ahead: the cell m = c + df along the ray's octant diagonal.  If its own empty cube has half-width >= df it
+      // contains this cell too, and the box [c, c + df + df(m) - 1] (forward only) lies inside it: a ray never needs
+      // what is behind it, so rays leaving or skimming a surface take steps about twice as long for one more byte.
+      const int mx = ex + ((df ^ gx) - gx), my = ey + ((df ^ gy) - gy), mz = ez + ((df ^ gz) - gz);
+      if ((unsigned)mx < (unsigned)v.ddims[0] && (unsigned)my < (unsigned)v.ddims[1] && (unsigned)mz < (unsigned)v.ddims[2]) {
+        const int d2 = (int)__ldg(&v.df[mx + v.ddims[0] * (my + v.ddims[1] * mz)]);
+        if (d2 > df) kdf = df + d2;
+      }
+    } else {
       const int ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
       if (ci != w.ci) { w.ci = ci; w.wtag = -1; }
       if (STATS) {
@@ -253,21 +261,18 @@ __device__ __forceinline__ uint4 shade_record(const Done& dn) {
                     __float_as_uint(dn.t), r | (g << 8) | (b << 16));
 }
 
-struct ShadowJob { float px, py, pz; int cx, cy, cz; int owner; };
-
 // CTA = one 32x8 screen tile; warp = 8x4 pixels (four full 128 B lines per record store).  All primary rays of a warp
-// start together from the same eye, so the lanes stay at similar levels of the hierarchy (measured: mixing rays of
-// different phases in one warp -- a persistent "refill idle lanes" loop -- dropped SIMT efficiency from 20/32 to 8/32).
-// Shadow rays are compacted across the CTA (ballot + prefix through shared memory) and start together as well.
+// start together from the same eye, so the lanes stay at similar levels of the walk; when all of them are done, the lanes
+// that hit a lit-facing face trace that pixel's shadow ray, again all starting together.  Keeping phases apart matters:
+// refilling idle lanes with new pixels (v4) or letting a lane continue as its shadow ray inside the primary loop (v9)
+// both raise lane occupancy and both cost 30 % or more extra warp instructions (profiles/README.md).
+// No shared memory, no barriers: the CTA is only the unit of tile ownership.
 template <bool STATS>
 __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
                                                               int rank, int world, int layout, int tiles_x, int n_tiles,
                                                               int local_tile0,
                                                               MesoHitRecord* __restrict__ out, RayStatsDev* stats,
                                                               uint8_t* touch_chunk, uint8_t* touch_brick) {
-  __shared__ ShadowJob s_jobs[RM_THREADS];
-  __shared__ uint8_t s_shadow[RM_THREADS];
-  __shared__ int s_warp_cnt[RM_THREADS / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int local_tile = local_tile0 + blockIdx.x;
   const int tile = local_tile * world + rank;
@@ -323,9 +328,8 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
   }
 
   const unsigned steps_p = steps;
-  // ---- phase 2: shadow rays, compacted across the CTA ----
+  // ---- phase 2: shadow ray of the same pixel (origin = hit point, start cell = the empty cell in front of the face) ----
   if (flags & MESO_FLAG_SHADOW) {
-#if RM_WARP_SHADOW
     if (want_shadow) {
       const int nrm = (dn.face & 1) ? 1 : -1;
       Ray r; r.ox = dn.px; r.oy = dn.py; r.oz = dn.pz;
@@ -338,39 +342,6 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
       dn.shadow = res == W_HIT ? 1 : 0;
       n_shadow = 1;
     }
-  }
-  if (false) {
-#endif
-    const unsigned bal = __ballot_sync(0xffffffffu, want_shadow);
-    if (lane == 0) s_warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int k = 0; k < RM_THREADS / 32; k++) { const int n = s_warp_cnt[k]; if (k < warp) base += n; total += n; }
-    if (want_shadow) {
-      // origin = hit point, start cell = the empty cell in front of the hit face
-      const int nrm = (dn.face & 1) ? 1 : -1;
-      ShadowJob j;
-      j.px = dn.px; j.py = dn.py; j.pz = dn.pz;
-      j.cx = dn.cx + (hit_axis == 0 ? nrm : 0); j.cy = dn.cy + (hit_axis == 1 ? nrm : 0); j.cz = dn.cz + (hit_axis == 2 ? nrm : 0);
-      j.owner = threadIdx.x;
-      s_jobs[base + __popc(bal & ((1u << lane) - 1u))] = j;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < total) {
-      const ShadowJob j = s_jobs[threadIdx.x];
-      Ray r; r.ox = j.px; r.oy = j.py; r.oz = j.pz;
-      ray_dir(r, Lx, Ly, Lz);
-      Walk w;
-      int cx = 0, cy = 0, cz = 0, res = W_EXIT;
-      if (walk_begin(v, r, j.cx, j.cy, j.cz, w, steps)) {
-        do { res = walk_iter<STATS>(sc, r, w, cx, cy, cz, steps); } while (res == W_CONTINUE);
-      }
-      s_shadow[j.owner] = res == W_HIT ? 1 : 0;
-      n_shadow = 1;
-    }
-    __syncthreads();
-    if (want_shadow) dn.shadow = s_shadow[threadIdx.x];
   }
 
   // ---- phase 3: shade + store ----
