@@ -86,16 +86,18 @@ struct Scene {
 };
 
 // Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every aligned step is "(cs | mask) + 1".
-// After a brick step only the stepped axis is exact; the other two hold an older true coordinate inside the same brick
-// (`gran` = 3) and are made exact before the walk looks at voxels.  Distance-field steps make all three exact at once.
-// need: 2 = the 32^3 cell may have changed (look the distance field up), 1 = the brick changed, 0 = same brick.
+// After a step out of a box of 2^gran voxels (gran 1: 2^3 cell, 3: brick, 5: distance-field cube) only the stepped axis
+// is exact; the other two hold an older true coordinate inside that box and are made exact before the walk looks at
+// anything finer than the box.
+// need: 3 = the 32^3 cell may have changed (look the distance field up), 2 = the brick changed, 1 = the 2^3 cell
+// changed, 0 = same 2^3 cell.
 struct Walk {
   int csx, csy, csz;
   int la; float lt;
   int gran, need;
   int ci, wtag, ztag;
   uint32_t slot;
-  unsigned long long wocc, wfull, slice;
+  unsigned long long wocc, wfull, slice, cm;
 };
 
 enum { W_CONTINUE = 0, W_HIT = 1, W_EXIT = 2 };
@@ -132,8 +134,8 @@ __device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int c
     }
   }
   w.csx = cx ^ (r.sx >> 31); w.csy = cy ^ (r.sy >> 31); w.csz = cz ^ (r.sz >> 31);
-  w.gran = 0; w.need = 2; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0;
-  w.wocc = 0; w.wfull = 0; w.slice = 0;
+  w.gran = 0; w.need = 3; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0;
+  w.wocc = 0; w.wfull = 0; w.slice = 0; w.cm = 0;
   return alive;
 }
 
@@ -147,7 +149,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   const int gx = r.sx >> 31, gy = r.sy >> 31, gz = r.sz >> 31;
   cx = w.csx ^ gx; cy = w.csy ^ gy; cz = w.csz ^ gz;
   bool go = true;  // keep looking finer
-  int sh = 0;      // level of the step: 0 voxel, 3 brick, 5 distance-field cube
+  int sh = 0;      // level of the step: 0 voxel, 1 2^3 cell, 3 brick, 5 distance-field cube
   int kdf = 1;     // cells to advance at that level (> 1 only for distance-field steps)
 #define MESO_SYNC_IF_COARSER(S)                                                                                 \
   if (go && w.gran > (S)) { /* looking finer than the box that was stepped: make the other two axes exact */    \
@@ -155,7 +157,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
     w.csx = cx ^ gx; w.csy = cy ^ gy; w.csz = cz ^ gz;                                                          \
     w.gran = 0;                                                                                                 \
   }
-  if (w.need >= 2) {
+  if (w.need >= 3) {
     // After a brick step (gran 3) the other two axes are still inside their brick, so the cell is known; after a
     // distance-field step (gran 5) they can be anywhere in the cube that was left: make them exact first.
     MESO_SYNC_IF_COARSER(3)
@@ -180,7 +182,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
       }
     }
   }
-  if (go && w.need >= 1) {
+  if (go && w.need >= 2) {
     const int bx = (cx >> 3) & 15, by = (cy >> 3) & 15, bz = (cz >> 3) & 15;
     const int wi = bz * 4 + (by >> 2);
     if (wi != w.wtag) {
@@ -195,9 +197,16 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
         return W_HIT;
       }
       w.slot = __ldg(&v.bptr[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
+      w.cm = __ldg(&v.pool_cm[w.slot]);
       if (STATS) s.touch_brick[w.slot] = 1;
       w.ztag = -1;
     }
+  }
+  if (go && w.need >= 1) {
+    // 2^3-voxel cells of the partial brick: after a step out of such a cell (gran 1) the other two axes are still inside
+    // their cell, so the bit of the new cell is known without making them exact; after a brick step they are not
+    MESO_SYNC_IF_COARSER(1)
+    if (!((w.cm >> (((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3))) & 1ull)) { sh = 1; go = false; }
   }
   MESO_SYNC_IF_COARSER(0)
   if (go) {
@@ -223,11 +232,11 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   const int news = SEL3(a, nxx, nxy, nxz);
   if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
   w.la = a; w.lt = ta; steps++;
-  if (STATS) s.lv[sh == 0 ? 0 : (sh == 3 ? 1 : (kdf == 1 ? 2 : (kdf <= 4 ? 3 : 4)))]++;
+  if (STATS) s.lv[sh == 0 ? 0 : (sh == 1 ? 1 : (sh == 3 ? 2 : (kdf <= 2 ? 3 : 4)))]++;
   w.gran = sh;
   const unsigned ucross = (unsigned)(olds ^ news);
-  w.need = (ucross >> 5) ? 2 : ((ucross >> 3) ? 1 : 0);
-  if (w.need >= 2) {
+  w.need = (ucross >> 5) ? 3 : ((ucross >> 3) ? 2 : ((ucross >> 1) ? 1 : 0));
+  if (w.need >= 3) {
     const int st = SEL3(a, r.sx, r.sy, r.sz);
     const int nv = SEL3(a, v.nvox[0], v.nvox[1], v.nvox[2]);
     if (news >= (st > 0 ? nv : 0)) return W_EXIT;   // mirrored coordinate at which the ray has left the grid

@@ -330,6 +330,32 @@ __global__ void region_kernel(DVolume v) {
   if (any) atomicOr(&v.region_any[r >> 5], 1u << (r & 31));
 }
 
+// ---- 2^3-cell masks of the partial bricks (raymarch: skipping inside a brick) ----------------------------------
+// One thread per payload slot in use: OR the eight slices pairwise in z, then in x and y with shifts, and gather the
+// sixteen 2x2 results of every z pair.
+__global__ void __launch_bounds__(256) coarse_mask_kernel(DVolume v) {
+  const uint32_t slot = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t n = min(*v.pool_count, v.max_bricks);
+  if (slot >= n) return;
+  const uint64_t* p = v.pool + (size_t)slot * 8;
+  uint64_t cm = 0;
+#pragma unroll
+  for (int ez = 0; ez < 4; ez++) {
+    uint64_t q = p[2 * ez] | p[2 * ez + 1];
+    q |= q >> 1;    // even x: OR of the x pair
+    q |= q >> 8;    // even y rows: OR of the y pair
+#pragma unroll
+    for (int ey = 0; ey < 4; ey++)
+#pragma unroll
+      for (int ex = 0; ex < 4; ex++) cm |= ((q >> (2 * ex + 16 * ey)) & 1ull) << (ex + 4 * ey + 16 * ez);
+  }
+  v.pool_cm[slot] = cm;
+}
+void launch_coarse_masks(const LaunchCtx& lc, const DVolume& v) {
+  coarse_mask_kernel<<<(v.max_bricks + 255) / 256, 256, 0, lc.stream>>>(v);
+  (*lc.launches)++;
+}
+
 // ---- cell distance field (raymarch empty-space skipping) -------------------------------------------------------
 // df(c) = min over non-empty 32^3 cells e of max(|cx-ex|, |cy-ey|, |cz-ez|), capped at K + 1: the cube of half-width
 // df - 1 cells around c is empty.  The L-infinity transform is separable: three identical passes
@@ -427,6 +453,7 @@ void launch_voxelize_list(const LaunchCtx& lc, const DVolume& v, int kind, const
   }
   finalize_list_kernel<<<(max_n + 7) / 8, 256, 0, lc.stream>>>(v, d_list, d_n);
   (*lc.launches) += 2;
+  launch_coarse_masks(lc, v);
   launch_df_build(lc, v);   // voxels were added: the distance field must not overestimate
 }
 
@@ -438,6 +465,7 @@ void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v, bool rebuild_
   const int nr = v.rdims[0] * v.rdims[1] * v.rdims[2];
   region_kernel<<<(nr + 127) / 128, 128, 0, lc.stream>>>(v);
   (*lc.launches) += 2;
+  launch_coarse_masks(lc, v);
   if (rebuild_df) launch_df_build(lc, v);
 }
 

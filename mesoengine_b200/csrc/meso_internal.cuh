@@ -26,6 +26,7 @@ struct DVolume {
   uint64_t* mips;       // nchunks*3*64 erode Mip1..3
   uint32_t* bptr;       // nchunks*4096 payload slot of partial bricks (0xFFFFFFFF otherwise)
   uint64_t* pool;       // max_bricks*8 words
+  uint64_t* pool_cm;    // max_bricks: per payload slot, bit per 2^3-voxel cell of the brick (index x/2 + 4(y/2) + 16(z/2)) (derived)
   uint32_t* chunk_any;  // bit per chunk: has >=1 block
   uint32_t* chunk_full; // bit per chunk: all 4096 bricks full
   uint64_t* cells;      // per chunk: bit per 32^3-voxel cell (4x4x4 bricks), index x + 4y + 16z (derived)
@@ -58,6 +59,7 @@ struct LaunchCtx {
 void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* d_overflow);
 void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v, bool rebuild_df = true);  // derived data: of, cells, chunk/region bits, df
 void launch_df_build(const LaunchCtx& lc, const DVolume& v);
+void launch_coarse_masks(const LaunchCtx& lc, const DVolume& v);
 void launch_scatter_payload(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, const uint64_t* d_payload, int64_t n);
 void launch_gather_partial(const LaunchCtx& lc, const DVolume& v, uint64_t* d_keys, uint64_t* d_payload, uint32_t* d_count);
 
