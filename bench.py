@@ -408,6 +408,32 @@ def run_ours(args):
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_rays = sum(rays_cam[k % 8] for k in range(e2e_steps))
     e2e_value = e2e_rays / float(e2e_dt.item()) / 1e6
+    # same loop with MESO_FLAG_RGBA8: the reference's own output format (RGBA_UN8 colour target), 4 B instead of 16 B per pixel
+    e2e_rgba8 = None
+    if world == 1:
+        imgs = [torch.empty((height, width), dtype=torch.int32).pin_memory() for _ in range(RING)]
+        imgs_np = [t.numpy().view(np.uint32) for t in imgs]
+
+        def rgba_run(nsteps):
+            nonlocal consumed
+            for k in range(nsteps):
+                slot = k % RING
+                if k >= RING:
+                    ctx.frame_wait(slot)
+                    consumed += int(imgs_np[slot][0, 0]) + int(imgs_np[slot][-1, -1])
+                ctx.raymarch_async(cams[k % 8], width, height, imgs_np[slot], slot, shadow=True, light=LIGHT, rgba8=True)
+            for slot in range(RING):
+                ctx.frame_wait(slot)
+                consumed += int(imgs_np[slot][0, 0]) + int(imgs_np[slot][-1, -1])
+
+        rgba_run(RING)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rgba_run(e2e_steps)
+        torch.cuda.synchronize()
+        e2e_rgba8 = {"value": e2e_rays / (time.perf_counter() - t0) / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": 4 * px,
+                     "note": "MESO_FLAG_RGBA8: only the colour word of every record is written and copied (the reference's RGBA_UN8 offscreen target)"}
+        del imgs
     clocks = sampler.stop() if sampler else None
 
     line = None
@@ -427,7 +453,7 @@ def run_ours(args):
                        "gather": gather, "gather_verified_equal_to_1gpu_frame": gather_verified,
                        "scene_build_s": t_build},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "rgba8": e2e_rgba8,
                     "note": ("meso_raymarch_async()/meso_frame_wait() frame ring of 4: FGPUUniformCamera from host memory (kernel parameters), records copied to pinned host memory, copy of frame k overlapping frame k+1"
                              if world == 1 else "frame gathered on rank 0 (fused p2p stores or NCCL), then copied to pinned host memory on that frame's stream, overlapping the next frame in flight")},
             "gpu_launches": int(launches),

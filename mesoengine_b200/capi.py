@@ -33,7 +33,7 @@ StreamStats = np.dtype([("generated", "<u4"), ("missing", "<u4"), ("candidates",
 
 SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
-FLAG_SHADOW = 1
+FLAG_SHADOW, FLAG_RGBA8 = 1, 2
 LAYOUT_FRAME, LAYOUT_TILES = 0, 1
 TILE_W, TILE_H = 32, 8
 
@@ -212,27 +212,27 @@ class Context:
         _ck(lib.meso_download_instances(self.h, _p(inst), C.c_int64(max(n_inst, 1))))
         return table, mips, inst[:n_inst]
 
-    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None):
-        """End-to-end call: camera from host memory, records into host memory."""
-        rec = out if out is not None else np.zeros((height, width), dtype=HitRecord)
+    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False):
+        """End-to-end call: camera from host memory, records (or, rgba8=True, the colour image as uint32) into host memory."""
+        rec = out if out is not None else np.zeros((height, width), dtype=np.uint32 if rgba8 else HitRecord)
         l = np.ascontiguousarray(light, dtype=np.float32)
-        _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(FLAG_SHADOW if shadow else 0),
-                              _p(l), _p(rec)))
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0)
+        _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(rec)))
         return rec
 
-    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8)):
+    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False):
         """Frame-ring call: enqueue frame + copy into `out` (pinned numpy array); pair with frame_wait(slot)."""
         l = np.ascontiguousarray(light, dtype=np.float32)
-        _ck(lib.meso_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(FLAG_SHADOW if shadow else 0),
-                                    _p(l), _p(out), C.c_int(slot)))
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0)
+        _ck(lib.meso_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(out), C.c_int(slot)))
 
     def frame_wait(self, slot):
         _ck(lib.meso_frame_wait(self.h, C.c_int(slot)))
 
-    def raymarch_device(self, cam, width, height, d_records, shadow=True, light=(0.3, 0.5, 0.8), layout=LAYOUT_FRAME):
+    def raymarch_device(self, cam, width, height, d_records, shadow=True, light=(0.3, 0.5, 0.8), layout=LAYOUT_FRAME, flags_extra=0):
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
-                                     C.c_uint32(FLAG_SHADOW if shadow else 0), _p(l), C.c_void_p(d_records), C.c_int(layout)))
+                                     C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
 
     def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8)):
         st = np.zeros(1, dtype=RayStats)

@@ -205,6 +205,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   if (go && w.need >= 1) {
     // 2^3-voxel cells of the partial brick: after a step out of such a cell (gran 1) the other two axes are still inside
     // their cell, so the bit of the new cell is known without making them exact; after a brick step they are not
+    // (a 4^3 level on top of this one was measured: 9 % fewer steps, 7 % slower -- one more divergent path per iteration)
     MESO_SYNC_IF_COARSER(1)
     if (!((w.cm >> (((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3))) & 1ull)) { sh = 1; go = false; }
   }
@@ -232,7 +233,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   const int news = SEL3(a, nxx, nxy, nxz);
   if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
   w.la = a; w.lt = ta; steps++;
-  if (STATS) s.lv[sh == 0 ? 0 : (sh == 1 ? 1 : (sh == 3 ? 2 : (kdf <= 2 ? 3 : 4)))]++;
+  if (STATS) s.lv[sh == 0 ? 0 : (sh <= 2 ? 1 : (sh == 3 ? 2 : (kdf <= 2 ? 3 : 4)))]++;
   w.gran = sh;
   const unsigned ucross = (unsigned)(olds ^ news);
   w.need = (ucross >> 5) ? 3 : ((ucross >> 3) ? 2 : ((ucross >> 1) ? 1 : 0));
@@ -357,7 +358,9 @@ __global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, Meso
   if (valid) {
     const size_t dst = layout == MESO_LAYOUT_FRAME ? (size_t)py * width + px
                                                    : (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
-    reinterpret_cast<uint4*>(out)[dst] = shade_record(dn);
+    const uint4 rec = shade_record(dn);
+    if (flags & MESO_FLAG_RGBA8) reinterpret_cast<uint32_t*>(out)[dst] = rec.w;
+    else reinterpret_cast<uint4*>(out)[dst] = rec;
   }
 
   if (STATS) {

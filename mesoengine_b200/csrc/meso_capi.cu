@@ -441,6 +441,7 @@ int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width,
   NEED_SCENE(c);
   if (!cam || !d_records || width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad argument");
   if (layout != MESO_LAYOUT_FRAME && layout != MESO_LAYOUT_TILES) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad layout");
+  if ((flags & MESO_FLAG_RGBA8) && layout != MESO_LAYOUT_FRAME) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: MESO_FLAG_RGBA8 needs MESO_LAYOUT_FRAME");
   MesoRaySetup rs;
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
@@ -454,14 +455,16 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
   if (!host || !cam) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: null argument");
   if (width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_raymarch: bad size");
   const size_t px = (size_t)width * height;
+  const size_t bpp = (flags & MESO_FLAG_RGBA8) ? 4 : sizeof(MesoHitRecord);   // bytes per pixel of the output
+  char* const host_b = reinterpret_cast<char*>(host);
   int r = ensure_frame(c, px);
   if (r != MESO_OK) return r;
   if (c->world > 1) {
     // other ranks' tiles stay all-ones; single launch + one copy
-    CK(cudaMemsetAsync(c->d_frame, 0xFF, px * sizeof(MesoHitRecord), c->stream));
+    CK(cudaMemsetAsync(c->d_frame, 0xFF, px * bpp, c->stream));
     r = meso_raymarch_device(c, cam, width, height, flags, light, c->d_frame, MESO_LAYOUT_FRAME);
     if (r != MESO_OK) return r;
-    CK(cudaMemcpyAsync(host, c->d_frame, px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(host, c->d_frame, px * bpp, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return MESO_OK;
   }
@@ -490,7 +493,8 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
     CK(cudaEventRecord(c->band_done[b], lc.stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->band_done[b], 0));
     const size_t y0 = (size_t)ty0 * MESO_TILE_H, y1 = std::min((size_t)height, (size_t)ty1 * MESO_TILE_H);
-    CK(cudaMemcpyAsync(host + y0 * width, c->d_frame + y0 * width, (y1 - y0) * width * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaMemcpyAsync(host_b + y0 * width * bpp, reinterpret_cast<const char*>(c->d_frame) + y0 * width * bpp, (y1 - y0) * width * bpp,
+                       cudaMemcpyDeviceToHost, c->copy_stream));
   }
   CK(cudaStreamSynchronize(c->copy_stream));   // every band kernel precedes its copy, so this covers both band streams
   return MESO_OK;
@@ -518,13 +522,14 @@ int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   lc.stream = c->band_stream[slot & 1];
   CK(cudaEventRecord(c->band_fork, c->stream));
   CK(cudaStreamWaitEvent(lc.stream, c->band_fork, 0));
-  if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * sizeof(MesoHitRecord), lc.stream));
+  const size_t bpp = (flags & MESO_FLAG_RGBA8) ? 4 : sizeof(MesoHitRecord);
+  if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * bpp, lc.stream));
   launch_raymarch(lc, c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr,
                   c->d_tile_counter);
   CK_LAST("raymarch async");
   CK(cudaEventRecord(c->ring_traced[slot], lc.stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ring_traced[slot], 0));
-  CK(cudaMemcpyAsync(host, c->d_ring[slot], px * sizeof(MesoHitRecord), cudaMemcpyDeviceToHost, c->copy_stream));
+  CK(cudaMemcpyAsync(host, c->d_ring[slot], px * bpp, cudaMemcpyDeviceToHost, c->copy_stream));
   CK(cudaEventRecord(c->ring_copied[slot], c->copy_stream));
   c->ring_busy[slot] = true;
   return MESO_OK;

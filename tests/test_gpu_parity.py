@@ -247,6 +247,28 @@ def test_frame_ring_async_equals_sync(ctx, capi, orc):
         ctx.raymarch_async(cams[0], w, h, views[0], 7)   # slot out of range -> ArgumentOutOfRange-class error
 
 
+def test_rgba8_output_is_the_colour_word_of_the_records(ctx, capi, orc):
+    """MESO_FLAG_RGBA8 (the reference's RGBA_UN8 offscreen colour target): 4 B per pixel, equal to record.rgba, through the
+    synchronous banded call (ragged height: bands end on different rows) and through the frame ring; oracle-checked."""
+    import torch
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 322, 531
+    cam = _cams(orc, origin, dims, w, h)[2]
+    ref = vol.raymarch(orc.ray_setup(cam, origin, w, h), w, h)
+    img = ctx.raymarch(cam, w, h, rgba8=True)
+    assert img.dtype == np.uint32 and img.shape == (h, w)
+    assert np.array_equal(img, ref["rgba"])
+    assert np.array_equal(ctx.raymarch(cam, w, h)["rgba"], img)
+    pinned = torch.empty((h, w), dtype=torch.int32).pin_memory()
+    view = pinned.numpy().view(np.uint32)
+    ctx.raymarch_async(cam, w, h, view, 1, rgba8=True)
+    ctx.frame_wait(1)
+    assert np.array_equal(view, img)
+    with pytest.raises(capi.MesoError):   # packed tile layout carries whole records only
+        ctx.raymarch_device(cam, w, h, ctx.device_alloc(w * h * 16), layout=capi.LAYOUT_TILES, flags_extra=capi.FLAG_RGBA8)
+
+
 def test_device_alloc_download(ctx, capi, orc):
     """The buffer path of the fused multi-GPU gather on one device: library-owned frame, kernel stores, download."""
     origin, dims, params = scenes.sphere_scene(256)
