@@ -61,7 +61,8 @@ __device__ __forceinline__ int advance_axis(float o, float d, float inv, int st,
   // Fast path (DESIGN.md "advance_axis shortcut"): when the estimated position is farther than eps from every voxel
   // plane, every plane behind it has a computed crossing time < ts and every plane ahead > ts (fp32 error of
   // t_b(p) <= 1.8e-7 |t|, of pos <= 6e-8 (|ts| + |pos|)), so the exact answer is floor(pos).  Otherwise decide with
-  // the keys themselves.  Same result either way; the oracle only has the slow path.
+  // the keys themselves.  Same result either way; the oracle only has the slow path.  (One launch-wide bound for eps
+  // instead of the per-call value saves six instructions and was 2 % slower: more lanes end up in the slow path.)
   const float fr = __fsub_rn(pos, fl);
   const float eps = __fadd_rn(__fmul_rn(__fadd_rn(fabsf(ts), fabsf(pos)), 5e-7f), 1e-5f);
   if (fr > eps && fr < __fsub_rn(1.0f, eps)) return e;
@@ -86,15 +87,15 @@ struct Scene {
 };
 
 // Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every aligned step is "(cs | mask) + 1".
-// After a step out of a box of 2^gran voxels (gran 1: 2^3 cell, 3: brick, 5: distance-field cube) only the stepped axis
-// is exact; the other two hold an older true coordinate inside that box and are made exact before the walk looks at
-// anything finer than the box.
+// All three are exact between iterations: a step out of a box bigger than a voxel re-derives the two other axes from
+// the consumed key right away (one sync site in the step section; syncing lazily, only when the walk looks finer, needs
+// the same ~35 instructions at three places of the cascade, and a warp pays for every place any of its lanes visits).
 // need: 3 = the 32^3 cell may have changed (look the distance field up), 2 = the brick changed, 1 = the 2^3 cell
 // changed, 0 = same 2^3 cell.
 struct Walk {
   int csx, csy, csz;
   int la; float lt;
-  int gran, need;
+  int need;
   int ci, wtag, ztag;
   uint32_t slot;
   unsigned long long wocc, wfull, slice, cm;
@@ -134,7 +135,7 @@ __device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int c
     }
   }
   w.csx = cx ^ (r.sx >> 31); w.csy = cy ^ (r.sy >> 31); w.csz = cz ^ (r.sz >> 31);
-  w.gran = 0; w.need = 3; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0;
+  w.need = 3; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0;
   w.wocc = 0; w.wfull = 0; w.slice = 0; w.cm = 0;
   return alive;
 }
@@ -151,16 +152,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   bool go = true;  // keep looking finer
   int sh = 0;      // level of the step: 0 voxel, 1 2^3 cell, 3 brick, 5 distance-field cube
   int kdf = 1;     // cells to advance at that level (> 1 only for distance-field steps)
-#define MESO_SYNC_IF_COARSER(S)                                                                                 \
-  if (go && w.gran > (S)) { /* looking finer than the box that was stepped: make the other two axes exact */    \
-    sync_axes(r, w, cx, cy, cz);                                                                                \
-    w.csx = cx ^ gx; w.csy = cy ^ gy; w.csz = cz ^ gz;                                                          \
-    w.gran = 0;                                                                                                 \
-  }
   if (w.need >= 3) {
-    // After a brick step (gran 3) the other two axes are still inside their brick, so the cell is known; after a
-    // distance-field step (gran 5) they can be anywhere in the cube that was left: make them exact first.
-    MESO_SYNC_IF_COARSER(3)
     const int ex = cx >> 5, ey = cy >> 5, ez = cz >> 5;
     const int df = (int)__ldg(&v.df[ex + v.ddims[0] * (ey + v.ddims[1] * ez)]);
     if (df > 0) {   // the cube of half-width df - 1 cells around this cell is empty
@@ -192,10 +184,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
     const int bit = bx + 16 * (by & 3);
     if (!((w.wocc >> bit) & 1ull)) { sh = 3; go = false; }
     else {
-      if ((w.wfull >> bit) & 1ull) {
-        if (w.gran > 0) sync_axes(r, w, cx, cy, cz);
-        return W_HIT;
-      }
+      if ((w.wfull >> bit) & 1ull) return W_HIT;
       w.slot = __ldg(&v.bptr[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
       w.cm = __ldg(&v.pool_cm[w.slot]);
       if (STATS) s.touch_brick[w.slot] = 1;
@@ -203,19 +192,15 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
     }
   }
   if (go && w.need >= 1) {
-    // 2^3-voxel cells of the partial brick: after a step out of such a cell (gran 1) the other two axes are still inside
-    // their cell, so the bit of the new cell is known without making them exact; after a brick step they are not
+    // 2^3-voxel cells of the partial brick
     // (a 4^3 level on top of this one was measured: 9 % fewer steps, 7 % slower -- one more divergent path per iteration)
-    MESO_SYNC_IF_COARSER(1)
     if (!((w.cm >> (((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3))) & 1ull)) { sh = 1; go = false; }
   }
-  MESO_SYNC_IF_COARSER(0)
   if (go) {
     const int z = cz & 7;
     if (z != w.ztag) { w.slice = __ldg(&v.pool[(size_t)w.slot * 8 + z]); w.ztag = z; }
     if ((w.slice >> ((cx & 7) + 8 * (cy & 7))) & 1ull) return W_HIT;
   }
-#undef MESO_SYNC_IF_COARSER
   // ---- one step at level sh: consume the smallest of the three pending keys (ties: lower axis first) ----
   // mirrored coordinate after crossing: kdf cells of size 2^sh ahead, never beyond the grid end (nvox if step > 0, else 0);
   // for the aligned levels (kdf = 1) this is (cs | mask) + 1 and the clamp never binds
@@ -234,13 +219,18 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
   w.la = a; w.lt = ta; steps++;
   if (STATS) s.lv[sh == 0 ? 0 : (sh <= 2 ? 1 : (sh == 3 ? 2 : (kdf <= 2 ? 3 : 4)))]++;
-  w.gran = sh;
   const unsigned ucross = (unsigned)(olds ^ news);
   w.need = (ucross >> 5) ? 3 : ((ucross >> 3) ? 2 : ((ucross >> 1) ? 1 : 0));
   if (w.need >= 3) {
     const int st = SEL3(a, r.sx, r.sy, r.sz);
     const int nv = SEL3(a, v.nvox[0], v.nvox[1], v.nvox[2]);
     if (news >= (st > 0 ? nv : 0)) return W_EXIT;   // mirrored coordinate at which the ray has left the grid
+  }
+  // the one place where the two other axes are made exact: right after every step that left a box bigger than a voxel
+  if (sh > 0) {
+    cx = w.csx ^ gx; cy = w.csy ^ gy; cz = w.csz ^ gz;
+    sync_axes(r, w, cx, cy, cz);
+    w.csx = cx ^ gx; w.csy = cy ^ gy; w.csz = cz ^ gz;
   }
   return W_CONTINUE;
 }
