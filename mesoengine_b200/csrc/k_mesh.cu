@@ -105,7 +105,7 @@ __device__ __forceinline__ int greedy_image(uint64_t img, int dir, int layer, in
   return n;
 }
 
-#define MQ_CAP 128   // quads staged per brick in shared memory (a smooth surface brick yields ~20)
+#define MQ_CAP 224   // quads staged per warp iteration (two bricks) in shared memory (a smooth surface brick yields ~20)
 
 // Same greedy merge, staging the quads in shared memory; slots come from a shared-memory atomic counter.
 __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count) {
@@ -131,28 +131,40 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
 }
 
 // Persistent, grid-stride over the work list (count read from device memory: no host round trip between the passes).
+// A warp takes TWO bricks per iteration, one per half-warp, through the slice phase (lanes 0..6 of each half resolve the
+// seven bricks involved, lanes 0..7 own one z-slice each).  The 2 x 48 (direction, layer) images are then built in three
+// full rounds, the non-empty ones (typically 6..12 of 48) are queued in shared memory, and the greedy merge runs over the
+// queue densely: one round of busy lanes instead of three rounds of mostly idle ones.
 __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
                                                           uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
-  __shared__ uint64_t s_e[8][6][8];
+  __shared__ uint64_t s_e[8][2][6][8];
+  __shared__ uint64_t s_img[8][96];
+  __shared__ uint8_t s_meta[8][96];
+  __shared__ int s_org[8][2][3];
   __shared__ uint4 s_q[8][MQ_CAP];
   __shared__ int s_n[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, hl = lane & 15;
   const uint32_t n_work = work_count_ptr ? *work_count_ptr : work_count_imm;
-  for (int64_t item = (int64_t)blockIdx.x * 8 + warp; item < n_work; item += (int64_t)gridDim.x * 8) {
+  const int64_t n_pairs = ((int64_t)n_work + 1) >> 1;
+  for (int64_t pair = (int64_t)blockIdx.x * 8 + warp; pair < n_pairs; pair += (int64_t)gridDim.x * 8) {
   __syncwarp();
-  const uint64_t key = work[item];
+  const int64_t item = pair * 2 + half;
+  const bool valid = item < (int64_t)n_work;
+  const uint64_t key = valid ? work[item] : 0ull;
   const int64_t c = (int64_t)(key >> 12); const int b = (int)(key & 4095);
   const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
   const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
+  if (hl == 0) { s_org[warp][half][0] = bx * 8; s_org[warp][half][1] = by * 8; s_org[warp][half][2] = bz * 8; }
 
-  const int z = lane & 7;
-  // Step 1: lanes 0..6 resolve the seven bricks involved (self, -x, +x, -y, +y, -z, +z) in parallel: one 16 B
-  // {occ,full} load each, then the payload slot of the partial ones.  state: 0 empty / outside, 1 full, 2 partial.
+  const int z = hl & 7;
+  // Step 1: lanes 0..6 of each half resolve the seven bricks involved (self, -x, +x, -y, +y, -z, +z) in parallel: one
+  // 16 B {occ,full} load each, then the payload slot of the partial ones.  state: 0 empty / outside, 1 full, 2 partial.
   int st = 0; uint32_t slot = 0;
-  if (lane < 7) {
-    const int nx = bx + (lane == 1 ? -1 : (lane == 2 ? 1 : 0));
-    const int ny = by + (lane == 3 ? -1 : (lane == 4 ? 1 : 0));
-    const int nz = bz + (lane == 5 ? -1 : (lane == 6 ? 1 : 0));
+  if (valid && hl < 7) {
+    const int nx = bx + (hl == 1 ? -1 : (hl == 2 ? 1 : 0));
+    const int ny = by + (hl == 3 ? -1 : (hl == 4 ? 1 : 0));
+    const int nz = bz + (hl == 5 ? -1 : (hl == 6 ? 1 : 0));
     if ((unsigned)nx < (unsigned)(v.dims[0] * 16) && (unsigned)ny < (unsigned)(v.dims[1] * 16) && (unsigned)nz < (unsigned)(v.dims[2] * 16)) {
       const int64_t nc = chunk_index(v, nx >> 4, ny >> 4, nz >> 4);
       const int nb = block_bit(nx & 15, ny & 15, nz & 15);
@@ -163,20 +175,20 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
       }
     }
   }
-  // Step 2: every slice needed is one independent 8 B load (lanes 0..7: slice z of self and of the four lateral
-  // neighbours; lane 0 / 7: the facing slice of the -z / +z neighbour).
+  // Step 2: every slice needed is one independent 8 B load (lanes 0..7 of the half: slice z of self and of the four
+  // lateral neighbours; lane 0 / 7: the facing slice of the -z / +z neighbour).
   auto slice_of = [&](int which, int zz) -> uint64_t {
-    const int s_st = __shfl_sync(0xffffffffu, st, which);
-    const uint32_t s_slot = __shfl_sync(0xffffffffu, slot, which);
-    if (s_st == 2 && lane < 8) return __ldg(&v.pool[(size_t)s_slot * 8 + zz]);
+    const int s_st = __shfl_sync(0xffffffffu, st, (lane & 16) | which);
+    const uint32_t s_slot = __shfl_sync(0xffffffffu, slot, (lane & 16) | which);
+    if (s_st == 2 && hl < 8) return __ldg(&v.pool[(size_t)s_slot * 8 + zz]);
     return s_st == 1 ? ~0ull : 0ull;
   };
   uint64_t s = slice_of(0, z);   // every lane takes part in the shuffles
-  if (lane >= 8) s = 0ull;
+  if (hl >= 8) s = 0ull;
   const uint64_t xm = slice_of(1, z), xp = slice_of(2, z), ym = slice_of(3, z), yp = slice_of(4, z);
   const uint64_t nzm = slice_of(5, 7), nzp = slice_of(6, 0);
   const uint64_t s_dn = __shfl_up_sync(0xffffffffu, s, 1), s_up = __shfl_down_sync(0xffffffffu, s, 1);
-  if (lane < 8) {
+  if (hl < 8) {
     const uint64_t C0 = 0x0101010101010101ull;
     const uint64_t n_xm = ((s << 1) & ~C0) | ((xm >> 7) & C0);
     const uint64_t n_xp = ((s >> 1) & ~(C0 << 7)) | ((xp & C0) << 7);
@@ -184,42 +196,48 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
     const uint64_t n_yp = (s >> 8) | (yp << 56);
     const uint64_t n_zm = z > 0 ? s_dn : nzm;
     const uint64_t n_zp = z < 7 ? s_up : nzp;
-    s_e[warp][0][z] = s & ~n_xm; s_e[warp][1][z] = s & ~n_xp;
-    s_e[warp][2][z] = s & ~n_ym; s_e[warp][3][z] = s & ~n_yp;
-    s_e[warp][4][z] = s & ~n_zm; s_e[warp][5][z] = s & ~n_zp;
+    s_e[warp][half][0][z] = s & ~n_xm; s_e[warp][half][1][z] = s & ~n_xp;
+    s_e[warp][half][2][z] = s & ~n_ym; s_e[warp][half][3][z] = s & ~n_yp;
+    s_e[warp][half][4][z] = s & ~n_zm; s_e[warp][half][5][z] = s & ~n_zp;
   }
-  __syncwarp();
-  // 48 (dir, layer) images over 32 lanes: task = lane and lane + 32
-  uint64_t img[2]; int tdir[2], tlay[2]; int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    const int task = lane + 32 * k;
-    img[k] = 0; tdir[k] = task >> 3; tlay[k] = task & 7;
-    if (task < 48) {
-      const int dir = tdir[k], l = tlay[k];
-      if (dir >= 4) img[k] = s_e[warp][dir][l];
-      else {
-        uint64_t im = 0;
-#pragma unroll
-        for (int zz = 0; zz < 8; zz++) {
-          const uint64_t e = s_e[warp][dir][zz];
-          const uint32_t row = dir < 2 ? gather_col(e, l) : ((uint32_t)(e >> (8 * l)) & 0xFFu);
-          im |= (uint64_t)row << (8 * zz);
-        }
-        img[k] = im;
-      }
-    }
-  }
-  // Fast path: one greedy pass that stages the quads of the brick in shared memory (slot = shared atomic, order
-  // inside a brick is irrelevant), then one global atomicAdd and a coalesced copy of 16 B records.
   if (lane == 0) s_n[warp] = 0;
   __syncwarp();
+  // 2 x 48 (dir, layer) images over 32 lanes in three full rounds; the non-empty ones are queued (order irrelevant)
+  int ni = 0;
 #pragma unroll
-  for (int k = 0; k < 2; k++)
-    if (lane + 32 * k < 48 && img[k]) greedy_stage(img[k], tdir[k], tlay[k], bx * 8, by * 8, bz * 8, s_q[warp], &s_n[warp]);
+  for (int k = 0; k < 3; k++) {
+    const int task = lane + 32 * k;
+    const int h = task >= 48 ? 1 : 0;
+    const int t48 = task - 48 * h;
+    const int dir = t48 >> 3, l = t48 & 7;
+    uint64_t im = 0;
+    if (dir >= 4) im = s_e[warp][h][dir][l];
+    else {
+#pragma unroll
+      for (int zz = 0; zz < 8; zz++) {
+        const uint64_t e = s_e[warp][h][dir][zz];
+        const uint32_t row = dir < 2 ? gather_col(e, l) : ((uint32_t)(e >> (8 * l)) & 0xFFu);
+        im |= (uint64_t)row << (8 * zz);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, im != 0ull);
+    if (im) {
+      const int idx = ni + __popc(bal & ((1u << lane) - 1u));
+      s_img[warp][idx] = im;
+      s_meta[warp][idx] = (uint8_t)(dir | (l << 3) | (h << 6));
+    }
+    ni += __popc(bal);
+  }
+  __syncwarp();
+  if (ni == 0) continue;
+  // Fast path: greedy passes over the queue stage the quads of both bricks in shared memory (slot = shared atomic, order
+  // is irrelevant), then one global atomicAdd and a coalesced copy of 16 B records.
+  for (int i = lane; i < ni; i += 32) {
+    const int m = s_meta[warp][i], h = m >> 6;
+    greedy_stage(s_img[warp][i], m & 7, (m >> 3) & 7, s_org[warp][h][0], s_org[warp][h][1], s_org[warp][h][2], s_q[warp], &s_n[warp]);
+  }
   __syncwarp();
   const int staged = s_n[warp];
-  if (staged == 0) continue;
   if (staged <= MQ_CAP) {
     unsigned long long sbase = 0;
     if (lane == 0) sbase = atomicAdd(quad_count, (unsigned long long)staged);
@@ -229,21 +247,19 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
     continue;
   }
   // Rare: more quads than the staging area holds -> count, prefix, emit straight to global memory.
-#pragma unroll
-  for (int k = 0; k < 2; k++)
-    if (lane + 32 * k < 48 && img[k]) cnt += greedy_image<false>(img[k], tdir[k], tlay[k], 0, 0, 0, nullptr, 0, 0);
+  int cnt = 0;
+  for (int i = lane; i < ni; i += 32) cnt += greedy_image<false>(s_img[warp][i], 0, 0, 0, 0, 0, nullptr, 0, 0);
   int incl = cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) continue;
   unsigned long long base = 0;
   if (lane == 0) base = atomicAdd(quad_count, (unsigned long long)total);
   base = __shfl_sync(0xffffffffu, base, 0);
   int64_t pos = (int64_t)base + incl - cnt;
-#pragma unroll
-  for (int k = 0; k < 2; k++) {
-    if (lane + 32 * k < 48 && img[k]) pos += greedy_image<true>(img[k], tdir[k], tlay[k], bx * 8, by * 8, bz * 8, quads, pos, cap);
+  for (int i = lane; i < ni; i += 32) {
+    const int m = s_meta[warp][i], h = m >> 6;
+    pos += greedy_image<true>(s_img[warp][i], m & 7, (m >> 3) & 7, s_org[warp][h][0], s_org[warp][h][1], s_org[warp][h][2], quads, pos, cap);
   }
 }
 }
