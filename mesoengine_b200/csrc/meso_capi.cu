@@ -139,7 +139,7 @@ int meso_ctx_create(int device, MesoCtx** out) {
 static void free_scene(MesoCtx* c) {
   DVolume& v = c->v;
   cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.cells); cudaFree(v.region_any); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
-  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count); cudaFree(v.df); cudaFree(v.df_tmp); cudaFree(v.pool_cm);
+  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count); cudaFree(v.df); cudaFree(v.df_tmp); cudaFree(v.pool_cm); cudaFree(v.words); cudaFree(v.n_words);
   cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
@@ -232,6 +232,7 @@ int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const in
   CK(cudaMalloc(&v.bptr, nc * MESO_BLOCKS * 4));
   CK(cudaMalloc(&v.pool, (size_t)max_bricks * 64));
   CK(cudaMalloc(&v.pool_cm, (size_t)max_bricks * 8));
+  CK(cudaMalloc(&v.words, nc * 64 * 4)); CK(cudaMalloc(&v.n_words, 4));
   CK(cudaMalloc(&v.chunk_any, (size_t)v.chunk_words * 4)); CK(cudaMalloc(&v.chunk_full, (size_t)v.chunk_words * 4));
   CK(cudaMalloc(&v.pool_count, 4));
   CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));

@@ -35,6 +35,8 @@ struct DVolume {
                         // 0 = non-empty.  Conservative: never larger than the true distance (derived; rebuilt whenever
                         // voxels may have been ADDED, left alone by the carve, which only removes)
   uint8_t* df_tmp;      // scratch of the separable passes
+  uint32_t* words;      // nchunks*64: K1 scratch, occupancy words the per-voxel kernel has to visit (mixed words)
+  uint32_t* n_words;    // device counter of `words`
   int ddims[3];         // cells per axis = dims * 4
   int rdims[3];         // regions per axis = ceil(dims / 4)
   int region_words;
