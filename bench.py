@@ -360,9 +360,53 @@ def run_ours(args):
     e2e_steps = max(8, min(args.steps, 40))
     consumed = 0
 
+    # N > 1: fused gather straight into HOST memory.  One shared-memory segment holds the R frames in flight; every rank
+    # maps it, registers it with its own GPU (meso_host_register) and its raymarch kernel stores its tiles there over its
+    # own PCIe link while tracing: N links instead of rank 0's one, no device-side frame, no copy.  Falls back to
+    # "gather on rank 0, then copy" if the segment cannot be created or registered.
+    host_fused = False
+    shm = None
+    if world > 1 and not args.no_host_fused:
+        shm_path = "/dev/shm/meso_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid())
+        try:
+            if rank == 0:
+                with open(shm_path, "wb") as f:
+                    f.truncate(R * px * 16)
+            dist.barrier()
+            shm = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(R * px * 16,))
+            shm_dptr = ctx.host_register(shm)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as e:
+            sys.stderr.write("bench: host-fused gather unavailable on rank %d (%s)\n" % (rank, e))
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        host_fused = int(ok.item()) == 1
+        if host_fused:
+            shm_views = [shm[i * px * 16:(i + 1) * px * 16].view(capi.HitRecord).reshape(height, width) for i in range(R)]
+
     def e2e_run(nsteps):
         nonlocal consumed
-        if world == 1:
+        if world > 1 and host_fused:
+            pend = [None] * R
+            for k in range(nsteps):
+                slot = k % R
+                if pend[slot] is not None:
+                    pend[slot].synchronize()
+                    if rank == 0:
+                        consumed += int(shm_views[slot]["w1"][0, 0]) + int(shm_views[slot]["w1"][-1, -1])
+                s = streams[slot]
+                ctx.set_stream(s.cuda_stream)
+                with torch.cuda.stream(s):
+                    ctx.raymarch_device(cams[k % 8], width, height, shm_dptr + slot * px * 16, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+                    dist.all_reduce(flags[slot])   # stream-ordered rendezvous: behind it every rank's tiles are in host memory
+                    e = torch.cuda.Event()
+                    e.record(s)
+                    pend[slot] = e
+                ctx.set_stream(stream.cuda_stream)
+            for slot in range(R):
+                if pend[slot] is not None:
+                    pend[slot].synchronize()
+        elif world == 1:
             for k in range(nsteps):
                 slot = k % RING
                 if k >= RING:
@@ -408,6 +452,26 @@ def run_ours(args):
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_rays = sum(rays_cam[k % 8] for k in range(e2e_steps))
     e2e_value = e2e_rays / float(e2e_dt.item()) / 1e6
+    host_fused_verified = None
+    if host_fused:
+        # the frame the ranks assembled in host memory equals the frame one GPU renders on its own
+        ctx.raymarch_device(cams[0], width, height, shm_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+        barrier()
+        if rank == 0:
+            ctx.set_partition(0, 1)
+            ref = ctx.raymarch(cams[0], width, height, shadow=True, light=LIGHT)
+            ctx.set_partition(rank, world)
+            host_fused_verified = bool(shm_views[0].tobytes() == ref.tobytes())
+        barrier()
+        ctx.host_unregister(shm)
+        del shm_views
+        shm = None
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.unlink(shm_path)
+            except OSError:
+                pass
     # same loop with MESO_FLAG_RGBA8: the reference's own output format (RGBA_UN8 colour target), 4 B instead of 16 B per pixel
     e2e_rgba8 = None
     if world == 1:
@@ -455,7 +519,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
                     "steps": e2e_steps, "rgba8": e2e_rgba8,
                     "note": ("meso_raymarch_async()/meso_frame_wait() frame ring of 4: FGPUUniformCamera from host memory (kernel parameters), records copied to pinned host memory, copy of frame k overlapping frame k+1"
-                             if world == 1 else "frame gathered on rank 0 (fused p2p stores or NCCL), then copied to pinned host memory on that frame's stream, overlapping the next frame in flight")},
+                             if world == 1 else
+                             ("fused gather into host memory: one shared-memory segment registered by every rank (meso_host_register); each rank's kernel stores its tile records there over its own PCIe link, 4-byte NCCL all-reduce as the rendezvous, frames consumed on rank 0"
+                              if host_fused else
+                              "frame gathered on rank 0 (fused p2p stores or NCCL), then copied to pinned host memory on that frame's stream, overlapping the next frame in flight")),
+                    "host_fused": host_fused, "host_fused_verified_equal_to_1gpu_frame": host_fused_verified},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "raymarch_kernel<false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -628,6 +696,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="frame ring depth of the timed loop (reference: kNumBufferedFrames = 4)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame gather (p2p falls back to nccl if IPC is unavailable)")
+    ap.add_argument("--no-host-fused", action="store_true", help="N > 1 e2e: gather on rank 0 and copy instead of storing straight into shared host memory")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -49,6 +49,7 @@ SYMBOLS = [
     "meso_raymarch_async", "meso_frame_wait", "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download", "meso_download_async",
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
+    "meso_host_register", "meso_host_unregister",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -327,6 +328,16 @@ class Context:
         words = np.zeros((nchunks + 31) // 32, dtype=np.uint32)
         _ck(lib.meso_stream_loaded(self.h, _p(words), C.c_int64(words.shape[0])))
         return np.unpackbits(words.view(np.uint8), bitorder="little")[:nchunks].astype(bool)
+
+    # ---- fused gather into host memory ----
+    def host_register(self, host_array):
+        """Page-lock + map a host numpy buffer (e.g. an mmap of a shared-memory file); returns the device address."""
+        d = C.c_void_p()
+        _ck(lib.meso_host_register(self.h, _p(host_array), C.c_size_t(host_array.nbytes), C.byref(d)))
+        return d.value
+
+    def host_unregister(self, host_array):
+        _ck(lib.meso_host_unregister(self.h, _p(host_array)))
 
     # ---- peer memory (fused gather) ----
     def device_alloc(self, nbytes):

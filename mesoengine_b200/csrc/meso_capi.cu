@@ -859,6 +859,25 @@ int meso_stream_loaded(MesoCtx* c, uint32_t* host_words, int64_t n_words) {
   return MESO_OK;
 }
 
+int meso_host_register(MesoCtx* c, void* host_ptr, size_t bytes, void** device_ptr) {
+  if (!c || !host_ptr || !device_ptr || bytes == 0) return fail(MESO_ERR_ARGUMENT, "meso_host_register: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  const cudaError_t e = cudaHostGetDevicePointer(device_ptr, host_ptr, 0);
+  if (e != cudaSuccess) {
+    cudaHostUnregister(host_ptr);
+    return fail(MESO_ERR_RUNTIME, std::string("meso_host_register: ") + cudaGetErrorString(e));
+  }
+  return MESO_OK;
+}
+int meso_host_unregister(MesoCtx* c, void* host_ptr) {
+  if (!c || !host_ptr) return fail(MESO_ERR_ARGUMENT, "meso_host_unregister: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaHostUnregister(host_ptr));
+  return MESO_OK;
+}
+
 int meso_device_alloc(MesoCtx* c, size_t bytes, void** dptr) {
   if (!c || !dptr || bytes == 0) return fail(MESO_ERR_ARGUMENT, "meso_device_alloc: bad argument");
   CK(cudaSetDevice(c->device));

@@ -1,5 +1,7 @@
 """GPU parity tests: every kernel, called through the C ABI (libmeso_b200.so), against the CPU oracle on the same
 inputs.  Bar: bit-exact (integer/bit outputs and, because both sides avoid fma, also t and rgba)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -267,6 +269,37 @@ def test_rgba8_output_is_the_colour_word_of_the_records(ctx, capi, orc):
     assert np.array_equal(view, img)
     with pytest.raises(capi.MesoError):   # packed tile layout carries whole records only
         ctx.raymarch_device(cam, w, h, ctx.device_alloc(w * h * 16), layout=capi.LAYOUT_TILES, flags_extra=capi.FLAG_RGBA8)
+
+
+def test_host_registered_frame_receives_kernel_stores(ctx, capi, orc, tmp_path):
+    """Fused gather into host memory on one device: a file-backed shared mapping is registered (meso_host_register), two
+    'ranks' (tile partitions 0/2 and 1/2) store their tiles into it straight from the kernel, and the mapping then holds
+    exactly the frame of the synchronous call."""
+    origin, dims, params = scenes.sphere_scene(256)
+    _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    w, h = 320, 184
+    cam = _cams(orc, origin, dims, w, h)[3]
+    expect = ctx.raymarch(cam, w, h).copy()
+    path = "/dev/shm/meso_test_%d" % os.getpid()
+    try:
+        with open(path, "wb") as f:
+            f.truncate(w * h * 16)
+        shm = np.memmap(path, dtype=np.uint8, mode="r+", shape=(w * h * 16,))
+        shm[:] = 0xEE
+        dptr = ctx.host_register(shm)
+        for r in (0, 1):
+            ctx.set_partition(r, 2)
+            ctx.raymarch_device(cam, w, h, dptr)
+        ctx.set_partition(0, 1)
+        ctx.sync()
+        assert shm.view(capi.HitRecord).reshape(h, w).tobytes() == expect.tobytes()
+        ctx.host_unregister(shm)
+        del shm
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+    with pytest.raises(capi.MesoError):
+        ctx.host_unregister(np.zeros(64, dtype=np.uint8))   # never registered
 
 
 def test_device_alloc_download(ctx, capi, orc):
