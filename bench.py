@@ -47,13 +47,26 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic(workload):
-    """dram bytes per launch of the raymarch kernel from the committed ncu --set full capture (profiles/), or None."""
+def load_traffic(workload, key=None):
+    """dram bytes per launch of the raymarch kernel from the committed ncu capture (profiles/), or None.
+    key="<workload>_warp_instructions": smsp__inst_executed.sum of the same capture."""
     p = os.path.join(ROOT, "profiles", "raymarch_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get(workload)
+            return json.load(f).get(key or workload)
     return None
+
+
+def issue_roofline(ctx, world, workload, kernel_ms, clocks):
+    """What actually bounds the walk: warp instructions of one launch (ncu smsp__inst_executed.sum of the committed
+    capture, 1-GPU launch) against the issue peak = SMs x 4 schedulers x SM clock.  Explanatory, next to the HBM figure."""
+    w = load_traffic(workload, workload + "_warp_instructions")
+    if w is None or world != 1:
+        return None
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = ctx.sm_count() * 4 * mhz * 1e6
+    return {"warp_instructions_per_launch": w, "peak_warp_instructions_per_s": peak, "achieved_per_s": w / (kernel_ms * 1e-3),
+            "frac": w / (kernel_ms * 1e-3) / peak, "source": "profiles/raymarch_traffic.json (ncu capture of the shipped kernel)"}
 
 
 class ClockSampler:
@@ -529,7 +542,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "raymarch_kernel<false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "latency/divergence-bound traversal; working set is L2-resident (SURVEY.md 8d)"},
+                         "issue": issue_roofline(ctx, world, args.workload, kms, clocks),
+                         "note": "divergence/instruction-issue-bound traversal; working set is L2-resident (SURVEY.md 8d); 'issue' relates the ncu-counted warp instructions of one launch to the SMs' issue peak"},
         }
 
     # ---- BASELINE.json configs[4]: interactive edit loop (1 GPU leg; carve is replicated compute on N GPUs) ----

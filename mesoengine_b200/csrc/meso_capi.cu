@@ -16,8 +16,10 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CK(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e__ = (call);                                                                            \
-    if (e__ != cudaSuccess)                                                                              \
+    if (e__ != cudaSuccess) {                                                                            \
+      (void)cudaGetLastError(); /* reported here: do not let it surface again in a later CK_LAST */      \
       return fail(MESO_ERR_RUNTIME, std::string(#call) + ": " + cudaGetErrorString(e__));                \
+    }                                                                                                    \
   } while (0)
 #define CK_LAST(what)                                                                                    \
   do {                                                                                                   \
@@ -211,6 +213,8 @@ int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const in
   for (int i = 0; i < 3; i++)
     if (dims[i] < 1 || dims[i] > 512) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: dims_chunks out of range [1,512]");
   if (max_bricks == 0) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: max_bricks must be > 0");
+  // 32-bit word / cell indices inside the kernels (64 words and 64 cells per chunk); 2^24 chunks would need > 300 GB anyway
+  if ((int64_t)dims[0] * dims[1] * dims[2] > (1ll << 24)) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: more than 2^24 chunks");
   CK(cudaSetDevice(c->device));
   if (c->has_scene) { cudaStreamSynchronize(c->stream); free_scene(c); }
   c->cfg = *cfg;

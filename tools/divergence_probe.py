@@ -21,9 +21,9 @@ for i, eye in enumerate(eyes):
                  "steps_per_primary": sp / max(1, int(st["primary"])), "steps_per_shadow": ss / max(1, int(st["shadow"])),
                  "lane_use_primary": sp / max(1, int(st["warp_slots_primary"])), "lane_use_shadow": ss / max(1, int(st["warp_slots_shadow"])),
                  "warp_slots_primary": int(st["warp_slots_primary"]), "warp_slots_shadow": int(st["warp_slots_shadow"]),
-                 "level_steps(voxel,brick,cell32,chunk,region)": [int(x) for x in st["level_steps"]]})
+                 "level_steps(voxel,cell2,brick,df_le2,df_gt2)": [int(x) for x in st["level_steps"]]})
     print(json.dumps(rows[-1]))
 tot = {k: sum(r[k] for r in rows) for k in ("primary", "shadow", "warp_slots_primary", "warp_slots_shadow")}
-lv = np.sum([r["level_steps(voxel,brick,cell32,chunk,region)"] for r in rows], axis=0)
+lv = np.sum([r["level_steps(voxel,cell2,brick,df_le2,df_gt2)"] for r in rows], axis=0)
 print(json.dumps({"all_cameras": tot, "level_share": (lv / lv.sum()).round(4).tolist(),
                   "slots_share_shadow": tot["warp_slots_shadow"] / (tot["warp_slots_primary"] + tot["warp_slots_shadow"])}))
