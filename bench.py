@@ -466,6 +466,7 @@ def run_ours(args):
     e2e_rays = sum(rays_cam[k % 8] for k in range(e2e_steps))
     e2e_value = e2e_rays / float(e2e_dt.item()) / 1e6
     host_fused_verified = None
+    edit_multi = None
     if host_fused:
         # the frame the ranks assembled in host memory equals the frame one GPU renders on its own
         ctx.raymarch_device(cams[0], width, height, shm_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
@@ -475,6 +476,11 @@ def run_ours(args):
             ref = ctx.raymarch(cams[0], width, height, shadow=True, light=LIGHT)
             ctx.set_partition(rank, world)
             host_fused_verified = bool(shm_views[0].tobytes() == ref.tobytes())
+        barrier()
+        # BASELINE.json configs[4] on N GPUs: carve replicated on every rank, render split by tiles into the shared frame
+        edit_multi = None
+        if not args.no_mesh:
+            edit_multi = bench_edit_loop_multi(ctx, capi, cams, width, height, shm_views[0], shm_dptr, flags[0], stream, rank, dist, torch)
         barrier()
         ctx.host_unregister(shm)
         del shm_views
@@ -549,6 +555,8 @@ def run_ours(args):
     # ---- BASELINE.json configs[4]: interactive edit loop (1 GPU leg; carve is replicated compute on N GPUs) ----
     if world == 1 and not args.no_mesh and rank == 0:
         line["edit_loop"] = bench_edit_loop(ctx, capi, cams, width, height)
+    if world > 1 and rank == 0 and edit_multi is not None:
+        line["edit_loop"] = edit_multi
 
     # ---- secondary metric of BASELINE.json: meshed voxels/s (configs[2]-style, 1 GPU leg only) ----
     if world == 1 and not args.no_mesh and rank == 0:
@@ -600,6 +608,48 @@ def bench_edit_loop(ctx, capi, cams, width, height, frames=48):
             "ms_remesh_dirty": t_mesh / frames * 1e3, "ms_render_to_host": t_render / frames * 1e3,
             "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": quads_total / frames,
             "note": "carve r=24 voxels at the centre-pixel hit, re-mesh dirty bricks + neighbours, re-render 3840x2160 to host memory (synchronous API)"}
+
+
+def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, flag, stream, rank, dist, torch, frames=48):
+    """The edit loop on N GPUs: every rank reads the centre-pixel hit of the last frame from the shared host frame, carves
+    the same sphere into its replica of the volume (replicated compute), rank 0 re-meshes the dirty bricks, and the next 4K
+    frame is rendered split by tiles, every rank's kernel storing its records into the shared host frame.  One rendezvous
+    per frame (the next carve needs the frame), wall clock between two barriers."""
+    dist.barrier()
+    torch.cuda.synchronize()
+
+    def render(k):
+        ctx.raymarch_device(cams[k % 8], width, height, frame_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+        with torch.cuda.stream(stream):
+            dist.all_reduce(flag)
+        stream.synchronize()
+
+    render(0)
+    t_carve = t_mesh = t_render = 0.0
+    dirty_total = quads_total = 0
+    t_all = time.perf_counter()
+    for k in range(frames):
+        r = frame[height // 2, width // 2]
+        if (int(r["w1"]) >> 20) & 1:
+            center = [int(r["w0"]) & 0xFFFF, int(r["w0"]) >> 16, int(r["w1"]) & 0xFFFF]
+            t0 = time.perf_counter()
+            nd = ctx.carve_sphere(center, 24)
+            t1 = time.perf_counter()
+            if rank == 0:
+                quads, keys = ctx.remesh_dirty(1 << 16, 1 << 13)
+                quads_total += len(quads)
+            t2 = time.perf_counter()
+            t_carve += t1 - t0; t_mesh += t2 - t1
+            dirty_total += nd
+        t0 = time.perf_counter()
+        render(k + 1)
+        t_render += time.perf_counter() - t0
+    t_all = time.perf_counter() - t_all
+    dist.barrier()
+    return {"frames": frames, "fps": frames / t_all, "ms_per_frame": t_all / frames * 1e3, "ms_carve": t_carve / frames * 1e3,
+            "ms_remesh_dirty": t_mesh / frames * 1e3, "ms_render_to_host": t_render / frames * 1e3,
+            "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": quads_total / frames,
+            "note": "rank 0's clock; carve r=24 voxels at the centre-pixel hit on every rank's replica, dirty bricks re-meshed on rank 0, 3840x2160 re-rendered by all ranks into the shared host frame (host-fused gather), one rendezvous per frame"}
 
 
 def bench_stream(ctx, capi, torch, stream):
