@@ -397,7 +397,7 @@ def run_ours(args):
         if host_fused:
             shm_views = [shm[i * px * 16:(i + 1) * px * 16].view(capi.HitRecord).reshape(height, width) for i in range(R)]
 
-    def e2e_run(nsteps):
+    def e2e_run(nsteps, rgba8=False):
         nonlocal consumed
         if world > 1 and host_fused:
             pend = [None] * R
@@ -406,11 +406,15 @@ def run_ours(args):
                 if pend[slot] is not None:
                     pend[slot].synchronize()
                     if rank == 0:
-                        consumed += int(shm_views[slot]["w1"][0, 0]) + int(shm_views[slot]["w1"][-1, -1])
+                        if rgba8:
+                            consumed += int(shm[slot * px * 16]) + int(shm[slot * px * 16 + 4 * px - 1])
+                        else:
+                            consumed += int(shm_views[slot]["w1"][0, 0]) + int(shm_views[slot]["w1"][-1, -1])
                 s = streams[slot]
                 ctx.set_stream(s.cuda_stream)
                 with torch.cuda.stream(s):
-                    ctx.raymarch_device(cams[k % 8], width, height, shm_dptr + slot * px * 16, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+                    ctx.raymarch_device(cams[k % 8], width, height, shm_dptr + slot * px * 16, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME,
+                                        flags_extra=capi.FLAG_RGBA8 if rgba8 else 0)
                     dist.all_reduce(flags[slot])   # stream-ordered rendezvous: behind it every rank's tiles are in host memory
                     e = torch.cuda.Event()
                     e.record(s)
@@ -467,7 +471,18 @@ def run_ours(args):
     e2e_value = e2e_rays / float(e2e_dt.item()) / 1e6
     host_fused_verified = None
     edit_multi = None
+    e2e_rgba8 = None
     if host_fused:
+        # the same ring with MESO_FLAG_RGBA8: 4 B per pixel into the shared host frame
+        e2e_run(R, rgba8=True)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps, rgba8=True)
+        barrier()
+        dt8 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt8, op=dist.ReduceOp.MAX)
+        e2e_rgba8 = {"value": e2e_rays / float(dt8.item()) / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": 4 * px,
+                     "note": "MESO_FLAG_RGBA8 through the host-fused gather: only the colour word of every record travels"}
         # the frame the ranks assembled in host memory equals the frame one GPU renders on its own
         ctx.raymarch_device(cams[0], width, height, shm_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
         barrier()
@@ -492,7 +507,6 @@ def run_ours(args):
             except OSError:
                 pass
     # same loop with MESO_FLAG_RGBA8: the reference's own output format (RGBA_UN8 colour target), 4 B instead of 16 B per pixel
-    e2e_rgba8 = None
     if world == 1:
         imgs = [torch.empty((height, width), dtype=torch.int32).pin_memory() for _ in range(RING)]
         imgs_np = [t.numpy().view(np.uint32) for t in imgs]
