@@ -342,6 +342,11 @@ def run_ours(args):
             gather_verified = bool(got.tobytes() == ref.tobytes())
         barrier()
 
+    # ---- meshing on N GPUs (BASELINE.json: meshed voxels/s at 1/2/4/8): the resident scene, fused quad gather ----
+    mesh_multi = None
+    if world > 1 and not args.no_mesh:
+        mesh_multi = bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n)
+
     # ---- dominant kernel alone (this rank's tiles), for the roofline ----
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world == 1:
@@ -571,10 +576,12 @@ def run_ours(args):
         line["edit_loop"] = bench_edit_loop(ctx, capi, cams, width, height)
     if world > 1 and rank == 0 and edit_multi is not None:
         line["edit_loop"] = edit_multi
+    if world > 1 and rank == 0 and mesh_multi is not None:
+        line["mesh"] = {"sphere_%d_voxels" % n: mesh_multi}
 
     # ---- secondary metric of BASELINE.json: meshed voxels/s (configs[2]-style, 1 GPU leg only) ----
     if world == 1 and not args.no_mesh and rank == 0:
-        line["mesh"] = bench_mesh(ctx, capi, scenes, torch, stream, args, dev)
+        line["mesh"] = bench_mesh(ctx, capi, scenes, torch, stream, args, dev, n_work=n)
 
     # ---- the reference's own streaming loop on its own scene (1 GPU leg) ----
     if world == 1 and not args.no_mesh and rank == 0:
@@ -666,6 +673,77 @@ def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, fla
             "note": "rank 0's clock; carve r=24 voxels at the centre-pixel hit on every rank's replica, dirty bricks re-meshed on rank 0, 3840x2160 re-rendered by all ranks into the shared host frame (host-fused gather), one rendezvous per frame"}
 
 
+def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels, steps=8):
+    """Meshing on N GPUs with a fused quad gather: chunk c belongs to rank c % world; rank 0 owns the quad list and its
+    8-byte counter (exported over CUDA IPC); every rank's mesh kernel reserves slots with a system-scope atomicAdd on the
+    counter and stores its 16 B quads into the list over NVLink.  The scene is the resident raymarch scene.  Returns None
+    if IPC is unavailable.  Time = CUDA events on every rank around kernel + rendezvous, max over ranks."""
+    cap = 1 << 25
+    try:
+        hq = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        hc = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            qptr0, cptr0 = ctx.device_alloc(cap * 16), ctx.device_alloc(8)
+            hq.copy_(torch.from_numpy(ctx.ipc_export(qptr0)))
+            hc.copy_(torch.from_numpy(ctx.ipc_export(cptr0)))
+        dist.broadcast(hq, src=0)
+        dist.broadcast(hc, src=0)
+        qptr = qptr0 if rank == 0 else ctx.ipc_open(hq.cpu().numpy())
+        cptr = cptr0 if rank == 0 else ctx.ipc_open(hc.cpu().numpy())
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+    except Exception as e:
+        sys.stderr.write("bench: fused quad gather unavailable on rank %d (%s)\n" % (rank, e))
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        return None
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def one():
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                ctx.device_memset(cptr, 0, 8)
+            dist.all_reduce(flag)            # nobody starts before the counter is zero
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.mesh_device_shared(qptr, cptr, cap)
+            dist.all_reduce(flag)            # behind it every rank's quads are in the list
+            b.record(stream)
+        stream.synchronize()
+        return a.elapsed_time(b)
+
+    one()
+    ts = [one() for _ in range(steps)]
+    t = torch.tensor([sum(ts) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = None
+    if rank == 0:
+        cnt = np.zeros(1, dtype=np.uint64)
+        ctx.download(cnt, cptr)
+        nq = int(cnt[0])
+        got = np.zeros((nq, 4), dtype=np.uint32)
+        ctx.download(got, qptr, nq * 16)
+        # the same mesh on one GPU, compared through an order-independent fingerprint (the list order is scheduling-dependent)
+        ctx.set_partition(0, 1)
+        ref_t = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+        nref = ctx.mesh_device(ref_t.data_ptr(), cap)
+        ref = ref_t[:nref].cpu().numpy().view(np.uint32)
+        ctx.set_partition(rank, world)
+        fp = lambda q: (int(q.shape[0]), [int(x) for x in q.astype(np.uint64).sum(axis=0)], [int(x) for x in np.bitwise_xor.reduce(q, axis=0)])
+        ms = float(t.item())
+        out = {"scene_voxels": n_voxels, "quads": nq, "ms": ms, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms * 1e-3),
+               "equal_to_1gpu_mesh": bool(fp(got) == fp(ref)),
+               "note": "chunk c -> rank c % N; fused quad gather into rank 0's list over NVLink (system-scope atomicAdd per warp, 16 B stores); fingerprint = (count, column sums, column xors)"}
+        del ref_t
+    dist.barrier()
+    if rank != 0:
+        ctx.ipc_close(qptr); ctx.ipc_close(cptr)
+    dist.barrier()
+    if rank == 0:
+        ctx.device_free(qptr0); ctx.device_free(cptr0)
+    return out
+
+
 def bench_stream(ctx, capi, torch, stream):
     """K6: FChunkManage::UpdateChunks + UpdateLoadingQueue on the reference's defaults (TestGenerator terrain, one sample
     per block, view radius 24 / 6 chunks, 120 degrees, 256 chunks per update) in a 49 x 6 x 49-chunk window around the
@@ -702,16 +780,19 @@ def bench_stream(ctx, capi, torch, stream):
             "note": "select (117 649 offsets -> desired set, rank-sorted) + dispatch list + generation of <= 256 chunks + derived data per update, no host round trip inside an update"}
 
 
-def bench_mesh(ctx, capi, scenes, torch, stream, args, dev):
-    """Face-cull + greedy meshing throughput on a 1024^3 grid (meshed voxels/s = N^3 / time)."""
+def bench_mesh(ctx, capi, scenes, torch, stream, args, dev, n_work=1024):
+    """Face-cull + greedy meshing throughput (meshed voxels/s = N^3 / time): BASELINE.json configs[2] (1024^3 terrain), the
+    1024^3 sphere, and the raymarch workload's own scene (the one the N-GPU mesh leg uses)."""
     out = {}
-    n = 1024
-    for name, kind, gran, scene in (("terrain_1024_blocks", capi.SDF_TERRAIN, capi.GRAN_BLOCK, scenes.terrain_scene(n)),
-                                    ("sphere_1024_voxels", capi.SDF_SPHERE, capi.GRAN_VOXEL, scenes.sphere_scene(n))):
+    cases = [("terrain_1024_blocks", 1024, capi.SDF_TERRAIN, capi.GRAN_BLOCK, scenes.terrain_scene(1024)),
+             ("sphere_1024_voxels", 1024, capi.SDF_SPHERE, capi.GRAN_VOXEL, scenes.sphere_scene(1024))]
+    if n_work != 1024:
+        cases.append(("sphere_%d_voxels" % n_work, n_work, capi.SDF_SPHERE, capi.GRAN_VOXEL, scenes.sphere_scene(n_work)))
+    for name, n, kind, gran, scene in cases:
         origin, dims, params = scene
-        ctx.scene_create(origin, dims, 1 << 18)
+        ctx.scene_create(origin, dims, (1 << 20) if n > 1024 else (1 << 18))
         ctx.voxelize_sdf(kind, params, gran)
-        cap = 1 << 24
+        cap = (1 << 25) if n > 1024 else (1 << 24)
         quads = torch.empty((cap, 4), dtype=torch.int32, device=dev)
         nq = ctx.mesh_device(quads.data_ptr(), cap)
         steps = max(5, min(args.steps, 30))
@@ -724,7 +805,7 @@ def bench_mesh(ctx, capi, scenes, torch, stream, args, dev):
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in evs) / steps
         occ, full, keys, _ = ctx.volume_download()
-        populated = int(sum(bin(int(x)).count("1") for x in occ.ravel()[occ.ravel() != 0]))
+        populated = int(np.unpackbits(occ.view(np.uint8)).sum())
         alg = 64.0 * len(keys) + 1024.0 * int(np.prod(dims)) + 16.0 * nq + 4
         out[name] = {"meshed_voxels_per_s": n ** 3 / (ms * 1e-3), "ms": ms, "quads": int(nq), "populated_bricks": populated,
                      "partial_bricks": int(len(keys)), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9}

@@ -49,7 +49,7 @@ SYMBOLS = [
     "meso_raymarch_async", "meso_frame_wait", "meso_device_alloc", "meso_device_free", "meso_ipc_export", "meso_ipc_open", "meso_ipc_close", "meso_download", "meso_download_async",
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
-    "meso_host_register", "meso_host_unregister",
+    "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -259,6 +259,10 @@ class Context:
         _ck(lib.meso_mesh_device(self.h, C.c_void_p(d_quads), C.c_int64(cap), C.byref(n) if want_count else None))
         return n.value
 
+    def mesh_device_shared(self, d_quads, d_counter, cap):
+        """Fused quad gather: append this rank's quads to a list (and 8-byte counter) that may live in a peer GPU."""
+        _ck(lib.meso_mesh_device_shared(self.h, C.c_void_p(d_quads), C.c_void_p(d_counter), C.c_int64(cap)))
+
     def carve_sphere(self, center, radius):
         c = np.ascontiguousarray(center, dtype=np.int32)
         n = C.c_int64(0)
@@ -344,6 +348,9 @@ class Context:
         p = C.c_void_p()
         _ck(lib.meso_device_alloc(self.h, C.c_size_t(nbytes), C.byref(p)))
         return p.value
+
+    def device_memset(self, dptr, value, nbytes):
+        _ck(lib.meso_device_memset(self.h, C.c_void_p(dptr), C.c_int(value), C.c_size_t(nbytes)))
 
     def device_free(self, dptr):
         _ck(lib.meso_device_free(self.h, C.c_void_p(dptr)))

@@ -105,7 +105,8 @@ __device__ __forceinline__ int greedy_image(uint64_t img, int dir, int layer, in
   return n;
 }
 
-#define MQ_CAP 224   // quads staged per warp iteration (two bricks) in shared memory (a smooth surface brick yields ~20)
+#define MQ_CAP 224   // quads a warp can stage in shared memory (a smooth surface brick yields ~20)
+#define MQ_FLUSH 128 // staged quads are written out once this many have accumulated (and at the end of the warp's work)
 
 // Same greedy merge, staging the quads in shared memory; slots come from a shared-memory atomic counter.
 __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count) {
@@ -147,7 +148,22 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
   const int half = lane >> 4, hl = lane & 15;
   const uint32_t n_work = work_count_ptr ? *work_count_ptr : work_count_imm;
   const int64_t n_pairs = ((int64_t)n_work + 1) >> 1;
-  for (int64_t pair = (int64_t)blockIdx.x * 8 + warp; pair < n_pairs; pair += (int64_t)gridDim.x * 8) {
+  if (lane == 0) s_n[warp] = 0;
+  __syncwarp();
+  // write the first `count` staged quads behind one reservation and empty the staging area
+  auto flush = [&](int count) {
+    if (count > 0) {
+      unsigned long long sbase = 0;
+      if (lane == 0) sbase = atomicAdd_system(quad_count, (unsigned long long)count);   // system scope: the counter may live in a peer GPU
+      sbase = __shfl_sync(0xffffffffu, sbase, 0);
+      for (int i = lane; i < count; i += 32)
+        if ((int64_t)sbase + i < cap) reinterpret_cast<uint4*>(quads)[sbase + i] = s_q[warp][i];
+    }
+    __syncwarp();
+    if (lane == 0) s_n[warp] = 0;
+    __syncwarp();
+  };
+  for (int64_t pair =(int64_t)blockIdx.x * 8 + warp; pair < n_pairs; pair += (int64_t)gridDim.x * 8) {
   __syncwarp();
   const int64_t item = pair * 2 + half;
   const bool valid = item < (int64_t)n_work;
@@ -200,7 +216,6 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
     s_e[warp][half][2][z] = s & ~n_ym; s_e[warp][half][3][z] = s & ~n_yp;
     s_e[warp][half][4][z] = s & ~n_zm; s_e[warp][half][5][z] = s & ~n_zp;
   }
-  if (lane == 0) s_n[warp] = 0;
   __syncwarp();
   // 2 x 48 (dir, layer) images over 32 lanes in three full rounds; the non-empty ones are queued (order irrelevant)
   int ni = 0;
@@ -231,22 +246,20 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
   __syncwarp();
   if (ni == 0) continue;
   // Fast path: greedy passes over the queue stage the quads of both bricks in shared memory (slot = shared atomic, order
-  // is irrelevant), then one global atomicAdd and a coalesced copy of 16 B records.
+  // is irrelevant).  Staged quads accumulate over several iterations and leave in batches of >= MQ_FLUSH: one
+  // (system-scope) atomicAdd and one coalesced copy of 16 B records per batch -- the reservation is a round trip over
+  // NVLink when the list lives in a peer GPU.
+  int before = s_n[warp];
+  if (before >= MQ_FLUSH) { flush(before); before = 0; }
   for (int i = lane; i < ni; i += 32) {
     const int m = s_meta[warp][i], h = m >> 6;
     greedy_stage(s_img[warp][i], m & 7, (m >> 3) & 7, s_org[warp][h][0], s_org[warp][h][1], s_org[warp][h][2], s_q[warp], &s_n[warp]);
   }
   __syncwarp();
-  const int staged = s_n[warp];
-  if (staged <= MQ_CAP) {
-    unsigned long long sbase = 0;
-    if (lane == 0) sbase = atomicAdd(quad_count, (unsigned long long)staged);
-    sbase = __shfl_sync(0xffffffffu, sbase, 0);
-    for (int i = lane; i < staged; i += 32)
-      if ((int64_t)sbase + i < cap) reinterpret_cast<uint4*>(quads)[sbase + i] = s_q[warp][i];
-    continue;
-  }
-  // Rare: more quads than the staging area holds -> count, prefix, emit straight to global memory.
+  if (s_n[warp] <= MQ_CAP) continue;
+  // Rare: more quads than the staging area holds -> write out what earlier iterations staged, then count, prefix and emit
+  // this pair's quads straight to global memory.
+  flush(before);
   int cnt = 0;
   for (int i = lane; i < ni; i += 32) cnt += greedy_image<false>(s_img[warp][i], 0, 0, 0, 0, 0, nullptr, 0, 0);
   int incl = cnt;
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
   for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
   unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd(quad_count, (unsigned long long)total);
+  if (lane == 0) base = atomicAdd_system(quad_count, (unsigned long long)total);
   base = __shfl_sync(0xffffffffu, base, 0);
   int64_t pos = (int64_t)base + incl - cnt;
   for (int i = lane; i < ni; i += 32) {
@@ -262,12 +275,14 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
     pos += greedy_image<true>(s_img[warp][i], m & 7, (m >> 3) & 7, s_org[warp][h][0], s_org[warp][h][1], s_org[warp][h][2], quads, pos, cap);
   }
 }
+  __syncwarp();
+  flush(s_n[warp]);
 }
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
-                 MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count) {
+                 MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count) {
   cudaMemsetAsync(d_work_count, 0, sizeof(uint32_t), lc.stream);
-  cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
+  if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   const int64_t n = v.nchunks * MESO_WORDS;
   mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, d_work, d_work_count);
   mesh_bricks_kernel<<<lc.sm_count * 8, 256, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count);

@@ -619,6 +619,17 @@ int meso_mesh_device(MesoCtx* c, void* d_quads, int64_t cap, int64_t* n_quads) {
   return MESO_OK;
 }
 
+int meso_mesh_device_shared(MesoCtx* c, void* d_quads, void* d_counter, int64_t cap) {
+  NEED_SCENE(c);
+  if (cap <= 0 || !d_quads || !d_counter) return fail(MESO_ERR_ARGUMENT, "meso_mesh_device_shared: bad argument");
+  int r = ensure_mesh_buffers(c);
+  if (r != MESO_OK) return r;
+  launch_mesh(c->lc(), c->v, c->rank, c->world, c->d_work, c->d_work_count, (MesoQuad*)d_quads, cap, (unsigned long long*)d_counter,
+              /*reset_count=*/false);
+  CK_LAST("mesh (shared list)");
+  return MESO_OK;
+}
+
 int meso_mesh(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads) {
   NEED_SCENE(c);
   if (!n_quads) return fail(MESO_ERR_ARGUMENT, "meso_mesh: n_quads is null");
@@ -886,6 +897,12 @@ int meso_device_alloc(MesoCtx* c, size_t bytes, void** dptr) {
   if (!c || !dptr || bytes == 0) return fail(MESO_ERR_ARGUMENT, "meso_device_alloc: bad argument");
   CK(cudaSetDevice(c->device));
   CK(cudaMalloc(dptr, bytes));   // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+  return MESO_OK;
+}
+int meso_device_memset(MesoCtx* c, void* dptr, int value, size_t bytes) {
+  if (!c || !dptr) return fail(MESO_ERR_ARGUMENT, "meso_device_memset: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(dptr, value, bytes, c->stream));
   return MESO_OK;
 }
 int meso_device_free(MesoCtx* c, void* dptr) {

@@ -76,7 +76,7 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
-                 MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count);
+                 MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count = true);
 void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
                       int64_t cap, unsigned long long* d_quad_count);
 
