@@ -392,6 +392,28 @@ def test_mesh_partition_union(ctx, orc):
     assert got.tobytes() == ref.tobytes()
 
 
+def test_mesh_shared_list_fused_gather(ctx, capi, orc):
+    """The buffer path of the fused quad gather on one device: three 'ranks' append their chunks' quads to ONE list behind
+    ONE counter (meso_mesh_device_shared); the list is the 1-GPU mesh."""
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+    ref = orc.sort_quads(vol.mesh())
+    cap = len(ref) + 64
+    qptr, cptr = ctx.device_alloc(cap * 16), ctx.device_alloc(8)
+    ctx.device_memset(cptr, 0, 8)
+    for rank in range(3):
+        ctx.set_partition(rank, 3)
+        ctx.mesh_device_shared(qptr, cptr, cap)
+    ctx.set_partition(0, 1)
+    cnt = np.zeros(1, dtype=np.uint64)
+    ctx.download(cnt, cptr)
+    assert int(cnt[0]) == len(ref)
+    got = np.zeros(len(ref), dtype=capi.Quad)
+    ctx.download(got, qptr, len(ref) * 16)
+    ctx.device_free(qptr); ctx.device_free(cptr)
+    assert orc.sort_quads(got).tobytes() == ref.tobytes()
+
+
 # ---- K5 -------------------------------------------------------------------------------------------------------
 
 def test_carve_and_remesh(ctx, orc):
