@@ -716,6 +716,25 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
     ts = [one() for _ in range(steps)]
     t = torch.tensor([sum(ts) / steps], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+    # the same partition with the lists left where they are made (one list per GPU, no gather): what the meshing itself costs
+    local = torch.empty(((cap // world) + (1 << 20), 4), dtype=torch.int32, device=dev)
+
+    def one_sharded():
+        with torch.cuda.stream(stream):
+            dist.all_reduce(flag)
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.mesh_device(local.data_ptr(), local.shape[0], want_count=False)
+            b.record(stream)
+        stream.synchronize()
+        return a.elapsed_time(b)
+
+    one_sharded()
+    tl = [one_sharded() for _ in range(steps)]
+    t_sh = torch.tensor([sum(tl) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t_sh, op=dist.ReduceOp.MAX)
+    del local
     out = None
     if rank == 0:
         cnt = np.zeros(1, dtype=np.uint64)
@@ -731,8 +750,11 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
         ctx.set_partition(rank, world)
         fp = lambda q: (int(q.shape[0]), [int(x) for x in q.astype(np.uint64).sum(axis=0)], [int(x) for x in np.bitwise_xor.reduce(q, axis=0)])
         ms = float(t.item())
+        ms_sh = float(t_sh.item())
         out = {"scene_voxels": n_voxels, "quads": nq, "ms": ms, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms * 1e-3),
                "equal_to_1gpu_mesh": bool(fp(got) == fp(ref)),
+               "sharded_lists": {"ms": ms_sh, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms_sh * 1e-3),
+                                 "note": "same partition, every rank keeps its own quad list (no gather): max over ranks of the mesh kernels"},
                "note": "chunk c -> rank c % N; fused quad gather into rank 0's list over NVLink (system-scope atomicAdd per warp, 16 B stores); fingerprint = (count, column sums, column xors)"}
         del ref_t
     dist.barrier()
