@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(256) compose_tiles_kernel(const uint4* __restr
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick, unsigned int* /*d_tile_counter*/, int local_tile0, int local_tile_count) {
+                     uint8_t* d_touch_brick, int local_tile0, int local_tile_count) {
   const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
   const int n_tiles = tiles_x * tiles_y;
   const int all_local = (n_tiles - rank + world - 1) / world;

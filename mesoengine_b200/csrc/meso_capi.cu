@@ -83,7 +83,6 @@ struct MesoCtx {
   uint32_t* d_flush = nullptr;
   size_t flush_words = 0;
   uint32_t* d_tmp_count = nullptr;
-  unsigned int* d_tile_counter = nullptr;
   cudaStream_t copy_stream = nullptr;       // D2H of finished bands overlaps the next band's kernel (meso_raymarch)
   cudaEvent_t band_done[16] = {nullptr};
   cudaStream_t band_stream[2] = {nullptr, nullptr};
@@ -123,7 +122,6 @@ int meso_ctx_create(int device, MesoCtx** out) {
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CK(cudaMalloc(&c->d_tmp_count, 16));
-  CK(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&c->band_done[i], cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&c->band_stream[i], cudaStreamNonBlocking));
@@ -161,7 +159,7 @@ int meso_ctx_destroy(MesoCtx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_scene(c);
-  cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow); cudaFree(c->d_tile_counter);
+  cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow);
   cudaFree(c->d_sel_keys); cudaFree(c->d_sel_out); cudaFree(c->d_sel_count);
   for (int i = 0; i < 16; i++) if (c->band_done[i]) cudaEventDestroy(c->band_done[i]);
   cudaStreamDestroy(c->copy_stream);
@@ -450,7 +448,7 @@ int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width,
   MesoRaySetup rs;
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr, c->d_tile_counter);
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr);
   CK_LAST("raymarch");
   return MESO_OK;
 }
@@ -493,7 +491,7 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
     LaunchCtx lc = c->lc();
     lc.stream = c->band_stream[b & 1];
     launch_raymarch(lc, c->v, rs, width, height, flags, 0, 1, MESO_LAYOUT_FRAME, c->d_frame, nullptr, nullptr, nullptr,
-                    c->d_tile_counter, ty0 * tiles_x, (ty1 - ty0) * tiles_x);
+                    ty0 * tiles_x, (ty1 - ty0) * tiles_x);
     CK_LAST("raymarch band");
     CK(cudaEventRecord(c->band_done[b], lc.stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->band_done[b], 0));
@@ -529,8 +527,7 @@ int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaStreamWaitEvent(lc.stream, c->band_fork, 0));
   const size_t bpp = (flags & MESO_FLAG_RGBA8) ? 4 : sizeof(MesoHitRecord);
   if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * bpp, lc.stream));
-  launch_raymarch(lc, c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr,
-                  c->d_tile_counter);
+  launch_raymarch(lc, c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr);
   CK_LAST("raymarch async");
   CK(cudaEventRecord(c->ring_traced[slot], lc.stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ring_traced[slot], 0));
@@ -560,7 +557,7 @@ int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaMemsetAsync(c->d_stats, 0, sizeof(RayStatsDev), c->stream));
   CK(cudaMemsetAsync(c->d_touch_chunk, 0, (size_t)c->v.nchunks, c->stream));
   CK(cudaMemsetAsync(c->d_touch_brick, 0, c->v.max_bricks, c->stream));
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick, c->d_tile_counter);
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick);
   CK_LAST("raymarch stats");
   RayStatsDev h;
   std::vector<uint8_t> tc((size_t)c->v.nchunks), tb(c->v.max_bricks);

@@ -31,7 +31,7 @@ struct DVolume {
   uint32_t* chunk_full; // bit per chunk: all 4096 bricks full
   uint64_t* cells;      // per chunk: bit per 32^3-voxel cell (4x4x4 bricks), index x + 4y + 16z (derived)
   uint32_t* region_any; // bit per 512^3-voxel region (4x4x4 chunks) (derived)
-  uint8_t* df;          // per 32^3 cell: Chebyshev distance (in cells, capped at MESO_DF_CAP) to the nearest non-empty cell;
+  uint8_t* df;          // per 32^3 cell: Chebyshev distance (in cells, capped at MESO_DF_K + 1) to the nearest non-empty cell;
                         // 0 = non-empty.  Conservative: never larger than the true distance (derived; rebuilt whenever
                         // voxels may have been ADDED, left alone by the carve, which only removes)
   uint8_t* df_tmp;      // scratch of the separable passes
@@ -72,7 +72,7 @@ void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick, unsigned int* d_tile_counter, int local_tile0 = 0, int local_tile_count = -1);
+                     uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
