@@ -386,21 +386,40 @@ def run_ours(args):
     shm = None
     if world > 1 and not args.no_host_fused:
         shm_path = "/dev/shm/meso_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid())
-        try:
-            if rank == 0:
+        # every rank runs the same two collectives whatever fails where (no rank may be left waiting in one of them)
+        created = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            try:
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize < R * px * 16 + (64 << 20):   # a short tmpfs would SIGBUS on first touch
+                    raise OSError("/dev/shm has %d MB free, need %d MB" % (st.f_bavail * st.f_frsize >> 20, R * px * 16 >> 20))
                 with open(shm_path, "wb") as f:
                     f.truncate(R * px * 16)
-            dist.barrier()
-            shm = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(R * px * 16,))
-            shm_dptr = ctx.host_register(shm)
-            ok = torch.ones(1, dtype=torch.int32, device=dev)
-        except Exception as e:
-            sys.stderr.write("bench: host-fused gather unavailable on rank %d (%s)\n" % (rank, e))
-            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+                created.fill_(1)
+            except Exception as e:
+                sys.stderr.write("bench: cannot create the shared host frame (%s)\n" % e)
+        dist.broadcast(created, src=0)
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        if int(created.item()) == 1:
+            try:
+                shm = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(R * px * 16,))
+                shm_dptr = ctx.host_register(shm)
+                ok.fill_(1)
+            except Exception as e:
+                sys.stderr.write("bench: host-fused gather unavailable on rank %d (%s)\n" % (rank, e))
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         host_fused = int(ok.item()) == 1
+        if not host_fused:
+            if shm is not None:
+                try:
+                    ctx.host_unregister(shm)
+                except Exception:
+                    pass
+                shm = None
+            if rank == 0 and os.path.exists(shm_path):
+                os.unlink(shm_path)
         if host_fused:
-            shm_views = [shm[i * px * 16:(i + 1) * px * 16].view(capi.HitRecord).reshape(height, width) for i in range(R)]
+            shm_views =[shm[i * px * 16:(i + 1) * px * 16].view(capi.HitRecord).reshape(height, width) for i in range(R)]
 
     def e2e_run(nsteps, rgba8=False):
         nonlocal consumed
@@ -679,23 +698,40 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
     counter and stores its 16 B quads into the list over NVLink.  The scene is the resident raymarch scene.  Returns None
     if IPC is unavailable.  Time = CUDA events on every rank around kernel + rendezvous, max over ranks."""
     cap = 1 << 25
-    try:
-        hq = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
-        hc = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
-        if rank == 0:
+    # every rank runs the same collectives whatever fails where
+    hq = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+    hc = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+    ok = torch.zeros(1, dtype=torch.int32, device=dev)
+    qptr0 = cptr0 = qptr = cptr = None
+    if rank == 0:
+        try:
             qptr0, cptr0 = ctx.device_alloc(cap * 16), ctx.device_alloc(8)
             hq.copy_(torch.from_numpy(ctx.ipc_export(qptr0)))
             hc.copy_(torch.from_numpy(ctx.ipc_export(cptr0)))
-        dist.broadcast(hq, src=0)
-        dist.broadcast(hc, src=0)
-        qptr = qptr0 if rank == 0 else ctx.ipc_open(hq.cpu().numpy())
-        cptr = cptr0 if rank == 0 else ctx.ipc_open(hc.cpu().numpy())
-        ok = torch.ones(1, dtype=torch.int32, device=dev)
-    except Exception as e:
-        sys.stderr.write("bench: fused quad gather unavailable on rank %d (%s)\n" % (rank, e))
-        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+            ok.fill_(1)
+        except Exception as e:
+            sys.stderr.write("bench: fused quad gather unavailable (%s)\n" % e)
+    dist.broadcast(ok, src=0)
+    dist.broadcast(hq, src=0)
+    dist.broadcast(hc, src=0)
+    if int(ok.item()) == 1:
+        try:
+            qptr = qptr0 if rank == 0 else ctx.ipc_open(hq.cpu().numpy())
+            cptr = cptr0 if rank == 0 else ctx.ipc_open(hc.cpu().numpy())
+        except Exception as e:
+            sys.stderr.write("bench: fused quad gather unavailable on rank %d (%s)\n" % (rank, e))
+            ok.fill_(0)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if int(ok.item()) != 1:
+        if rank != 0:
+            for p in (qptr, cptr):
+                if p is not None:
+                    ctx.ipc_close(p)
+        dist.barrier()
+        if rank == 0:
+            for p in (qptr0, cptr0):
+                if p is not None:
+                    ctx.device_free(p)
         return None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
