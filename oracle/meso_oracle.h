@@ -71,7 +71,7 @@ enum { ORC_SDF_SPHERE = 0, ORC_SDF_TERRAIN = 1 };
 enum { ORC_GRAN_BLOCK = 0, ORC_GRAN_VOXEL = 1 };
 enum { ORC_SIN_LIBM = 0, ORC_SIN_PORTABLE = 1 };
 enum { ORC_FLAG_SHADOW = 1 };
-enum { ORC_DDA_FLAT = 0, ORC_DDA_HIER = 1 };
+enum { ORC_DDA_FLAT = 0, ORC_DDA_HIER = 1, ORC_DDA_BOX = 2 };  /* BOX: HIER + unaligned empty cubes from a cell distance field */
 
 /* ---- a8/a9: SDFs and per-chunk generators (GeneratorHelper.h:19-150, VoxelMathHelper.h:25-33) */
 double orc_sin_portable(double x);

@@ -10,7 +10,10 @@
  *     and crossings are consumed in the total order key = (t, axis).  ORC_DDA_FLAT walks one voxel per step on
  *     an unbounded grid and is the definition; ORC_DDA_HIER skips empty chunks (128^3) / empty bricks (8^3) and
  *     re-derives the other two coordinates from the same keys, so it is bit-identical to FLAT by construction
- *     (tests/test_oracle_raymarch.py checks it).  The CUDA kernel implements HIER.
+ *     (tests/test_oracle_raymarch.py checks it).  ORC_DDA_BOX additionally leaves whole UNALIGNED cubes of empty
+ *     32^3 cells in one step (cubes from a brute-force Chebyshev distance over cells, cap 8): the kind of skip the
+ *     CUDA kernel makes (its own field: separable passes, cap 32, probe-ahead).  FLAT == HIER == BOX, byte for byte,
+ *     is the CPU-side evidence that the records do not depend on which empty boxes a walk skips.
  */
 #include "orc_internal.h"
 
@@ -27,6 +30,8 @@ typedef struct {
   const uint8_t* chunk_any;
   uint8_t* touched_chunk; /* may be NULL */
   uint8_t* touched_brick; /* indexed by payload slot; may be NULL */
+  const uint8_t* df;      /* ORC_DDA_BOX only: per 32^3 cell, Chebyshev distance in cells to the nearest non-empty cell */
+  int dd[3];              /* cells per axis */
 } Scene;
 
 static inline void ray_init(Ray* r, const float o[3], const float d[3]) {
@@ -131,6 +136,29 @@ static Trace trace(const Scene* s, const Ray* r, const int c0[3], int mode) {
     for (;;) {
       int L = cell_level(s, c);
       if (L == 0) { tr.hit = 1; break; }
+      if (mode == ORC_DDA_BOX && L >= ORC_BR) {
+        /* Empty brick or chunk: if the distance field certifies an empty cube of cells around this 32^3 cell, leave the
+         * whole cube (clamped to the grid) in one step -- an UNALIGNED box, unlike the aligned cells of ORC_DDA_HIER.
+         * Same keys, same order: any empty box is a legal skip. */
+        int k = s->df[(c[0] >> 5) + s->dd[0] * ((c[1] >> 5) + s->dd[1] * (c[2] >> 5))];
+        if (k > 0) {
+          int a = -1; float ta = 0.0f; int pl_a = 0;
+          for (int i = 0; i < 3; i++) {
+            if (!r->step[i]) continue;
+            int e = c[i] >> 5, pl;
+            if (r->step[i] > 0) { pl = (e + k) * 32; if (pl > s->n[i]) pl = s->n[i]; }
+            else { pl = (e - k + 1) * 32; if (pl < 0) pl = 0; }
+            float ti = plane_t(r, i, pl);
+            if (a < 0 || key_less(ti, i, ta, a)) { a = i; ta = ti; pl_a = pl; }
+          }
+          if (a < 0) break;
+          c[a] = r->step[a] > 0 ? pl_a : pl_a - 1;
+          for (int b = 0; b < 3; b++) if (b != a) c[b] = advance_axis(r, b, c[b], ta, a);
+          tr.axis = a; tr.t = ta; tr.steps++;
+          if (!inside(s, c)) break;
+          continue;
+        }
+      }
       int a = -1; float ta = 0.0f; int pl_a = 0;
       for (int i = 0; i < 3; i++) {
         if (!r->step[i]) continue;
@@ -236,6 +264,40 @@ void orc_raymarch(const OrcVolume* v, const OrcRaySetup* rs, int width, int heig
     any[c] = o != 0;
   }
   a.sc.chunk_any = any;
+  uint8_t* df = NULL;
+  if (mode == ORC_DDA_BOX) {
+    /* cell occupancy from the block masks, then a brute-force Chebyshev distance (cap 8 cells): deliberately not the
+     * device's algorithm, cap or data -- the point of this mode is that the records do not depend on the boxes */
+    const int dd0 = v->dims[0] * 4, dd1 = v->dims[1] * 4, dd2 = v->dims[2] * 4, CAP = 8;
+    const size_t nc = (size_t)dd0 * dd1 * dd2;
+    uint8_t* occ_cell = (uint8_t*)calloc(nc, 1);
+    df = (uint8_t*)calloc(nc, 1);
+    for (int ez = 0; ez < dd2; ez++) for (int ey = 0; ey < dd1; ey++) for (int ex = 0; ex < dd0; ex++) {
+      const int64_t ci = orc_cidx(v, ex >> 2, ey >> 2, ez >> 2);
+      uint64_t m = 0;
+      for (int bz = 4 * (ez & 3); bz < 4 * (ez & 3) + 4; bz++)
+        m |= v->occ[ci * ORC_WORDS + bz * 4 + (ey & 3)] & (0x000F000F000F000Full << (4 * (ex & 3)));
+      occ_cell[ex + (size_t)dd0 * (ey + (size_t)dd1 * ez)] = m != 0;
+    }
+    for (int ez = 0; ez < dd2; ez++) for (int ey = 0; ey < dd1; ey++) for (int ex = 0; ex < dd0; ex++) {
+      const size_t i = ex + (size_t)dd0 * (ey + (size_t)dd1 * ez);
+      int k = 0;
+      if (!occ_cell[i]) {
+        for (k = 1; k <= CAP; k++) {   /* k = smallest Chebyshev radius with a non-empty cell inside the cube */
+          int found = 0;
+          for (int z = ez - k; z <= ez + k && !found; z++) for (int y = ey - k; y <= ey + k && !found; y++) for (int x = ex - k; x <= ex + k; x++) {
+            if (x < 0 || y < 0 || z < 0 || x >= dd0 || y >= dd1 || z >= dd2) continue;
+            if (occ_cell[x + (size_t)dd0 * (y + (size_t)dd1 * z)]) { found = 1; break; }
+          }
+          if (found) break;
+        }
+        if (k > CAP) k = CAP + 1;
+      }
+      df[i] = (uint8_t)k;
+    }
+    free(occ_cell);
+    a.sc.df = df; a.sc.dd[0] = dd0; a.sc.dd[1] = dd1; a.sc.dd[2] = dd2;
+  }
   if (stats) {
     a.sc.touched_chunk = (uint8_t*)calloc((size_t)v->nchunks, 1);
     a.sc.touched_brick = (uint8_t*)calloc((size_t)(v->pool_n > 0 ? v->pool_n : 1), 1);
@@ -255,6 +317,7 @@ void orc_raymarch(const OrcVolume* v, const OrcRaySetup* rs, int width, int heig
     free(a.sc.touched_chunk); free(a.sc.touched_brick);
   }
   free(any);
+  free(df);
 }
 
 /* ---- reference-semantics restatement of the instanced draw ------------------------------------ */

@@ -42,7 +42,7 @@ SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
 SIN_LIBM, SIN_PORTABLE = 0, 1
 FLAG_SHADOW = 1
-DDA_FLAT, DDA_HIER = 0, 1
+DDA_FLAT, DDA_HIER, DDA_BOX = 0, 1, 2
 REF_SPHERE = (100.0, 0.0, 0.0, 50.0)   # GeneratorHelper.h:134
 
 
