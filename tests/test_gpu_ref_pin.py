@@ -1,0 +1,48 @@
+"""K1 + K2 on the GPU against rows produced by the REFERENCE'S OWN CODE (tests/golden/ref_build.npz, see
+tests/test_ref_pin.py): block lists in generator order, the four erode mips, the hidden-block cull, the emitted
+FGPUBlock instances and the FGPUChunk table of every chunk of the reference sphere (448 chunks, 523 155 blocks,
+201 936 instances) and of 48 terrain chunks -- no oracle in between.  The checker is the one the CPU suite feeds with
+the oracle's outputs (refprobe.check_grid_against_golden)."""
+import numpy as np
+import pytest
+
+import refprobe
+
+pytestmark = pytest.mark.gpu
+
+GOLD = dict(np.load(refprobe.GOLDEN))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from mesoengine_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _run(ctx, origin, dims, kind, params, stamp):
+    from mesoengine_b200 import capi
+    ctx.scene_create(origin, dims, 1 << 16)
+    ctx.voxelize_sdf(kind, params, capi.GRAN_BLOCK)
+    occ = ctx.volume_download()[0]
+    n = ctx.build_occupancy(stamp=stamp)
+    table, mips, inst = ctx.download_occupancy(n)
+    return occ, mips, table, inst[:n]
+
+
+def test_reference_sphere_on_gpu_equals_reference_rows(ctx):
+    from mesoengine_b200 import capi, scenes
+    origin, dims = (2, -4, -4), (8, 8, 8)
+    occ, mips, table, inst = _run(ctx, origin, dims, capi.SDF_SPHERE, scenes.REF_SPHERE, 9)
+    assert len(inst) == 201936
+    assert refprobe.check_grid_against_golden(GOLD, "sphere", refprobe.SPHERE_CHUNKS, origin, dims, occ, mips, table, inst, 9) == 448
+
+
+def test_terrain_on_gpu_equals_reference_rows(ctx):
+    """The device evaluates TestGenerator's hash with the portable sin; on these 48 chunks
+    (196 608 samples, 98 057 solid) every block comes out as the reference's libm build decided it."""
+    from mesoengine_b200 import capi
+    origin, dims = refprobe.TERRAIN_GRID
+    occ, mips, table, inst = _run(ctx, origin, dims, capi.SDF_TERRAIN, None, 5)
+    assert refprobe.check_grid_against_golden(GOLD, "terrain", refprobe.TERRAIN_CHUNKS, origin, dims, occ, mips, table, inst, 5) == 48

@@ -1,0 +1,88 @@
+"""The oracle pinned by the REFERENCE'S OWN CODE.
+
+oracle/_ref/libmeso_ref.so is the reference's hot-path headers (GeneratorHelper.h, VoxelMathHelper.h, Chunk.h,
+BinaryOccupancyVolume.h, ChunkManagerHelper.h, NearestMap.h, Comparator.h, TriplePlanarCube.h, GPUStructures.h,
+VoxelSceneConfig.h) compiled unmodified from /root/reference against stand-ins for the un-vendored third-party headers
+(oracle/ref_shim/, oracle/ref_driver.cpp).  tests/golden/ref_build.npz holds what that build answered on the battery
+in tests/refprobe.py (tools/gen_golden_from_ref_build.py).  Here:
+
+  * the repo oracle must answer the same battery bit for bit (runs anywhere; this is the pin);
+  * where the reference build is present, it must still reproduce the committed file (the file is not stale);
+  * whole-grid K1/K2 outputs in the layout the GPU produces are compared with the reference's rows chunk by chunk
+    (the same checker the GPU test uses, fed by the oracle here).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import refprobe
+
+GOLD = dict(np.load(refprobe.GOLDEN))
+
+
+def _diff(a, b):
+    bad = []
+    for k in sorted(set(a) | set(b)):
+        if k not in a or k not in b:
+            bad.append(k + " (missing)")
+            continue
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        if x.shape != y.shape or x.dtype != y.dtype or x.tobytes() != y.tobytes():
+            bad.append(k)
+    return bad
+
+
+@pytest.fixture(scope="module")
+def orc_answers(orc):
+    return refprobe.probe(refprobe.OrcBackend())
+
+
+def test_oracle_equals_reference_build_bit_for_bit(orc_answers):
+    assert _diff(orc_answers, GOLD) == []
+
+
+def test_reference_build_reproduces_committed_vectors():
+    so = refprobe.build_ref()
+    if so is None:
+        pytest.skip("no /root/reference and no prebuilt oracle/_ref/libmeso_ref.so here; the committed vectors stand in")
+    assert _diff(refprobe.probe(refprobe.RefBackend(so)), GOLD) == []
+
+
+def test_hand_derived_known_answers_hold_in_the_reference_build():
+    """SURVEY.md section 4's de-facto KATs, now answered by the reference's own GenerateSphere + cull."""
+    assert int(GOLD["sphere_counts"].sum()) == 523155
+    assert int(GOLD["sphere_instances"].sum()) == 201936
+    assert GOLD["layouts"].tolist()[:12] == [12, 0, 4, 8, 16, 0, 12, 160, 64, 128, 144, 16]
+    assert GOLD["triplanar_indices"].tolist() == [0, 1, 2, 3, 4, 5, 6, 1]
+    assert int(GOLD["view0_mode0_count"][0]) == 19661
+    # terrain rows are not trivial: full, empty and mixed chunks all occur
+    tc = GOLD["terrain_counts"]
+    assert (tc == 4096).any() and (tc == 0).any() and ((tc > 0) & (tc < 4096)).sum() >= 20
+
+
+def test_probe_covers_edge_inputs():
+    """empty block list, solid chunk, camera's own chunk (max(0, NaN)), non-normalised and axis-aligned views."""
+    assert GOLD["erode_mips"].shape == (9, 4, 512)
+    assert not GOLD["erode_mips"][7].any()                      # the empty list
+    solid = np.unpackbits(GOLD["erode_mips"][3], axis=1, bitorder="little")
+    assert solid[0].sum() == 4096 and solid[1].sum() == 14 ** 3 and solid[2].sum() == 12 ** 3 and solid[3].sum() == 10 ** 3
+    assert GOLD["chunk_importance"][7] == np.float32(1.0e6)      # own chunk sits inside the +-2 cube
+    assert np.isfinite(GOLD["chunk_importance"]).all()
+
+
+@pytest.mark.parametrize("sin_mode", ["libm", "portable"])
+def test_whole_grid_outputs_match_reference_rows(orc, sin_mode):
+    """The layout K1/K2 produce (block masks, mips 1..3, chunk table, instance list), from the oracle, against the
+    reference's per-chunk rows.  `portable` is the sin the GPU uses: on these chunks it decides every block as libm does."""
+    mode = orc.SIN_LIBM if sin_mode == "libm" else orc.SIN_PORTABLE
+    origin, dims = (2, -4, -4), (8, 8, 8)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, orc.REF_SPHERE, granularity=orc.GRAN_BLOCK, sin_mode=mode)
+    table, mips, inst = vol.build_occupancy(stamp=9)
+    n = refprobe.check_grid_against_golden(GOLD, "sphere", refprobe.SPHERE_CHUNKS, origin, dims, vol.occ(), mips, table, inst, 9)
+    assert n == 448 and len(inst) == 201936
+
+    origin, dims = refprobe.TERRAIN_GRID
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_TERRAIN, None, granularity=orc.GRAN_BLOCK, sin_mode=mode)
+    table, mips, inst = vol.build_occupancy(stamp=5)
+    assert refprobe.check_grid_against_golden(GOLD, "terrain", refprobe.TERRAIN_CHUNKS, origin, dims, vol.occ(), mips, table, inst, 5) == 48
