@@ -6,9 +6,15 @@
  * The product path (mesoengine_b200/, include/meso_cuda.h) never links or calls it.
  *
  * Parity status: the reference ships no tests, golden vectors or fixtures
- * and cannot be compiled or run in this image (needs glm, Boost 1.83, Vulkan, GLFW, MSVC).
- * The functions below that restate reference code cite the file:line they follow and are pinned
- * by the hand-derivable known-answer facts of SURVEY.md section 4 (tests/test_oracle_kat.py).
+ * and its application cannot be built or run in this image (needs glm, Boost 1.83, Vulkan, GLFW,
+ * MSVC).  Its hot-path HEADERS are compiled unmodified into oracle/_ref/libmeso_ref.so against
+ * stand-ins for the absent third-party headers (ref_driver.cpp, ref_shim/); the functions below that
+ * restate reference code cite the file:line they follow and are pinned (a) bit for bit by that
+ * build -- generators, hash/noise, index helpers, erosion/mips/cull, importance, view-cone set,
+ * Fibonacci directions, re-centring (tests/test_ref_pin.py, tests/golden/ref_build.npz) -- and
+ * (b) by the hand-derivable known-answer facts of SURVEY.md section 4 (tests/test_oracle_kat.py).
+ * The per-pixel result (GLSL) and the camera matrices (un-vendored Cookbook/glm code) are restated
+ * from the text / the published definitions only.
  * Everything the reference does not contain (voxel-in-brick level, DDA order, shadow rays,
  * face-cull + greedy merge, sphere carve) is DEFINED here: "parity unpinned by reference;
  * bit-exact vs repo oracle".
