@@ -458,3 +458,56 @@ def check_grid_against_golden(gold, prefix, chunks, origin, dims, occ, mips123, 
         else:
             assert tuple(t["ChunkLocation"]) == (0x7FFFFFFF,) * 3      # FGPUChunk's default = invalid (Chunk.h:29)
     return len(chunks)
+
+
+# ---- the reference's voxel shaders, executed (oracle/ref_glsl_driver.cpp) ---------------------------------------------
+DRAW_GOLDEN = os.path.join(_ROOT, "tests", "golden", "ref_draw.npz")
+DRAW_W, DRAW_H, DRAW_EYES, DRAW_STAMP = 96, 54, (0, 2, 5), 5
+
+
+def draw_scene(orc):
+    """The scene of the draw comparison: the block-granular 256^3 V-sphere after the hidden-block cull (FGPUChunk table +
+    FGPUBlock instances from the oracle, themselves pinned by the reference build above) and three orbit cameras."""
+    import scenes
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_BLOCK)
+    table, _, inst = vol.build_occupancy(stamp=DRAW_STAMP)
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cams = [orc.camera_uniform(eyes[i], ctr, width=DRAW_W, height=DRAW_H) for i in DRAW_EYES]
+    return origin, dims, vol, table, inst, cams
+
+
+def ref_draw(lib, cam, scene_cfg, table, inst, indices, w, h):
+    """cmdDrawIndexed through the reference's own VS/FS text.  -> depth, instance, colour, normal, n_behind"""
+    depth = np.zeros((h, w), dtype=np.float32)
+    instance = np.zeros((h, w), dtype=np.int32)
+    color = np.zeros((h, w, 4), dtype=np.float32)
+    normal = np.zeros((h, w, 3), dtype=np.float32)
+    idx = np.ascontiguousarray(indices, dtype=np.uint16)
+    lib.ref_draw_instanced.restype = C.c_int64
+    behind = lib.ref_draw_instanced(_p(cam), _p(scene_cfg), _p(np.ascontiguousarray(table)), _p(np.ascontiguousarray(inst)),
+                                    C.c_int64(len(inst)), _p(idx), C.c_int(len(idx)), C.c_int(w), C.c_int(h),
+                                    _p(depth), _p(instance), _p(color), _p(normal))
+    return depth, instance, color, normal, int(behind)
+
+
+def probe_draw(backend, orc):
+    """-> {name: array}: per camera, what the reference's shaders + the fixed-function rules put into every pixel."""
+    _, _, _, table, inst, cams = draw_scene(orc)
+    scene_cfg = orc.default_scene_config()
+    idx = backend.triplanar_indices()
+    out = {}
+    for i, cam in zip(DRAW_EYES, cams):
+        depth, instance, color, normal, behind = ref_draw(backend.lib, cam, scene_cfg, table, inst, idx, DRAW_W, DRAW_H)
+        assert behind == 0
+        out[f"eye{i}_depth"], out[f"eye{i}_instance"], out[f"eye{i}_color"], out[f"eye{i}_normal"] = depth, instance, color, normal
+    out["vs_invalid_instance"] = np.stack([_vs(backend.lib, cams[0], scene_cfg, table, 0x7FFFFFFF, 0, DRAW_STAMP, 0),
+                                           _vs(backend.lib, cams[0], scene_cfg, table, int(inst["ChunkIndex"][0]), 0, DRAW_STAMP + 1, 3)])
+    return out
+
+
+def _vs(lib, cam, scene_cfg, table, chunk_index, packed_loc, stamp, vertex):
+    out = np.zeros(10, dtype=np.float32)
+    lib.ref_vs_invoke(_p(cam), _p(scene_cfg), _p(np.ascontiguousarray(table)), C.c_uint32(chunk_index), C.c_uint32(packed_loc),
+                      C.c_uint32(stamp), C.c_int(vertex), _p(out))
+    return out

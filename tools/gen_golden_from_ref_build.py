@@ -14,6 +14,7 @@ import sys
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refprobe  # noqa: E402
 
@@ -26,6 +27,10 @@ def main():
     np.savez_compressed(refprobe.GOLDEN, **out)
     n = sum(np.asarray(v).nbytes for v in out.values())
     print(f"{refprobe.GOLDEN}: {len(out)} arrays, {n} bytes raw, {os.path.getsize(refprobe.GOLDEN)} bytes on disk")
+    import orc
+    draw = refprobe.probe_draw(refprobe.RefBackend(so), orc)
+    np.savez_compressed(refprobe.DRAW_GOLDEN, **draw)
+    print(f"{refprobe.DRAW_GOLDEN}: {len(draw)} arrays, {os.path.getsize(refprobe.DRAW_GOLDEN)} bytes on disk")
     print("sphere: %d blocks, %d instances over %d chunks" % (out["sphere_counts"].sum(), out["sphere_instances"].sum(), len(out["sphere_counts"])))
     print("terrain: %d blocks, %d instances over %d chunks" % (out["terrain_counts"].sum(), out["terrain_instances"].sum(), len(out["terrain_counts"])))
 
