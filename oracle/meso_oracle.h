@@ -13,8 +13,9 @@
  * build -- generators, hash/noise, index helpers, erosion/mips/cull, importance, view-cone set,
  * Fibonacci directions, re-centring (tests/test_ref_pin.py, tests/golden/ref_build.npz) -- and
  * (b) by the hand-derivable known-answer facts of SURVEY.md section 4 (tests/test_oracle_kat.py).
- * The per-pixel result (GLSL) and the camera matrices (un-vendored Cookbook/glm code) are restated
- * from the text / the published definitions only.
+ * The per-pixel result is pinned by executing the reference's own GLSL text (ref_glsl_driver.cpp:
+ * block, face, colour <= 1 LSB, depth 1e-5); the camera matrices (un-vendored Cookbook/glm code)
+ * are restated from the published definitions only.
  * Everything the reference does not contain (voxel-in-brick level, DDA order, shadow rays,
  * face-cull + greedy merge, sphere carve) is DEFINED here: "parity unpinned by reference;
  * bit-exact vs repo oracle".

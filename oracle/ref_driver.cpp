@@ -11,8 +11,9 @@
  *
  * What this pins: oracle/orc_sdf.c, orc_occupancy.c, orc_resident.c and parts of orc_camera.c
  * (tests/test_ref_pin.py, and the golden vectors tools/gen_golden_from_ref_build.py writes into tests/golden/).
- * What it cannot pin: the per-pixel result (GLSL in Samples/SimpleVoxel.cpp:72-224, needs Vulkan), the camera
- * matrices (Cookbook Camera.h is un-vendored), FChunkPool placement (threads + LVK buffers).
+ * The per-pixel result (GLSL in Samples/SimpleVoxel.cpp:72-224) is handled next door in ref_glsl_driver.cpp.
+ * What cannot be pinned this way: the camera matrices (Cookbook Camera.h is un-vendored), FChunkPool placement
+ * (threads + LVK buffers).
  *
  * Only tests/, tools/gen_golden_from_ref_build.py and __graft_entry__.build() touch this file or its output.
  */
