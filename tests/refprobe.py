@@ -18,6 +18,8 @@ REF_SO = os.path.join(_ROOT, "oracle", "_ref", "libmeso_ref.so")
 GOLDEN = os.path.join(_ROOT, "tests", "golden", "ref_build.npz")
 
 Candidate = np.dtype([("Importance", "<f4"), ("Offset", "<i4", (3,))])
+Camera160 = np.dtype([("Projection", "<f4", (16,)), ("View", "<f4", (16,)), ("CameraChunkLocation", "<i4", (4,)),
+                      ("SubCameraLocation", "<f4", (4,))])      # FGPUUniformCamera, GPUStructures.h:36-41
 
 
 def build_ref():
@@ -501,6 +503,13 @@ def probe_draw(backend, orc):
         depth, instance, color, normal, behind = ref_draw(backend.lib, cam, scene_cfg, table, inst, idx, DRAW_W, DRAW_H)
         assert behind == 0
         out[f"eye{i}_depth"], out[f"eye{i}_instance"], out[f"eye{i}_color"], out[f"eye{i}_normal"] = depth, instance, color, normal
+        # what the draw was given, so that a consumer needs nothing but this file: the camera block and, per covered
+        # pixel, the winning instance's ViewChunkRelativeBlockOffset (SimpleVoxel.cpp:177) from its FGPUBlock / FGPUChunk
+        out[f"eye{i}_camera"] = np.frombuffer(cam.tobytes(), dtype=np.uint8).copy()
+        k = np.maximum(instance, 0)
+        cam_chunk = cam["CameraChunkLocation"][0][:3].astype(np.int64)
+        blk = (table["ChunkLocation"][inst["ChunkIndex"][k]].astype(np.int64) - cam_chunk) * 16 + inst["BlockLocation"][k][..., :3].astype(np.int64)
+        out[f"eye{i}_block"] = np.where((instance >= 0)[..., None], blk, 0).astype(np.int32)
     out["vs_invalid_instance"] = np.stack([_vs(backend.lib, cams[0], scene_cfg, table, 0x7FFFFFFF, 0, DRAW_STAMP, 0),
                                            _vs(backend.lib, cams[0], scene_cfg, table, int(inst["ChunkIndex"][0]), 0, DRAW_STAMP + 1, 3)])
     return out
@@ -511,3 +520,46 @@ def _vs(lib, cam, scene_cfg, table, chunk_index, packed_loc, stamp, vertex):
     lib.ref_vs_invoke(_p(cam), _p(scene_cfg), _p(np.ascontiguousarray(table)), C.c_uint32(chunk_index), C.c_uint32(packed_loc),
                       C.c_uint32(stamp), C.c_int(vertex), _p(out))
     return out
+
+
+def check_records_against_ref_draw(draw, eye, rec, origin_chunk, edge=1e-3):
+    """rec: (H,W) hit records of the DDA (from the CUDA kernel, or from the oracle it is bit-identical to) for camera
+    draw[f"eye{eye}_camera"] over the draw_scene() volume.  Against the frame the reference's own shaders produced:
+    same hit / miss, same block, same face, colour within 1 LSB -- on every pixel farther than `edge` block units from
+    a face edge (for hits: read off the interpolated varying, which is the local position - 0.5) and, for misses, not
+    adjacent to a covered pixel.  Returns (#hits compared, #misses compared, #skipped)."""
+    inst, nrm, col = draw[f"eye{eye}_instance"], draw[f"eye{eye}_normal"].astype(np.float64), draw[f"eye{eye}_color"]
+    cam = np.frombuffer(draw[f"eye{eye}_camera"].tobytes(), dtype=Camera160)[0]
+    cam_chunk = cam["CameraChunkLocation"][:3].astype(np.int64)
+    w0, w1 = rec["w0"].astype(np.int64), rec["w1"].astype(np.int64)
+    d_hit = ((w1 >> 20) & 1).astype(bool)
+    d_face = (w1 >> 16) & 7
+    vox = np.stack([w0 & 0xFFFF, w0 >> 16, w1 & 0xFFFF], -1)
+    d_blk = (vox >> 3) + (np.asarray(origin_chunk, dtype=np.int64) - cam_chunk) * 16
+    d_rgba = np.stack([(rec["rgba"].astype(np.int64) >> (8 * c)) & 0xFF for c in range(4)], -1)
+
+    covered = inst >= 0
+    a = np.abs(nrm)
+    ax = a.argmax(-1)
+    top = np.take_along_axis(a, ax[..., None], -1)[..., 0]
+    second = np.sort(a, -1)[..., 1]
+    safe_hit = covered & (np.abs(top - 0.5) < 1e-6) & (second < 0.5 - edge)
+    grown = covered.copy()
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            sh = np.zeros_like(covered)
+            ys, yd = (slice(max(dy, 0), covered.shape[0] + min(dy, 0)), slice(max(-dy, 0), covered.shape[0] + min(-dy, 0)))
+            xs, xd = (slice(max(dx, 0), covered.shape[1] + min(dx, 0)), slice(max(-dx, 0), covered.shape[1] + min(-dx, 0)))
+            sh[yd, xd] = covered[ys, xs]
+            grown |= sh
+    safe_miss = ~grown
+    assert d_hit[safe_hit].all(), "DDA misses where the reference draw covers the pixel"
+    assert not d_hit[safe_miss].any(), "DDA hits where the reference draw leaves the clear colour"
+    assert np.array_equal(d_blk[safe_hit], draw[f"eye{eye}_block"].astype(np.int64)[safe_hit]), "block"
+    sign = np.take_along_axis(nrm, ax[..., None], -1)[..., 0] > 0
+    assert np.array_equal(d_face[safe_hit], (2 * ax + sign)[safe_hit]), "face"
+    r8 = np.floor(col.astype(np.float64) * 255.0 + 0.5).astype(np.int64)
+    assert (np.abs(d_rgba - r8)[safe_hit] <= 1).all(), "colour differs by more than 1 LSB"
+    miss_rgba = d_rgba[safe_miss]
+    assert (miss_rgba == np.array([0, 0, 0, 255])).all(), "miss colour is not the clear colour (0,0,0,1)"
+    return int(safe_hit.sum()), int(safe_miss.sum()), int((~safe_hit & ~safe_miss).sum())

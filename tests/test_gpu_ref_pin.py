@@ -46,3 +46,20 @@ def test_terrain_on_gpu_equals_reference_rows(ctx):
     origin, dims = refprobe.TERRAIN_GRID
     occ, mips, table, inst = _run(ctx, origin, dims, capi.SDF_TERRAIN, None, 5)
     assert refprobe.check_grid_against_golden(GOLD, "terrain", refprobe.TERRAIN_CHUNKS, origin, dims, occ, mips, table, inst, 5) == 48
+
+
+DRAW = dict(np.load(refprobe.DRAW_GOLDEN))
+
+
+@pytest.mark.parametrize("eye_idx", refprobe.DRAW_EYES)
+def test_raymarch_on_gpu_against_the_executed_reference_shaders(ctx, eye_idx):
+    """K4 against the frame the reference's own vertex / fragment shader text produced (tests/golden/ref_draw.npz, see
+    oracle/ref_glsl_driver.cpp): same hit / miss, block, face, colour within 1 LSB away from face edges."""
+    from mesoengine_b200 import capi, scenes
+    origin, dims, params = scenes.sphere_scene(256)
+    ctx.scene_create(origin, dims, 1 << 16)
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_BLOCK)
+    cam = np.frombuffer(DRAW[f"eye{eye_idx}_camera"].tobytes(), dtype=capi.Camera).copy()
+    rec = ctx.raymarch(cam, refprobe.DRAW_W, refprobe.DRAW_H, shadow=False)
+    hits, misses, skipped = refprobe.check_records_against_ref_draw(DRAW, eye_idx, rec, origin)
+    assert hits > 2000 and misses > 1500 and skipped < 0.15 * rec.size, (hits, misses, skipped)

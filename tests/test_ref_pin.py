@@ -160,3 +160,14 @@ def test_restated_draw_and_dda_match_the_executed_reference_shaders(orc, eye_idx
             d8 = [(int(rec["rgba"][py, px]) >> (8 * c)) & 0xFF for c in range(4)]
             assert all(abs(a - e) <= 1 for a, e in zip(d8, r8)), (px, py, d8, r8)                  # (D) colour ~ (R) colour
     assert checked > 1500 and skipped < 0.08 * w * h, (checked, skipped)
+
+
+@pytest.mark.parametrize("eye_idx", refprobe.DRAW_EYES)
+def test_dda_frame_against_reference_draw_whole_frame(orc, eye_idx):
+    """The checker tests/test_gpu_ref_pin.py applies to the CUDA kernel's frame, fed here with the oracle's DDA frame."""
+    origin, dims, vol, table, inst, cams = refprobe.draw_scene(orc)
+    cam = np.frombuffer(DRAW[f"eye{eye_idx}_camera"].tobytes(), dtype=orc.Camera)
+    assert cam.tobytes() == cams[refprobe.DRAW_EYES.index(eye_idx)].tobytes()
+    rec = vol.raymarch(orc.ray_setup(cam, origin, refprobe.DRAW_W, refprobe.DRAW_H), refprobe.DRAW_W, refprobe.DRAW_H, shadow=False)
+    hits, misses, skipped = refprobe.check_records_against_ref_draw(DRAW, eye_idx, rec, origin)
+    assert hits > 2000 and misses > 1500 and skipped < 0.15 * rec.size, (hits, misses, skipped)
