@@ -164,7 +164,7 @@ def test_restated_draw_and_dda_match_the_executed_reference_shaders(orc, eye_idx
 
 @pytest.mark.parametrize("eye_idx", refprobe.DRAW_EYES)
 def test_dda_frame_against_reference_draw_whole_frame(orc, eye_idx):
-    """The checker tests/test_gpu_ref_pin.py applies to the CUDA kernel's frame, fed here with the oracle's DDA frame."""
+    """The checker tests/test_zz_gpu_ref_pin.py applies to the CUDA kernel's frame, fed here with the oracle's DDA frame."""
     origin, dims, vol, table, inst, cams = refprobe.draw_scene(orc)
     cam = np.frombuffer(DRAW[f"eye{eye_idx}_camera"].tobytes(), dtype=orc.Camera)
     assert cam.tobytes() == cams[refprobe.DRAW_EYES.index(eye_idx)].tobytes()
