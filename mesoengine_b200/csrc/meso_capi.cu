@@ -102,6 +102,8 @@ extern "C" {
 const char* meso_last_error(void) { return g_err.c_str(); }
 int meso_abi_version(void) { return 1; }
 
+static int ctx_init(MesoCtx* c);
+
 int meso_ctx_create(int device, MesoCtx** out) {
   if (!out) return fail(MESO_ERR_ARGUMENT, "meso_ctx_create: out is null");
   *out = nullptr;
@@ -119,6 +121,13 @@ int meso_ctx_create(int device, MesoCtx** out) {
   MesoCtx* c = new MesoCtx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  const int r = ctx_init(c);
+  if (r != MESO_OK) { meso_ctx_destroy(c); return r; }   // g_err keeps the failing call's message
+  *out = c;
+  return MESO_OK;
+}
+
+static int ctx_init(MesoCtx* c) {
   CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   CK(cudaMalloc(&c->d_tmp_count, 16));
@@ -132,7 +141,6 @@ int meso_ctx_create(int device, MesoCtx** out) {
   }
   CK(cudaMalloc(&c->d_overflow, sizeof(int)));
   CK(cudaMemset(c->d_overflow, 0, sizeof(int)));
-  *out = c;
   return MESO_OK;
 }
 
@@ -203,7 +211,16 @@ int meso_ctx_set_partition(MesoCtx* c, int rank, int world) {
 int meso_device_sm_count(MesoCtx* c) { return c ? c->sm_count : 0; }
 int64_t meso_launch_count(MesoCtx* c) { return c ? c->launches : 0; }
 
+static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const int32_t origin[3], const int32_t dims[3], uint32_t max_bricks);
+
 int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const int32_t origin[3], const int32_t dims[3], uint32_t max_bricks) {
+  const int r = scene_alloc(c, cfg, origin, dims, max_bricks);
+  // an allocation that failed half-way (out of memory at a large grid) leaves no scene and no device memory behind
+  if (r != MESO_OK && c && !c->has_scene) free_scene(c);
+  return r;
+}
+
+static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const int32_t origin[3], const int32_t dims[3], uint32_t max_bricks) {
   if (!c || !cfg || !origin || !dims) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: null argument");
   // the kernels are specialised for the reference's constants (VoxelSceneConfig.h:22-24)
   if (cfg->BlockResolution != 8 || cfg->ChunkResolution != 16 || cfg->BlockSize != 1.0f || cfg->ChunkSize != 16.0f)
@@ -266,6 +283,16 @@ int meso_scene_create(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const in
     CK(cudaSetDevice((c)->device));                                                 \
   } while (0)
 
+// Frames started with meso_raymarch_async are traced on the band streams and may still be reading the volume when the
+// call returns.  Every entry point that rewrites the volume in place orders its work on the context's stream behind the
+// traversal (not the host copy) of the frames still in flight; with no frame in flight this does nothing.
+static int join_frames(MesoCtx* c) {
+  for (int i = 0; i < MESO_FRAME_RING; i++)
+    if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
+  return MESO_OK;
+}
+#define JOIN_FRAMES(c) do { const int jr__ = join_frames(c); if (jr__ != MESO_OK) return jr__; } while (0)
+
 static int check_overflow(MesoCtx* c, const char* what) {
   int h = 0;
   CK(cudaMemcpyAsync(&h, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -283,6 +310,7 @@ int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granular
   if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown granularity");
   if (kind == MESO_SDF_SPHERE && !params) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: sphere needs params");
   c->streaming = false;  // the whole grid is regenerated: a stream in progress ends (meso_stream_begin starts a new one)
+  JOIN_FRAMES(c);
   launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
   CK_LAST("voxelize");
   return check_overflow(c, "meso_voxelize_sdf");
@@ -295,6 +323,7 @@ int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, co
   const size_t nc = (size_t)c->v.nchunks;
   for (int64_t i = 0; i < n; i++)
     if (keys[i] >= (uint64_t)nc * MESO_BLOCKS) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: key out of range");
+  JOIN_FRAMES(c);
   CK(cudaMemcpyAsync(c->v.occ, occ, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->v.full, full, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(c->v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
@@ -648,6 +677,7 @@ int meso_mesh(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads) {
 int meso_carve_sphere(MesoCtx* c, const int32_t center[3], int32_t radius, int64_t* n_dirty) {
   NEED_SCENE(c);
   if (!center || radius < 0 || radius > 30000) return fail(MESO_ERR_ARGUMENT, "meso_carve_sphere: bad argument");
+  JOIN_FRAMES(c);
   launch_carve(c->lc(), c->v, center, radius, c->d_dirty, c->cap_dirty, c->d_dirty_count, c->d_overflow);
   CK_LAST("carve");
   uint32_t n = 0;
@@ -803,6 +833,7 @@ int meso_stream_begin(MesoCtx* c, int kind, const double params[4], int granular
   const size_t nc = (size_t)v.nchunks;
   if (!c->d_loaded) CK(cudaMalloc(&c->d_loaded, (size_t)v.chunk_words * 4));
   if (!c->d_stream_stats) CK(cudaMalloc(&c->d_stream_stats, 16));
+  JOIN_FRAMES(c);
   // empty volume: nothing is generated yet (FChunkPool::Initialize, ChunkPool.h:283-345)
   CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
   CK(cudaMemsetAsync(v.of, 0, nc * 64 * 16, c->stream)); CK(cudaMemsetAsync(v.cells, 0, nc * 8, c->stream));
@@ -836,6 +867,7 @@ int meso_stream_update_async(MesoCtx* c, const int32_t cam[3], const float forwa
     CK(cudaMalloc(&c->d_stream_list, (size_t)max_new * 4));
     c->stream_list_cap = max_new;
   }
+  JOIN_FRAMES(c);
   launch_select_view(c->lc(), forward, *view, c->d_sel_keys, c->d_sel_count, c->d_sel_out, c->sel_cap);
   launch_stream_worklist(c->lc(), c->v, c->d_sel_out, c->d_sel_count, c->sel_cap, cam, c->d_loaded, max_new, c->d_stream_list, c->d_stream_stats);
   launch_voxelize_list(c->lc(), c->v, c->stream_kind, c->stream_params, c->stream_gran, c->d_overflow, c->d_stream_list, c->d_stream_stats, max_new);
