@@ -365,12 +365,16 @@ def probe(b):
     r["fibonacci_f64_8"] = b.fibonacci_f64(8, True)
     r["fibonacci_f64_100_raw"] = b.fibonacci_f64(100, False)
 
-    cams = rng.integers(-50, 50, (1500, 3)).astype(np.int32)
+    # 30 cameras x 50 chunk locations (inputs are stored too: the GPU test feeds them to meso_chunk_importance)
+    cams = np.repeat(rng.integers(-50, 50, (30, 3)).astype(np.int32), 50, axis=0)
+    fw30 = rng.normal(size=(30, 3)).astype(np.float32)
+    fw30[::3] /= np.linalg.norm(fw30[::3], axis=1, keepdims=True)
+    fw = np.repeat(fw30, 50, axis=0)
     offs = np.concatenate([rng.integers(-3, 4, (500, 3)), rng.integers(-70, 70, (1000, 3))]).astype(np.int32)
-    fw = rng.normal(size=(1500, 3)).astype(np.float32)
-    fw[::3] /= np.linalg.norm(fw[::3], axis=1, keepdims=True)
+    offs = offs[rng.permutation(1500)]
     offs[7] = 0                                              # the camera's own chunk: max(0, NaN)
-    r["chunk_importance"] = np.array([b.chunk_importance(c, f, c + o) for c, f, o in zip(cams, fw, offs)], dtype=np.float32)
+    r["chunk_importance_cam"], r["chunk_importance_fwd"], r["chunk_importance_loc"] = cams, fw, cams + offs
+    r["chunk_importance"] = np.array([b.chunk_importance(c, f, l) for c, f, l in zip(cams, fw, cams + offs)], dtype=np.float32)
     blocks = rng.integers(0, 16, (1500, 3)).astype(np.uint8)
     r["block_importance"] = np.array([b.block_importance(c, f, c + o, bl) for c, f, o, bl in zip(cams, fw, offs // 8, blocks)], dtype=np.float32)
 
@@ -390,6 +394,7 @@ def probe(b):
 
     dirs = b.fibonacci_f32(256)
     qs = rng.normal(size=(400, 3)).astype(np.float32)
+    r["nearest_direction_query"] = qs
     r["nearest_direction"] = np.array([b.nearest_direction(dirs, q) for q in qs], dtype=np.uint32)
     n, first = b.bake_and_query(16, 8, 3, 120.0, (0.3, 0.1, -0.9))
     r["bake_query_count"] = np.array([n], dtype=np.int64)

@@ -67,6 +67,7 @@ def test_probe_covers_edge_inputs():
     assert not GOLD["erode_mips"][7].any()                      # the empty list
     solid = np.unpackbits(GOLD["erode_mips"][3], axis=1, bitorder="little")
     assert solid[0].sum() == 4096 and solid[1].sum() == 14 ** 3 and solid[2].sum() == 12 ** 3 and solid[3].sum() == 10 ** 3
+    assert (GOLD["chunk_importance_loc"][7] == GOLD["chunk_importance_cam"][7]).all()
     assert GOLD["chunk_importance"][7] == np.float32(1.0e6)      # own chunk sits inside the +-2 cube
     assert np.isfinite(GOLD["chunk_importance"]).all()
 
@@ -171,3 +172,15 @@ def test_dda_frame_against_reference_draw_whole_frame(orc, eye_idx):
     rec = vol.raymarch(orc.ray_setup(cam, origin, refprobe.DRAW_W, refprobe.DRAW_H), refprobe.DRAW_W, refprobe.DRAW_H, shadow=False)
     hits, misses, skipped = refprobe.check_records_against_ref_draw(DRAW, eye_idx, rec, origin)
     assert hits > 2000 and misses > 1500 and skipped < 0.15 * rec.size, (hits, misses, skipped)
+
+
+# ---- the product's pure-host ABI functions against the reference build (no device needed) ------------------------------
+def test_product_baked_direction_equals_reference_nearest_map():
+    """meso_baked_direction (libmeso_b200.so, host code) == TNearestMap::Query over GetFibonacciSphere<float>(256), the
+    table lookup of ChunkManager.h:106-124, on the 400 queries the reference build answered."""
+    from mesoengine_b200 import capi
+    dirs = GOLD["fibonacci_f32_256"]
+    for q, want in zip(GOLD["nearest_direction_query"], GOLD["nearest_direction"]):
+        d, idx = capi.baked_direction(256, q)
+        assert idx == int(want)
+        assert d.view(np.uint32).tolist() == dirs[idx].view(np.uint32).tolist()

@@ -63,3 +63,27 @@ def test_raymarch_on_gpu_against_the_executed_reference_shaders(ctx, eye_idx):
     rec = ctx.raymarch(cam, refprobe.DRAW_W, refprobe.DRAW_H, shadow=False)
     hits, misses, skipped = refprobe.check_records_against_ref_draw(DRAW, eye_idx, rec, origin)
     assert hits > 2000 and misses > 1500 and skipped < 0.15 * rec.size, (hits, misses, skipped)
+
+
+@pytest.mark.parametrize("i,mode", [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (0, 1), (1, 1)])
+def test_select_view_on_gpu_equals_reference_queue(ctx, i, mode):
+    """K6 selection against FChunkManageHelper::GetDesiredShowChunkLocationByView / ...Simple as the reference build ran
+    them: same candidate set with the same importance bits, and the same importance sequence in pop order (the order
+    among equal importances is unspecified in std::priority_queue)."""
+    from mesoengine_b200 import capi
+    got = ctx.select_view_chunks(refprobe.VIEWS[i], capi.view_config(24, 6, 120.0, mode))
+    assert len(got) == int(GOLD[f"view{i}_mode{mode}_count"][0])
+    canon = got[np.lexsort((got["Offset"][:, 2], got["Offset"][:, 1], got["Offset"][:, 0]))]
+    assert canon.dtype.itemsize == 16
+    assert np.array_equal(refprobe._sha(canon), GOLD[f"view{i}_mode{mode}_set_sha1"])
+    assert np.array_equal(refprobe._sha(got["Importance"].copy()), GOLD[f"view{i}_mode{mode}_pop_importance_sha1"])
+
+
+def test_chunk_importance_on_gpu_equals_reference(ctx):
+    """K6 importance against FImportanceComputeInfo::CalculateChunkImportance as the reference build ran it
+    (30 cameras x 50 chunks, incl. the camera's own chunk where the reference relies on max(0, NaN) = 0)."""
+    cam, fwd, loc = GOLD["chunk_importance_cam"], GOLD["chunk_importance_fwd"], GOLD["chunk_importance_loc"]
+    want = GOLD["chunk_importance"]
+    for g in range(0, len(want), 50):
+        got = ctx.chunk_importance(cam[g], fwd[g], loc[g:g + 50])
+        assert np.array_equal(got.view(np.uint32), want[g:g + 50].view(np.uint32)), g
