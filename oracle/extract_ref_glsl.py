@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Cut the voxel vertex / fragment shader bodies out of the reference's Samples/SimpleVoxel.cpp into oracle/_ref/*.inc
+"""Cut the voxel vertex / fragment shader bodies out of the reference's Samples/SimpleVoxel.cpp into a scratch directory (oracle/_ref/.gen, removed after the compile)
 so that ref_driver.cpp can compile and EXECUTE the reference's own shader text (ref_shim/glsl_compat.h supplies the
 GLSL vocabulary).  The output is a build product under oracle/_ref/ (git-ignored); nothing from the reference is copied
 into the repository.  TEST INFRASTRUCTURE.

@@ -1,7 +1,7 @@
 /*
  * ref_glsl_driver.cpp -- the reference's voxel VERTEX and FRAGMENT shader text, executed on the CPU.  TEST INFRASTRUCTURE.
  *
- * oracle/_ref/ref_voxel_vs.inc / ref_voxel_fs.inc are cut out of /root/reference/Samples/SimpleVoxel.cpp at build time
+ * ref_voxel_vs.inc / ref_voxel_fs.inc are cut out of /root/reference/Samples/SimpleVoxel.cpp at build time
  * (oracle/extract_ref_glsl.py; syntax-only edits) and compiled here against ref_shim/glsl_compat.h.  What is the
  * reference's: instance validity, chunk/block offset arithmetic, octant choice, the 56-corner table, vertex
  * positions, Projection * View * position, the fragment colour.  What is NOT the reference's and is written here from

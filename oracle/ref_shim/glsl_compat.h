@@ -3,7 +3,7 @@
  *
  * oracle/extract_ref_glsl.py cuts the function bodies of the reference's voxel vertex and fragment shaders out of
  * Samples/SimpleVoxel.cpp (from `ivec3 UnpackU8Vec3` to the end of `main`, and the fragment `main`) into
- * oracle/_ref/*.inc with three textual changes (array constructor -> braces, `.xyz` -> `.xyz()`, `main` renamed).
+ * a scratch directory (removed after the compile) with three textual changes (array constructor -> braces, `.xyz` -> `.xyz()`, `main` renamed).
  * This header supplies what that text needs to compile as C++: fp32 vectors / matrices with GLSL's operator set
  * (literals such as 0.5 are GLSL floats: every scalar operand is converted to float first), column-major mat4, and the
  * interface variables the shader's declarations (built from C++ string pieces in the reference, SimpleVoxel.cpp:41-62)
