@@ -155,6 +155,54 @@ def cpu_step(orc, vol, cam, width, height, bands, nthreads):
     return rays, recs
 
 
+def reference_code_timings(nthreads):
+    """The REFERENCE'S OWN CODE, where it could be compiled (oracle/_ref/libmeso_ref.so: the reference's hot-path headers
+    and shader text, built in the authoring container from /root/reference, see oracle/ref_driver.cpp): its CPU
+    generator-worker body (GenerateSphere + CalculateOccupancyErodeMipmaps + hidden-block test, ChunkManager.h:160-170)
+    over the 448 chunks of the reference sphere on all host threads, and its instanced draw (the voxel VS/FS text through a
+    scalar software pipeline) over the resulting 201 936 instances on one thread.  Reported beside the restated path;
+    neither is the timed headline workload (the reference has no voxel-in-brick level and no shadow rays)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import numpy as np
+        import orc
+        import refprobe
+        from concurrent.futures import ThreadPoolExecutor
+        if not os.path.exists(refprobe.REF_SO):
+            return {"unavailable": "oracle/_ref/libmeso_ref.so not present (it is built where /root/reference exists)"}
+        ref = refprobe.RefBackend(refprobe.REF_SO)
+        chunks = refprobe.SPHERE_CHUNKS
+
+        def gen(loc):
+            xyz, _, cull = ref.generate_chunk(0, loc)      # ctypes releases the GIL; the call uses locals only
+            return len(xyz), int(len(xyz) - cull.sum())
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            rows = list(ex.map(gen, chunks))
+        dt_gen = time.perf_counter() - t0
+        blocks, inst = sum(r[0] for r in rows), sum(r[1] for r in rows)
+        out = {"kind": "reference", "generate": {"chunks": len(chunks), "blocks": blocks, "instances": inst, "cores": nthreads,
+                                                 "s": dt_gen, "chunks_per_s": len(chunks) / dt_gen,
+                                                 "what": "GenerateSphere + CalculateOccupancyErodeMipmaps(16, 4) + bShouldVoxelOccupancyCull(.., 1) per chunk"}}
+        # the draw: block-granular reference sphere (the reference's own scene), 1280x720 (BASELINE.json configs[0])
+        origin, dims = (2, -4, -4), (8, 8, 8)
+        vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, orc.REF_SPHERE, granularity=orc.GRAN_BLOCK)
+        table, _, instances = vol.build_occupancy(stamp=1)
+        w, h = 1280, 720
+        cam = orc.camera_uniform((5.0, 2.0, 2.0), (100.0, 0.0, 0.0), width=w, height=h)   # reference start pose, looking at the sphere
+        t0 = time.perf_counter()
+        depth, instance, color, normal, behind = refprobe.ref_draw(ref.lib, cam, orc.default_scene_config(), table, instances,
+                                                                  ref.triplanar_indices(), w, h)
+        dt_draw = time.perf_counter() - t0
+        out["instanced_draw"] = {"instances": int(len(instances)), "resolution": [w, h], "cores": 1, "s": dt_draw,
+                                 "mpixels_per_s": w * h / dt_draw / 1e6, "covered_pixels": int((instance >= 0).sum()),
+                                 "vertices_behind_camera": behind,
+                                 "what": "cmdDrawIndexed(8, instances) through the reference's vertex/fragment shader text, scalar software pipeline"}
+        return out
+    except Exception as e:  # the reported baseline must never take the arm down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -184,9 +232,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "scene": "V-sphere %d^3 voxel-granular" % n, "resolution": [width, height],
-                   "note": "reference cannot be built here (SURVEY.md 8c); this is the CPU restatement (oracle/) of the same path"},
+                   "note": "the reference application cannot be built here (SURVEY.md 8c) and has no voxel-in-brick level or shadow rays; the timed path is the CPU restatement (oracle/), which oracle/_ref pins against the reference's own code; 'reference_code' times that code itself"},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_code": reference_code_timings(nthreads),
     }
     print(json.dumps(line), flush=True)
     return 0
