@@ -819,6 +819,41 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
     tl = [one_sharded() for _ in range(steps)]
     t_sh = torch.tensor([sum(tl) / steps], dtype=torch.float64, device=dev)
     dist.all_reduce(t_sh, op=dist.ReduceOp.MAX)
+
+    # Opt-in (MESO_BENCH_PREFIX_GATHER=1; written after the round's GPU budget was spent, not yet measured): the gather
+    # DESIGN.md section 8 item 5 proposes for N >= 4 -- every rank meshes into its own list, the counts are all-gathered,
+    # and each rank sends its list in ONE bulk copy (meso_device_copy over NVLink) into rank 0's list at its prefix
+    # offset: one reservation per rank instead of one per warp.  Runs after the fused leg, so the list rank 0 verifies
+    # below is the one this leg assembled.
+    prefix = None
+    if os.environ.get("MESO_BENCH_PREFIX_GATHER") == "1":
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def one_prefix():
+            with torch.cuda.stream(stream):
+                dist.all_reduce(flag)
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                nloc = ctx.mesh_device(local.data_ptr(), local.shape[0])      # reads its 8-byte count back
+                mine.fill_(nloc)
+                dist.all_gather_into_tensor(counts, mine)
+                c = counts.cpu()
+                off = int(c[:rank].sum())
+                if off + nloc > cap:
+                    raise RuntimeError("prefix gather: quad list capacity exceeded")
+                ctx.device_copy(qptr + off * 16, local.data_ptr(), nloc * 16)
+                dist.all_reduce(flag)        # behind it every rank's list has landed
+                b.record(stream)
+            stream.synchronize()
+            return a.elapsed_time(b), int(c.sum())
+
+        one_prefix()
+        tp = [one_prefix() for _ in range(steps)]
+        t_px = torch.tensor([sum(x[0] for x in tp) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_px, op=dist.ReduceOp.MAX)
+        prefix = {"ms": float(t_px.item()), "quads": tp[-1][1],
+                  "note": "per-rank lists + all-gather of counts + one bulk NVLink copy per rank at prefix offsets into rank 0's list"}
     del local
     out = None
     if rank == 0:
@@ -841,6 +876,8 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
                "sharded_lists": {"ms": ms_sh, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms_sh * 1e-3),
                                  "note": "same partition, every rank keeps its own quad list (no gather): max over ranks of the mesh kernels"},
                "note": "chunk c -> rank c % N; fused quad gather into rank 0's list over NVLink (system-scope atomicAdd per warp, 16 B stores); fingerprint = (count, column sums, column xors)"}
+        if prefix is not None:
+            out["prefix_gather"] = prefix
         del ref_t
     dist.barrier()
     if rank != 0:

@@ -50,6 +50,7 @@ SYMBOLS = [
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
+    "meso_device_copy",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -351,6 +352,10 @@ class Context:
 
     def device_memset(self, dptr, value, nbytes):
         _ck(lib.meso_device_memset(self.h, C.c_void_p(dptr), C.c_int(value), C.c_size_t(nbytes)))
+
+    def device_copy(self, dst_dptr, src_dptr, nbytes):
+        """device -> device on the context's stream (enqueue only); either side may be an ipc_open()ed peer pointer."""
+        _ck(lib.meso_device_copy(self.h, C.c_void_p(dst_dptr), C.c_void_p(src_dptr), C.c_size_t(nbytes)))
 
     def device_free(self, dptr):
         _ck(lib.meso_device_free(self.h, C.c_void_p(dptr)))

@@ -934,6 +934,12 @@ int meso_device_memset(MesoCtx* c, void* dptr, int value, size_t bytes) {
   CK(cudaMemsetAsync(dptr, value, bytes, c->stream));
   return MESO_OK;
 }
+int meso_device_copy(MesoCtx* c, void* dst, const void* src, size_t bytes) {
+  if (!c || (bytes > 0 && (!dst || !src))) return fail(MESO_ERR_ARGUMENT, "meso_device_copy: bad argument");
+  CK(cudaSetDevice(c->device));
+  if (bytes > 0) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, c->stream));   // UVA resolves local and peer addresses
+  return MESO_OK;
+}
 int meso_device_free(MesoCtx* c, void* dptr) {
   if (!c) return fail(MESO_ERR_ARGUMENT, "null context");
   CK(cudaSetDevice(c->device));
