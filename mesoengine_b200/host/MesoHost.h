@@ -48,6 +48,9 @@ struct FVoxelSceneConfig {
   uint32_t MaxVolumeCount = 65536 * 16;   // brick payload pool (meso_scene_create max_bricks)
   uint32_t MaxChunkCount = 8192 * 2;
   uint32_t MaxEmptyChunkCount = 8192 * 4;
+  uint32_t MaxChunkCheckTimes = 128;       // unused (pool probing, ChunkPool.h:447-622): the window holds every chunk it covers;
+  uint32_t MaxEmptyChunkCheckTimes = 128;  // kept so that code written against the reference's struct compiles unchanged
+  uint32_t MaxBlockCheckTimes = 16;        // (oracle/ref_host_mirror_check.cpp compares this struct with the reference's)
   uint32_t BakeVisibilityViewNum = 256;   // > 0: snap the forward vector to the nearest of this many baked directions
   uint32_t ViewForwardLoadChunkSize = 24;
   uint32_t ViewBackwardLoadChunkSize = 6;

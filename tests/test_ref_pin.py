@@ -184,3 +184,14 @@ def test_product_baked_direction_equals_reference_nearest_map():
         d, idx = capi.baked_direction(256, q)
         assert idx == int(want)
         assert d.view(np.uint32).tolist() == dirs[idx].view(np.uint32).tolist()
+
+
+def test_host_mirror_declarations_equal_the_reference_headers():
+    """mesoengine_b200/host/MesoHost.h compiled side by side with the reference's VoxelSceneConfig.h / VoxelMathHelper.h:
+    every FVoxelSceneConfig field (type, default, offset), EChunkOverrideMode, ConvertToChunkLocation bits."""
+    import subprocess
+    if refprobe.build_ref() is None or not os.path.isdir(refprobe.REF_ROOT):
+        pytest.skip("needs /root/reference (compares against the reference's own headers)")
+    exe = os.path.join(os.path.dirname(refprobe.REF_SO), "host_mirror_check")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.startswith("ok:"), out.stdout + out.stderr
