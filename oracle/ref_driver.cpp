@@ -34,6 +34,31 @@
 #include "Helper/Comparator.h"
 #include "Shape/TriplePlanarCube.h"
 
+/* ---- the drop-in boundary against the reference's own declarations (INTEGRATION.md "The binding itself") ---------
+ * include/meso_cuda.h next to the reference's record types: the reinterpret_casts the binding relies on are layout-exact.
+ * (glm's vector types come from ref_shim/; like glm's they are plain packed scalars.) */
+#include "../include/meso_cuda.h"
+#define SAME_LAYOUT(RefT, MesoT, rf, mf) \
+  static_assert(offsetof(RefT, rf) == offsetof(MesoT, mf) && sizeof(RefT::rf) == sizeof(MesoT::mf), #RefT "::" #rf " vs " #MesoT "::" #mf)
+static_assert(sizeof(FGPUBlock) == sizeof(MesoGPUBlock) && sizeof(FGPUChunk) == sizeof(MesoGPUChunk), "record sizes");
+static_assert(sizeof(FGPUUniformCamera) == sizeof(MesoGPUUniformCamera) && sizeof(FGPUUniformSceneConfig) == sizeof(MesoGPUUniformSceneConfig), "uniform sizes");
+SAME_LAYOUT(FGPUBlock, MesoGPUBlock, ChunkIndex, ChunkIndex);
+SAME_LAYOUT(FGPUBlock, MesoGPUBlock, BlockLocation, BlockLocation);
+SAME_LAYOUT(FGPUBlock, MesoGPUBlock, BlockFrameStamp, BlockFrameStamp);
+SAME_LAYOUT(FGPUChunk, MesoGPUChunk, ChunkLocation, ChunkLocation);
+SAME_LAYOUT(FGPUChunk, MesoGPUChunk, ChunkFrameStamp, ChunkFrameStamp);
+SAME_LAYOUT(FGPUUniformCamera, MesoGPUUniformCamera, Projection, Projection);
+SAME_LAYOUT(FGPUUniformCamera, MesoGPUUniformCamera, View, View);
+SAME_LAYOUT(FGPUUniformCamera, MesoGPUUniformCamera, CameraChunkLocation, CameraChunkLocation);
+SAME_LAYOUT(FGPUUniformCamera, MesoGPUUniformCamera, SubCameraLocation, SubCameraLocation);
+SAME_LAYOUT(FGPUUniformSceneConfig, MesoGPUUniformSceneConfig, BlockSize, BlockSize);
+SAME_LAYOUT(FGPUUniformSceneConfig, MesoGPUUniformSceneConfig, BlockResolution, BlockResolution);
+SAME_LAYOUT(FGPUUniformSceneConfig, MesoGPUUniformSceneConfig, ChunkSize, ChunkSize);
+SAME_LAYOUT(FGPUUniformSceneConfig, MesoGPUUniformSceneConfig, ChunkResolution, ChunkResolution);
+/* std::pair<float, ivec3> (ChunkManagerHelper.h:76) is what meso_select_view_chunks returns as MesoChunkCandidate */
+static_assert(sizeof(FChunkManageHelper::FTempChunkDataType) == sizeof(MesoChunkCandidate), "candidate size");
+#undef SAME_LAYOUT
+
 namespace lvk {
 /* LVK.h:52 declares it, LVK.cpp defines it; LVK_ASSERT in inline members refers to it in debug builds. */
 bool Assert(bool cond, const char*, int, const char*, ...) { return cond; }
