@@ -78,7 +78,7 @@ enum { ORC_SDF_SPHERE = 0, ORC_SDF_TERRAIN = 1 };
 enum { ORC_GRAN_BLOCK = 0, ORC_GRAN_VOXEL = 1 };
 enum { ORC_SIN_LIBM = 0, ORC_SIN_PORTABLE = 1 };
 enum { ORC_FLAG_SHADOW = 1 };
-enum { ORC_DDA_FLAT = 0, ORC_DDA_HIER = 1, ORC_DDA_BOX = 2 };  /* BOX: HIER + unaligned empty cubes from a cell distance field */
+enum { ORC_DDA_FLAT = 0, ORC_DDA_HIER = 1, ORC_DDA_BOX = 2, ORC_DDA_MODEL = 3 };  /* BOX: HIER + unaligned empty cubes from a cell distance field; MODEL: see orc_step_model_* */
 
 /* ---- a8/a9: SDFs and per-chunk generators (GeneratorHelper.h:19-150, VoxelMathHelper.h:25-33) */
 double orc_sin_portable(double x);
@@ -171,6 +171,14 @@ int64_t orc_select_view_chunks(const float fwd[3], uint32_t forward_load, uint32
                                int mode, OrcChunkCandidate* out, int64_t cap);
 void orc_fibonacci_sphere_f32(uint32_t samples, float* out_xyz);
 uint32_t orc_nearest_direction(const float* dirs, uint32_t n, const float q[3]);
+
+/* ---- instrumentation: step-count model of acceleration structures (ORC_DDA_MODEL; orc_raymarch.c) ---------------
+ * Same records as every other mode; counts steps by kind for a configurable hierarchy.  Not thread-safe to reconfigure
+ * while a frame is being traced.  counts: 0 voxel, 1 2^3 cell, 2 brick, 3 field step <= 2 cells, 4 field step > 2 cells,
+ * 5 grid-entry steps. */
+void orc_step_model_config(int df_shift, int df_cap, int probe, int directional, int brick_cap, int cell2);
+int orc_step_model_build(const OrcVolume* v);
+void orc_step_model_counts(uint64_t out[6], int reset);
 
 int orc_hardware_threads(void);
 

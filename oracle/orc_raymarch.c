@@ -21,6 +21,26 @@
 static uint64_t* orc_debug_level_hist = NULL;
 void orc_debug_set_level_hist(uint64_t* hist3) { orc_debug_level_hist = hist3; }
 
+/* ---- step-count MODEL of acceleration structures (ORC_DDA_MODEL; instrumentation, never part of parity) ----------
+ * Any certified-empty box is a legal skip, so one walker can stand in for candidate kernel designs: it asks a
+ * configurable hierarchy for a box around the current voxel, leaves it, and counts the steps by kind.  The records it
+ * produces are byte-identical to ORC_DDA_FLAT / HIER (checked in tests/test_oracle_raymarch.py), only the counts
+ * differ.  tools/step_model.py calibrates it against the step counts measured on the GPU (profiles/) and evaluates
+ * variants (finer field, per-octant forward cubes, brick-level cubes) before any GPU time is spent on them. */
+typedef struct {
+  int df_shift;      /* log2 of the distance-field cell in voxels: 5 = 32^3 (shipped kernel), 4 = 16^3                   */
+  int df_cap;        /* cap of the field in cells (shipped: 32)                                                         */
+  int probe;         /* 1: second lookup along the octant diagonal as the shipped kernel does                            */
+  int directional;   /* 1: per-octant forward-cube field (largest empty cube starting at the cell, towards the octant)   */
+  int brick_cap;     /* > 1: forward cubes of empty bricks at the brick level, up to this many bricks per step           */
+  int cell2;         /* 1: 2^3-voxel cells inside partial bricks (shipped)                                               */
+} OrcStepModel;
+static OrcStepModel g_model = {5, 32, 1, 0, 0, 1};
+static uint64_t g_model_steps[6];   /* 0 voxel, 1 2^3 cell, 2 brick, 3 field step <= 2 cells, 4 field step > 2 cells, 5 entry */
+static uint8_t* g_model_sym = NULL;       /* symmetric field, dd cells                      */
+static uint8_t* g_model_fwd = NULL;       /* forward-cube field, 8 octants x dd cells       */
+static int g_model_dd[3] = {0, 0, 0};
+
 typedef struct { float o[3], d[3], inv[3]; int step[3]; } Ray;
 typedef struct { int hit; int c[3]; int axis; float t; uint64_t steps; } Trace;
 
@@ -102,6 +122,99 @@ static inline int cell_level(const Scene* s, const int c[3]) {
   return (int)((p[c[2] & 7] >> ((c[0] & 7) + 8 * (c[1] & 7))) & 1u) ? 0 : 1;
 }
 
+/* leave the axis-aligned box [lo, hi) (voxel planes, already clamped to the grid) that contains c; returns 0 if the ray has no direction */
+static int leave_box(const Ray* r, int c[3], const int lo[3], const int hi[3], Trace* tr) {
+  int a = -1; float ta = 0.0f; int pl_a = 0;
+  for (int i = 0; i < 3; i++) {
+    if (!r->step[i]) continue;
+    int pl = r->step[i] > 0 ? hi[i] : lo[i];
+    float ti = plane_t(r, i, pl);
+    if (a < 0 || key_less(ti, i, ta, a)) { a = i; ta = ti; pl_a = pl; }
+  }
+  if (a < 0) return 0;
+  c[a] = r->step[a] > 0 ? pl_a : pl_a - 1;
+  for (int b = 0; b < 3; b++) if (b != a) c[b] = advance_axis(r, b, c[b], ta, a);
+  tr->axis = a; tr->t = ta; tr->steps++;
+  return 1;
+}
+
+static int brick_occupied(const Scene* s, int bx, int by, int bz) {   /* brick coordinates in the grid; outside = empty */
+  const OrcVolume* v = s->v;
+  if (bx < 0 || by < 0 || bz < 0 || bx >= v->dims[0] * 16 || by >= v->dims[1] * 16 || bz >= v->dims[2] * 16) return 0;
+  int64_t ci = orc_cidx(v, bx >> 4, by >> 4, bz >> 4);
+  return orc_getbit(v->occ + ci * ORC_WORDS, orc_bidx(bx & 15, by & 15, bz & 15));
+}
+
+static void model_walk(const Scene* s, const Ray* r, int c[3], Trace* tr) {
+  const OrcStepModel* m = &g_model;
+  const int sh = m->df_shift;
+  const int oct = (r->step[0] < 0 ? 1 : 0) | (r->step[1] < 0 ? 2 : 0) | (r->step[2] < 0 ? 4 : 0);
+  const size_t ncell = (size_t)g_model_dd[0] * g_model_dd[1] * g_model_dd[2];
+  for (;;) {
+    /* field level */
+    const int e[3] = {c[0] >> sh, c[1] >> sh, c[2] >> sh};
+    const size_t ei = (size_t)e[0] + (size_t)g_model_dd[0] * ((size_t)e[1] + (size_t)g_model_dd[1] * (size_t)e[2]);
+    int k = m->directional ? g_model_fwd[(size_t)oct * ncell + ei] : g_model_sym[ei];
+    if (k > 0) {
+      if (!m->directional && m->probe) {
+        int q[3]; int in = 1;
+        for (int i = 0; i < 3; i++) { q[i] = e[i] + (r->step[i] < 0 ? -k : k); if (q[i] < 0 || q[i] >= g_model_dd[i]) in = 0; }
+        if (in) { int d2 = g_model_sym[(size_t)q[0] + (size_t)g_model_dd[0] * ((size_t)q[1] + (size_t)g_model_dd[1] * (size_t)q[2])]; if (d2 > k) k += d2; }
+      }
+      int lo[3], hi[3];
+      for (int i = 0; i < 3; i++) {
+        hi[i] = (e[i] + k) << sh; if (hi[i] > s->n[i]) hi[i] = s->n[i];
+        lo[i] = (e[i] - k + 1) << sh; if (lo[i] < 0) lo[i] = 0;
+      }
+      if (!leave_box(r, c, lo, hi, tr)) return;
+      __atomic_fetch_add(&g_model_steps[k <= 2 ? 3 : 4], 1, __ATOMIC_RELAXED);
+      if (!inside(s, c)) return;
+      continue;
+    }
+    int L = cell_level(s, c);
+    if (L == 0) { tr->hit = 1; return; }
+    if (L >= ORC_BR) {
+      /* empty brick: aligned brick step, or the largest empty cube of bricks towards the octant (direct test, cap brick_cap) */
+      int kb = 1;
+      const int b[3] = {c[0] >> 3, c[1] >> 3, c[2] >> 3};
+      for (int t = 2; t <= m->brick_cap; t++) {
+        int empty = 1;
+        for (int z = 0; z < t && empty; z++) for (int y = 0; y < t && empty; y++) for (int x = 0; x < t; x++) {
+          if (x < t - 1 && y < t - 1 && z < t - 1) continue;   /* the (t-1)-cube was tested already */
+          if (brick_occupied(s, b[0] + (r->step[0] < 0 ? -x : x), b[1] + (r->step[1] < 0 ? -y : y), b[2] + (r->step[2] < 0 ? -z : z))) { empty = 0; break; }
+        }
+        if (!empty) break;
+        kb = t;
+      }
+      int lo[3], hi[3];
+      for (int i = 0; i < 3; i++) {
+        hi[i] = (b[i] + kb) << 3; if (hi[i] > s->n[i]) hi[i] = s->n[i];
+        lo[i] = (b[i] - kb + 1) << 3; if (lo[i] < 0) lo[i] = 0;
+      }
+      if (!leave_box(r, c, lo, hi, tr)) return;
+      __atomic_fetch_add(&g_model_steps[2], 1, __ATOMIC_RELAXED);
+      if (!inside(s, c)) return;
+      continue;
+    }
+    /* empty voxel inside a partial brick */
+    int size = 1;
+    if (m->cell2) {
+      const OrcVolume* v = s->v;
+      int64_t ci = orc_cidx(v, c[0] >> 7, c[1] >> 7, c[2] >> 7);
+      uint32_t slot = v->bptr[ci][orc_bidx((c[0] >> 3) & 15, (c[1] >> 3) & 15, (c[2] >> 3) & 15)];
+      const uint64_t* p = v->pool + (size_t)slot * 8;
+      const int x0 = c[0] & 6, y0 = c[1] & 6, z0 = c[2] & 6;
+      uint64_t mask = (3ull << (x0 + 8 * y0)) | (3ull << (x0 + 8 * (y0 + 1)));
+      if (((p[z0] | p[z0 + 1]) & mask) == 0) size = 2;
+    }
+    int lo[3], hi[3];
+    for (int i = 0; i < 3; i++) { lo[i] = c[i] & ~(size - 1); hi[i] = lo[i] + size; }
+    if (!leave_box(r, c, lo, hi, tr)) return;
+    __atomic_fetch_add(&g_model_steps[size == 2 ? 1 : 0], 1, __ATOMIC_RELAXED);
+    if (!inside(s, c)) return;
+  }
+}
+
 static Trace trace(const Scene* s, const Ray* r, const int c0[3], int mode) {
   Trace tr; tr.hit = 0; tr.axis = -1; tr.t = 0.0f; tr.steps = 0;
   int c[3] = {c0[0], c0[1], c0[2]};
@@ -133,6 +246,7 @@ static Trace trace(const Scene* s, const Ray* r, const int c0[3], int mode) {
       tr.axis = a; tr.t = ta; tr.steps++;
       if (!inside(s, c)) goto done;
     }
+    if (mode == ORC_DDA_MODEL) { if (tr.steps) __atomic_fetch_add(&g_model_steps[5], 1, __ATOMIC_RELAXED); model_walk(s, r, c, &tr); goto done; }
     for (;;) {
       int L = cell_level(s, c);
       if (L == 0) { tr.hit = 1; break; }
@@ -392,4 +506,99 @@ int orc_ref_instanced_pixel(const OrcGPUUniformCamera* cam, const OrcGPUUniformS
   out_rgba[3] = 0.0f;
   *out_face = best_face; *out_t = best_t; *out_margin = best_margin;
   return 1;
+}
+
+/* ---- step-count model: fields and control (instrumentation; see the comment at the top of this file) --------------- */
+void orc_step_model_config(int df_shift, int df_cap, int probe, int directional, int brick_cap, int cell2) {
+  g_model.df_shift = df_shift; g_model.df_cap = df_cap; g_model.probe = probe; g_model.directional = directional;
+  g_model.brick_cap = brick_cap; g_model.cell2 = cell2;
+}
+void orc_step_model_counts(uint64_t out[6], int reset) {
+  for (int i = 0; i < 6; i++) { out[i] = g_model_steps[i]; if (reset) g_model_steps[i] = 0; }
+}
+/* Builds the field the current configuration needs over cells of 2^df_shift voxels (3 <= df_shift <= 7). */
+int orc_step_model_build(const OrcVolume* v) {
+  const int sh = g_model.df_shift, cap = g_model.df_cap;
+  if (sh < 3 || sh > 7 || cap < 1 || cap > 255) return -1;
+  const int bpc = 1 << (sh - 3);                        /* bricks per cell axis */
+  int dd[3];
+  for (int i = 0; i < 3; i++) dd[i] = (v->dims[i] * 16 + bpc - 1) / bpc;
+  const size_t n = (size_t)dd[0] * dd[1] * dd[2];
+  free(g_model_sym); free(g_model_fwd); g_model_sym = NULL; g_model_fwd = NULL;
+  for (int i = 0; i < 3; i++) g_model_dd[i] = dd[i];
+  uint8_t* occ = (uint8_t*)calloc(n, 1);
+  if (!occ) return -1;
+  for (int64_t c = 0; c < v->nchunks; c++) {
+    const int cx = (int)(c % v->dims[0]), cy = (int)((c / v->dims[0]) % v->dims[1]), cz = (int)(c / ((int64_t)v->dims[0] * v->dims[1]));
+    for (int w = 0; w < ORC_WORDS; w++) {
+      uint64_t bits = v->occ[c * ORC_WORDS + w];
+      while (bits) {
+        const int b = w * 64 + __builtin_ctzll(bits); bits &= bits - 1;
+        const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
+        occ[(size_t)(bx / bpc) + (size_t)dd[0] * ((size_t)(by / bpc) + (size_t)dd[1] * (size_t)(bz / bpc))] = 1;
+      }
+    }
+  }
+  if (!g_model.directional) {
+    /* Chebyshev distance to the nearest occupied cell, capped: k-fold box dilation, one cell per round */
+    uint8_t* dist = (uint8_t*)malloc(n); uint8_t* cur = (uint8_t*)malloc(n); uint8_t* tmp = (uint8_t*)malloc(n);
+    if (!dist || !cur || !tmp) { free(occ); free(dist); free(cur); free(tmp); return -1; }
+    for (size_t i = 0; i < n; i++) { dist[i] = occ[i] ? 0 : (uint8_t)cap; cur[i] = occ[i]; }
+    for (int k = 1; k < cap; k++) {
+      /* x */
+      for (size_t row = 0; row < (size_t)dd[1] * dd[2]; row++) {
+        const uint8_t* a = cur + row * dd[0]; uint8_t* o = tmp + row * dd[0];
+        for (int x = 0; x < dd[0]; x++) o[x] = a[x] | (x > 0 ? a[x - 1] : 0) | (x + 1 < dd[0] ? a[x + 1] : 0);
+      }
+      /* y */
+      for (int z = 0; z < dd[2]; z++) for (int y = 0; y < dd[1]; y++) {
+        const size_t base = (size_t)dd[0] * ((size_t)y + (size_t)dd[1] * z);
+        for (int x = 0; x < dd[0]; x++) {
+          uint8_t r = tmp[base + x];
+          if (y > 0) r |= tmp[base - dd[0] + x];
+          if (y + 1 < dd[1]) r |= tmp[base + dd[0] + x];
+          cur[base + x] = r;
+        }
+      }
+      /* z */
+      const size_t plane = (size_t)dd[0] * dd[1];
+      int changed = 0;
+      for (int z = 0; z < dd[2]; z++) for (size_t i = 0; i < plane; i++) {
+        const size_t at = (size_t)z * plane + i;
+        uint8_t r = cur[at];
+        if (z > 0) r |= cur[at - plane];
+        if (z + 1 < dd[2]) r |= cur[at + plane];
+        tmp[at] = r;
+        if (r && dist[at] == cap && !occ[at]) { dist[at] = (uint8_t)k; changed = 1; }
+      }
+      uint8_t* sw = cur; cur = tmp; tmp = sw;
+      (void)changed;
+    }
+    free(cur); free(tmp);
+    g_model_sym = dist;
+  } else {
+    uint8_t* fwd = (uint8_t*)malloc(8 * n);
+    if (!fwd) { free(occ); return -1; }
+    for (int o = 0; o < 8; o++) {
+      const int sx = (o & 1) ? -1 : 1, sy = (o & 2) ? -1 : 1, sz = (o & 4) ? -1 : 1;
+      uint8_t* f = fwd + (size_t)o * n;
+      for (int zi = 0; zi < dd[2]; zi++) for (int yi = 0; yi < dd[1]; yi++) for (int xi = 0; xi < dd[0]; xi++) {
+        /* visit forward neighbours first: walk against the octant direction */
+        const int x = sx > 0 ? dd[0] - 1 - xi : xi, y = sy > 0 ? dd[1] - 1 - yi : yi, z = sz > 0 ? dd[2] - 1 - zi : zi;
+        const size_t at = (size_t)x + (size_t)dd[0] * ((size_t)y + (size_t)dd[1] * (size_t)z);
+        if (occ[at]) { f[at] = 0; continue; }
+        int best = cap;
+        for (int q = 1; q < 8; q++) {
+          const int nx = x + ((q & 1) ? sx : 0), ny = y + ((q & 2) ? sy : 0), nz = z + ((q & 4) ? sz : 0);
+          if (nx < 0 || ny < 0 || nz < 0 || nx >= dd[0] || ny >= dd[1] || nz >= dd[2]) continue;   /* beyond the grid: empty */
+          const int fn = f[(size_t)nx + (size_t)dd[0] * ((size_t)ny + (size_t)dd[1] * (size_t)nz)];
+          if (fn < best) best = fn;
+        }
+        f[at] = (uint8_t)(best + 1 > cap ? cap : best + 1);
+      }
+    }
+    g_model_fwd = fwd;
+  }
+  free(occ);
+  return 0;
 }

@@ -42,7 +42,7 @@ SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
 SIN_LIBM, SIN_PORTABLE = 0, 1
 FLAG_SHADOW = 1
-DDA_FLAT, DDA_HIER, DDA_BOX = 0, 1, 2
+DDA_FLAT, DDA_HIER, DDA_BOX, DDA_MODEL = 0, 1, 2, 3
 REF_SPHERE = (100.0, 0.0, 0.0, 50.0)   # GeneratorHelper.h:134
 
 
@@ -292,6 +292,21 @@ class Volume:
         n = int(lib.orc_carve_sphere(self.h, _p(_i3(center)), C.c_int32(radius), _p(dirty), C.c_int64(cap)))
         assert n <= cap
         return dirty[:n].copy()
+
+
+def step_model(vol, df_shift=5, df_cap=32, probe=True, directional=False, brick_cap=0, cell2=True):
+    """Configure the step-count model (ORC_DDA_MODEL) and build its field for `vol`. Instrumentation, not parity."""
+    lib.orc_step_model_config(C.c_int(df_shift), C.c_int(df_cap), C.c_int(1 if probe else 0), C.c_int(1 if directional else 0),
+                              C.c_int(brick_cap), C.c_int(1 if cell2 else 0))
+    if lib.orc_step_model_build(vol.h) != 0:
+        raise MemoryError("orc_step_model_build")
+
+
+def step_model_counts(reset=True):
+    """-> steps by kind: voxel, 2^3 cell, brick, field step <= 2 cells, field step > 2 cells, grid entry."""
+    out = np.zeros(6, dtype=np.uint64)
+    lib.orc_step_model_counts(_p(out), C.c_int(1 if reset else 0))
+    return out
 
 
 def sort_quads(q):

@@ -134,3 +134,25 @@ def test_dda_matches_reference_instanced_draw(orc, eye_idx):
             assert all(abs(g - e) <= 1 for g, e in zip(got, exp)), (px, py, got, exp)
             assert got[face >> 1] in ((191, 192) if face & 1 else (63, 64))   # the pinned channel identifies the face
     assert checked > 300
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(probe=False), dict(directional=True), dict(df_shift=4), dict(df_shift=4, directional=True),
+                                 dict(brick_cap=4), dict(cell2=False), dict(df_shift=3, df_cap=16, directional=True, brick_cap=0)])
+def test_step_model_walks_produce_the_same_records(orc, cfg):
+    """ORC_DDA_MODEL (the step-count model of candidate acceleration structures, tools/step_model.py) skips different
+    boxes for every configuration and must still produce the records of the plain hierarchical walk, byte for byte --
+    which also proves every box its fields certify is really empty."""
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL)
+    w, h = 96, 54
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    orc.step_model(vol, **cfg)
+    orc.step_model_counts(reset=True)
+    for eye in (eyes[1], eyes[6], (ctr[0] + 1.5, ctr[1] + 0.5, ctr[2] + 9.0)):     # two orbit cameras and one close to the surface
+        cam = orc.camera_uniform(eye, ctr, width=w, height=h)
+        rs = orc.ray_setup(cam, origin, w, h)
+        ref = vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_HIER)
+        got = vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_MODEL)
+        assert got.tobytes() == ref.tobytes()
+    counts = orc.step_model_counts()
+    assert counts.sum() > 0 and (cfg.get("cell2", True) or counts[1] == 0)
