@@ -33,7 +33,8 @@ typedef struct {
   int probe;         /* 1: second lookup along the octant diagonal as the shipped kernel does                            */
   int directional;   /* 1: per-octant forward-cube field (largest empty cube starting at the cell, towards the octant)   */
   int brick_cap;     /* > 1: forward cubes of empty bricks at the brick level, up to this many bricks per step           */
-  int cell2;         /* 1: 2^3-voxel cells inside partial bricks (shipped)                                               */
+  int cell2;         /* 1: 2^3-voxel cells inside partial bricks (shipped); t > 1: forward cubes of up to t empty cells,     */
+                     /*    confined to the brick (what a per-brick table of 64 cells x 8 octants x 2 bits would certify)     */
 } OrcStepModel;
 static OrcStepModel g_model = {5, 32, 1, 0, 0, 1};
 static uint64_t g_model_steps[6];   /* 0 voxel, 1 2^3 cell, 2 brick, 3 field step <= 2 cells, 4 field step > 2 cells, 5 entry */
@@ -206,6 +207,34 @@ static void model_walk(const Scene* s, const Ray* r, int c[3], Trace* tr) {
       const int x0 = c[0] & 6, y0 = c[1] & 6, z0 = c[2] & 6;
       uint64_t mask = (3ull << (x0 + 8 * y0)) | (3ull << (x0 + 8 * (y0 + 1)));
       if (((p[z0] | p[z0 + 1]) & mask) == 0) size = 2;
+      if (size == 2 && m->cell2 > 1) {
+        /* largest cube of empty 2^3 cells starting at this cell towards the octant, inside the brick */
+        const int q0[3] = {(c[0] & 7) >> 1, (c[1] & 7) >> 1, (c[2] & 7) >> 1};
+        int kc = 1;
+        for (int t = 2; t <= m->cell2; t++) {
+          int ok = 1;
+          for (int z = 0; z < t && ok; z++) for (int y = 0; y < t && ok; y++) for (int x = 0; x < t; x++) {
+            if (x < t - 1 && y < t - 1 && z < t - 1) continue;
+            const int qx = q0[0] + (r->step[0] < 0 ? -x : x), qy = q0[1] + (r->step[1] < 0 ? -y : y), qz = q0[2] + (r->step[2] < 0 ? -z : z);
+            if (qx < 0 || qy < 0 || qz < 0 || qx > 3 || qy > 3 || qz > 3) { ok = 0; break; }
+            const uint64_t mk = (3ull << (2 * qx + 16 * qy)) | (3ull << (2 * qx + 16 * qy + 8));
+            if ((p[2 * qz] | p[2 * qz + 1]) & mk) { ok = 0; break; }
+          }
+          if (!ok) break;
+          kc = t;
+        }
+        if (kc > 1) {
+          int lo2[3], hi2[3];
+          for (int i = 0; i < 3; i++) {
+            const int base = c[i] & ~1;
+            hi2[i] = base + 2 * kc; lo2[i] = base + 2 - 2 * kc;
+          }
+          if (!leave_box(r, c, lo2, hi2, tr)) return;
+          __atomic_fetch_add(&g_model_steps[1], 1, __ATOMIC_RELAXED);
+          if (!inside(s, c)) return;
+          continue;
+        }
+      }
     }
     int lo[3], hi[3];
     for (int i = 0; i < 3; i++) { lo[i] = c[i] & ~(size - 1); hi[i] = lo[i] + size; }

@@ -297,7 +297,7 @@ class Volume:
 def step_model(vol, df_shift=5, df_cap=32, probe=True, directional=False, brick_cap=0, cell2=True):
     """Configure the step-count model (ORC_DDA_MODEL) and build its field for `vol`. Instrumentation, not parity."""
     lib.orc_step_model_config(C.c_int(df_shift), C.c_int(df_cap), C.c_int(1 if probe else 0), C.c_int(1 if directional else 0),
-                              C.c_int(brick_cap), C.c_int(1 if cell2 else 0))
+                              C.c_int(brick_cap), C.c_int(int(cell2)))
     if lib.orc_step_model_build(vol.h) != 0:
         raise MemoryError("orc_step_model_build")
 

@@ -137,7 +137,7 @@ def test_dda_matches_reference_instanced_draw(orc, eye_idx):
 
 
 @pytest.mark.parametrize("cfg", [dict(), dict(probe=False), dict(directional=True), dict(df_shift=4), dict(df_shift=4, directional=True),
-                                 dict(brick_cap=4), dict(cell2=False), dict(df_shift=3, df_cap=16, directional=True, brick_cap=0)])
+                                 dict(brick_cap=4), dict(cell2=False), dict(cell2=4), dict(directional=True, brick_cap=8, cell2=2), dict(df_shift=3, df_cap=16, directional=True, brick_cap=0)])
 def test_step_model_walks_produce_the_same_records(orc, cfg):
     """ORC_DDA_MODEL (the step-count model of candidate acceleration structures, tools/step_model.py) skips different
     boxes for every configuration and must still produce the records of the plain hierarchical walk, byte for byte --

@@ -34,6 +34,10 @@ CONFIGS = [
     ("8^3 (brick) per-octant forward cubes cap 32: replaces field AND brick level", dict(df_shift=3, directional=True)),
     ("v8 + brick-level forward cubes up to 4 bricks", dict(brick_cap=4)),
     ("32^3 per-octant cubes + brick-level forward cubes up to 4 bricks", dict(directional=True, brick_cap=4)),
+    ("32^3 per-octant cubes + brick-level forward cubes up to 8 bricks", dict(directional=True, brick_cap=8)),
+    ("v8 + forward cubes of up to 4 empty 2^3 cells inside the brick", dict(cell2=4)),
+    ("32^3 per-octant cubes + brick cubes <= 4 + 2^3-cell cubes <= 4", dict(directional=True, brick_cap=4, cell2=4)),
+    ("v8 without the 2^3-cell level (v7-like)", dict(cell2=False)),
 ]
 KINDS = ["voxel", "cell2", "brick", "field_le2", "field_gt2", "entry"]
 
@@ -64,7 +68,8 @@ def main():
     if args.n == 4096 and os.path.exists(mpath):
         for line in open(mpath):
             d = json.loads(line)
-            measured[d["camera"]] = d
+            if "camera" in d:
+                measured[d["camera"]] = d
 
     results = []
     ref_records = {}
