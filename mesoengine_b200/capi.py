@@ -33,7 +33,7 @@ StreamStats = np.dtype([("generated", "<u4"), ("missing", "<u4"), ("candidates",
 
 SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
-FLAG_SHADOW, FLAG_RGBA8 = 1, 2
+FLAG_SHADOW, FLAG_RGBA8, FLAG_CUBES = 1, 2, 4
 LAYOUT_FRAME, LAYOUT_TILES = 0, 1
 TILE_W, TILE_H = 32, 8
 
@@ -50,7 +50,7 @@ SYMBOLS = [
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
-    "meso_device_copy",
+    "meso_device_copy", "meso_build_cubes",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -214,18 +214,22 @@ class Context:
         _ck(lib.meso_download_instances(self.h, _p(inst), C.c_int64(max(n_inst, 1))))
         return table, mips, inst[:n_inst]
 
-    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False):
+    def build_cubes(self):
+        """(Re)build the per-octant forward-cube tables that FLAG_CUBES reads (opt-in raymarch path)."""
+        _ck(lib.meso_build_cubes(self.h))
+
+    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False, cubes=False):
         """End-to-end call: camera from host memory, records (or, rgba8=True, the colour image as uint32) into host memory."""
         rec = out if out is not None else np.zeros((height, width), dtype=np.uint32 if rgba8 else HitRecord)
         l = np.ascontiguousarray(light, dtype=np.float32)
-        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0)
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0)
         _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(rec)))
         return rec
 
-    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False):
+    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False, cubes=False):
         """Frame-ring call: enqueue frame + copy into `out` (pinned numpy array); pair with frame_wait(slot)."""
         l = np.ascontiguousarray(light, dtype=np.float32)
-        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0)
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0)
         _ck(lib.meso_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(out), C.c_int(slot)))
 
     def frame_wait(self, slot):
@@ -236,11 +240,11 @@ class Context:
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
                                      C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
 
-    def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8)):
+    def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), cubes=False):
         st = np.zeros(1, dtype=RayStats)
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_stats(self.h, _p(cam), C.c_int(width), C.c_int(height),
-                                    C.c_uint32(FLAG_SHADOW if shadow else 0), _p(l), _p(st)))
+                                    C.c_uint32((FLAG_SHADOW if shadow else 0) | (FLAG_CUBES if cubes else 0)), _p(l), _p(st)))
         return st[0]
 
     def compose_tiles_device(self, d_tiles, world, width, height, d_frame):

@@ -86,6 +86,7 @@ struct Scene {
   uint8_t* touch_chunk;
   uint8_t* touch_brick;
   unsigned* lv;              // STATS only: per-thread steps per level
+  CubeTables ct;             // CUBES only: per-octant forward cubes (meso_build_cubes)
 };
 
 // Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every aligned step is "(cs | mask) + 1".
@@ -146,7 +147,11 @@ __device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int c
 // solid voxel), then take one step at that level.  Levels: the distance field over 32^3 cells (a step leaves the whole
 // empty cube of half-width df - 1 cells around the current cell, clamped to the grid), bricks (8^3), voxels.
 // On W_HIT (cx,cy,cz) is the exact hit voxel.
-template <bool STATS>
+// CUBES (opt-in, MESO_FLAG_CUBES; chosen by the step model in profiles/README.md, not yet measured on hardware): every
+// level reads the edge of the largest empty cube that STARTS at the current cell / brick / 2^3 cell and extends towards
+// the ray's octant (CubeTables) where the shipped walk reads a symmetric distance or an occupancy bit.  Same levels, same
+// single step section, bigger boxes; any empty box is a legal skip, so the records cannot change.
+template <bool STATS, bool CUBES = false>
 __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, int& cx, int& cy, int& cz, unsigned& steps) {
   const DVolume& v = *s.v;
   const int gx = r.sx >> 31, gy = r.sy >> 31, gz = r.sz >> 31;
@@ -154,6 +159,48 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
   bool go = true;  // keep looking finer
   int sh = 0;      // level of the step: 0 voxel, 1 2^3 cell, 3 brick, 5 distance-field cube
   int kdf = 1;     // cells to advance at that level (> 1 only for distance-field steps)
+  if (CUBES) {
+    const int oct = (gx & 1) | (gy & 2) | (gz & 4);
+    if (w.need >= 3) {
+      const int ex = cx >> 5, ey = cy >> 5, ez = cz >> 5;
+      const int k = (int)__ldg(&s.ct.cell[(size_t)oct * (size_t)s.ct.ncells + (size_t)(ex + v.ddims[0] * (ey + v.ddims[1] * ez))]);
+      if (k > 0) { sh = 5; kdf = k; go = false; }
+      else {
+        const int ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
+        if (ci != w.ci) { w.ci = ci; w.wtag = -1; }
+        if (STATS) {
+          const int e = ((cx >> 5) & 3) + 4 * ((cy >> 5) & 3) + 16 * ((cz >> 5) & 3);
+          if ((v.cells[ci] >> e) & 1ull) s.touch_chunk[ci] = 1;
+        }
+      }
+    }
+    if (go && w.need >= 2) {
+      const int bx = (cx >> 3) & 15, by = (cy >> 3) & 15, bz = (cz >> 3) & 15;
+      const int wi = bz * 4 + (by >> 2);
+      if (wi != w.wtag) {
+        const ulonglong2 p = __ldg(&v.of[(size_t)w.ci * 64 + wi]);
+        w.wocc = p.x; w.wfull = p.y; w.wtag = wi;
+      }
+      const int bit = bx + 16 * (by & 3);
+      if (!((w.wocc >> bit) & 1ull)) {
+        sh = 3; go = false;
+        kdf = 1 + (((int)__ldg(&s.ct.brick[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]) >> (2 * oct)) & 3);
+      } else {
+        if ((w.wfull >> bit) & 1ull) return W_HIT;
+        w.slot = __ldg(&v.bptr[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
+        w.cm = __ldg(&v.pool_cm[w.slot]);
+        if (STATS) s.touch_brick[w.slot] = 1;
+        w.ztag = -1;
+      }
+    }
+    if (go && w.need >= 1) {
+      const int ce = ((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3);
+      if (!((w.cm >> ce) & 1ull)) {
+        sh = 1; go = false;
+        kdf = 1 + (((int)__ldg(&s.ct.cell2[(size_t)w.slot * 64 + ce]) >> (2 * oct)) & 3);
+      }
+    }
+  } else {
   if (w.need >= 3) {
     const int ex = cx >> 5, ey = cy >> 5, ez = cz >> 5;
     const int df = (int)__ldg(&v.df[ex + v.ddims[0] * (ey + v.ddims[1] * ez)]);
@@ -198,6 +245,7 @@ __device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, 
     // (a 4^3 level on top of this one was measured: 9 % fewer steps, 7 % slower -- one more divergent path per iteration)
     if (!((w.cm >> (((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3))) & 1ull)) { sh = 1; go = false; }
   }
+  }  // !CUBES
   if (go) {
     const int z = cz & 7;
     if (z != w.ztag) { w.slice = __ldg(&v.pool[(size_t)w.slot * 8 + z]); w.ztag = z; }
@@ -269,119 +317,26 @@ __device__ __forceinline__ uint4 shade_record(const Done& dn) {
 // refilling idle lanes with new pixels (v4) or letting a lane continue as its shadow ray inside the primary loop (v9)
 // both raise lane occupancy and both cost 30 % or more extra warp instructions (profiles/README.md).
 // No shared memory, no barriers: the CTA is only the unit of tile ownership.
-template <bool STATS>
-__global__ void __launch_bounds__(RM_THREADS, 5) raymarch_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
-                                                              int rank, int world, int layout, int tiles_x, int n_tiles,
-                                                              int local_tile0,
-                                                              MesoHitRecord* __restrict__ out, RayStatsDev* stats,
-                                                              uint8_t* touch_chunk, uint8_t* touch_brick) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int local_tile = local_tile0 + blockIdx.x;
-  const int tile = local_tile * world + rank;
-  const int tx = (warp & 3) * 8 + (lane & 7), ty = (warp >> 2) * 4 + (lane >> 3);
-  const int px = (tile % tiles_x) * MESO_TILE_W + tx;
-  const int py = (tile / tiles_x) * MESO_TILE_H + ty;
-  const bool valid = tile < n_tiles && px < width && py < height;
-  Scene sc; sc.v = &v; sc.touch_chunk = touch_chunk; sc.touch_brick = touch_brick;
-  unsigned lv[5] = {0, 0, 0, 0, 0};
-  sc.lv = lv;
-  const float Lx = rs.L[0], Ly = rs.L[1], Lz = rs.L[2];
+#define RM_KERNEL_NAME raymarch_kernel
+#define RM_EXTRA_PARAM
+#define RM_CUBES false
+#define RM_SET_CUBES(sc)
+#include "raymarch_kernel.inc"
+#undef RM_KERNEL_NAME
+#undef RM_EXTRA_PARAM
+#undef RM_CUBES
+#undef RM_SET_CUBES
 
-  // ---- phase 1: primary ray ----
-  Done dn; dn.cx = dn.cy = dn.cz = 0; dn.face = 7; dn.shadow = 0; dn.t = 0.f; dn.px = dn.py = dn.pz = 0.f;
-  bool want_shadow = false;
-  int hit_axis = -1;
-  unsigned steps = 0, n_shadow = 0;
-  if (valid) {
-    const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)px, 0.5f), rs.two_over_w), 1.0f);
-    const float fy = __fsub_rn(1.0f, __fmul_rn(__fadd_rn((float)py, 0.5f), rs.two_over_h));
-    float dx = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[0]), __fmul_rn(fy, rs.V[0])), rs.F[0]);
-    float dy = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[1]), __fmul_rn(fy, rs.V[1])), rs.F[1]);
-    float dz = __fadd_rn(__fadd_rn(__fmul_rn(fx, rs.U[2]), __fmul_rn(fy, rs.V[2])), rs.F[2]);
-    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
-    Ray r; r.ox = rs.o[0]; r.oy = rs.o[1]; r.oz = rs.o[2];
-    ray_dir(r, dx, dy, dz);
-    Walk w;
-    int cx = 0, cy = 0, cz = 0, res = W_EXIT;
-    if (walk_begin(v, r, clamp_floor_to_int(r.ox), clamp_floor_to_int(r.oy), clamp_floor_to_int(r.oz), w, steps)) {
-      do { res = walk_iter<STATS>(sc, r, w, cx, cy, cz, steps); } while (res == W_CONTINUE);
-    }
-    if (res == W_HIT) {
-      dn.t = w.lt; dn.cx = cx; dn.cy = cy; dn.cz = cz;
-      dn.px = __fadd_rn(r.ox, __fmul_rn(r.dx, w.lt)); dn.py = __fadd_rn(r.oy, __fmul_rn(r.dy, w.lt)); dn.pz = __fadd_rn(r.oz, __fmul_rn(r.dz, w.lt));
-      if (w.la >= 0) {
-        const int st_ax = SEL3(w.la, r.sx, r.sy, r.sz);
-        const float l_ax = SEL3(w.la, Lx, Ly, Lz);
-        const int c_ax = SEL3(w.la, cx, cy, cz);
-        const float pl = (float)(st_ax > 0 ? c_ax : c_ax + 1);
-        if (w.la == 0) dn.px = pl; else if (w.la == 1) dn.py = pl; else dn.pz = pl;
-        dn.face = w.la * 2 + (st_ax > 0 ? 0 : 1);
-        hit_axis = w.la;
-        if (flags & MESO_FLAG_SHADOW) {
-          const bool facing = st_ax > 0 ? (l_ax < 0.0f) : (l_ax > 0.0f);
-          if (!facing) dn.shadow = 1; else want_shadow = true;
-        }
-      } else {
-        dn.face = 6;
-        dn.px = r.ox; dn.py = r.oy; dn.pz = r.oz;
-      }
-    }
-  }
-
-  const unsigned steps_p = steps;
-  // ---- phase 2: shadow ray of the same pixel (origin = hit point, start cell = the empty cell in front of the face) ----
-  if (flags & MESO_FLAG_SHADOW) {
-    if (want_shadow) {
-      const int nrm = (dn.face & 1) ? 1 : -1;
-      Ray r; r.ox = dn.px; r.oy = dn.py; r.oz = dn.pz;
-      ray_dir(r, Lx, Ly, Lz);
-      Walk w;
-      int cx = 0, cy = 0, cz = 0, res = W_EXIT;
-      if (walk_begin(v, r, dn.cx + (hit_axis == 0 ? nrm : 0), dn.cy + (hit_axis == 1 ? nrm : 0), dn.cz + (hit_axis == 2 ? nrm : 0), w, steps)) {
-        do { res = walk_iter<STATS>(sc, r, w, cx, cy, cz, steps); } while (res == W_CONTINUE);
-      }
-      dn.shadow = res == W_HIT ? 1 : 0;
-      n_shadow = 1;
-    }
-  }
-
-  // ---- phase 3: shade + store ----
-  if (valid) {
-    const size_t dst = layout == MESO_LAYOUT_FRAME ? (size_t)py * width + px
-                                                   : (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
-    const uint4 rec = shade_record(dn);
-    if (flags & MESO_FLAG_RGBA8) reinterpret_cast<uint32_t*>(out)[dst] = rec.w;
-    else reinterpret_cast<uint4*>(out)[dst] = rec;
-  }
-
-  if (STATS) {
-    unsigned long long v0 = valid ? 1 : 0, v1 = n_shadow, v2 = dn.face != 7 ? 1 : 0, v3 = steps;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-      v2 += __shfl_xor_sync(0xffffffffu, v2, o); v3 += __shfl_xor_sync(0xffffffffu, v3, o);
-    }
-    unsigned long long v4 = steps_p;
-    unsigned mp = steps_p, ms = steps - steps_p;
-    unsigned long long l0 = lv[0], l1 = lv[1], l2 = lv[2], l3 = lv[3], l4 = lv[4];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      v4 += __shfl_xor_sync(0xffffffffu, v4, o);
-      mp = max(mp, __shfl_xor_sync(0xffffffffu, mp, o)); ms = max(ms, __shfl_xor_sync(0xffffffffu, ms, o));
-      l0 += __shfl_xor_sync(0xffffffffu, l0, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o); l2 += __shfl_xor_sync(0xffffffffu, l2, o);
-      l3 += __shfl_xor_sync(0xffffffffu, l3, o); l4 += __shfl_xor_sync(0xffffffffu, l4, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&stats->primary, v0); atomicAdd(&stats->shadow, v1);
-      atomicAdd(&stats->hits, v2); atomicAdd(&stats->steps, v3);
-      atomicAdd(&stats->steps_primary, v4);
-      atomicAdd(&stats->warp_slots_primary, 32ull * mp); atomicAdd(&stats->warp_slots_shadow, 32ull * ms);
-      atomicAdd(&stats->level_steps[0], l0); atomicAdd(&stats->level_steps[1], l1); atomicAdd(&stats->level_steps[2], l2);
-      atomicAdd(&stats->level_steps[3], l3); atomicAdd(&stats->level_steps[4], l4);
-    }
-  }
-}
+// the same frame through the per-octant forward cubes (MESO_FLAG_CUBES)
+#define RM_KERNEL_NAME raymarch_cubes_kernel
+#define RM_EXTRA_PARAM , CubeTables ct
+#define RM_CUBES true
+#define RM_SET_CUBES(sc) (sc).ct = ct
+#include "raymarch_kernel.inc"
+#undef RM_KERNEL_NAME
+#undef RM_EXTRA_PARAM
+#undef RM_CUBES
+#undef RM_SET_CUBES
 
 __global__ void __launch_bounds__(256) compose_tiles_kernel(const uint4* __restrict__ tiles, int world, int width, int height,
                                                             int tiles_x, int n_tiles, int64_t tiles_per_rank, uint4* __restrict__ frame) {
@@ -396,7 +351,7 @@ __global__ void __launch_bounds__(256) compose_tiles_kernel(const uint4* __restr
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick, int local_tile0, int local_tile_count) {
+                     uint8_t* d_touch_brick, int local_tile0, int local_tile_count, const CubeTables* cubes) {
   const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
   const int n_tiles = tiles_x * tiles_y;
   const int all_local = (n_tiles - rank + world - 1) / world;
@@ -405,6 +360,16 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
   const size_t smem = 0;
   // (Dispatching the tiles in a golden-ratio permuted order, to spread the expensive silhouette tiles over the launch,
   // was measured: no gain in the pipelined loop, 2 % slower alone -- neighbouring tiles share distance-field and brick lines.)
+  if (cubes) {
+    if (d_stats)
+      raymarch_cubes_kernel<true><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
+                                                                                     n_tiles, local_tile0, d_out, d_stats, d_touch_chunk, d_touch_brick, *cubes);
+    else
+      raymarch_cubes_kernel<false><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
+                                                                                      n_tiles, local_tile0, d_out, nullptr, nullptr, nullptr, *cubes);
+    (*lc.launches)++;
+    return;
+  }
   if (d_stats)
     raymarch_kernel<true><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
                                                                              n_tiles, local_tile0, d_out, d_stats, d_touch_chunk, d_touch_brick);

@@ -79,6 +79,12 @@ struct MesoCtx {
   bool streaming = false;
   int stream_kind = 0, stream_gran = 0;
   double stream_params[4] = {0, 0, 0, 0};
+  // forward cubes (MESO_FLAG_CUBES)
+  uint8_t* d_cube_cell = nullptr;
+  uint16_t* d_cube_brick = nullptr;
+  uint16_t* d_cube_cell2 = nullptr;
+  CubeTables cubes{};
+  bool cubes_valid = false;
   // misc
   uint32_t* d_flush = nullptr;
   size_t flush_words = 0;
@@ -153,6 +159,8 @@ static void free_scene(MesoCtx* c) {
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
   cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
   cudaFree(c->d_loaded); cudaFree(c->d_stream_list); cudaFree(c->d_stream_stats);
+  cudaFree(c->d_cube_cell); cudaFree(c->d_cube_brick); cudaFree(c->d_cube_cell2);
+  c->d_cube_cell = nullptr; c->d_cube_brick = nullptr; c->d_cube_cell2 = nullptr; c->cubes = CubeTables{}; c->cubes_valid = false;
   c->d_loaded = nullptr; c->d_stream_list = nullptr; c->stream_list_cap = 0; c->d_stream_stats = nullptr; c->streaming = false;
   v = DVolume{};
   c->d_table = nullptr; c->d_counts = c->d_offsets = nullptr; c->d_total = nullptr; c->d_inst = nullptr;
@@ -287,6 +295,7 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
 // call returns.  Every entry point that rewrites the volume in place orders its work on the context's stream behind the
 // traversal (not the host copy) of the frames still in flight; with no frame in flight this does nothing.
 static int join_frames(MesoCtx* c) {
+  c->cubes_valid = false;   // the same entry points invalidate the forward-cube tables (meso_build_cubes)
   for (int i = 0; i < MESO_FRAME_RING; i++)
     if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
   return MESO_OK;
@@ -461,6 +470,31 @@ int meso_ray_setup(const MesoGPUUniformCamera* cam, const int32_t origin_chunk[3
   return MESO_OK;
 }
 
+int meso_build_cubes(MesoCtx* c) {
+  NEED_SCENE(c);
+  const DVolume& v = c->v;
+  const size_t ncells = (size_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
+  if (!c->d_cube_cell) CK(cudaMalloc(&c->d_cube_cell, 8 * ncells));
+  if (!c->d_cube_brick) CK(cudaMalloc(&c->d_cube_brick, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t)));
+  if (!c->d_cube_cell2) CK(cudaMalloc(&c->d_cube_cell2, (size_t)v.max_bricks * 64 * sizeof(uint16_t)));
+  for (int i = 0; i < MESO_FRAME_RING; i++)     // frames in flight may be reading the old tables
+    if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
+  launch_build_cubes(c->lc(), v, c->d_cube_cell, c->d_cube_brick, c->d_cube_cell2);
+  CK_LAST("build cubes");
+  c->cubes.cell = c->d_cube_cell; c->cubes.brick = c->d_cube_brick; c->cubes.cell2 = c->d_cube_cell2; c->cubes.ncells = (int64_t)ncells;
+  c->cubes_valid = true;
+  return MESO_OK;
+}
+
+// the tables a raymarch launch should use: nullptr for the shipped walk, an error if MESO_FLAG_CUBES has nothing valid to read
+static int cubes_for(MesoCtx* c, uint32_t flags, const CubeTables** out) {
+  *out = nullptr;
+  if (!(flags & MESO_FLAG_CUBES)) return MESO_OK;
+  if (!c->cubes_valid) return fail(MESO_ERR_ARGUMENT, "MESO_FLAG_CUBES: call meso_build_cubes after the last change of the volume");
+  *out = &c->cubes;
+  return MESO_OK;
+}
+
 static int ensure_frame(MesoCtx* c, size_t px) {
   if (c->frame_px >= px) return MESO_OK;
   cudaFree(c->d_frame); c->d_frame = nullptr; c->frame_px = 0;
@@ -477,7 +511,11 @@ int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width,
   MesoRaySetup rs;
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr);
+  const CubeTables* cubes = nullptr;
+  r = cubes_for(c, flags, &cubes);
+  if (r != MESO_OK) return r;
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr,
+                  0, -1, cubes);
   CK_LAST("raymarch");
   return MESO_OK;
 }
@@ -505,6 +543,9 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
   MesoRaySetup rs;
   r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
+  const CubeTables* cubes = nullptr;
+  r = cubes_for(c, flags, &cubes);
+  if (r != MESO_OK) return r;
   const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
   int bands = tiles_y >= 64 ? 4 : (tiles_y >= 16 ? 2 : 1);   // measured on B200 at 4K: 1 -> 5.6 ms, 4 -> 4.0 ms, 16 -> 5.7 ms
   if (const char* e = getenv("MESO_E2E_BANDS")) bands = std::max(1, std::min(16, atoi(e)));  // tuning knob
@@ -520,7 +561,7 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
     LaunchCtx lc = c->lc();
     lc.stream = c->band_stream[b & 1];
     launch_raymarch(lc, c->v, rs, width, height, flags, 0, 1, MESO_LAYOUT_FRAME, c->d_frame, nullptr, nullptr, nullptr,
-                    ty0 * tiles_x, (ty1 - ty0) * tiles_x);
+                    ty0 * tiles_x, (ty1 - ty0) * tiles_x, cubes);
     CK_LAST("raymarch band");
     CK(cudaEventRecord(c->band_done[b], lc.stream));
     CK(cudaStreamWaitEvent(c->copy_stream, c->band_done[b], 0));
@@ -548,6 +589,9 @@ int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   MesoRaySetup rs;
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
+  const CubeTables* cubes = nullptr;
+  r = cubes_for(c, flags, &cubes);
+  if (r != MESO_OK) return r;
   // Frames of the ring alternate between the two band streams so that the tail of frame k (a few tiles with grazing
   // rays) overlaps the body of frame k+1; each is ordered after whatever the caller enqueued on the context's stream.
   LaunchCtx lc = c->lc();
@@ -556,7 +600,8 @@ int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaStreamWaitEvent(lc.stream, c->band_fork, 0));
   const size_t bpp = (flags & MESO_FLAG_RGBA8) ? 4 : sizeof(MesoHitRecord);
   if (c->world > 1) CK(cudaMemsetAsync(c->d_ring[slot], 0xFF, px * bpp, lc.stream));
-  launch_raymarch(lc, c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr);
+  launch_raymarch(lc, c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_ring[slot], nullptr, nullptr, nullptr,
+                  0, -1, cubes);
   CK_LAST("raymarch async");
   CK(cudaEventRecord(c->ring_traced[slot], lc.stream));
   CK(cudaStreamWaitEvent(c->copy_stream, c->ring_traced[slot], 0));
@@ -586,7 +631,11 @@ int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaMemsetAsync(c->d_stats, 0, sizeof(RayStatsDev), c->stream));
   CK(cudaMemsetAsync(c->d_touch_chunk, 0, (size_t)c->v.nchunks, c->stream));
   CK(cudaMemsetAsync(c->d_touch_brick, 0, c->v.max_bricks, c->stream));
-  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick);
+  const CubeTables* cubes = nullptr;
+  r = cubes_for(c, flags, &cubes);
+  if (r != MESO_OK) return r;
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick,
+                  0, -1, cubes);
   CK_LAST("raymarch stats");
   RayStatsDev h;
   std::vector<uint8_t> tc((size_t)c->v.nchunks), tb(c->v.max_bricks);

@@ -45,6 +45,16 @@ struct DVolume {
   int chunk_words;      // number of u32 words in chunk_any / chunk_full
 };
 
+// Per-octant forward cubes (k_cubes.cu, meso_build_cubes; opt-in raymarch path MESO_FLAG_CUBES).  Octant of a ray =
+// (step_x < 0) | (step_y < 0) << 1 | (step_z < 0) << 2; "forward" = towards that octant.  Every entry certifies an EMPTY
+// cube that starts at the cell / brick / 2^3 cell and is `edge` units long on each axis (outside the grid counts as empty).
+struct CubeTables {
+  const uint8_t* cell;    // [8][ncells]       edge in 32^3 cells (1 .. MESO_DF_K + 1); 0 = the cell is not empty
+  const uint16_t* brick;  // [nchunks * 4096]  2 bits per octant: edge - 1 in bricks (1..4); defined for empty bricks of non-empty cells
+  const uint16_t* cell2;  // [max_bricks * 64] 2 bits per octant: edge - 1 in 2^3 cells (1..4, inside the brick); defined for empty cells
+  int64_t ncells;
+};
+
 struct RayStatsDev {
   unsigned long long primary, shadow, hits, steps;
   unsigned long long steps_primary, warp_slots_primary, warp_slots_shadow;
@@ -72,7 +82,9 @@ void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1);
+                     uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1, const CubeTables* cubes = nullptr);
+// k_cubes.cu: (re)build the three tables for the current volume
+void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint16_t* d_brick, uint16_t* d_cell2);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
