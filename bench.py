@@ -276,6 +276,10 @@ def run_ours(args):
     ctx.scene_create(origin, dims, max_bricks=(1 << 20) if n >= 4096 else (1 << 18))
     t_build = time.perf_counter()
     ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)  # replicated on every rank
+    if capi.ENV_CUBES:
+        # A/B switch (MESO_CUBES=1, off by default): the opt-in forward-cube walk for every raymarch call on this scene
+        # until an edit invalidates the tables (the edit loop then falls back to the shipped walk)
+        ctx.build_cubes()
     ctx.sync()
     t_build = time.perf_counter() - t_build
     cams = make_cameras(scene, width, height)
@@ -621,7 +625,8 @@ def run_ours(args):
                        "cache": "no flush inside the timed region: every step writes its own 132.7 MB frame (%d frame buffers cycled) and re-reads the scene, a per-step footprint above the 126 MB L2; the kernel-alone roofline loop flushes L2 (256 MiB write) between launches" % R,
                        "frames_in_flight": R,
                        "gather": gather, "gather_verified_equal_to_1gpu_frame": gather_verified,
-                       "scene_build_s": t_build},
+                       "scene_build_s": t_build,
+                       "walk": "forward cubes (MESO_CUBES=1, opt-in)" if capi.ENV_CUBES else "shipped (v8)"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
                     "steps": e2e_steps, "rgba8": e2e_rgba8,
                     "note": ("meso_raymarch_async()/meso_frame_wait() frame ring of 4: FGPUUniformCamera from host memory (kernel parameters), records copied to pinned host memory, copy of frame k overlapping frame k+1"

@@ -53,6 +53,9 @@ SYMBOLS = [
     "meso_device_copy", "meso_build_cubes",
 ]
 IPC_HANDLE_BYTES = 64
+# A/B switch for measurements (off unless MESO_CUBES=1): every raymarch call of a Context whose forward-cube tables are
+# current (build_cubes() since the last volume change) adds FLAG_CUBES.  bench.py builds the tables when it is set.
+ENV_CUBES = os.environ.get("MESO_CUBES") == "1"
 
 
 class MesoError(RuntimeError):
@@ -170,6 +173,7 @@ class Context:
         return int(lib.meso_launch_count(self.h))
 
     def scene_create(self, origin_chunk, dims_chunks, max_bricks, cfg=None):
+        self._cubes_ready = False
         cfg = default_scene_config() if cfg is None else cfg
         self.origin = np.ascontiguousarray(origin_chunk, dtype=np.int32)
         self.dims = np.ascontiguousarray(dims_chunks, dtype=np.int32)
@@ -177,12 +181,14 @@ class Context:
         _ck(lib.meso_scene_create(self.h, _p(cfg), _p(self.origin), _p(self.dims), C.c_uint32(max_bricks)))
 
     def voxelize_sdf(self, kind, params=None, granularity=GRAN_VOXEL):
+        self._cubes_ready = False
         p = np.zeros(4, dtype=np.float64)
         if params is not None:
             p[: len(params)] = np.asarray(params, dtype=np.float64)
         _ck(lib.meso_voxelize_sdf(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
 
     def volume_upload(self, occ, full, keys, payload):
+        self._cubes_ready = False
         occ = np.ascontiguousarray(occ, dtype=np.uint64)
         full = np.ascontiguousarray(full, dtype=np.uint64)
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -217,19 +223,23 @@ class Context:
     def build_cubes(self):
         """(Re)build the per-octant forward-cube tables that FLAG_CUBES reads (opt-in raymarch path)."""
         _ck(lib.meso_build_cubes(self.h))
+        self._cubes_ready = True
+
+    def _auto_cubes(self):
+        return FLAG_CUBES if (ENV_CUBES and getattr(self, "_cubes_ready", False)) else 0
 
     def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False, cubes=False):
         """End-to-end call: camera from host memory, records (or, rgba8=True, the colour image as uint32) into host memory."""
         rec = out if out is not None else np.zeros((height, width), dtype=np.uint32 if rgba8 else HitRecord)
         l = np.ascontiguousarray(light, dtype=np.float32)
-        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0)
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0) | self._auto_cubes()
         _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(rec)))
         return rec
 
     def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False, cubes=False):
         """Frame-ring call: enqueue frame + copy into `out` (pinned numpy array); pair with frame_wait(slot)."""
         l = np.ascontiguousarray(light, dtype=np.float32)
-        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0)
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0) | self._auto_cubes()
         _ck(lib.meso_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(out), C.c_int(slot)))
 
     def frame_wait(self, slot):
@@ -238,7 +248,7 @@ class Context:
     def raymarch_device(self, cam, width, height, d_records, shadow=True, light=(0.3, 0.5, 0.8), layout=LAYOUT_FRAME, flags_extra=0):
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
-                                     C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
+                                     C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra | self._auto_cubes()), _p(l), C.c_void_p(d_records), C.c_int(layout)))
 
     def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), cubes=False):
         st = np.zeros(1, dtype=RayStats)
@@ -269,6 +279,7 @@ class Context:
         _ck(lib.meso_mesh_device_shared(self.h, C.c_void_p(d_quads), C.c_void_p(d_counter), C.c_int64(cap)))
 
     def carve_sphere(self, center, radius):
+        self._cubes_ready = False
         c = np.ascontiguousarray(center, dtype=np.int32)
         n = C.c_int64(0)
         _ck(lib.meso_carve_sphere(self.h, _p(c), C.c_int32(radius), C.byref(n)))
@@ -312,11 +323,13 @@ class Context:
         return out
 
     def stream_begin(self, kind, params=None, granularity=GRAN_VOXEL):
+        self._cubes_ready = False
         p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
         _ck(lib.meso_stream_begin(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
 
     def stream_update(self, camera_chunk, forward, max_new, view=None, wait=True):
         """FChunkManage::UpdateChunks + UpdateLoadingQueue; returns StreamStats (wait=True) or None (enqueue only)."""
+        self._cubes_ready = False
         view = view_config() if view is None else view
         cc = np.ascontiguousarray(camera_chunk, dtype=np.int32)
         f = np.ascontiguousarray(forward, dtype=np.float32)
