@@ -279,7 +279,6 @@ class Context:
         _ck(lib.meso_mesh_device_shared(self.h, C.c_void_p(d_quads), C.c_void_p(d_counter), C.c_int64(cap)))
 
     def carve_sphere(self, center, radius):
-        self._cubes_ready = False
         c = np.ascontiguousarray(center, dtype=np.int32)
         n = C.c_int64(0)
         _ck(lib.meso_carve_sphere(self.h, _p(c), C.c_int32(radius), C.byref(n)))

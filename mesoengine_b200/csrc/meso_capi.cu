@@ -295,7 +295,6 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
 // call returns.  Every entry point that rewrites the volume in place orders its work on the context's stream behind the
 // traversal (not the host copy) of the frames still in flight; with no frame in flight this does nothing.
 static int join_frames(MesoCtx* c) {
-  c->cubes_valid = false;   // the same entry points invalidate the forward-cube tables (meso_build_cubes)
   for (int i = 0; i < MESO_FRAME_RING; i++)
     if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
   return MESO_OK;
@@ -319,6 +318,7 @@ int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granular
   if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown granularity");
   if (kind == MESO_SDF_SPHERE && !params) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: sphere needs params");
   c->streaming = false;  // the whole grid is regenerated: a stream in progress ends (meso_stream_begin starts a new one)
+  c->cubes_valid = false;
   JOIN_FRAMES(c);
   launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
   CK_LAST("voxelize");
@@ -332,6 +332,7 @@ int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, co
   const size_t nc = (size_t)c->v.nchunks;
   for (int64_t i = 0; i < n; i++)
     if (keys[i] >= (uint64_t)nc * MESO_BLOCKS) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: key out of range");
+  c->cubes_valid = false;
   JOIN_FRAMES(c);
   CK(cudaMemcpyAsync(c->v.occ, occ, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->v.full, full, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
@@ -479,6 +480,10 @@ int meso_build_cubes(MesoCtx* c) {
   if (!c->d_cube_cell2) CK(cudaMalloc(&c->d_cube_cell2, (size_t)v.max_bricks * 64 * sizeof(uint16_t)));
   for (int i = 0; i < MESO_FRAME_RING; i++)     // frames in flight may be reading the old tables
     if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
+  // Entries of payload slots that do not exist yet read as "one cell": a carve only REMOVES voxels, so every cube the
+  // tables certify stays empty afterwards, and the slots it allocates (full bricks that became partial) are covered by
+  // this zero fill -- the tables survive carves (like the distance field) and are rebuilt only when voxels may be added.
+  CK(cudaMemsetAsync(c->d_cube_cell2, 0, (size_t)v.max_bricks * 64 * sizeof(uint16_t), c->stream));
   launch_build_cubes(c->lc(), v, c->d_cube_cell, c->d_cube_brick, c->d_cube_cell2);
   CK_LAST("build cubes");
   c->cubes.cell = c->d_cube_cell; c->cubes.brick = c->d_cube_brick; c->cubes.cell2 = c->d_cube_cell2; c->cubes.ncells = (int64_t)ncells;
@@ -882,6 +887,7 @@ int meso_stream_begin(MesoCtx* c, int kind, const double params[4], int granular
   const size_t nc = (size_t)v.nchunks;
   if (!c->d_loaded) CK(cudaMalloc(&c->d_loaded, (size_t)v.chunk_words * 4));
   if (!c->d_stream_stats) CK(cudaMalloc(&c->d_stream_stats, 16));
+  c->cubes_valid = false;
   JOIN_FRAMES(c);
   // empty volume: nothing is generated yet (FChunkPool::Initialize, ChunkPool.h:283-345)
   CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
@@ -916,6 +922,7 @@ int meso_stream_update_async(MesoCtx* c, const int32_t cam[3], const float forwa
     CK(cudaMalloc(&c->d_stream_list, (size_t)max_new * 4));
     c->stream_list_cap = max_new;
   }
+  c->cubes_valid = false;
   JOIN_FRAMES(c);
   launch_select_view(c->lc(), forward, *view, c->d_sel_keys, c->d_sel_count, c->d_sel_out, c->sel_cap);
   launch_stream_worklist(c->lc(), c->v, c->d_sel_out, c->d_sel_count, c->sel_cap, cam, c->d_loaded, max_new, c->d_stream_list, c->d_stream_stats);

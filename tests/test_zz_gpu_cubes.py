@@ -8,7 +8,8 @@ has run on hardware yet -- so these tests are skipped unless asked for, and are 
 What they pin: (1) frames through the cubes are byte-identical to the oracle's (any certified-empty box is a legal skip, so
 a wrong table shows up as a wrong record); (2) the kernel takes exactly the steps the oracle's step model takes with the
 same cubes (directional cells cap 32, brick cubes <= 4, 2^3-cell cubes <= 4) -- equality of the totals pins the three
-tables themselves; (3) the tables are invalidated by every call that rewrites the volume."""
+tables themselves; (3) the tables survive carves (which only remove voxels) and are invalidated by every call that may add
+voxels."""
 import os
 
 import numpy as np
@@ -82,18 +83,25 @@ def test_cubes_steps_equal_the_step_model(ctx, orc):
         assert int(st["steps"]) < int(shipped["steps"])
 
 
-def test_cubes_are_invalidated_by_edits(ctx, capi, orc):
+def test_cubes_survive_carves_and_are_invalidated_when_voxels_may_be_added(ctx, capi, orc):
     origin, dims, params = scenes.sphere_scene(256)
     vol = _scene(ctx, orc, orc.SDF_SPHERE, origin, dims, params, orc.GRAN_VOXEL)
-    cam = orc.camera_uniform(scenes.orbit_eyes(origin, dims, 8)[0][2], scenes.grid_center_world(origin, dims), width=64, height=40)
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cam = orc.camera_uniform(eyes[2], ctr, width=96, height=60)
     with pytest.raises(capi.MesoError):
-        ctx.raymarch(cam, 64, 40, cubes=True)            # never built for this volume
+        ctx.raymarch(cam, 96, 60, cubes=True)            # never built for this volume
     ctx.build_cubes()
-    ctx.raymarch(cam, 64, 40, cubes=True)
-    ctx.carve_sphere((128, 128, 40), 30)
-    vol.carve_sphere((128, 128, 40), 30)
+    # carves only remove voxels: the tables stay valid (conservative), incl. full bricks that become partial (new slots)
+    for center, radius in (((128, 128, 40), 30), ((60, 128, 128), 45), ((128, 200, 128), 12)):
+        ctx.carve_sphere(center, radius)
+        vol.carve_sphere(center, radius)
+        for eye in (eyes[2], eyes[5]):
+            cam = orc.camera_uniform(eye, ctr, width=96, height=60)
+            ref = vol.raymarch(orc.ray_setup(cam, origin, 96, 60), 96, 60, shadow=True)
+            assert ctx.raymarch(cam, 96, 60, shadow=True, cubes=True).tobytes() == ref.tobytes()
+    ctx.build_cubes()                                     # a rebuild after the edits gives the same frames with longer steps
+    ref = vol.raymarch(orc.ray_setup(cam, origin, 96, 60), 96, 60, shadow=True)
+    assert ctx.raymarch(cam, 96, 60, shadow=True, cubes=True).tobytes() == ref.tobytes()
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)     # voxels may have been added: the tables are gone
     with pytest.raises(capi.MesoError):
-        ctx.raymarch(cam, 64, 40, cubes=True)            # a full brick may have become partial: new payload slot, no table yet
-    ctx.build_cubes()
-    ref = vol.raymarch(orc.ray_setup(cam, origin, 64, 40), 64, 40, shadow=True)
-    assert ctx.raymarch(cam, 64, 40, shadow=True, cubes=True).tobytes() == ref.tobytes()
+        ctx.raymarch(cam, 96, 60, cubes=True)
