@@ -119,6 +119,7 @@ int64_t orc_volume_num_chunks(const OrcVolume*);
 const uint64_t* orc_volume_occ(const OrcVolume*);   /* nchunks*64 words */
 const uint64_t* orc_volume_full(const OrcVolume*);  /* nchunks*64 words */
 int64_t orc_volume_num_partial(const OrcVolume*);
+int64_t orc_volume_pool_slots(const OrcVolume*);   /* payload slots ever allocated (sizes the cell2 cube table) */
 /* Canonical export of partial bricks sorted by (chunk, block): keys[i] = chunk*4096+block, payload 8 words each. */
 int64_t orc_volume_export_partial(const OrcVolume*, uint64_t* keys, uint64_t* payload, int64_t cap);
 /* Import from canonical form (used to hand the GPU a host-generated volume and vice versa). */
@@ -179,6 +180,11 @@ uint32_t orc_nearest_direction(const float* dirs, uint32_t n, const float q[3]);
 void orc_step_model_config(int df_shift, int df_cap, int probe, int directional, int brick_cap, int cell2);
 int orc_step_model_build(const OrcVolume* v);
 void orc_step_model_counts(uint64_t out[6], int reset);
+/* The three forward-cube tables of csrc/k_cubes.cu (opt-in raymarch path), built with the GPU's algorithms in the GPU's
+ * layouts: cell [8][ncells] u8, brick [nchunks*4096] u16, cell2 [pool_n*64] u16 (oracle payload-slot order).
+ * orc_cube_tables_use makes ORC_DDA_MODEL read them (NULLs: back to on-the-fly cubes). */
+int orc_cube_tables(const OrcVolume* v, uint8_t* cell, uint16_t* brick, uint16_t* cell2);
+void orc_cube_tables_use(const OrcVolume* v, const uint8_t* cell, const uint16_t* brick, const uint16_t* cell2);
 
 int orc_hardware_threads(void);
 

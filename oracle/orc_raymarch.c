@@ -41,6 +41,9 @@ static uint64_t g_model_steps[6];   /* 0 voxel, 1 2^3 cell, 2 brick, 3 field ste
 static uint8_t* g_model_sym = NULL;       /* symmetric field, dd cells                      */
 static uint8_t* g_model_fwd = NULL;       /* forward-cube field, 8 octants x dd cells       */
 static int g_model_dd[3] = {0, 0, 0};
+/* table-driven variant: the three tables of csrc/k_cubes.cu, built by orc_cube_tables with the GPU's algorithms */
+static const uint8_t* g_tab_cell = NULL; static const uint16_t* g_tab_brick = NULL; static const uint16_t* g_tab_cell2 = NULL;
+static int64_t g_tab_ncells = 0;
 
 typedef struct { float o[3], d[3], inv[3]; int step[3]; } Ray;
 typedef struct { int hit; int c[3]; int axis; float t; uint64_t steps; } Trace;
@@ -155,9 +158,9 @@ static void model_walk(const Scene* s, const Ray* r, int c[3], Trace* tr) {
     /* field level */
     const int e[3] = {c[0] >> sh, c[1] >> sh, c[2] >> sh};
     const size_t ei = (size_t)e[0] + (size_t)g_model_dd[0] * ((size_t)e[1] + (size_t)g_model_dd[1] * (size_t)e[2]);
-    int k = m->directional ? g_model_fwd[(size_t)oct * ncell + ei] : g_model_sym[ei];
+    int k = g_tab_cell ? g_tab_cell[(size_t)oct * (size_t)g_tab_ncells + ei] : (m->directional ? g_model_fwd[(size_t)oct * ncell + ei] : g_model_sym[ei]);
     if (k > 0) {
-      if (!m->directional && m->probe) {
+      if (!g_tab_cell && !m->directional && m->probe) {
         int q[3]; int in = 1;
         for (int i = 0; i < 3; i++) { q[i] = e[i] + (r->step[i] < 0 ? -k : k); if (q[i] < 0 || q[i] >= g_model_dd[i]) in = 0; }
         if (in) { int d2 = g_model_sym[(size_t)q[0] + (size_t)g_model_dd[0] * ((size_t)q[1] + (size_t)g_model_dd[1] * (size_t)q[2])]; if (d2 > k) k += d2; }
@@ -178,6 +181,10 @@ static void model_walk(const Scene* s, const Ray* r, int c[3], Trace* tr) {
       /* empty brick: aligned brick step, or the largest empty cube of bricks towards the octant (direct test, cap brick_cap) */
       int kb = 1;
       const int b[3] = {c[0] >> 3, c[1] >> 3, c[2] >> 3};
+      if (g_tab_brick) {
+        const int64_t ci = orc_cidx(s->v, b[0] >> 4, b[1] >> 4, b[2] >> 4);
+        kb = 1 + ((g_tab_brick[(size_t)ci * ORC_BLOCKS + orc_bidx(b[0] & 15, b[1] & 15, b[2] & 15)] >> (2 * oct)) & 3);
+      } else
       for (int t = 2; t <= m->brick_cap; t++) {
         int empty = 1;
         for (int z = 0; z < t && empty; z++) for (int y = 0; y < t && empty; y++) for (int x = 0; x < t; x++) {
@@ -207,7 +214,18 @@ static void model_walk(const Scene* s, const Ray* r, int c[3], Trace* tr) {
       const int x0 = c[0] & 6, y0 = c[1] & 6, z0 = c[2] & 6;
       uint64_t mask = (3ull << (x0 + 8 * y0)) | (3ull << (x0 + 8 * (y0 + 1)));
       if (((p[z0] | p[z0 + 1]) & mask) == 0) size = 2;
-      if (size == 2 && m->cell2 > 1) {
+      if (size == 2 && g_tab_cell2) {
+        const int ce = ((c[0] >> 1) & 3) + 4 * ((c[1] >> 1) & 3) + 16 * ((c[2] >> 1) & 3);
+        const int kc = 1 + ((g_tab_cell2[(size_t)slot * 64 + ce] >> (2 * oct)) & 3);
+        if (kc > 1) {
+          int lo2[3], hi2[3];
+          for (int i = 0; i < 3; i++) { const int base = c[i] & ~1; hi2[i] = base + 2 * kc; lo2[i] = base + 2 - 2 * kc; }
+          if (!leave_box(r, c, lo2, hi2, tr)) return;
+          __atomic_fetch_add(&g_model_steps[1], 1, __ATOMIC_RELAXED);
+          if (!inside(s, c)) return;
+          continue;
+        }
+      } else if (size == 2 && m->cell2 > 1) {
         /* largest cube of empty 2^3 cells starting at this cell towards the octant, inside the brick */
         const int q0[3] = {(c[0] & 7) >> 1, (c[1] & 7) >> 1, (c[2] & 7) >> 1};
         int kc = 1;
@@ -630,4 +648,111 @@ int orc_step_model_build(const OrcVolume* v) {
   }
   free(occ);
   return 0;
+}
+
+
+/* ---- the tables of csrc/k_cubes.cu, built on the CPU with the GPU's algorithms (same layouts; cell2 indexed by the
+ * oracle's own payload slots) -- reference data for the opt-in forward-cube path and a check of the builders' logic ---- */
+int orc_cube_tables(const OrcVolume* v, uint8_t* cell, uint16_t* brick, uint16_t* cell2) {
+  const int dd[3] = {v->dims[0] * 4, v->dims[1] * 4, v->dims[2] * 4};
+  const int64_t n = (int64_t)dd[0] * dd[1] * dd[2];
+  const int cap = 32;
+  uint8_t* ne = (uint8_t*)calloc((size_t)n, 1);   /* cell not empty */
+  if (!ne) return -1;
+  for (int z = 0; z < dd[2]; z++) for (int y = 0; y < dd[1]; y++) for (int x = 0; x < dd[0]; x++) {
+    const int64_t ci = orc_cidx(v, x >> 2, y >> 2, z >> 2);
+    uint64_t m = 0;
+    for (int bz = 4 * (z & 3); bz < 4 * (z & 3) + 4; bz++) m |= v->occ[ci * ORC_WORDS + bz * 4 + (y & 3)] & (0x000F000F000F000Full << (4 * (x & 3)));
+    ne[x + (int64_t)dd[0] * (y + (int64_t)dd[1] * z)] = m != 0;
+  }
+  /* cube_cell_init_kernel + cube_cell_pass_kernel: relaxation rounds t = 2 .. 32, in place */
+  for (int o = 0; o < 8; o++) for (int64_t i = 0; i < n; i++) cell[(size_t)o * n + i] = ne[i] ? 0 : 1;
+  for (int t = 2; t <= cap; t++)
+    for (int o = 0; o < 8; o++) {
+      uint8_t* f = cell + (size_t)o * n;
+      const int sx = (o & 1) ? -1 : 1, sy = (o & 2) ? -1 : 1, sz = (o & 4) ? -1 : 1;
+      for (int z = 0; z < dd[2]; z++) for (int y = 0; y < dd[1]; y++) for (int x = 0; x < dd[0]; x++) {
+        const int64_t i = x + (int64_t)dd[0] * (y + (int64_t)dd[1] * z);
+        if (f[i] != t - 1) continue;
+        int ok = 1;
+        for (int q = 1; q < 8 && ok; q++) {
+          const int nx = x + ((q & 1) ? sx : 0), ny = y + ((q & 2) ? sy : 0), nz = z + ((q & 4) ? sz : 0);
+          if (nx < 0 || ny < 0 || nz < 0 || nx >= dd[0] || ny >= dd[1] || nz >= dd[2]) continue;
+          if (f[nx + (int64_t)dd[0] * (ny + (int64_t)dd[1] * nz)] < t - 1) ok = 0;
+        }
+        if (ok) f[i] = (uint8_t)t;
+      }
+    }
+  /* cube_brick_kernel: bricks of non-empty cells, shell tests up to 4 */
+  Scene sc; memset(&sc, 0, sizeof(sc)); sc.v = v;
+  memset(brick, 0, (size_t)v->nchunks * ORC_BLOCKS * sizeof(uint16_t));
+  for (int ez = 0; ez < dd[2]; ez++) for (int ey = 0; ey < dd[1]; ey++) for (int ex = 0; ex < dd[0]; ex++) {
+    if (!ne[ex + (int64_t)dd[0] * (ey + (int64_t)dd[1] * ez)]) continue;
+    for (int l = 0; l < 64; l++) {
+      const int bx = ex * 4 + (l & 3), by = ey * 4 + ((l >> 2) & 3), bz = ez * 4 + (l >> 4);
+      unsigned r = 0;
+      if (!brick_occupied(&sc, bx, by, bz)) {
+        for (int o = 0; o < 8; o++) {
+          const int sx = (o & 1) ? -1 : 1, sy = (o & 2) ? -1 : 1, sz = (o & 4) ? -1 : 1;
+          int k = 1;
+          for (int t = 2; t <= 4; t++) {
+            int empty = 1;
+            for (int z = 0; z < t && empty; z++) for (int y = 0; y < t && empty; y++) for (int x = 0; x < t; x++) {
+              if (x < t - 1 && y < t - 1 && z < t - 1) continue;
+              if (brick_occupied(&sc, bx + sx * x, by + sy * y, bz + sz * z)) { empty = 0; break; }
+            }
+            if (!empty) break;
+            k = t;
+          }
+          r |= (unsigned)(k - 1) << (2 * o);
+        }
+      }
+      const int64_t ci = orc_cidx(v, bx >> 4, by >> 4, bz >> 4);
+      brick[(size_t)ci * ORC_BLOCKS + orc_bidx(bx & 15, by & 15, bz & 15)] = (uint16_t)r;
+    }
+  }
+  /* cube_cell2_kernel: per payload slot, from the 2^3-cell mask */
+  for (int64_t slot = 0; slot < v->pool_n; slot++) {
+    const uint64_t* p = v->pool + (size_t)slot * 8;
+    uint64_t cm = 0;
+    for (int c = 0; c < 64; c++) {
+      const int x0 = 2 * (c & 3), y0 = 2 * ((c >> 2) & 3), z0 = 2 * (c >> 4);
+      const uint64_t mk = (3ull << (x0 + 8 * y0)) | (3ull << (x0 + 8 * (y0 + 1)));
+      if ((p[z0] | p[z0 + 1]) & mk) cm |= 1ull << c;
+    }
+    for (int c = 0; c < 64; c++) {
+      const int cx = c & 3, cy = (c >> 2) & 3, cz = c >> 4;
+      unsigned r = 0;
+      if (!((cm >> c) & 1ull)) {
+        for (int o = 0; o < 8; o++) {
+          const int sx = (o & 1) ? -1 : 1, sy = (o & 2) ? -1 : 1, sz = (o & 4) ? -1 : 1;
+          int k = 1;
+          for (int t = 2; t <= 4; t++) {
+            int empty = 1;
+            for (int z = 0; z < t && empty; z++) for (int y = 0; y < t && empty; y++) for (int x = 0; x < t; x++) {
+              if (x < t - 1 && y < t - 1 && z < t - 1) continue;
+              const int qx = cx + sx * x, qy = cy + sy * y, qz = cz + sz * z;
+              if (qx < 0 || qy < 0 || qz < 0 || qx > 3 || qy > 3 || qz > 3 || ((cm >> (qx + 4 * qy + 16 * qz)) & 1ull)) { empty = 0; break; }
+            }
+            if (!empty) break;
+            k = t;
+          }
+          r |= (unsigned)(k - 1) << (2 * o);
+        }
+      }
+      cell2[(size_t)slot * 64 + c] = (uint16_t)r;
+    }
+  }
+  free(ne);
+  return 0;
+}
+
+/* ORC_DDA_MODEL reads these tables instead of computing cubes on the fly (NULLs switch back). */
+void orc_cube_tables_use(const OrcVolume* v, const uint8_t* cell, const uint16_t* brick, const uint16_t* cell2) {
+  g_tab_cell = cell; g_tab_brick = brick; g_tab_cell2 = cell2;
+  if (cell) {
+    g_model.df_shift = 5;
+    for (int i = 0; i < 3; i++) g_model_dd[i] = v->dims[i] * 4;
+    g_tab_ncells = (int64_t)g_model_dd[0] * g_model_dd[1] * g_model_dd[2];
+  }
 }

@@ -261,3 +261,6 @@ int64_t orc_volume_build_occupancy(const OrcVolume* v, uint32_t stamp, OrcGPUChu
   }
   return total;
 }
+
+/* payload slots ever allocated (>= live partial bricks: a carve retires slots without reusing them) */
+int64_t orc_volume_pool_slots(const OrcVolume* v) { return v->pool_n; }

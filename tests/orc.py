@@ -232,6 +232,10 @@ class Volume:
     def num_partial(self):
         return int(lib.orc_volume_num_partial(self.h))
 
+    def num_partial_slots(self):
+        lib.orc_volume_pool_slots.restype = C.c_int64
+        return int(lib.orc_volume_pool_slots(self.h))
+
     def export_partial(self):
         n = self.num_partial()
         keys = np.zeros(max(n, 1), dtype=np.uint64)
@@ -307,6 +311,27 @@ def step_model_counts(reset=True):
     out = np.zeros(6, dtype=np.uint64)
     lib.orc_step_model_counts(_p(out), C.c_int(1 if reset else 0))
     return out
+
+
+def cube_tables(vol, extra_slots=0):
+    """The forward-cube tables of csrc/k_cubes.cu built on the CPU: (cell [8, ncells] u8, brick [nchunks*4096] u16,
+    cell2 [(pool_n + extra_slots)*64] u16; the extra entries stay zero = "one cell", as on the GPU, for payload slots a
+    later carve allocates)."""
+    ncells = int(np.prod(vol.dims.astype(np.int64) * 4))
+    cell = np.zeros((8, ncells), dtype=np.uint8)
+    brick = np.zeros(vol.nchunks * 4096, dtype=np.uint16)
+    cell2 = np.zeros((max(int(vol.num_partial_slots()), 1) + extra_slots) * 64, dtype=np.uint16)
+    if lib.orc_cube_tables(vol.h, _p(cell), _p(brick), _p(cell2)) != 0:
+        raise MemoryError("orc_cube_tables")
+    return cell, brick, cell2
+
+
+def cube_tables_use(vol, tables):
+    """Make DDA_MODEL read `tables` (as returned by cube_tables; keep them alive) or, with None, compute cubes on the fly."""
+    if tables is None:
+        lib.orc_cube_tables_use(vol.h, None, None, None)
+    else:
+        lib.orc_cube_tables_use(vol.h, _p(tables[0]), _p(tables[1]), _p(tables[2]))
 
 
 def sort_quads(q):

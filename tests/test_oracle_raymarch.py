@@ -156,3 +156,65 @@ def test_step_model_walks_produce_the_same_records(orc, cfg):
         assert got.tobytes() == ref.tobytes()
     counts = orc.step_model_counts()
     assert counts.sum() > 0 and (cfg.get("cell2", True) or counts[1] == 0)
+
+
+@pytest.mark.parametrize("scene", ["sphere", "terrain", "carved"])
+def test_cube_tables_built_with_the_gpu_algorithms_drive_the_same_walk(orc, scene):
+    """csrc/k_cubes.cu's three tables, built on the CPU with the same algorithms and layouts (relaxation rounds for the
+    cells, shell tests for bricks and 2^3 cells, 2 bits per octant): a walk that READS them produces the records of the
+    plain walk and takes exactly the steps of the walk that computes its cubes on the fly -- the builders, the packing and
+    the indexing agree with the definition of the cubes."""
+    if scene == "terrain":
+        origin, dims = (0, -1, 0), (2, 2, 2)
+        vol = orc.Volume(origin, dims).voxelize(orc.SDF_TERRAIN, None, granularity=orc.GRAN_VOXEL)
+    else:
+        origin, dims, params = scenes.sphere_scene(256)
+        vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL)
+        if scene == "carved":
+            vol.carve_sphere((128, 128, 40), 30)
+            vol.carve_sphere((60, 128, 128), 45)
+    w, h = 96, 54
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    tables = orc.cube_tables(vol)
+    assert tables[0].max() <= 32 and (tables[0] > 1).any() and (tables[1] != 0).any() and (tables[2] != 0).any()
+    orc.step_model(vol, df_shift=5, df_cap=32, probe=False, directional=True, brick_cap=4, cell2=4)
+    try:
+        for eye in (eyes[0], eyes[3], eyes[6]):
+            cam = orc.camera_uniform(eye, ctr, width=w, height=h)
+            rs = orc.ray_setup(cam, origin, w, h)
+            ref = vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_HIER)
+            orc.cube_tables_use(vol, None)
+            orc.step_model_counts(reset=True)
+            fly = vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_MODEL)
+            c_fly = orc.step_model_counts()
+            orc.cube_tables_use(vol, tables)
+            tab = vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_MODEL)
+            c_tab = orc.step_model_counts()
+            assert fly.tobytes() == ref.tobytes() and tab.tobytes() == ref.tobytes()
+            assert c_tab.tolist() == c_fly.tolist()
+    finally:
+        orc.cube_tables_use(vol, None)
+
+
+def test_cube_tables_stay_valid_after_carves(orc):
+    """Tables built BEFORE a carve, used AFTER it: a carve only removes voxels, so every certified cube is still empty; full
+    bricks that became partial get new payload slots whose (zero) entries mean "one cell".  Records == plain walk."""
+    origin, dims, params = scenes.sphere_scene(256)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL)
+    tables = orc.cube_tables(vol, extra_slots=1 << 15)
+    slots_before = vol.num_partial_slots()
+    for center, radius in (((128, 128, 40), 30), ((60, 128, 128), 45), ((128, 200, 128), 12)):
+        vol.carve_sphere(center, radius)
+    assert vol.num_partial_slots() > slots_before and vol.num_partial_slots() <= slots_before + (1 << 15)
+    w, h = 96, 54
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    orc.step_model(vol, df_shift=5, df_cap=32, probe=False, directional=True, brick_cap=4, cell2=4)
+    orc.cube_tables_use(vol, tables)
+    try:
+        for eye in (eyes[0], eyes[2], eyes[5], (ctr[0] - 2.0, ctr[1], ctr[2] - 9.5)):
+            cam = orc.camera_uniform(eye, ctr, width=w, height=h)
+            rs = orc.ray_setup(cam, origin, w, h)
+            ref = vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_HIER)
+            assert vol.raymarch(rs, w, h, shadow=True, mode=orc.DDA_MODEL).tobytes() == ref.tobytes()
+    finally:
+        orc.cube_tables_use(vol, None)
