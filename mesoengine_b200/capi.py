@@ -50,7 +50,7 @@ SYMBOLS = [
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
-    "meso_device_copy", "meso_build_cubes",
+    "meso_device_copy", "meso_build_cubes", "meso_download_cubes",
 ]
 IPC_HANDLE_BYTES = 64
 # A/B switch for measurements (off unless MESO_CUBES=1): every raymarch call of a Context whose forward-cube tables are
@@ -224,6 +224,14 @@ class Context:
         """(Re)build the per-octant forward-cube tables that FLAG_CUBES reads (opt-in raymarch path)."""
         _ck(lib.meso_build_cubes(self.h))
         self._cubes_ready = True
+
+    def download_cubes(self):
+        """-> (cell [8, ncells] u8, brick [nchunks*4096] u16) as built by build_cubes (debug / tests)."""
+        ncells = int(np.prod(self.dims.astype(np.int64) * 4))
+        cell = np.zeros((8, ncells), dtype=np.uint8)
+        brick = np.zeros(self.nchunks * 4096, dtype=np.uint16)
+        _ck(lib.meso_download_cubes(self.h, _p(cell), _p(brick)))
+        return cell, brick
 
     def _auto_cubes(self):
         return FLAG_CUBES if (ENV_CUBES and getattr(self, "_cubes_ready", False)) else 0

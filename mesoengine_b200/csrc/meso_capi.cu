@@ -491,6 +491,15 @@ int meso_build_cubes(MesoCtx* c) {
   return MESO_OK;
 }
 
+int meso_download_cubes(MesoCtx* c, uint8_t* cell, uint16_t* brick) {
+  NEED_SCENE(c);
+  if (!c->cubes_valid) return fail(MESO_ERR_ARGUMENT, "meso_download_cubes: call meso_build_cubes first");
+  if (cell) CK(cudaMemcpyAsync(cell, c->d_cube_cell, 8 * (size_t)c->cubes.ncells, cudaMemcpyDeviceToHost, c->stream));
+  if (brick) CK(cudaMemcpyAsync(brick, c->d_cube_brick, (size_t)c->v.nchunks * MESO_BLOCKS * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return MESO_OK;
+}
+
 // the tables a raymarch launch should use: nullptr for the shipped walk, an error if MESO_FLAG_CUBES has nothing valid to read
 static int cubes_for(MesoCtx* c, uint32_t flags, const CubeTables** out) {
   *out = nullptr;

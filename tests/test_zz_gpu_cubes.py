@@ -65,6 +65,22 @@ def test_cubes_frames_equal_oracle_terrain(ctx, orc):
     _frames_equal(ctx, orc, vol, origin, dims, 128, 72)
 
 
+@pytest.mark.parametrize("scene", ["sphere", "terrain"])
+def test_cube_tables_equal_the_cpu_tables(ctx, orc, scene):
+    """cell and brick tables (independent of payload-slot order) against oracle/orc_raymarch.c:orc_cube_tables, bit for bit."""
+    if scene == "sphere":
+        origin, dims, params = scenes.sphere_scene(256)
+        vol = _scene(ctx, orc, orc.SDF_SPHERE, origin, dims, params, orc.GRAN_VOXEL)
+    else:
+        origin, dims = (0, -1, 0), (2, 2, 3)
+        vol = _scene(ctx, orc, orc.SDF_TERRAIN, origin, dims, None, orc.GRAN_VOXEL)
+    ctx.build_cubes()
+    cell, brick = ctx.download_cubes()
+    ref_cell, ref_brick, _ = orc.cube_tables(vol)
+    assert np.array_equal(cell, ref_cell)
+    assert np.array_equal(brick, ref_brick)
+
+
 def test_cubes_steps_equal_the_step_model(ctx, orc):
     origin, dims, params = scenes.sphere_scene(256)
     vol = _scene(ctx, orc, orc.SDF_SPHERE, origin, dims, params, orc.GRAN_VOXEL)
