@@ -180,6 +180,8 @@ uint32_t orc_nearest_direction(const float* dirs, uint32_t n, const float q[3]);
 void orc_step_model_config(int df_shift, int df_cap, int probe, int directional, int brick_cap, int cell2);
 int orc_step_model_build(const OrcVolume* v);
 void orc_step_model_counts(uint64_t out[6], int reset);
+/* per-pixel steps of the primary and the shadow ray (2 x u32 per pixel of the full frame); NULL switches it off */
+void orc_debug_set_step_image(uint32_t* img, int width);
 /* The three forward-cube tables of csrc/k_cubes.cu (opt-in raymarch path), built with the GPU's algorithms in the GPU's
  * layouts: cell [8][ncells] u8, brick [nchunks*4096] u16, cell2 [pool_n*64] u16 (oracle payload-slot order).
  * orc_cube_tables_use makes ORC_DDA_MODEL read them (NULLs: back to on-the-fly cubes). */

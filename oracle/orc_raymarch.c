@@ -45,6 +45,11 @@ static int g_model_dd[3] = {0, 0, 0};
 static const uint8_t* g_tab_cell = NULL; static const uint16_t* g_tab_brick = NULL; static const uint16_t* g_tab_cell2 = NULL;
 static int64_t g_tab_ncells = 0;
 
+/* optional instrumentation: steps of every pixel's primary and shadow ray (2 x u32 per pixel, row-major full frame) --
+ * lets tools/step_model.py apply the kernel's warp shape (8x4 pixels) and predict warp iterations, not only steps */
+static uint32_t* g_step_image = NULL; static int g_step_image_w = 0;
+void orc_debug_set_step_image(uint32_t* img, int width) { g_step_image = img; g_step_image_w = width; }
+
 typedef struct { float o[3], d[3], inv[3]; int step[3]; } Ray;
 typedef struct { int hit; int c[3]; int axis; float t; uint64_t steps; } Trace;
 
@@ -364,6 +369,7 @@ static void shade_pixel(RmArg* a, int px, int py, uint64_t cnt[4]) {
   for (int i = 0; i < 3; i++) { float f = floorf(rs->o[i]); if (f > 1.0e9f) f = 1.0e9f; if (f < -1.0e9f) f = -1.0e9f; c0[i] = (int)f; }
   Trace tr = trace(&a->sc, &r, c0, a->mode);
   cnt[0]++; cnt[3] += tr.steps;
+  if (g_step_image) { g_step_image[2 * ((size_t)py * g_step_image_w + px)] = (uint32_t)tr.steps; g_step_image[2 * ((size_t)py * g_step_image_w + px) + 1] = 0; }
   OrcHitRecord* out = &a->rec[(size_t)py * a->width + px];
   if (!tr.hit) { out->w0 = 0xFFFFFFFFu; out->w1 = 0x0007FFFFu; out->t = INFINITY; out->rgba = 0xFF000000u; return; }
   cnt[2]++;
@@ -382,6 +388,7 @@ static void shade_pixel(RmArg* a, int px, int py, uint64_t cnt[4]) {
         sc0[ax] -= r.step[ax];
         Trace st = trace(&a->sc, &sr, sc0, a->mode);
         cnt[1]++; cnt[3] += st.steps;
+        if (g_step_image) g_step_image[2 * ((size_t)py * g_step_image_w + px) + 1] = (uint32_t)st.steps;
         shadow = st.hit;
       }
     }

@@ -306,6 +306,11 @@ def step_model(vol, df_shift=5, df_cap=32, probe=True, directional=False, brick_
         raise MemoryError("orc_step_model_build")
 
 
+def set_step_image(img, width=0):
+    """img: (H, W, 2) uint32 array receiving every pixel's primary / shadow step counts, or None to switch it off."""
+    lib.orc_debug_set_step_image(_p(img) if img is not None else None, C.c_int(width))
+
+
 def step_model_counts(reset=True):
     """-> steps by kind: voxel, 2^3 cell, brick, field step <= 2 cells, field step > 2 cells, grid entry."""
     out = np.zeros(6, dtype=np.uint64)

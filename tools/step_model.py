@@ -73,6 +73,15 @@ def main():
 
     results = []
     ref_records = {}
+    step_img = np.zeros((h, w, 2), dtype=np.uint32)
+    orc.set_step_image(step_img, w)
+
+    def warp_slots(y0, y1):
+        """32 x the longest lane of every warp (8 x 4 pixels, as the kernel maps them), primary and shadow phase."""
+        blk = step_img[y0:y1].reshape((y1 - y0) // 4, 4, w // 8, 8, 2)
+        mx = blk.max(axis=(1, 3)).astype(np.int64)
+        return 32 * int(mx[..., 0].sum()), 32 * int(mx[..., 1].sum())
+
     for name, cfg in CONFIGS:
         t0 = time.time()
         orc.step_model(vol, **cfg)
@@ -84,20 +93,25 @@ def main():
             orc.step_model_counts(reset=True)
             prim = shad = 0
             sig = 0
+            slots_p = slots_s = 0
             for (y0, y1) in bands:
                 rec, st = vol.raymarch(rs, w, h, rect=(0, y0, w, y1), shadow=True, mode=orc.DDA_MODEL, stats=True)
                 prim += int(st["primary"]); shad += int(st["shadow"])
                 sig ^= hash(rec[y0:y1].tobytes())
+                a, b = warp_slots(y0, y1)
+                slots_p += a; slots_s += b
             # every configuration must see the same frame
             assert ref_records.setdefault(ci, sig) == sig, "records differ between configurations"
             c = orc.step_model_counts()
-            per_cam[ci] = {"primary": prim, "shadow": shad, "steps": {k: int(v) for k, v in zip(KINDS, c)}}
+            per_cam[ci] = {"primary": prim, "shadow": shad, "steps": {k: int(v) for k, v in zip(KINDS, c)},
+                           "warp_slots_primary": slots_p, "warp_slots_shadow": slots_s}
         tot = {k: sum(per_cam[ci]["steps"][k] for ci in cams) for k in KINDS}
         rays = sum(per_cam[ci]["primary"] + per_cam[ci]["shadow"] for ci in cams)
         total_steps = sum(tot.values())
+        slots = sum(per_cam[ci]["warp_slots_primary"] + per_cam[ci]["warp_slots_shadow"] for ci in cams)
         results.append({"config": name, "params": cfg, "field_build_s": t_build, "rays_sampled": rays,
-                        "steps_per_ray": total_steps / rays, "by_kind_per_ray": {k: tot[k] / rays for k in KINDS}, "per_camera": per_cam})
-        print("%-82s %6.2f steps/ray  %s" % (name, total_steps / rays, "  ".join("%s %.2f" % (k, tot[k] / rays) for k in KINDS)), flush=True)
+                        "steps_per_ray": total_steps / rays, "warp_slots_per_ray": slots / rays, "lane_use": total_steps / slots, "by_kind_per_ray": {k: tot[k] / rays for k in KINDS}, "per_camera": per_cam})
+        print("%-82s %6.2f steps/ray  %6.2f warp slots/ray  %s" % (name, total_steps / rays, slots / rays, "  ".join("%s %.2f" % (k, tot[k] / rays) for k in KINDS)), flush=True)
 
     calib = None
     if measured:
@@ -111,16 +125,22 @@ def main():
             mrays = m["primary"] + m["shadow"]
             mod = base["per_camera"][ci]
             mo_rays = mod["primary"] + mod["shadow"]
-            rows_out.append({"camera": ci, "gpu_steps_per_ray": sum(mv.values()) / mrays,
+            rows_out.append({"camera": ci, "gpu_warp_slots_per_ray": (m["warp_slots_primary"] + m["warp_slots_shadow"]) / mrays,
+                             "model_warp_slots_per_ray": (mod["warp_slots_primary"] + mod["warp_slots_shadow"]) / mo_rays,
+                             "gpu_steps_per_ray": sum(mv.values()) / mrays,
                              "model_steps_per_ray": sum(v for k, v in mod["steps"].items() if k != "entry") / mo_rays,
                              "gpu_by_kind_per_ray": {k: v / mrays for k, v in mv.items()},
                              "model_by_kind_per_ray": {k: v / mo_rays for k, v in mod["steps"].items()}})
         calib = rows_out
         for r in rows_out:
-            print("camera %d: GPU %.2f steps/ray, model %.2f" % (r["camera"], r["gpu_steps_per_ray"], r["model_steps_per_ray"]))
+            print("camera %d: GPU %.2f steps/ray, model %.2f;  GPU %.2f warp slots/ray, model %.2f" %
+                  (r["camera"], r["gpu_steps_per_ray"], r["model_steps_per_ray"], r["gpu_warp_slots_per_ray"], r["model_warp_slots_per_ray"]))
     base_spr = results[0]["steps_per_ray"]
+    base_slots = results[0]["warp_slots_per_ray"]
     for r in results:
         r["relative_to_shipped"] = r["steps_per_ray"] / base_spr
+        r["warp_slots_relative_to_shipped"] = r["warp_slots_per_ray"] / base_slots
+    orc.set_step_image(None)
     with open(args.out, "w") as f:
         json.dump({"scene": "V-sphere %d^3 voxel-granular" % args.n, "resolution": [w, h], "sample": "%d bands x %d rows (1/%.2f of the frame), primary + shadow" % (len(bands), rows, scale),
                    "cameras": cams, "configs": results, "calibration_vs_gpu_stats_build": calib}, f, indent=1)
