@@ -125,13 +125,13 @@ def make_cameras(scene, width, height):
     return [camera.camera_uniform(e, ctr, width, height) for e in eyes]
 
 
-def sample_bands(height, n_bands=8, rows=8):
-    """The bounded CPU sample: n_bands bands of `rows` scanlines spread evenly over the frame."""
+def sample_rows(height, n_bands=8, rows=8):
+    """The bounded CPU sample: n_bands bands of `rows` scanlines spread evenly over the frame, as one list of scanlines."""
     out = []
     for b in range(n_bands):
         y0 = int((b + 0.5) * height / n_bands) - rows // 2
         y0 = max(0, min(height - rows, y0))
-        out.append((y0, y0 + rows))
+        out.extend(range(y0, y0 + rows))
     return out
 
 
@@ -144,15 +144,24 @@ def cpu_build_volume(orc, scene):
     return orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL, fast=True)
 
 
-def cpu_step(orc, vol, cam, width, height, bands, nthreads):
+def cpu_step(orc, vol, cam, width, height, rows, nthreads, out=None):
+    """One step of the CPU arm: the sampled scanlines of one frame in ONE parallel region over (row, 128-pixel span) items
+    (oracle/orc_raymarch.c:orc_raymarch_rows), so every one of `nthreads` threads has work for the whole call."""
     rs = orc.ray_setup(cam, vol.origin, width, height, LIGHT)
-    rays = 0
-    recs = []
-    for (y0, y1) in bands:
-        rec, st = vol.raymarch(rs, width, height, rect=(0, y0, width, y1), shadow=True, mode=orc.DDA_HIER, nthreads=nthreads, stats=True)
-        rays += int(st["primary"]) + int(st["shadow"])
-        recs.append(rec[y0:y1])
-    return rays, recs
+    rec, st = vol.raymarch_rows(rs, width, height, rows, shadow=True, mode=orc.DDA_HIER, nthreads=nthreads, out=out)
+    return int(st["primary"]) + int(st["shadow"]), rec
+
+
+def cpu_thread_scaling(orc, vol, cam, width, height, rows, nthreads):
+    """Mrays/s of the same sample on 1 thread and on all of them: what `cores` in cpu_baseline actually buys."""
+    out = {}
+    for nt in sorted({1, max(1, nthreads // 2), nthreads}):
+        r = rows if nt > 1 else rows[::8]            # one thread gets an eighth of the sample
+        t0 = time.perf_counter()
+        rays, _ = cpu_step(orc, vol, cam, width, height, r, nt)
+        out[str(nt)] = rays / (time.perf_counter() - t0) / 1e6
+    out["speedup_all_over_1"] = out[str(nthreads)] / out["1"]
+    return out
 
 
 def reference_code_timings(nthreads):
@@ -207,33 +216,38 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # oracle only: this arm must not load the product library (tests/scenes.py loads the scene formulas by file path)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
-    from mesoengine_b200 import scenes
+    import scenes
     n, width, height, desc = WORKLOADS[args.workload]
     scene = scenes.sphere_scene(n)
+    origin, dims, _ = scene
     nthreads = orc.hw_threads()
     vol = cpu_build_volume(orc, scene)
-    cams = make_cameras(scene, width, height)
-    bands = sample_bands(height)
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cams = [orc.camera_uniform(e, ctr, width=width, height=height) for e in eyes]
+    n_bands = max(8, min(64, 2 * nthreads))            # >= 16 items per thread whatever the box
+    rows = sample_rows(height, n_bands, 8)
+    buf = np.zeros((height, width), dtype=orc.HitRecord)
     for k in range(max(1, min(args.warmup, 2))):
-        cpu_step(orc, vol, cams[k % 8], width, height, bands, nthreads)
+        cpu_step(orc, vol, cams[k % 8], width, height, rows, nthreads, out=buf)
     t0 = time.perf_counter()
     rays = 0
     for k in range(args.steps):
-        r, _ = cpu_step(orc, vol, cams[k % 8], width, height, bands, nthreads)
+        r, _ = cpu_step(orc, vol, cams[k % 8], width, height, rows, nthreads, out=buf)
         rays += r
     dt = time.perf_counter() - t0
     value = rays / dt / 1e6
-    sample = "%d bands x %d rows x %d px per step (%.1f%% of the frame), cameras cycled" % (len(bands), bands[0][1] - bands[0][0], width,
-                                                                                           100.0 * sum(b[1] - b[0] for b in bands) / height)
+    scaling = cpu_thread_scaling(orc, vol, cams[0], width, height, rows, nthreads)
+    sample = "%d bands x 8 rows x %d px per step (%.1f%% of the frame) in one parallel region, cameras cycled" % (n_bands, width, 100.0 * len(rows) / height)
     line = {
         "impl": "reference", "metric": "Mrays/s voxel raymarch (primary + shadow)", "value": value, "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "scene": "V-sphere %d^3 voxel-granular" % n, "resolution": [width, height],
                    "note": "the reference application cannot be built here (SURVEY.md 8c) and has no voxel-in-brick level or shadow rays; the timed path is the CPU restatement (oracle/), which oracle/_ref pins against the reference's own code; 'reference_code' times that code itself"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": nthreads, "kind": "port", "sample": sample, "thread_scaling_mrays_s": scaling},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_code": reference_code_timings(nthreads),
     }
@@ -972,25 +986,27 @@ def cpu_baseline(ctx, capi, scene, cams, width, height, args):
     occ, full, keys, payload = ctx.volume_download()
     vol = orc.Volume(origin, dims).import_(occ, full, keys, payload)
     nthreads = orc.hw_threads()
-    bands = sample_bands(height, 32, 8)
-    cpu_step(orc, vol, cams[0], width, height, bands, nthreads)
+    n_bands = max(8, min(64, 2 * nthreads))
+    rows = sample_rows(height, n_bands, 8)
+    buf = np.zeros((height, width), dtype=orc.HitRecord)
+    cpu_step(orc, vol, cams[0], width, height, rows, nthreads, out=buf)
     rays = 0
     mism = 0
     n_steps = 16
     dt = 0.0
     for k in range(n_steps):
         t1 = time.perf_counter()
-        r, recs = cpu_step(orc, vol, cams[k % 8], width, height, bands, nthreads)
+        r, rec = cpu_step(orc, vol, cams[k % 8], width, height, rows, nthreads, out=buf)
         dt += time.perf_counter() - t1
         rays += r
         # byte-compare the same scanlines of the GPU frame (outside the CPU timing)
         gpu = ctx.raymarch(cams[k % 8], width, height, shadow=True, light=LIGHT)
-        for (y0, y1), rec in zip(bands, recs):
-            mism += int((gpu[y0:y1].view(np.uint32).reshape(-1, 4) != rec.view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
+        mism += int((gpu[rows].view(np.uint32).reshape(-1, 4) != rec[rows].view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
+    scaling = cpu_thread_scaling(orc, vol, cams[0], width, height, rows, nthreads)
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": nthreads, "kind": "port",
-            "sample": "%d steps x %d bands x %d rows x %d px (cameras cycled); records byte-compared with the GPU frame: %d mismatching pixels"
-                      % (n_steps, len(bands), bands[0][1] - bands[0][0], width, mism),
-            "parity_mismatches": mism}
+            "sample": "%d steps x %d bands x 8 rows x %d px in one parallel region per step (cameras cycled); records byte-compared with the GPU frame: %d mismatching pixels"
+                      % (n_steps, n_bands, width, mism),
+            "thread_scaling_mrays_s": scaling, "parity_mismatches": mism}
 
 
 def main():

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmeso_b200.so")
+# MESO_SO: measurement tools load an A/B build of the same library (tools/rm_ab.py); unset everywhere else
+SO_PATH = os.environ.get("MESO_SO") or os.path.join(_HERE, "libmeso_b200.so")
 
 GPUBlock = np.dtype([("ChunkIndex", "<u4"), ("BlockLocation", "u1", (4,)), ("BlockFrameStamp", "<u4")])
 GPUChunk = np.dtype([("ChunkLocation", "<i4", (3,)), ("ChunkFrameStamp", "<u4")])

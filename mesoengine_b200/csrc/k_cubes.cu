@@ -125,14 +125,31 @@ __global__ void __launch_bounds__(256) cube_cell2_kernel(DVolume v, uint16_t* __
   out[(size_t)slot * 64 + c] = (uint16_t)r;
 }
 
-void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint16_t* d_brick, uint16_t* d_cell2) {
+// cellp: the cell cubes with a one-cell border that reads 255 (outside the grid)
+__global__ void __launch_bounds__(256) cube_cell_pad_kernel(DVolume v, const uint8_t* __restrict__ f, uint8_t* __restrict__ fp, int64_t ncells, int64_t npcells) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 8 * npcells) return;
+  const int o = (int)(g / npcells);
+  const int64_t i = g - (int64_t)o * npcells;
+  const int p0 = v.ddims[0] + 2, p1 = v.ddims[1] + 2;
+  const int x = (int)(i % p0) - 1, y = (int)((i / p0) % p1) - 1, z = (int)(i / ((int64_t)p0 * p1)) - 1;
+  uint8_t val = 255;
+  if ((unsigned)x < (unsigned)v.ddims[0] && (unsigned)y < (unsigned)v.ddims[1] && (unsigned)z < (unsigned)v.ddims[2])
+    val = f[(size_t)o * ncells + (size_t)x + (size_t)v.ddims[0] * ((size_t)y + (size_t)v.ddims[1] * (size_t)z)];
+  fp[g] = val;
+}
+
+void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint8_t* d_cellp, uint16_t* d_brick, uint16_t* d_cell2) {
   const int64_t ncells = (int64_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
+  const int64_t npcells = (int64_t)(v.ddims[0] + 2) * (v.ddims[1] + 2) * (v.ddims[2] + 2);
   cube_cell_init_kernel<<<(unsigned)((ncells + 255) / 256), 256, 0, lc.stream>>>(v, d_cell, ncells);
   (*lc.launches)++;
   for (int t = 2; t <= CUBE_CAP; t++) {
     cube_cell_pass_kernel<<<(unsigned)((8 * ncells + 255) / 256), 256, 0, lc.stream>>>(v, d_cell, ncells, t);
     (*lc.launches)++;
   }
+  cube_cell_pad_kernel<<<(unsigned)((8 * npcells + 255) / 256), 256, 0, lc.stream>>>(v, d_cell, d_cellp, ncells, npcells);
+  (*lc.launches)++;
   cudaMemsetAsync(d_brick, 0, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t), lc.stream);
   cube_brick_kernel<<<(unsigned)((ncells * 64 + 255) / 256), 256, 0, lc.stream>>>(v, d_brick, ncells);
   (*lc.launches)++;

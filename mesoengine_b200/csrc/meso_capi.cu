@@ -81,6 +81,7 @@ struct MesoCtx {
   double stream_params[4] = {0, 0, 0, 0};
   // forward cubes (MESO_FLAG_CUBES)
   uint8_t* d_cube_cell = nullptr;
+  uint8_t* d_cube_cellp = nullptr;
   uint16_t* d_cube_brick = nullptr;
   uint16_t* d_cube_cell2 = nullptr;
   CubeTables cubes{};
@@ -159,8 +160,8 @@ static void free_scene(MesoCtx* c) {
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
   cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
   cudaFree(c->d_loaded); cudaFree(c->d_stream_list); cudaFree(c->d_stream_stats);
-  cudaFree(c->d_cube_cell); cudaFree(c->d_cube_brick); cudaFree(c->d_cube_cell2);
-  c->d_cube_cell = nullptr; c->d_cube_brick = nullptr; c->d_cube_cell2 = nullptr; c->cubes = CubeTables{}; c->cubes_valid = false;
+  cudaFree(c->d_cube_cell); cudaFree(c->d_cube_cellp); cudaFree(c->d_cube_brick); cudaFree(c->d_cube_cell2);
+  c->d_cube_cell = nullptr; c->d_cube_cellp = nullptr; c->d_cube_brick = nullptr; c->d_cube_cell2 = nullptr; c->cubes = CubeTables{}; c->cubes_valid = false;
   c->d_loaded = nullptr; c->d_stream_list = nullptr; c->stream_list_cap = 0; c->d_stream_stats = nullptr; c->streaming = false;
   v = DVolume{};
   c->d_table = nullptr; c->d_counts = c->d_offsets = nullptr; c->d_total = nullptr; c->d_inst = nullptr;
@@ -236,8 +237,10 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   for (int i = 0; i < 3; i++)
     if (dims[i] < 1 || dims[i] > 512) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: dims_chunks out of range [1,512]");
   if (max_bricks == 0) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: max_bricks must be > 0");
-  // 32-bit word / cell indices inside the kernels (64 words and 64 cells per chunk); 2^24 chunks would need > 300 GB anyway
-  if ((int64_t)dims[0] * dims[1] * dims[2] > (1ll << 24)) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: more than 2^24 chunks");
+  // 32-bit word / cell / brick indices inside the kernels (64 words, 64 cells, 4096 bricks per chunk): 2^20 chunks = a 12 800^3-voxel window
+  if ((int64_t)dims[0] * dims[1] * dims[2] > (1ll << 20)) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: more than 2^20 chunks");
+  // 32-bit brick / 2^3-cell indices in the raymarch (chunk * 4096 + brick, slot * 64 + cell)
+  if (max_bricks > (1u << 26)) return fail(MESO_ERR_ARGUMENT, "meso_scene_create: max_bricks above 2^26");
   CK(cudaSetDevice(c->device));
   if (c->has_scene) { cudaStreamSynchronize(c->stream); free_scene(c); }
   c->cfg = *cfg;
@@ -475,7 +478,9 @@ int meso_build_cubes(MesoCtx* c) {
   NEED_SCENE(c);
   const DVolume& v = c->v;
   const size_t ncells = (size_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
+  const size_t npcells = (size_t)(v.ddims[0] + 2) * (v.ddims[1] + 2) * (v.ddims[2] + 2);
   if (!c->d_cube_cell) CK(cudaMalloc(&c->d_cube_cell, 8 * ncells));
+  if (!c->d_cube_cellp) CK(cudaMalloc(&c->d_cube_cellp, 8 * npcells));
   if (!c->d_cube_brick) CK(cudaMalloc(&c->d_cube_brick, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t)));
   if (!c->d_cube_cell2) CK(cudaMalloc(&c->d_cube_cell2, (size_t)v.max_bricks * 64 * sizeof(uint16_t)));
   for (int i = 0; i < MESO_FRAME_RING; i++)     // frames in flight may be reading the old tables
@@ -484,9 +489,10 @@ int meso_build_cubes(MesoCtx* c) {
   // tables certify stays empty afterwards, and the slots it allocates (full bricks that became partial) are covered by
   // this zero fill -- the tables survive carves (like the distance field) and are rebuilt only when voxels may be added.
   CK(cudaMemsetAsync(c->d_cube_cell2, 0, (size_t)v.max_bricks * 64 * sizeof(uint16_t), c->stream));
-  launch_build_cubes(c->lc(), v, c->d_cube_cell, c->d_cube_brick, c->d_cube_cell2);
+  launch_build_cubes(c->lc(), v, c->d_cube_cell, c->d_cube_cellp, c->d_cube_brick, c->d_cube_cell2);
   CK_LAST("build cubes");
-  c->cubes.cell = c->d_cube_cell; c->cubes.brick = c->d_cube_brick; c->cubes.cell2 = c->d_cube_cell2; c->cubes.ncells = (int64_t)ncells;
+  c->cubes.cell = c->d_cube_cell; c->cubes.cellp = c->d_cube_cellp; c->cubes.pd0 = v.ddims[0] + 2; c->cubes.pd01 = (v.ddims[0] + 2) * (v.ddims[1] + 2);
+  c->cubes.npcells = (int64_t)npcells; c->cubes.brick = c->d_cube_brick; c->cubes.cell2 = c->d_cube_cell2; c->cubes.ncells = (int64_t)ncells;
   c->cubes_valid = true;
   return MESO_OK;
 }

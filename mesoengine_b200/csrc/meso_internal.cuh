@@ -50,6 +50,10 @@ struct DVolume {
 // cube that starts at the cell / brick / 2^3 cell and is `edge` units long on each axis (outside the grid counts as empty).
 struct CubeTables {
   const uint8_t* cell;    // [8][ncells]       edge in 32^3 cells (1 .. MESO_DF_K + 1); 0 = the cell is not empty
+  const uint8_t* cellp;   // [8][npcells]      the same with a one-cell border all around that reads 255 = outside the grid:
+                          //                   cell (x, y, z) at (x + 1) + pd0 (y + 1) + pd01 (z + 1); the raymarch's only exit test
+  int pd0, pd01;          // row / slice pitch of cellp: ddims[0] + 2, (ddims[0] + 2) (ddims[1] + 2)
+  int64_t npcells;
   const uint16_t* brick;  // [nchunks * 4096]  2 bits per octant: edge - 1 in bricks (1..4); defined for empty bricks of non-empty cells
   const uint16_t* cell2;  // [max_bricks * 64] 2 bits per octant: edge - 1 in 2^3 cells (1..4, inside the brick); defined for empty cells
   int64_t ncells;
@@ -84,7 +88,7 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
                      uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1, const CubeTables* cubes = nullptr);
 // k_cubes.cu: (re)build the three tables for the current volume
-void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint16_t* d_brick, uint16_t* d_cell2);
+void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint8_t* d_cellp, uint16_t* d_brick, uint16_t* d_cell2);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,

@@ -137,6 +137,10 @@ typedef struct { uint64_t primary, shadow, hits, steps; uint64_t touched_chunks,
 /* Render the sub-rectangle [x0,x1) x [y0,y1) into records (row-major, full frame stride `width`). */
 void orc_raymarch(const OrcVolume*, const OrcRaySetup*, int width, int height, int x0, int y0, int x1, int y1,
                   uint32_t flags, int dda_mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats);
+/* The same for an explicit list of scanlines (records still row-major width x height): one call = one parallel region
+ * over (row, 128-pixel span) items -- bench.py's bounded CPU sample. */
+void orc_raymarch_rows(const OrcVolume* v, const OrcRaySetup* rs, int width, int height, const int32_t* rows, int nrows,
+                       uint32_t flags, int mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats);
 /* Reference-semantics restatement of the instanced draw (SimpleVoxel.cpp:146-192,220-224): nearest of the three
  * camera-facing faces of every valid instance along the pixel-centre ray, fp64. Returns 1 on hit.
  * out: block location in camera-chunk-relative block units, face id, t (world units), margin to nearest edge. */

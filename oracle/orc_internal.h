@@ -25,6 +25,9 @@ struct OrcVolume {
   uint64_t* pool;   /* 8 words per payload */
   int64_t pool_n, pool_cap;
   pthread_mutex_t lock;
+  uint8_t* any;     /* per chunk: has >= 1 block.  Cache of the raymarch walk; cleared with the volume and rebuilt by the
+                       first frame after it.  A carve only removes blocks, so a stale 1 is merely conservative.       */
+  int any_valid;
 };
 
 /* bit index of block (x,y,z) in a chunk: x + 16*y + 256*z  (VoxelMathHelper.h:73-76) */

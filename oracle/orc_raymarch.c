@@ -352,7 +352,7 @@ done:
 static inline uint32_t to_un8(float x) { return (uint32_t)(x * 255.0f + 0.5f); }
 
 typedef struct {
-  Scene sc; const OrcRaySetup* rs; int width, x0, x1, y0; uint32_t flags; int mode; OrcHitRecord* rec;
+  Scene sc; const OrcRaySetup* rs; int width, x0, x1, y0; const int32_t* rows; uint32_t flags; int mode; OrcHitRecord* rec;
   uint64_t primary, shadow, hits, steps; pthread_mutex_t mu;
 } RmArg;
 
@@ -408,30 +408,61 @@ static void shade_pixel(RmArg* a, int px, int py, uint64_t cnt[4]) {
   out->rgba = ch[0] | (ch[1] << 8) | (ch[2] << 16); /* alpha 0 on hits (SimpleVoxel.cpp:222), 1 on clear (:315) */
 }
 
+/* work item = RM_SPAN consecutive pixels of one sampled row: fine enough that a handful of rows keeps every thread busy */
+#define RM_SPAN 128
 static void rm_range(void* ctx, int64_t b, int64_t e, int tid) {
   (void)tid;
   RmArg* a = (RmArg*)ctx;
   uint64_t cnt[4] = {0, 0, 0, 0};
-  for (int64_t row = b; row < e; row++)
-    for (int px = a->x0; px < a->x1; px++) shade_pixel(a, px, a->y0 + (int)row, cnt);
+  const int spans = (a->x1 - a->x0 + RM_SPAN - 1) / RM_SPAN;
+  for (int64_t it = b; it < e; it++) {
+    const int row = a->rows ? a->rows[it / spans] : a->y0 + (int)(it / spans);
+    const int xa = a->x0 + (int)(it % spans) * RM_SPAN;
+    const int xb = xa + RM_SPAN < a->x1 ? xa + RM_SPAN : a->x1;
+    for (int px = xa; px < xb; px++) shade_pixel(a, px, row, cnt);
+  }
   pthread_mutex_lock(&a->mu);
   a->primary += cnt[0]; a->shadow += cnt[1]; a->hits += cnt[2]; a->steps += cnt[3];
   pthread_mutex_unlock(&a->mu);
 }
 
+static const uint8_t* chunk_any_cached(const OrcVolume* cv) {
+  OrcVolume* v = (OrcVolume*)cv;   /* the cache is not part of the volume's value */
+  pthread_mutex_lock(&v->lock);
+  if (!v->any_valid) {
+    if (!v->any) v->any = (uint8_t*)malloc((size_t)v->nchunks);
+    for (int64_t c = 0; c < v->nchunks; c++) {
+      uint64_t o = 0;
+      for (int w = 0; w < ORC_WORDS; w++) o |= v->occ[c * ORC_WORDS + w];
+      v->any[c] = o != 0;
+    }
+    v->any_valid = 1;
+  }
+  pthread_mutex_unlock(&v->lock);
+  return v->any;
+}
+
+static void raymarch_impl(const OrcVolume* v, const OrcRaySetup* rs, int width, int x0, int y0, int x1, int nrows, const int32_t* rows,
+                          uint32_t flags, int mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats);
+
 void orc_raymarch(const OrcVolume* v, const OrcRaySetup* rs, int width, int height, int x0, int y0, int x1, int y1,
                   uint32_t flags, int mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats) {
   (void)height;
+  raymarch_impl(v, rs, width, x0, y0, x1, y1 - y0, NULL, flags, mode, nthreads, records, stats);
+}
+/* the same for an explicit list of scanlines (bench.py's bounded CPU sample: one call, one parallel region) */
+void orc_raymarch_rows(const OrcVolume* v, const OrcRaySetup* rs, int width, int height, const int32_t* rows, int nrows,
+                       uint32_t flags, int mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats) {
+  (void)height;
+  raymarch_impl(v, rs, width, 0, 0, width, nrows, rows, flags, mode, nthreads, records, stats);
+}
+
+static void raymarch_impl(const OrcVolume* v, const OrcRaySetup* rs, int width, int x0, int y0, int x1, int nrows, const int32_t* rows,
+                          uint32_t flags, int mode, int nthreads, OrcHitRecord* records, OrcRayStats* stats) {
   RmArg a; memset(&a, 0, sizeof(a));
   a.sc.v = v;
   for (int i = 0; i < 3; i++) a.sc.n[i] = v->dims[i] * ORC_CV;
-  uint8_t* any = (uint8_t*)calloc((size_t)v->nchunks, 1);
-  for (int64_t c = 0; c < v->nchunks; c++) {
-    uint64_t o = 0;
-    for (int w = 0; w < ORC_WORDS; w++) o |= v->occ[c * ORC_WORDS + w];
-    any[c] = o != 0;
-  }
-  a.sc.chunk_any = any;
+  a.sc.chunk_any = chunk_any_cached(v);
   uint8_t* df = NULL;
   if (mode == ORC_DDA_BOX) {
     /* cell occupancy from the block masks, then a brute-force Chebyshev distance (cap 8 cells): deliberately not the
@@ -470,9 +501,9 @@ void orc_raymarch(const OrcVolume* v, const OrcRaySetup* rs, int width, int heig
     a.sc.touched_chunk = (uint8_t*)calloc((size_t)v->nchunks, 1);
     a.sc.touched_brick = (uint8_t*)calloc((size_t)(v->pool_n > 0 ? v->pool_n : 1), 1);
   }
-  a.rs = rs; a.width = width; a.x0 = x0; a.x1 = x1; a.y0 = y0; a.flags = flags; a.mode = mode; a.rec = records;
+  a.rs = rs; a.width = width; a.x0 = x0; a.x1 = x1; a.y0 = y0; a.rows = rows; a.flags = flags; a.mode = mode; a.rec = records;
   pthread_mutex_init(&a.mu, NULL);
-  orc_parallel_for(y1 - y0, nthreads, 4, rm_range, &a);
+  orc_parallel_for((int64_t)nrows * ((x1 - x0 + RM_SPAN - 1) / RM_SPAN), nthreads, 1, rm_range, &a);
   pthread_mutex_destroy(&a.mu);
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -484,7 +515,6 @@ void orc_raymarch(const OrcVolume* v, const OrcRaySetup* rs, int width, int heig
     stats->u_bytes = 2 * (uint64_t)((v->nchunks + 7) / 8) + 1024 * stats->touched_chunks + 68 * stats->touched_bricks;
     free(a.sc.touched_chunk); free(a.sc.touched_brick);
   }
-  free(any);
   free(df);
 }
 

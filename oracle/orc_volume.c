@@ -11,15 +11,12 @@ int orc_hardware_threads(void) {
   return n < 1 ? 1 : (int)n;
 }
 
-/* ---- tiny parallel-for --------------------------------------------------------------------- */
-typedef struct { orc_range_fn fn; void* ctx; int64_t n, grain; int64_t* next; pthread_mutex_t* mu; int tid; } PfArg;
+/* ---- tiny parallel-for: dynamic scheduling over [0, n) in grains, one atomic fetch-add per grain -------- */
+typedef struct { orc_range_fn fn; void* ctx; int64_t n, grain; int64_t* next; int tid; } PfArg;
 static void* pf_worker(void* p) {
   PfArg* a = (PfArg*)p;
   for (;;) {
-    pthread_mutex_lock(a->mu);
-    int64_t b = *a->next;
-    *a->next = b + a->grain;
-    pthread_mutex_unlock(a->mu);
+    const int64_t b = __atomic_fetch_add(a->next, a->grain, __ATOMIC_RELAXED);
     if (b >= a->n) break;
     int64_t e = b + a->grain; if (e > a->n) e = a->n;
     a->fn(a->ctx, b, e, a->tid);
@@ -32,13 +29,13 @@ void orc_parallel_for(int64_t n, int nthreads, int64_t grain, orc_range_fn fn, v
   if (nthreads <= 1) { fn(ctx, 0, n, 0); return; }
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256]; PfArg args[256];
-  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
   int64_t next = 0;
   for (int i = 0; i < nthreads; i++) {
-    args[i] = (PfArg){fn, ctx, n, grain, &next, &mu, i};
-    pthread_create(&th[i], NULL, pf_worker, &args[i]);
+    args[i] = (PfArg){fn, ctx, n, grain, &next, i};
+    if (i > 0) pthread_create(&th[i], NULL, pf_worker, &args[i]);
   }
-  for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+  pf_worker(&args[0]);   /* the calling thread works too: nthreads threads busy, not nthreads + 1 */
+  for (int i = 1; i < nthreads; i++) pthread_join(th[i], NULL);
 }
 
 /* ---- volume ---------------------------------------------------------------------------------- */
@@ -57,7 +54,7 @@ OrcVolume* orc_volume_create(const int32_t origin[3], const int32_t dims[3]) {
 void orc_volume_destroy(OrcVolume* v) {
   if (!v) return;
   for (int64_t c = 0; c < v->nchunks; c++) free(v->bptr[c]);
-  free(v->bptr); free(v->occ); free(v->full); free(v->pool);
+  free(v->bptr); free(v->occ); free(v->full); free(v->pool); free(v->any);
   pthread_mutex_destroy(&v->lock);
   free(v);
 }
@@ -66,6 +63,7 @@ static void clear_volume(OrcVolume* v) {
   memset(v->full, 0, sizeof(uint64_t) * ORC_WORDS * (size_t)v->nchunks);
   for (int64_t c = 0; c < v->nchunks; c++) { free(v->bptr[c]); v->bptr[c] = NULL; }
   v->pool_n = 0;
+  v->any_valid = 0;
 }
 uint32_t orc_alloc_payload(OrcVolume* v) { /* caller holds v->lock */
   if (v->pool_n == v->pool_cap) {

@@ -274,6 +274,15 @@ class Volume:
                          C.c_int(nthreads or hw_threads()), _p(rec), _p(st) if stats else None)
         return (rec, st[0]) if stats else rec
 
+    def raymarch_rows(self, rs, width, height, rows, shadow=True, mode=DDA_HIER, nthreads=None, out=None):
+        """Scanlines `rows` of the frame in one parallel region -> (records [height, width] with those rows filled, stats)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        rec = out if out is not None else np.zeros((height, width), dtype=HitRecord)
+        st = np.zeros(1, dtype=RayStats)
+        lib.orc_raymarch_rows(self.h, _p(rs), C.c_int(width), C.c_int(height), _p(rows), C.c_int(len(rows)),
+                              C.c_uint32(FLAG_SHADOW if shadow else 0), C.c_int(mode), C.c_int(nthreads or hw_threads()), _p(rec), _p(st))
+        return rec, st[0]
+
     def mesh(self, nthreads=None):
         n = int(lib.orc_mesh(self.h, C.c_int(nthreads or hw_threads()), None, C.c_int64(0)))
         q = np.zeros(max(n, 1), dtype=Quad)

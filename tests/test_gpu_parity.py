@@ -249,6 +249,34 @@ def test_frame_ring_async_equals_sync(ctx, capi, orc):
         ctx.raymarch_async(cams[0], w, h, views[0], 7)   # slot out of range -> ArgumentOutOfRange-class error
 
 
+def test_edits_are_ordered_behind_frames_in_flight(ctx, capi, orc):
+    """meso_carve_sphere between two meso_raymarch_async frames must not race the frame that was started before it (join_frames in meso_capi.cu).
+    Frame A (started before the carve) shows the uncarved volume, frame B the carved one; repeated to give a race a chance."""
+    import torch
+    origin, dims, params = scenes.sphere_scene(256)
+    w, h = 640, 368
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cam = orc.camera_uniform(eyes[2], ctr, width=w, height=h)
+    hosts = [torch.empty((h, w, 4), dtype=torch.int32).pin_memory() for _ in range(2)]
+    views = [t.numpy().view(capi.HitRecord).reshape(h, w) for t in hosts]
+    for rep in range(5):
+        vol = _make(ctx, orc, origin, dims, orc.SDF_SPHERE, params, orc.GRAN_VOXEL)
+        before = vol.raymarch(orc.ray_setup(cam, origin, w, h), w, h, shadow=True)
+        # the carve sits where this camera looks: radius grows per repetition so every round changes many pixels
+        hit = np.argwhere(((before["w1"] >> 20) & 1) == 1)
+        py, px = hit[len(hit) // 2]
+        center = (int(before["w0"][py, px] & 0xFFFF), int(before["w0"][py, px] >> 16), int(before["w1"][py, px] & 0xFFFF))
+        ctx.raymarch_async(cam, w, h, views[0], 0)
+        ctx.carve_sphere(center, 20 + 6 * rep)            # enqueued while frame 0 may still be tracing
+        ctx.raymarch_async(cam, w, h, views[1], 1)
+        vol.carve_sphere(center, 20 + 6 * rep)
+        after = vol.raymarch(orc.ray_setup(cam, origin, w, h), w, h, shadow=True)
+        ctx.frame_wait(0); ctx.frame_wait(1)
+        assert before.tobytes() != after.tobytes()
+        assert views[0].tobytes() == before.tobytes(), "the carve raced the frame started before it (rep %d)" % rep
+        assert views[1].tobytes() == after.tobytes(), rep
+
+
 def test_rgba8_output_is_the_colour_word_of_the_records(ctx, capi, orc):
     """MESO_FLAG_RGBA8 (the reference's RGBA_UN8 offscreen colour target): 4 B per pixel, equal to record.rgba, through the
     synchronous banded call (ragged height: bands end on different rows) and through the frame ring; oracle-checked."""

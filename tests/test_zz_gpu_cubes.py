@@ -1,11 +1,6 @@
-"""Opt-in (MESO_TEST_CUBES=1): the per-octant forward-cube raymarch path (MESO_FLAG_CUBES, csrc/k_cubes.cu).
+"""The per-octant forward-cube raymarch path (MESO_FLAG_CUBES, csrc/k_cubes.cu).
 
-Written after round 1's GPU budget was spent: the code compiles, the shipped kernel's SASS is unchanged, and nothing here
-has run on hardware yet -- so these tests are skipped unless asked for, and are the first thing to run in round 2:
-
-    MESO_TEST_CUBES=1 python -m pytest tests/test_zz_gpu_cubes.py -m gpu -x -q
-
-What they pin: (1) frames through the cubes are byte-identical to the oracle's (any certified-empty box is a legal skip, so
+What these tests pin: (1) frames through the cubes are byte-identical to the oracle's (any certified-empty box is a legal skip, so
 a wrong table shows up as a wrong record); (2) the kernel takes exactly the steps the oracle's step model takes with the
 same cubes (directional cells cap 32, brick cubes <= 4, 2^3-cell cubes <= 4) -- equality of the totals pins the three
 tables themselves; (3) the tables survive carves (which only remove voxels) and are invalidated by every call that may add
@@ -17,8 +12,7 @@ import pytest
 
 import scenes
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MESO_TEST_CUBES") != "1", reason="forward-cube path not yet run on hardware; set MESO_TEST_CUBES=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -121,32 +115,3 @@ def test_cubes_survive_carves_and_are_invalidated_when_voxels_may_be_added(ctx, 
     ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)     # voxels may have been added: the tables are gone
     with pytest.raises(capi.MesoError):
         ctx.raymarch(cam, 96, 60, cubes=True)
-
-
-def test_edits_are_ordered_behind_frames_in_flight(ctx, capi, orc):
-    """Not about cubes, but equally unverified on hardware (same opt-in switch): meso_carve_sphere between two
-    meso_raymarch_async frames must not race the frame that was started before it (join_frames in meso_capi.cu).
-    Frame A (started before the carve) shows the uncarved volume, frame B the carved one; repeated to give a race a chance."""
-    import torch
-    origin, dims, params = scenes.sphere_scene(256)
-    w, h = 640, 368
-    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
-    cam = orc.camera_uniform(eyes[2], ctr, width=w, height=h)
-    hosts = [torch.empty((h, w, 4), dtype=torch.int32).pin_memory() for _ in range(2)]
-    views = [t.numpy().view(capi.HitRecord).reshape(h, w) for t in hosts]
-    for rep in range(5):
-        vol = _scene(ctx, orc, orc.SDF_SPHERE, origin, dims, params, orc.GRAN_VOXEL)
-        before = vol.raymarch(orc.ray_setup(cam, origin, w, h), w, h, shadow=True)
-        # the carve sits where this camera looks: radius grows per repetition so every round changes many pixels
-        hit = np.argwhere(((before["w1"] >> 20) & 1) == 1)
-        py, px = hit[len(hit) // 2]
-        center = (int(before["w0"][py, px] & 0xFFFF), int(before["w0"][py, px] >> 16), int(before["w1"][py, px] & 0xFFFF))
-        ctx.raymarch_async(cam, w, h, views[0], 0)
-        ctx.carve_sphere(center, 20 + 6 * rep)            # enqueued while frame 0 may still be tracing
-        ctx.raymarch_async(cam, w, h, views[1], 1)
-        vol.carve_sphere(center, 20 + 6 * rep)
-        after = vol.raymarch(orc.ray_setup(cam, origin, w, h), w, h, shadow=True)
-        ctx.frame_wait(0); ctx.frame_wait(1)
-        assert before.tobytes() != after.tobytes()
-        assert views[0].tobytes() == before.tobytes(), "the carve raced the frame started before it (rep %d)" % rep
-        assert views[1].tobytes() == after.tobytes(), rep
