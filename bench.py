@@ -313,21 +313,44 @@ def run_ours(args):
     if world > 1 and args.gather == "p2p":
         # Fused gather: rank 0 owns the frame (cudaMalloc through the C ABI, exported over CUDA IPC); every rank's
         # raymarch kernel stores its tile records straight into it over NVLink.  No gather pass, no compose pass.
-        try:
-            for i in range(R):
-                handle = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
-                if rank == 0:
+        # every rank issues every broadcast whatever fails where (a rank that left the loop early would leave the others
+        # waiting in a collective); failures are recorded and agreed on by one MIN all-reduce afterwards
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        for i in range(R):
+            handle = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                try:
                     frame_owner_ptrs[i] = ctx.device_alloc(px * 16)
                     handle.copy_(torch.from_numpy(ctx.ipc_export(frame_owner_ptrs[i])))
-                dist.broadcast(handle, src=0)
-                frame_ptrs[i] = frame_owner_ptrs[i] if rank == 0 else ctx.ipc_open(handle.cpu().numpy())
-            ok = torch.ones(1, dtype=torch.int32, device=dev)
-        except Exception as e:  # e.g. IPC not permitted in this container
-            sys.stderr.write("bench: p2p gather unavailable on rank %d (%s); falling back to NCCL all_gather\n" % (rank, e))
-            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+                except Exception as e:  # e.g. IPC not permitted in this container
+                    sys.stderr.write("bench: p2p gather unavailable on rank 0 (%s); falling back to NCCL all_gather\n" % e)
+                    ok.zero_()
+            dist.broadcast(handle, src=0)
+            if rank == 0:
+                frame_ptrs[i] = frame_owner_ptrs[i]
+            elif int(ok.item()) == 1:
+                try:
+                    frame_ptrs[i] = ctx.ipc_open(handle.cpu().numpy())
+                except Exception as e:
+                    sys.stderr.write("bench: p2p gather unavailable on rank %d (%s); falling back to NCCL all_gather\n" % (rank, e))
+                    ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 1:
             gather = "p2p"
+        else:   # release what was opened / allocated before falling back
+            for i in range(R):
+                if rank != 0 and frame_ptrs[i] is not None:
+                    try:
+                        ctx.ipc_close(frame_ptrs[i])
+                    except Exception:
+                        pass
+            dist.barrier()
+            if rank == 0:
+                for i in range(R):
+                    if frame_owner_ptrs[i] is not None:
+                        ctx.device_free(frame_owner_ptrs[i])
+            frame_ptrs = [None] * R
+            frame_owner_ptrs = [None] * R
     if world == 1 or gather != "p2p":
         frames = [torch.empty((height, width, 4), dtype=torch.int32, device=dev) for _ in range(R)]
     if world > 1 and gather != "p2p":

@@ -51,9 +51,10 @@ SYMBOLS = [
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
-    "meso_device_copy", "meso_build_cubes", "meso_download_cubes",
+    "meso_device_copy", "meso_build_cubes", "meso_download_cubes", "meso_volume_upload_blocks",
 ]
 IPC_HANDLE_BYTES = 64
+UPLOAD_MERGE = 1
 # A/B switch for measurements (off unless MESO_CUBES=1): every raymarch call of a Context whose forward-cube tables are
 # current (build_cubes() since the last volume change) adds FLAG_CUBES.  bench.py builds the tables when it is set.
 ENV_CUBES = os.environ.get("MESO_CUBES") == "1"
@@ -195,6 +196,16 @@ class Context:
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         payload = np.ascontiguousarray(payload, dtype=np.uint64)
         _ck(lib.meso_volume_upload(self.h, _p(occ), _p(full), _p(keys), _p(payload), C.c_int64(len(keys))))
+
+    def volume_upload_blocks(self, chunks, blocks, merge=False):
+        """The reference's own records: FGPUChunk table + FGPUBlock pool (ChunkPool.h:662-679).  Returns the accepted count."""
+        self._cubes_ready = False
+        chunks = np.ascontiguousarray(chunks, dtype=GPUChunk)
+        blocks = np.ascontiguousarray(blocks, dtype=GPUBlock)
+        n = C.c_int64(0)
+        _ck(lib.meso_volume_upload_blocks(self.h, _p(chunks), C.c_int64(len(chunks)), _p(blocks), C.c_int64(len(blocks)),
+                                          C.c_uint32(UPLOAD_MERGE if merge else 0), C.byref(n)))
+        return n.value
 
     def volume_download(self):
         occ = np.zeros((self.nchunks, 64), dtype=np.uint64)

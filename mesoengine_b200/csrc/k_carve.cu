@@ -46,18 +46,27 @@ __global__ void __launch_bounds__(256) carve_kernel(DVolume v, CarveBox box, uin
   for (int o = 1; o < 8; o <<= 1) { chg |= __shfl_xor_sync(0xffffffffu, chg, o); any |= __shfl_xor_sync(0xffffffffu, any, o); }
   uint32_t slot = 0xFFFFFFFFu;
   if (valid && occupied && chg && z == 0) {
-    const uint32_t di = atomicAdd(dirty_count, 1u);
-    if (di < cap_dirty) dirty[di] = (uint64_t)c * MESO_BLOCKS + (uint64_t)b;
-    const unsigned long long bit = 1ull << (b & 63);
-    if (was_full) atomicAnd((unsigned long long*)&v.full[c * 64 + (b >> 6)], ~bit);
-    if (!any) {
-      atomicAnd((unsigned long long*)&v.occ[c * 64 + (b >> 6)], ~bit);
-      v.bptr[c * MESO_BLOCKS + b] = 0xFFFFFFFFu;  // payload slot (if any) is retired, not recycled
-    } else if (was_full) {
+    // A full brick that becomes partial needs a payload slot: take it BEFORE touching the masks.  If the pool is
+    // exhausted the brick is left exactly as it was (still full, not dirty), the allocator is rolled back and the call
+    // reports the overflow -- the volume stays consistent (no occ && !full brick without a payload).
+    bool ok = true;
+    if (was_full && any) {
       slot = atomicAdd(v.pool_count, 1u);
-      if (slot < v.max_bricks) v.bptr[c * MESO_BLOCKS + b] = slot; else { *overflow = 1; slot = 0xFFFFFFFFu; }
-    } else {
-      slot = v.bptr[c * MESO_BLOCKS + b];
+      if (slot >= v.max_bricks) { atomicSub(v.pool_count, 1u); *overflow = 1; slot = 0xFFFFFFFFu; ok = false; }
+    }
+    if (ok) {
+      const uint32_t di = atomicAdd(dirty_count, 1u);
+      if (di < cap_dirty) dirty[di] = (uint64_t)c * MESO_BLOCKS + (uint64_t)b;
+      const unsigned long long bit = 1ull << (b & 63);
+      if (was_full) atomicAnd((unsigned long long*)&v.full[c * 64 + (b >> 6)], ~bit);
+      if (!any) {
+        atomicAnd((unsigned long long*)&v.occ[c * 64 + (b >> 6)], ~bit);
+        v.bptr[c * MESO_BLOCKS + b] = 0xFFFFFFFFu;  // payload slot (if any) is retired, not recycled
+      } else if (was_full) {
+        v.bptr[c * MESO_BLOCKS + b] = slot;
+      } else {
+        slot = v.bptr[c * MESO_BLOCKS + b];
+      }
     }
   }
   slot = __shfl_sync(0xffffffffu, slot, lane & ~7);

@@ -168,6 +168,42 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(DVolume v, uint32_t
   for (uint32_t i = t; i < words; i += 256) out[i] = s_rec[i];
 }
 
+// The reference's own upload records (FChunkPool::UploadChunk / UploadBlock, ChunkPool.h:662-679) scattered into the block
+// masks: one thread per FGPUBlock.  A block counts iff the vertex shader would draw it (SimpleVoxel.cpp:160-166:
+// ChunkIndex valid, chunk record valid, stamps equal) and its chunk lies inside the window; it becomes an all-solid
+// brick (the reference has no voxel-in-brick level).  12 B read per block, two 8-byte atomics.
+__global__ void __launch_bounds__(256) scatter_blocks_kernel(DVolume v, const MesoGPUChunk* __restrict__ chunks, int64_t n_chunks,
+                                                             const MesoGPUBlock* __restrict__ blocks, int64_t n_blocks,
+                                                             unsigned long long* accepted) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  bool ok = false;
+  if (i < n_blocks) {
+    const MesoGPUBlock b = blocks[i];
+    if (b.ChunkIndex != 2147483647u && (int64_t)b.ChunkIndex < n_chunks) {
+      const MesoGPUChunk ch = chunks[b.ChunkIndex];
+      const bool chunk_valid = !(ch.ChunkLocation[0] == 2147483647 && ch.ChunkLocation[1] == 2147483647 && ch.ChunkLocation[2] == 2147483647);
+      const int lx = ch.ChunkLocation[0] - v.origin[0], ly = ch.ChunkLocation[1] - v.origin[1], lz = ch.ChunkLocation[2] - v.origin[2];
+      if (chunk_valid && ch.ChunkFrameStamp == b.BlockFrameStamp && (unsigned)lx < (unsigned)v.dims[0] && (unsigned)ly < (unsigned)v.dims[1] &&
+          (unsigned)lz < (unsigned)v.dims[2] && b.BlockLocation[0] < 16 && b.BlockLocation[1] < 16 && b.BlockLocation[2] < 16) {
+        const int64_t c = chunk_index(v, lx, ly, lz);
+        const int bit = block_bit(b.BlockLocation[0], b.BlockLocation[1], b.BlockLocation[2]);
+        const unsigned long long m = 1ull << (bit & 63);
+        atomicOr((unsigned long long*)&v.occ[c * 64 + (bit >> 6)], m);
+        atomicOr((unsigned long long*)&v.full[c * 64 + (bit >> 6)], m);
+        ok = true;
+      }
+    }
+  }
+  const unsigned n = __popc(__ballot_sync(0xffffffffu, ok));
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(accepted, (unsigned long long)n);
+}
+void launch_scatter_blocks(const LaunchCtx& lc, const DVolume& v, const MesoGPUChunk* d_chunks, int64_t n_chunks, const MesoGPUBlock* d_blocks,
+                           int64_t n_blocks, unsigned long long* d_accepted) {
+  if (n_blocks <= 0) return;
+  scatter_blocks_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, lc.stream>>>(v, d_chunks, n_chunks, d_blocks, n_blocks, d_accepted);
+  (*lc.launches)++;
+}
+
 // pass 1: mips + per-chunk instance counts + exclusive scan (d_total = number of instances)
 void launch_occupancy_count(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, MesoGPUChunk* d_table, uint32_t* d_counts,
                             uint32_t* d_offsets, uint64_t* d_total) {
@@ -178,9 +214,9 @@ void launch_occupancy_count(const LaunchCtx& lc, const DVolume& v, uint32_t stam
 // pass 2: compacted FGPUBlock list in generator order
 void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, const uint32_t* d_counts, const uint32_t* d_offsets,
                            MesoGPUBlock* d_inst, int64_t cap_inst) {
-  static bool attr_set = false;
   const int smem = MESO_BLOCKS * 12;
-  if (!attr_set) { cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  // function attributes are per device: set it on every launch (a host-side table write), not once per process
+  cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   emit_instances_kernel<<<(unsigned)v.nchunks, 256, smem, lc.stream>>>(v, stamp, d_counts, d_offsets, d_inst, cap_inst);
   (*lc.launches) += 1;
 }

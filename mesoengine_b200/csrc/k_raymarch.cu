@@ -25,6 +25,7 @@
 #include "meso_internal.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 
 #define F_INF __int_as_float(0x7F800000)
 #define RM_THREADS 256
@@ -485,6 +486,13 @@ __device__ __forceinline__ int walk10(const DVolume& v, const Scene10& s, const 
         const unsigned b12 = ((unsigned)(cx >> 3) & 15u) | (((unsigned)(cy >> 3) & 15u) << 4) | (((unsigned)(cz >> 3) & 15u) << 8);
         const int wi = (int)(b12 >> 6);
         const unsigned bit = b12 & 63u;
+#ifdef RM10_DEBUG
+        if (w.ci < 0 || w.ci >= (int)v.nchunks) {
+          printf("RM10 bad ci=%d c=(%d,%d,%d) cs=(%d,%d,%d) g=(%d,%d,%d) ux=%u steps=%u la=%d lt=%g o=(%g,%g,%g) d=(%g,%g,%g) i=(%g,%g,%g)\n", w.ci, cx, cy, cz,
+                 w.csx, w.csy, w.csz, gx, gy, gz, w.ux, steps, w.la, w.lt, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz);
+          return W_EXIT;
+        }
+#endif
         if (wi != w.wtag) {
           const ulonglong2 p = __ldg(v.of + ((unsigned)w.ci * 64u + (unsigned)wi));
           w.wocc = p.x; w.wfull = p.y; w.wtag = wi;

@@ -257,10 +257,9 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
     s |= __shfl_xor_sync(0xffffffffu, s, 2);
     const bool any = __any_sync(0xffffffffu, s != 0ull);
     const bool all = __all_sync(0xffffffffu, s == ~0ull);
-    if (lane == 0) {
-      if (any) atomicOr(&s_occ, 1ull << i);
-      if (all) atomicOr(&s_full, 1ull << i);
-    }
+    // a mixed brick needs a payload slot; if the pool is exhausted the brick is dropped (left empty), the allocator rolled
+    // back and the overflow reported: the volume never holds an occ && !full brick without a payload
+    bool keep = any;
     if (any && !all) {
       uint32_t slot = 0;
       if (lane == 0) slot = atomicAdd(v.pool_count, 1u);
@@ -268,9 +267,14 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
       if (slot < v.max_bricks) {
         if (q == 0) v.pool[(size_t)slot * 8 + vz] = s;
         if (lane == 0) v.bptr[c * MESO_BLOCKS + bi] = slot;
-      } else if (lane == 0) {
-        *overflow = 1;
+      } else {
+        keep = false;
+        if (lane == 0) { atomicSub(v.pool_count, 1u); *overflow = 1; }
       }
+    }
+    if (lane == 0) {
+      if (keep) atomicOr(&s_occ, 1ull << i);
+      if (all) atomicOr(&s_full, 1ull << i);
     }
   }
   __syncthreads();

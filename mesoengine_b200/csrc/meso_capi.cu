@@ -333,27 +333,80 @@ int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, co
   if (!occ || !full || n < 0 || (n > 0 && (!keys || !payload))) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: null argument");
   if ((uint64_t)n > c->v.max_bricks) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: more partial bricks than max_bricks");
   const size_t nc = (size_t)c->v.nchunks;
-  for (int64_t i = 0; i < n; i++)
+  // every occ && !full brick needs exactly one key (its payload), and a key may only name such a brick: a partial brick
+  // without a payload slot would be dereferenced out of bounds by the raymarch, mesh and gather kernels
+  int64_t n_need = 0;
+  for (size_t i = 0; i < nc * 64; i++) {
+    if (full[i] & ~occ[i]) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: a brick is marked full but not occupied");
+    n_need += __builtin_popcountll(occ[i] & ~full[i]);
+  }
+  if (n_need != n) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: n_partial does not match popcount(occ & ~full)");
+  for (int64_t i = 0; i < n; i++) {
     if (keys[i] >= (uint64_t)nc * MESO_BLOCKS) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: key out of range");
+    if (i > 0 && keys[i] <= keys[i - 1]) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: keys must be strictly ascending");
+    const uint64_t w = keys[i] >> 6, b = keys[i] & 63;
+    if (!(((occ[w] & ~full[w]) >> b) & 1ull)) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload: key names a brick that is not partial");
+  }
   c->cubes_valid = false;
   JOIN_FRAMES(c);
-  CK(cudaMemcpyAsync(c->v.occ, occ, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->v.full, full, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemsetAsync(c->v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
-  const uint32_t n32 = (uint32_t)n;
-  CK(cudaMemcpyAsync(c->v.pool_count, &n32, 4, cudaMemcpyHostToDevice, c->stream));
   uint64_t *d_k = nullptr, *d_p = nullptr;
-  if (n > 0) {
-    CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_p, (size_t)n * 64));
-    CK(cudaMemcpyAsync(d_k, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_p, payload, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream));
-    launch_scatter_payload(c->lc(), c->v, d_k, d_p, n);
-  }
-  launch_volume_finalize(c->lc(), c->v);
-  CK_LAST("volume upload");
-  CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_k); cudaFree(d_p);
-  return MESO_OK;
+  auto body = [&]() -> int {
+    CK(cudaMemcpyAsync(c->v.occ, occ, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v.full, full, nc * 64 * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
+    const uint32_t n32 = (uint32_t)n;
+    CK(cudaMemcpyAsync(c->v.pool_count, &n32, 4, cudaMemcpyHostToDevice, c->stream));
+    if (n > 0) {
+      CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_p, (size_t)n * 64));
+      CK(cudaMemcpyAsync(d_k, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(d_p, payload, (size_t)n * 64, cudaMemcpyHostToDevice, c->stream));
+      launch_scatter_payload(c->lc(), c->v, d_k, d_p, n);
+    }
+    launch_volume_finalize(c->lc(), c->v);
+    CK_LAST("volume upload");
+    CK(cudaStreamSynchronize(c->stream));
+    return MESO_OK;
+  };
+  const int r = body();
+  cudaFree(d_k); cudaFree(d_p);   // on every path
+  return r;
+}
+
+int meso_volume_upload_blocks(MesoCtx* c, const MesoGPUChunk* chunks, int64_t n_chunks, const MesoGPUBlock* blocks, int64_t n_blocks,
+                              uint32_t flags, int64_t* n_accepted) {
+  NEED_SCENE(c);
+  if (n_chunks < 0 || n_blocks < 0 || (n_chunks > 0 && !chunks) || (n_blocks > 0 && !blocks)) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload_blocks: bad argument");
+  if (flags & ~(uint32_t)MESO_UPLOAD_MERGE) return fail(MESO_ERR_ARGUMENT, "meso_volume_upload_blocks: unknown flag");
+  DVolume& v = c->v;
+  const size_t nc = (size_t)v.nchunks;
+  c->cubes_valid = false;
+  c->streaming = false;
+  JOIN_FRAMES(c);
+  MesoGPUChunk* d_c = nullptr; MesoGPUBlock* d_b = nullptr;
+  auto body = [&]() -> int {
+    if (!(flags & MESO_UPLOAD_MERGE)) {   // replace: the window is emptied first (the reference re-uploads whole pools)
+      CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
+      CK(cudaMemsetAsync(v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
+      CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
+    }
+    CK(cudaMemsetAsync(c->d_quad_count, 0, 8, c->stream));   // borrowed as the accepted-block counter
+    if (n_blocks > 0 && n_chunks > 0) {
+      CK(cudaMalloc(&d_c, (size_t)n_chunks * sizeof(MesoGPUChunk))); CK(cudaMalloc(&d_b, (size_t)n_blocks * sizeof(MesoGPUBlock)));
+      CK(cudaMemcpyAsync(d_c, chunks, (size_t)n_chunks * sizeof(MesoGPUChunk), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemcpyAsync(d_b, blocks, (size_t)n_blocks * sizeof(MesoGPUBlock), cudaMemcpyHostToDevice, c->stream));
+      launch_scatter_blocks(c->lc(), v, d_c, n_chunks, d_b, n_blocks, c->d_quad_count);
+    }
+    launch_volume_finalize(c->lc(), v);
+    CK_LAST("volume upload blocks");
+    unsigned long long acc = 0;
+    CK(cudaMemcpyAsync(&acc, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (n_accepted) *n_accepted = (int64_t)acc;
+    return MESO_OK;
+  };
+  const int r = body();
+  cudaFree(d_c); cudaFree(d_b);
+  return r;
 }
 
 int meso_volume_num_partial(MesoCtx* c, int64_t* out) {

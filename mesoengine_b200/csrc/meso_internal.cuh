@@ -84,6 +84,9 @@ void launch_occupancy_count(const LaunchCtx& lc, const DVolume& v, uint32_t stam
 void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, const uint32_t* d_counts, const uint32_t* d_offsets,
                            MesoGPUBlock* d_inst, int64_t cap_inst);
 
+void launch_scatter_blocks(const LaunchCtx& lc, const DVolume& v, const MesoGPUChunk* d_chunks, int64_t n_chunks, const MesoGPUBlock* d_blocks,
+                           int64_t n_blocks, unsigned long long* d_accepted);
+
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
                      uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1, const CubeTables* cubes = nullptr);

@@ -8,10 +8,16 @@
 //   FGPUUniformCamera / SceneConfig       Runtimes/Shader/GPUStructures.h:13-56
 //   FVoxelMathHelper::ConvertToChunkLocation  Runtimes/Helper/VoxelMathHelper.h:17-22
 //   FVoxelCamera                          Runtimes/Instance/VoxelCamera.{h,cpp}
+//   FBinaryOccupancyVolume / FOccupancyHelper  Runtimes/Voxel/Occupancy/BinaryOccupancyVolume.h:5-99
+//   FChunkBase / FChunk / FEmptyChunk     Runtimes/Voxel/Chunk/Chunk.h:44-106
+//   GeneratorType (the CPU plug-in point) Runtimes/Voxel/Chunk/ChunkManager.h:61; FGeneratorHelper::GenerateSphere GeneratorHelper.h:120-150
 //   FChunkManage (facade)                 Runtimes/Voxel/Chunk/ChunkManager.h:90-102,134-159,211-400
 //   VoxelWindowsInstance (headless)       Runtimes/Instance/VoxelWindowsInstance.{h,cpp}: Initialize, RunInstance, hooks
 // Header-only like the reference's Runtimes.  No glm/boost/GLFW/Vulkan: a 40-line vector layer replaces glm here.
-// There is no CPU compute in this layer: generation, occupancy, meshing and visibility all run in libmeso_b200.so.
+// The product path has no CPU compute in this layer: generation, occupancy, meshing and visibility all run in
+// libmeso_b200.so.  The host OBJECTS the north star says stay intact (FChunk, FBinaryOccupancyVolume, a user-written
+// GeneratorType callback) are kept as plain containers with the reference's methods; what a callback produces travels
+// to the device as the reference's own FGPUChunk / FGPUBlock records (meso_volume_upload_blocks).
 #pragma once
 #include <array>
 #include <climits>
@@ -21,6 +27,7 @@
 #include <functional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/meso_cuda.h"
@@ -147,8 +154,105 @@ class FVoxelCamera {
   }
 };
 
-// What the generator plug-in point (GeneratorType, ChunkManager.h:61) becomes: the SDF is evaluated on the device, so the
-// "generator" is a description, not a callback.
+// ---- host objects of the reference, kept intact (plain containers; the device path does not need them) --------------
+// BinaryOccupancyVolume.h:5-39.  Bit storage = 64-bit words instead of boost::dynamic_bitset; index x + y R + z R^2
+// (FVoxelMathHelper::Convert3DTo1D, VoxelMathHelper.h:73-76); Set / GetClamped clamp the location into the volume.
+struct FBinaryOccupancyVolume {
+  using FOccupancyValue = bool;
+  std::vector<uint64_t> OccupancyVolume;
+  uint32_t Resolution = 0;
+  FBinaryOccupancyVolume() = default;
+  explicit FBinaryOccupancyVolume(uint32_t Resolution_) : OccupancyVolume(((size_t)Resolution_ * Resolution_ * Resolution_ + 63) / 64, 0ull), Resolution(Resolution_) {}
+  static int32_t Clamp1(int32_t v, int32_t hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+  uint32_t Index(ivec3 L) const { return (uint32_t)L.x + (uint32_t)L.y * Resolution + (uint32_t)L.z * Resolution * Resolution; }
+  uint32_t IndexClamped(ivec3 L) const { const int32_t h = (int32_t)Resolution - 1; return Index({Clamp1(L.x, h), Clamp1(L.y, h), Clamp1(L.z, h)}); }
+  bool bIsOutOfBound(ivec3 L) const { const int32_t r = (int32_t)Resolution; return L.x < 0 || L.x >= r || L.y < 0 || L.y >= r || L.z < 0 || L.z >= r; }
+  void Set(FOccupancyValue Value, ivec3 Location) {
+    const uint32_t i = IndexClamped(Location);
+    if (Value) OccupancyVolume[i >> 6] |= 1ull << (i & 63); else OccupancyVolume[i >> 6] &= ~(1ull << (i & 63));
+  }
+  FOccupancyValue GetClamped(ivec3 Location) const { const uint32_t i = IndexClamped(Location); return (OccupancyVolume[i >> 6] >> (i & 63)) & 1ull; }
+  FOccupancyValue Get(ivec3 Location) const { const uint32_t i = Index(Location); return (OccupancyVolume[i >> 6] >> (i & 63)) & 1ull; }
+  FOccupancyValue GetWithBoundaryCondition(ivec3 Location, FOccupancyValue BoundaryValue = false) const {
+    return bIsOutOfBound(Location) ? BoundaryValue : Get(Location);
+  }
+};
+
+// BinaryOccupancyVolume.h:45-99: a location within one cell of the border erodes to 0; otherwise the AND of its 26
+// (bUseComplex, the default) or 6 neighbours.
+struct FOccupancyHelper {
+  template <bool bUseComplex = true>
+  static bool ErodeSingleVoxel(const FBinaryOccupancyVolume& Volume, ivec3 L) {
+    const int32_t r = (int32_t)Volume.Resolution;
+    if (L.x < 1 || L.x >= r - 1 || L.y < 1 || L.y >= r - 1 || L.z < 1 || L.z >= r - 1) return false;
+    for (int dz = -1; dz <= 1; dz++)
+      for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+          const int n = (dx != 0) + (dy != 0) + (dz != 0);
+          if (n == 0 || (!bUseComplex && n != 1)) continue;
+          if (!Volume.Get({L.x + dx, L.y + dy, L.z + dz})) return false;
+        }
+    return true;
+  }
+};
+
+struct FChunkBase {                       // Chunk.h:44-55
+  ivec3 ChunkLocation{INT_MAX, INT_MAX, INT_MAX};
+  uint32_t ChunkFrameStamp = 0;
+  bool bIsValid() const { return ChunkLocation != ivec3{INT_MAX, INT_MAX, INT_MAX}; }
+};
+struct FChunk : public FChunkBase {       // Chunk.h:57-101
+  std::vector<FBlock> Blocks;
+  std::vector<FBinaryOccupancyVolume> OccupancyVolumeErodeMipmaps;
+  void AddBlock(const FBlock& NewBlock) { Blocks.push_back(NewBlock); }
+  // Mip0 = the block set; Mip_d, evaluated at block locations only, = erode(Mip_{d-1}).  On the device this is K2
+  // (meso_build_occupancy); the host method exists for callers that inspect a chunk before handing it over.
+  void CalculateOccupancyErodeMipmaps(const uint32_t Resolution = 16, const uint32_t MaxDepth = 4) {
+    OccupancyVolumeErodeMipmaps.clear();
+    OccupancyVolumeErodeMipmaps.emplace_back(Resolution);
+    for (const FBlock& b : Blocks) OccupancyVolumeErodeMipmaps[0].Set(true, {b.BlockLocation[0], b.BlockLocation[1], b.BlockLocation[2]});
+    for (uint32_t d = 1; d < MaxDepth; d++) {
+      FBinaryOccupancyVolume Mip(Resolution);
+      for (const FBlock& b : Blocks) {
+        const ivec3 L{b.BlockLocation[0], b.BlockLocation[1], b.BlockLocation[2]};
+        Mip.Set(FOccupancyHelper::ErodeSingleVoxel(OccupancyVolumeErodeMipmaps[d - 1], L), L);
+      }
+      OccupancyVolumeErodeMipmaps.push_back(std::move(Mip));
+    }
+  }
+  bool bShouldVoxelOccupancyCull(ivec3 BlockLocation, uint32_t ThresholdDepth = 2) const {
+    return OccupancyVolumeErodeMipmaps[ThresholdDepth].GetWithBoundaryCondition(BlockLocation, true);
+  }
+};
+struct FEmptyChunk : public FChunkBase {};
+
+// The generator plug-in point, as the reference declares it (ChunkManager.h:61): called once per chunk on host worker
+// threads; FChunk.Blocks is what travels to the device.
+using GeneratorType = std::function<FChunk(ivec3, float, unsigned char, uint32_t)>;
+
+struct FGeneratorHelper {
+  // GeneratorHelper.h:120-150: block min corner against the sphere (100,0,0) r 50, fp64, X outer / Z inner
+  static FChunk GenerateSphere(ivec3 StartLocation, float BlockSize, unsigned char ChunkResolution, uint32_t /*MipmapLevel*/) {
+    FChunk Result;
+    Result.ChunkLocation = StartLocation;
+    const double s = (double)BlockSize, cr = (double)ChunkResolution;
+    const double ox = (double)StartLocation.x * s * cr, oy = (double)StartLocation.y * s * cr, oz = (double)StartLocation.z * s * cr;
+    for (uint32_t X = 0; X < ChunkResolution; X++)
+      for (uint32_t Y = 0; Y < ChunkResolution; Y++)
+        for (uint32_t Z = 0; Z < ChunkResolution; Z++) {
+          const double dx = (ox + (double)X * s) - 100.0, dy = (oy + (double)Y * s) - 0.0, dz = (oz + (double)Z * s) - 0.0;
+          if (std::sqrt((dx * dx + dy * dy) + dz * dz) - 50.0 < 0.0) {
+            FBlock b; b.ChunkIndex = 0; b.BlockLocation[0] = (uint8_t)X; b.BlockLocation[1] = (uint8_t)Y; b.BlockLocation[2] = (uint8_t)Z; b.VolumeIndex = 0;
+            Result.AddBlock(b);
+          }
+        }
+    Result.CalculateOccupancyErodeMipmaps();
+    return Result;
+  }
+};
+
+// The device-side form of the plug-in point: the SDF is evaluated by K1, so the "generator" is a description, not a
+// callback.  A GeneratorType callback (above) is the other way in: FChunkManage runs it on host threads and uploads.
 struct FGeneratorDesc {
   int Kind = MESO_SDF_SPHERE;                       // FGeneratorHelper::GenerateSphere / TestGenerator
   double Params[4] = {100.0, 0.0, 0.0, 50.0};       // GeneratorHelper.h:134
@@ -203,6 +307,15 @@ class FChunkManage {
   bool bDebugDisableUpdateChunk = false;                                   // ChunkManager.h:76
   uint32_t DebugVisibleChunkNum = 0, DebugLoadedChunkNum = 0, DebugMissingChunkNum = 0;  // ChunkManager.h:66-75 counters
 
+  // FChunkManage::SetGenerator (ChunkManager.h:62-65): a user-written CPU generator.  When set, UpdateLoadingQueue runs it for
+  // every chunk of the window on ThreadCount host threads (the reference's generator workers, SimpleVoxel.cpp:260-261) and
+  // uploads the blocks as the reference's own FGPUChunk / FGPUBlock records; K2 (mips, cull, instances) stays on the device.
+  void SetGenerator(GeneratorType Generator_, uint32_t ThreadCount_ = 0) {
+    HostGenerator = std::move(Generator_);
+    const uint32_t hc = std::max(1u, std::thread::hardware_concurrency());
+    ThreadCount = ThreadCount_ ? ThreadCount_ : std::max(hc > 2 ? hc - 2 : 1u, 1u);
+    bDirty = true;
+  }
   void Initialize(MesoCtx* Ctx_, const FVoxelSceneConfig& VoxelSceneConfig, FGeneratorDesc Generator_, ivec3 WindowOrigin_, ivec3 WindowDims_,
                   bool bStreaming_ = false) {
     Ctx = Ctx_; Generator = Generator_; WindowOrigin = WindowOrigin_; WindowDims = WindowDims_; bStreaming = bStreaming_;
@@ -232,6 +345,7 @@ class FChunkManage {
   // ChunkManager.h:211-400: generate what is missing, then publish chunk table + block instances (K1 + K2 on the device)
   void UpdateLoadingQueue(const FVoxelSceneConfig& VoxelSceneConfig, uint32_t /*RenderFrameIndex*/) {
     if (bStreaming) {
+      if (HostGenerator) throw std::runtime_error("FChunkManage: a host GeneratorType callback needs the static window mode (bStreaming = false)");
       if (!bHasView) return;
       const int32_t cc[3] = {CameraChunk.x, CameraChunk.y, CameraChunk.z};
       const float f[3] = {ViewDirection.x, ViewDirection.y, ViewDirection.z};
@@ -244,13 +358,58 @@ class FChunkManage {
       return;
     }
     if (!bDirty) return;
+    if (HostGenerator) {
+      RunHostGenerator(VoxelSceneConfig);
+      Check(meso_build_occupancy(Ctx, FrameStamp, &ChunkPool.CurrentBlockCount), "meso_build_occupancy");
+      bDirty = false;
+      return;
+    }
     Check(meso_voxelize_sdf(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_voxelize_sdf");
     Check(meso_build_occupancy(Ctx, FrameStamp, &ChunkPool.CurrentBlockCount), "meso_build_occupancy");
     bDirty = false;
   }
+  int64_t DebugUploadedBlockNum = 0;      // blocks the last host-generator pass handed to the device
  private:
+  // MultiThreadGeneratorBatched (ChunkManager.h:183-210) without the pool placement: chunks of the window are dealt to the
+  // workers round-robin; every worker fills its own record vectors (ChunkIndex = the chunk's row in the table).
+  void RunHostGenerator(const FVoxelSceneConfig& VoxelSceneConfig) {
+    const int64_t n = (int64_t)WindowDims.x * WindowDims.y * WindowDims.z;
+    std::vector<FGPUChunk> Table((size_t)n);
+    const uint32_t nt = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(ThreadCount, n));
+    std::vector<std::vector<FGPUBlock>> Parts(nt);
+    std::vector<std::string> Errors(nt);
+    auto Work = [&](uint32_t t) {
+      try {
+        for (int64_t i = t; i < n; i += nt) {
+          const ivec3 loc{WindowOrigin.x + (int32_t)(i % WindowDims.x), WindowOrigin.y + (int32_t)((i / WindowDims.x) % WindowDims.y),
+                          WindowOrigin.z + (int32_t)(i / ((int64_t)WindowDims.x * WindowDims.y))};
+          FChunk c = HostGenerator(loc, VoxelSceneConfig.BlockSize, VoxelSceneConfig.ChunkResolution, 0u);
+          c.ChunkLocation = loc;   // "just make sure" (ChunkManager.h:167)
+          FGPUChunk rec;
+          if (c.Blocks.empty()) { rec.ChunkLocation[0] = rec.ChunkLocation[1] = rec.ChunkLocation[2] = INT_MAX; rec.ChunkFrameStamp = 0; }
+          else { rec.ChunkLocation[0] = loc.x; rec.ChunkLocation[1] = loc.y; rec.ChunkLocation[2] = loc.z; rec.ChunkFrameStamp = FrameStamp; }
+          Table[(size_t)i] = rec;
+          for (const FBlock& b : c.Blocks)
+            Parts[t].push_back(FGPUBlock{(uint32_t)i, {b.BlockLocation[0], b.BlockLocation[1], b.BlockLocation[2], 255u}, FrameStamp});
+        }
+      } catch (const std::exception& e) { Errors[t] = e.what(); }
+    };
+    std::vector<std::thread> Workers;
+    for (uint32_t t = 1; t < nt; t++) Workers.emplace_back(Work, t);
+    Work(0);
+    for (auto& w : Workers) w.join();
+    for (const auto& e : Errors) if (!e.empty()) throw std::runtime_error("GeneratorType callback: " + e);
+    std::vector<FGPUBlock> Blocks;
+    size_t total = 0;
+    for (const auto& p : Parts) total += p.size();
+    Blocks.reserve(total);
+    for (const auto& p : Parts) Blocks.insert(Blocks.end(), p.begin(), p.end());
+    Check(meso_volume_upload_blocks(Ctx, Table.data(), n, Blocks.data(), (int64_t)Blocks.size(), 0u, &DebugUploadedBlockNum), "meso_volume_upload_blocks");
+  }
   MesoCtx* Ctx = nullptr;
   FGeneratorDesc Generator;
+  GeneratorType HostGenerator;
+  uint32_t ThreadCount = 1;
   ivec3 CameraChunk{0, 0, 0};
   vec3 ViewDirection{};
   bool bHasView = false;

@@ -3,7 +3,9 @@
 // instanced draw of Render() (cmdBindVertexBuffer / cmdPushConstants / cmdDrawIndexed(8, MaxBlockCount),
 // SimpleVoxel.cpp:352-398) is one call: meso_raymarch().
 //
-//   SimpleVoxel [--stream] [frames] [width height] [eye x y z] [target x y z] [out.bin]
+//   SimpleVoxel [--stream | --cpu-generator] [frames] [width height] [eye x y z] [target x y z] [out.bin]
+// --cpu-generator: the generator is the reference's std::function callback (SimpleVoxel.cpp:263-267) run on host worker
+// threads; its FChunk.Blocks reach the device as FGPUChunk / FGPUBlock records (meso_volume_upload_blocks).
 // --stream: the reference's loading loop -- chunks are generated as the view asks for them (FChunkManage::UpdateChunks +
 // UpdateLoadingQueue, at most MaxUnsyncedLoadChunkCount per frame), not all at once.
 // Prints an FNV-1a checksum of the last frame's records (tests/test_gpu_host_sample.py compares it with the Python path).
@@ -19,6 +21,7 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
  public:
   FChunkManage ChunkManager;
   bool bStream = false;
+  bool bCpuGenerator = false;
   uint32_t CameraUpdates = 0, ChunkUpdates = 0;
   double RenderMs = 0.0;
 
@@ -27,6 +30,12 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
     FGeneratorDesc Generator;   // FGeneratorHelper::GenerateSphere, the generator SimpleVoxel.cpp:263-267 wires in
     // the 8^3 chunks around the reference sphere (centre (100,0,0), radius 50 blocks)
     ChunkManager.Initialize(Context, VoxelSceneConfig, Generator, ivec3{2, -4, -4}, ivec3{8, 8, 8}, bStream);
+    if (bCpuGenerator) {
+      auto GeneratorInstance = [](ivec3 StartLocation, float BlockSize, unsigned char ChunkResolution, uint32_t MipmapLevel) {
+        return FGeneratorHelper::GenerateSphere(StartLocation, BlockSize, ChunkResolution, MipmapLevel);
+      };
+      ChunkManager.SetGenerator(GeneratorInstance);
+    }
   }
   void WhenCameraChunkUpdate() override { ChunkUpdates++; }
   void WhenCameraUpdate() override {
@@ -44,8 +53,9 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
 };
 
 int main(int argc, char* argv[]) {
-  bool stream = false;
+  bool stream = false, cpu_generator = false;
   if (argc > 1 && std::strcmp(argv[1], "--stream") == 0) { stream = true; argc--; argv++; }
+  else if (argc > 1 && std::strcmp(argv[1], "--cpu-generator") == 0) { cpu_generator = true; argc--; argv++; }
   const uint32_t frames = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 4;
   VoxelInstanceInitialConfig cfg;
   if (argc > 3) { cfg.WindowsWidth = std::atoi(argv[2]); cfg.WindowsHeight = std::atoi(argv[3]); }
@@ -57,6 +67,7 @@ int main(int argc, char* argv[]) {
   try {
     SimpleVoxelWindowsInstance Instance;
     Instance.bStream = stream;
+    Instance.bCpuGenerator = cpu_generator;
     Instance.WindowsCamera.SetPose(eye, target, {0.0f, 0.0f, 1.0f});
     Instance.Initialize(cfg);
     Instance.RunInstance(frames);

@@ -70,3 +70,21 @@ def test_cpp_sample_streaming_matches_python_streaming(frames, tmp_path):
     assert "loaded=%d missing=%d" % (loaded, int(st["missing"])) in log
     assert n_loaded == loaded and (frames > 1 or loaded == 256)
     assert got.tobytes() == rec.tobytes()
+
+
+def test_cpp_sample_cpu_generator_callback_equals_device_generator(tmp_path):
+    """--cpu-generator: the reference's std::function GeneratorType callback (FGeneratorHelper::GenerateSphere on host
+    worker threads) -> FChunk.Blocks -> FGPUChunk / FGPUBlock records -> meso_volume_upload_blocks.  Same instances
+    after the device cull and the same frame as the device generator (meso_voxelize_sdf)."""
+    from mesoengine_b200 import camera, capi
+    subprocess.check_call(["make", "-C", os.path.dirname(EXE), "CXX=g++"])
+    w, h = 320, 180
+    eye, target = (20.5, -61.25, 33.0), (100.0, 0.0, 0.0)
+    frames = {}
+    for mode in ("--cpu-generator", None):
+        out = tmp_path / ("frame%s.bin" % (mode or ""))
+        args = [EXE] + ([mode] if mode else []) + ["2", str(w), str(h)] + [repr(float(v)) for v in eye + target] + [str(out)]
+        log = subprocess.check_output(args, text=True)
+        assert "blocks=201936" in log, log
+        frames[mode] = np.fromfile(out, dtype=capi.HitRecord).reshape(h, w)
+    assert frames["--cpu-generator"].tobytes() == frames[None].tobytes()

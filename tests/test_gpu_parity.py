@@ -464,3 +464,105 @@ def test_carve_and_remesh(ctx, orc):
     got = ctx.mesh(len(ref) + 16)
     assert orc.sort_quads(got).tobytes() == orc.sort_quads(ref).tobytes()
     _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, 160, 96)[:2], 160, 96)
+
+
+def test_upload_blocks_reference_records(ctx, capi, orc):
+    """meso_volume_upload_blocks: the reference's own upload records (FGPUChunk table + FGPUBlock pool, ChunkPool.h:662-679).
+    Blocks of the reference sphere as records == the device generator's volume; invalid records (INT_MAX index, stale
+    stamp, invalid chunk, chunk outside the window) are skipped exactly like the vertex shader skips them; merge adds."""
+    origin, dims = (2, -4, -4), (8, 8, 8)
+    ctx.scene_create(origin, dims, 1 << 12)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, orc.REF_SPHERE, granularity=orc.GRAN_BLOCK)
+    occ = vol.occ()
+    n_chunks = int(np.prod(dims))
+    table = np.zeros(n_chunks + 2, dtype=capi.GPUChunk)
+    blocks = []
+    stamp = 7
+    for c in range(n_chunks):
+        bits = np.unpackbits(occ[c].view(np.uint8), bitorder="little")
+        idx = np.nonzero(bits)[0]
+        loc = (origin[0] + c % dims[0], origin[1] + (c // dims[0]) % dims[1], origin[2] + c // (dims[0] * dims[1]))
+        table[c] = ((loc if len(idx) else (2**31 - 1,) * 3), stamp if len(idx) else 0)
+        for b in idx:
+            blocks.append((c, (b & 15, (b >> 4) & 15, b >> 8, 255), stamp))
+    n_good = len(blocks)
+    table[n_chunks] = ((100, 100, 100), stamp)            # valid record, outside the window
+    table[n_chunks + 1] = ((2**31 - 1,) * 3, stamp)       # invalid chunk record
+    blocks += [(2**31 - 1, (1, 1, 1, 255), stamp), (0, (1, 1, 1, 255), stamp + 1), (n_chunks, (1, 1, 1, 255), stamp),
+               (n_chunks + 1, (1, 1, 1, 255), stamp), (n_chunks + 5, (1, 1, 1, 255), stamp)]
+    blocks = np.array(blocks, dtype=capi.GPUBlock)
+    rng = np.random.default_rng(3)
+    blocks = blocks[rng.permutation(len(blocks))]          # the pool order is thread-scheduled in the reference
+    assert ctx.volume_upload_blocks(table, blocks) == n_good
+    o2, f2, keys, _ = ctx.volume_download()
+    assert np.array_equal(o2, occ) and np.array_equal(f2, occ) and len(keys) == 0
+    n = ctx.build_occupancy(stamp=3)
+    _, _, inst = ctx.download_occupancy(n)
+    _, _, i_ref = vol.build_occupancy(stamp=3)
+    assert inst.tobytes() == i_ref.tobytes()
+    # the frame through the uploaded records == the oracle's
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cam = orc.camera_uniform(eyes[1], ctr, width=128, height=72)
+    ref = vol.raymarch(orc.ray_setup(cam, origin, 128, 72), 128, 72, shadow=True)
+    assert ctx.raymarch(cam, 128, 72, shadow=True).tobytes() == ref.tobytes()
+    # delta upload: half the records, then the other half merged
+    good = blocks[(blocks["ChunkIndex"] < n_chunks) & (blocks["BlockFrameStamp"] == stamp)]
+    assert ctx.volume_upload_blocks(table, good[: n_good // 2]) == n_good // 2
+    assert ctx.volume_upload_blocks(table, good[n_good // 2:], merge=True) == n_good - n_good // 2
+    o3, f3, _, _ = ctx.volume_download()
+    assert np.array_equal(o3, occ) and np.array_equal(f3, occ)
+    # replace empties the window
+    assert ctx.volume_upload_blocks(table, blocks[:0]) == 0
+    o4, _, _, _ = ctx.volume_download()
+    assert not o4.any()
+
+
+def test_volume_upload_rejects_inconsistent_input(ctx, capi, orc):
+    """meso_volume_upload validates what the kernels rely on: one key per occ && !full brick, ascending, naming a partial brick."""
+    origin, dims, params = scenes.sphere_scene(256)
+    ctx.scene_create(origin, dims, 1 << 16)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL)
+    keys, payload = vol.export_partial()
+    occ, full = vol.occ(), vol.full()
+    ctx.volume_upload(occ, full, keys, payload)
+    with pytest.raises(capi.MesoError):
+        ctx.volume_upload(occ, full, keys[:-1], payload[:-1])            # a partial brick without a payload
+    with pytest.raises(capi.MesoError):
+        ctx.volume_upload(occ, full, keys[::-1].copy(), payload)          # not ascending
+    bad = keys.copy(); bad[0] = bad[1]
+    with pytest.raises(capi.MesoError):
+        ctx.volume_upload(occ, full, bad, payload)                        # duplicate
+    f2 = full.copy(); f2.reshape(-1)[int(keys[0]) >> 6] |= np.uint64(1) << np.uint64(int(keys[0]) & 63)
+    with pytest.raises(capi.MesoError):
+        ctx.volume_upload(occ, f2, keys, payload)                         # a key naming a full brick
+    ctx.volume_upload(occ, full, keys, payload)                           # still usable afterwards
+    o2, f3, k2, p2 = ctx.volume_download()
+    assert np.array_equal(o2, occ) and np.array_equal(k2, keys) and np.array_equal(p2, payload)
+
+
+def test_pool_overflow_leaves_a_consistent_volume(ctx, capi, orc):
+    """Voxelise / carve with too small a payload pool: the call fails, and what is left renders and meshes without
+    touching memory it does not own (no occ && !full brick without a payload slot)."""
+    origin, dims, params = scenes.sphere_scene(256)
+    ctx.scene_create(origin, dims, 64)                     # far too few payload slots
+    with pytest.raises(capi.MesoError):
+        ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
+    occ, full, keys, payload = ctx.volume_download()
+    assert len(keys) <= 64
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cam = orc.camera_uniform(eyes[0], ctr, width=96, height=60)
+    vol = orc.Volume(origin, dims).import_(occ, full, keys, payload)
+    ref = vol.raymarch(orc.ray_setup(cam, origin, 96, 60), 96, 60, shadow=True)
+    assert ctx.raymarch(cam, 96, 60, shadow=True).tobytes() == ref.tobytes()
+    # carve: a block-granular sphere has no payload at all; carving its surface needs slots -> overflow, bricks left full
+    ctx.scene_create(origin, dims, 8)
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_BLOCK)
+    with pytest.raises(capi.MesoError):
+        ctx.carve_sphere((128, 128, 60), 30)
+    occ, full, keys, payload = ctx.volume_download()
+    assert len(keys) <= 8
+    vol = orc.Volume(origin, dims).import_(occ, full, keys, payload)
+    ref = vol.raymarch(orc.ray_setup(cam, origin, 96, 60), 96, 60, shadow=True)
+    assert ctx.raymarch(cam, 96, 60, shadow=True).tobytes() == ref.tobytes()
+    q = ctx.mesh(1 << 20)
+    assert orc.sort_quads(q).tobytes() == orc.sort_quads(vol.mesh()).tobytes()

@@ -195,3 +195,15 @@ def test_host_mirror_declarations_equal_the_reference_headers():
     exe = os.path.join(os.path.dirname(refprobe.REF_SO), "host_mirror_check")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and out.stdout.startswith("ok:"), out.stdout + out.stderr
+
+
+def test_host_objects_equal_the_reference_objects():
+    """FChunk / FBinaryOccupancyVolume / FOccupancyHelper / FGeneratorHelper::GenerateSphere / GeneratorType of the host
+    mirror next to the reference's own (oracle/ref_host_objects_check.cpp): block lists in order, four mips bit for bit,
+    the cull test incl. out-of-chunk locations, clamped and boundary reads, both erosion stencils."""
+    import subprocess
+    if refprobe.build_ref() is None or not os.path.isdir(refprobe.REF_ROOT):
+        pytest.skip("needs /root/reference (compares against the reference's own headers)")
+    exe = os.path.join(os.path.dirname(refprobe.REF_SO), "host_objects_check")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("ok:") and "523155 blocks" in out.stdout, out.stdout + out.stderr

@@ -5,10 +5,10 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from mesoengine_b200 import camera, capi, scenes
-N, W, H = 4096, 3840, 2160
+N, W, H = int(os.environ.get("RM_ONE_N", "4096")), int(os.environ.get("RM_ONE_W", "3840")), int(os.environ.get("RM_ONE_H", "2160"))
 origin, dims, params = scenes.sphere_scene(N)
 ctx = capi.Context(0)
-ctx.scene_create(origin, dims, max_bricks=1 << 20)
+ctx.scene_create(origin, dims, max_bricks=(1 << 20) if N >= 4096 else (1 << 18))
 ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
 ctx.build_cubes()
 eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
