@@ -535,25 +535,28 @@ __device__ __forceinline__ int walk10(const DVolume& v, const Scene10& s, const 
     if (!(ta < F_INF)) return W_EXIT;   // zero direction
     const int ox0 = w.csx, oy0 = w.csy, oz0 = w.csz;
     const int a = zm ? 2 : (yx ? 1 : 0);
-    if (zm) w.csz = nxz; else if (yx) w.csy = nxy; else w.csx = nxx;
     w.la = a; w.lt = ta; steps++;
     if (STATS) s.lv[sz == 1 ? 0 : (sz == 2 ? 1 : (sz == 8 ? 2 : (kdf <= 2 ? 3 : 4)))]++;
+    // the two axes that did not step are made exact here, the one place where that happens (a step out of a single voxel
+    // cannot have crossed a plane of another axis: those two stay as they are)
+    int ex = ox0, ey = oy0, ez = oz0;
     if (sz > 1) {
-      // the one place where the two other axes are made exact
       if (SLOW) {
-        if (a != 0) w.csx = sync1_slow(r.ox, r.dx, r.ix, 0, w.csx, ta, a);
-        if (a != 1) w.csy = sync1_slow(r.oy, r.dy, r.iy, 1, w.csy, ta, a);
-        if (a != 2) w.csz = sync1_slow(r.oz, r.dz, r.iz, 2, w.csz, ta, a);
+        ex = sync1_slow(r.ox, r.dx, r.ix, 0, ox0, ta, a);
+        ey = sync1_slow(r.oy, r.dy, r.iy, 1, oy0, ta, a);
+        ez = sync1_slow(r.oz, r.dz, r.iz, 2, oz0, ta, a);
       } else {
         const int ti = __float_as_int(ta);
-        const int sx = sync1(r.ox, r.dx, r.ix, w.csx, ta, ti + 1);              // axis 0 wins every tie
-        const int sy = sync1(r.oy, r.dy, r.iy, w.csy, ta, ti + (zm ? 1 : 0));   // axis 1 wins a tie against axis 2 only
-        const int sz2 = sync1(r.oz, r.dz, r.iz, w.csz, ta, ti);                 // axis 2 never does
-        if (zm || yx) w.csx = sx;
-        if (zm || !yx) w.csy = sy;
-        if (!zm) w.csz = sz2;
+        ex = sync1(r.ox, r.dx, r.ix, ox0, ta, ti + 1);              // axis 0 wins every tie
+        ey = sync1(r.oy, r.dy, r.iy, oy0, ta, ti + (zm ? 1 : 0));   // axis 1 wins a tie against axis 2 only
+        ez = sync1(r.oz, r.dz, r.iz, oz0, ta, ti);                 // axis 2 never does
       }
     }
+    // (written as three selects on `a`: an earlier form -- assign the stepped axis, then conditionally overwrite the two
+    // others under zm / yx predicates -- came out of the compiler with the stepped y coordinate reverted to its old value)
+    w.csx = a == 0 ? nxx : ex;
+    w.csy = a == 1 ? nxy : ey;
+    w.csz = a == 2 ? nxz : ez;
     // a forward cube of several bricks / 2^3 cells is unaligned: the synced axes may have crossed a brick, a 32^3 cell or
     // a chunk face inside it, so this looks at all three axes
     w.ux = (unsigned)((ox0 ^ w.csx) | (oy0 ^ w.csy) | (oz0 ^ w.csz));
@@ -644,7 +647,11 @@ __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS))
       scene10_octant<CL>(sc, ct, m);
       const bool far = ray_is_far(m);
       park_inactive(m, w);
+#ifdef RM10_NO_SLOW
+      (void)far; res = walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
+#else
       res = far ? walk10_slow<STATS, CL>(v, sc, m, w, cx, cy, cz, steps) : walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
+#endif
     }
     if (res == W_HIT) {
       dn.t = w.lt; dn.cx = cx; dn.cy = cy; dn.cz = cz;
@@ -660,6 +667,8 @@ __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS))
         if (w.la == 0) dn.px = pl; else if (w.la == 1) dn.py = pl; else dn.pz = pl;
         dn.face = w.la * 2 - g_ax;
         hit_axis = w.la;
+        // a crossing at t = 0 on a negative-direction axis: the defining key (+0) * (negative inv) is -0.0, the mirrored one +0.0
+        if (g_ax && w.lt == 0.0f) dn.t = -0.0f;
         if (flags & MESO_FLAG_SHADOW) {
           const bool facing = g_ax == 0 ? (l_ax < 0.0f) : (l_ax > 0.0f);
           if (!facing) dn.shadow = 1; else want_shadow = true;
@@ -684,7 +693,11 @@ __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS))
         scene10_octant<CL>(sc, ct, m);
         const bool far = ray_is_far(m);
         park_inactive(m, w);
+#ifdef RM10_NO_SLOW
+        (void)far; res = walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
+#else
         res = far ? walk10_slow<STATS, CL>(v, sc, m, w, cx, cy, cz, steps) : walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
+#endif
       }
       dn.shadow = res == W_HIT ? 1 : 0;
       n_shadow = 1;
