@@ -290,10 +290,6 @@ def run_ours(args):
     ctx.scene_create(origin, dims, max_bricks=(1 << 20) if n >= 4096 else (1 << 18))
     t_build = time.perf_counter()
     ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)  # replicated on every rank
-    if capi.ENV_CUBES:
-        # A/B switch (MESO_CUBES=1, off by default): the opt-in forward-cube walk for every raymarch call on this scene
-        # until an edit invalidates the tables (the edit loop then falls back to the shipped walk)
-        ctx.build_cubes()
     ctx.sync()
     t_build = time.perf_counter() - t_build
     cams = make_cameras(scene, width, height)
@@ -663,7 +659,7 @@ def run_ours(args):
                        "frames_in_flight": R,
                        "gather": gather, "gather_verified_equal_to_1gpu_frame": gather_verified,
                        "scene_build_s": t_build,
-                       "walk": "forward cubes (MESO_CUBES=1, opt-in)" if capi.ENV_CUBES else "shipped (v8)"},
+                       "walk": "mirrored-space stateless DDA over per-octant forward cubes (32^3 cells, bricks), built with the volume"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 16 * px,
                     "steps": e2e_steps, "rgba8": e2e_rgba8,
                     "note": ("meso_raymarch_async()/meso_frame_wait() frame ring of 4: FGPUUniformCamera from host memory (kernel parameters), records copied to pinned host memory, copy of frame k overlapping frame k+1"
@@ -674,7 +670,7 @@ def run_ours(args):
                     "host_fused": host_fused, "host_fused_verified_equal_to_1gpu_frame": host_fused_verified},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "raymarch_kernel<false>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "raymarch10_kernel<false, 2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
                          "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
                          "issue": issue_roofline(ctx, world, args.workload, kms, clocks),

@@ -34,7 +34,7 @@ StreamStats = np.dtype([("generated", "<u4"), ("missing", "<u4"), ("candidates",
 
 SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
-FLAG_SHADOW, FLAG_RGBA8, FLAG_CUBES = 1, 2, 4
+FLAG_SHADOW, FLAG_RGBA8, FLAG_CUBES, FLAG_NO_CUBES = 1, 2, 4, 8
 LAYOUT_FRAME, LAYOUT_TILES = 0, 1
 TILE_W, TILE_H = 32, 8
 
@@ -55,9 +55,6 @@ SYMBOLS = [
 ]
 IPC_HANDLE_BYTES = 64
 UPLOAD_MERGE = 1
-# A/B switch for measurements (off unless MESO_CUBES=1): every raymarch call of a Context whose forward-cube tables are
-# current (build_cubes() since the last volume change) adds FLAG_CUBES.  bench.py builds the tables when it is set.
-ENV_CUBES = os.environ.get("MESO_CUBES") == "1"
 
 
 class MesoError(RuntimeError):
@@ -175,7 +172,6 @@ class Context:
         return int(lib.meso_launch_count(self.h))
 
     def scene_create(self, origin_chunk, dims_chunks, max_bricks, cfg=None):
-        self._cubes_ready = False
         cfg = default_scene_config() if cfg is None else cfg
         self.origin = np.ascontiguousarray(origin_chunk, dtype=np.int32)
         self.dims = np.ascontiguousarray(dims_chunks, dtype=np.int32)
@@ -183,14 +179,12 @@ class Context:
         _ck(lib.meso_scene_create(self.h, _p(cfg), _p(self.origin), _p(self.dims), C.c_uint32(max_bricks)))
 
     def voxelize_sdf(self, kind, params=None, granularity=GRAN_VOXEL):
-        self._cubes_ready = False
         p = np.zeros(4, dtype=np.float64)
         if params is not None:
             p[: len(params)] = np.asarray(params, dtype=np.float64)
         _ck(lib.meso_voxelize_sdf(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
 
     def volume_upload(self, occ, full, keys, payload):
-        self._cubes_ready = False
         occ = np.ascontiguousarray(occ, dtype=np.uint64)
         full = np.ascontiguousarray(full, dtype=np.uint64)
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
@@ -199,7 +193,6 @@ class Context:
 
     def volume_upload_blocks(self, chunks, blocks, merge=False):
         """The reference's own records: FGPUChunk table + FGPUBlock pool (ChunkPool.h:662-679).  Returns the accepted count."""
-        self._cubes_ready = False
         chunks = np.ascontiguousarray(chunks, dtype=GPUChunk)
         blocks = np.ascontiguousarray(blocks, dtype=GPUBlock)
         n = C.c_int64(0)
@@ -235,7 +228,6 @@ class Context:
     def build_cubes(self):
         """(Re)build the per-octant forward-cube tables that FLAG_CUBES reads (opt-in raymarch path)."""
         _ck(lib.meso_build_cubes(self.h))
-        self._cubes_ready = True
 
     def download_cubes(self):
         """-> (cell [8, ncells] u8, brick [nchunks*4096] u16) as built by build_cubes (debug / tests)."""
@@ -245,21 +237,24 @@ class Context:
         _ck(lib.meso_download_cubes(self.h, _p(cell), _p(brick)))
         return cell, brick
 
-    def _auto_cubes(self):
-        return FLAG_CUBES if (ENV_CUBES and getattr(self, "_cubes_ready", False)) else 0
+    @staticmethod
+    def _cubes_flag(cubes):
+        """cubes=None: the library's default (forward cubes whenever the tables are current); True insists on them; False
+        forces the distance-field walk."""
+        return 0 if cubes is None else (FLAG_CUBES if cubes else FLAG_NO_CUBES)
 
-    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False, cubes=False):
+    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False, cubes=None):
         """End-to-end call: camera from host memory, records (or, rgba8=True, the colour image as uint32) into host memory."""
         rec = out if out is not None else np.zeros((height, width), dtype=np.uint32 if rgba8 else HitRecord)
         l = np.ascontiguousarray(light, dtype=np.float32)
-        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0) | self._auto_cubes()
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | self._cubes_flag(cubes)
         _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(rec)))
         return rec
 
-    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False, cubes=False):
+    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False, cubes=None):
         """Frame-ring call: enqueue frame + copy into `out` (pinned numpy array); pair with frame_wait(slot)."""
         l = np.ascontiguousarray(light, dtype=np.float32)
-        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | (FLAG_CUBES if cubes else 0) | self._auto_cubes()
+        flags = (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | self._cubes_flag(cubes)
         _ck(lib.meso_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(out), C.c_int(slot)))
 
     def frame_wait(self, slot):
@@ -268,13 +263,13 @@ class Context:
     def raymarch_device(self, cam, width, height, d_records, shadow=True, light=(0.3, 0.5, 0.8), layout=LAYOUT_FRAME, flags_extra=0):
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
-                                     C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra | self._auto_cubes()), _p(l), C.c_void_p(d_records), C.c_int(layout)))
+                                     C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
 
-    def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), cubes=False):
+    def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), cubes=None):
         st = np.zeros(1, dtype=RayStats)
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_stats(self.h, _p(cam), C.c_int(width), C.c_int(height),
-                                    C.c_uint32((FLAG_SHADOW if shadow else 0) | (FLAG_CUBES if cubes else 0)), _p(l), _p(st)))
+                                    C.c_uint32((FLAG_SHADOW if shadow else 0) | self._cubes_flag(cubes)), _p(l), _p(st)))
         return st[0]
 
     def compose_tiles_device(self, d_tiles, world, width, height, d_frame):
@@ -342,13 +337,11 @@ class Context:
         return out
 
     def stream_begin(self, kind, params=None, granularity=GRAN_VOXEL):
-        self._cubes_ready = False
         p = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
         _ck(lib.meso_stream_begin(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
 
     def stream_update(self, camera_chunk, forward, max_new, view=None, wait=True):
         """FChunkManage::UpdateChunks + UpdateLoadingQueue; returns StreamStats (wait=True) or None (enqueue only)."""
-        self._cubes_ready = False
         view = view_config() if view is None else view
         cc = np.ascontiguousarray(camera_chunk, dtype=np.int32)
         f = np.ascontiguousarray(forward, dtype=np.float32)

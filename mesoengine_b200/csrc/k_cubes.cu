@@ -1,10 +1,11 @@
-// k_cubes.cu -- per-octant FORWARD CUBES for the raymarch walk (opt-in path MESO_FLAG_CUBES).
+// k_cubes.cu -- per-octant FORWARD CUBES for the raymarch walk.
 //
-// Status: written after round 1's GPU budget was spent -- compiled, never run on hardware.  The design was chosen with the
-// calibrated step model (tools/step_model.py, profiles/README.md last section): reading, at every level of the walk, the
-// edge of the largest empty cube that starts at the current unit and extends towards the ray's octant takes the walk
-// from 15.6 to 10.4 steps per ray on the 4096^3 scene.  oracle/orc_raymarch.c (ORC_DDA_MODEL) states the same cubes on
-// the CPU; tests/test_zz_gpu_cubes.py (opt-in, MESO_TEST_CUBES=1) compares the tables and the frames.
+// Chosen with the calibrated step model (tools/step_model.py, profiles/README.md) and measured on B200 (profiles/
+// r2_rm_ab_*.jsonl): reading, at a level of the walk, the edge of the largest empty cube that starts at the current unit
+// and extends towards the ray's octant takes the walk on the 4096^3 scene from 15.9 to 12.0 steps per ray with cell and
+// brick cubes (the default; +14 % Mrays/s over the distance field) and to 10.7 with 2^3-cell cubes on top (not faster: two
+// more bytes per step).  oracle/orc_raymarch.c (ORC_DDA_MODEL) states the same cubes on the CPU;
+// tests/test_zz_gpu_cubes.py compares the tables and the frames.
 //
 // A ray only ever needs what lies ahead of it, so the boxes are anchored at the current unit and grow towards the octant
 // (step_x < 0) | (step_y < 0) << 1 | (step_z < 0) << 2.  Outside the grid counts as empty (the walk clamps its steps to
@@ -150,9 +151,13 @@ void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, 
   }
   cube_cell_pad_kernel<<<(unsigned)((8 * npcells + 255) / 256), 256, 0, lc.stream>>>(v, d_cell, d_cellp, ncells, npcells);
   (*lc.launches)++;
-  cudaMemsetAsync(d_brick, 0, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t), lc.stream);
-  cube_brick_kernel<<<(unsigned)((ncells * 64 + 255) / 256), 256, 0, lc.stream>>>(v, d_brick, ncells);
-  (*lc.launches)++;
-  cube_cell2_kernel<<<(unsigned)(((int64_t)v.max_bricks * 64 + 255) / 256), 256, 0, lc.stream>>>(v, d_cell2);
-  (*lc.launches)++;
+  if (d_brick) {   // only entries of non-empty 32^3 cells are ever read; the rest is zero-filled (0.05 ms at 4096^3)
+    cudaMemsetAsync(d_brick, 0, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t), lc.stream);
+    cube_brick_kernel<<<(unsigned)((ncells * 64 + 255) / 256), 256, 0, lc.stream>>>(v, d_brick, ncells);
+    (*lc.launches)++;
+  }
+  if (d_cell2) {
+    cube_cell2_kernel<<<(unsigned)(((int64_t)v.max_bricks * 64 + 255) / 256), 256, 0, lc.stream>>>(v, d_cell2);
+    (*lc.launches)++;
+  }
 }

@@ -5,30 +5,28 @@
 //
 // The DDA is STATELESS (DESIGN.md "DDA"): the crossing time of integer voxel plane p on axis a is always
 //     t_a(p) = (float(p) - o_a) * inv_a          one FSUB + one FMUL, never fused (-fmad=false)
-// and crossings are consumed in the total order (t, axis).  Skipping an empty box -- an aligned 8^3 brick, or the cube
-// of 32^3 cells the distance field DVolume.df certifies empty around the current cell -- consumes the smallest of the
-// box's three exit keys and re-derives the other two coordinates from the same keys (advance_axis), so the walk visits
-// exactly the voxels the oracle's flat walk would: hit voxel, face and t are bit-identical to oracle/orc_raymarch.c.
-// Any empty box is a legal skip; how big the boxes are only changes the number of steps, never the result.
+// and crossings are consumed in the total order (t, axis).  Skipping an empty box -- an aligned 8^3 brick or 2^3 cell, or
+// an unaligned cube of 32^3 cells / bricks that a table certifies empty -- consumes the smallest of the box's three exit
+// keys and re-derives the other two coordinates from the same keys (sync1), so the walk visits exactly the voxels the
+// oracle's flat walk would: hit voxel, face and t are bit-identical to oracle/orc_raymarch.c.  Any empty box is a legal
+// skip; how big the boxes are only changes the number of steps, never the result.
 //
-// Execution model: CTA = one 32x8 screen tile (tile t belongs to rank t % world), warp = 8x4 pixels.  All primary rays
-// of a warp start together at the eye and stay at similar levels of the walk; afterwards the lanes that hit a lit-facing
-// face trace their shadow rays, starting together again.  Every level of the walk shares ONE step section per
-// iteration: separate step code for the distance-field level was measured twice and costs 12 % more warp instructions.
-// Distance-field bytes come through L1/L2 (2 MB at 4096^3); {occ,full} word pairs (16 B loads) and brick slices are
-// cached in registers behind tags.
-// (A persistent "idle lanes pull the next pixel" variant was measured and dropped: mixing rays of different phases in
-// one warp cut SIMT efficiency from 20/32 to 8/32 active threads -- profiles/README.md.)
+// Execution model: 32x8 screen tile = 8 warps of 8x4 pixels (tile t belongs to rank t % world), two 128-thread CTAs per
+// tile.  All primary rays of a warp start together at the eye and stay at similar levels of the walk; afterwards the
+// lanes that hit a lit-facing face trace their shadow rays, starting together again.  Every level of the walk shares
+// ONE step section per iteration (separate step code per level costs more warp instructions than it saves: a warp pays
+// for every path any of its lanes takes).  Table bytes come through L1/L2; {occ,full} word pairs (16 B loads), the
+// 2^3-cell mask and the brick slice are cached in registers behind tags.
+// Measured and dropped (profiles/README.md): persistent warps refilling idle lanes, primary-into-shadow continuation,
+// CTA-wide / global shadow-ray compaction, a 4^3 level, per-level step code.
 //
-// All per-ray state is kept in named scalars (x/y/z members, SEL3 selects), never in indexable arrays: the compiler
-// turns "if (i == a) v = arr[i]" chains into a dynamically indexed load, which would push the whole state to local memory.
+// All per-ray state is kept in named scalars (x/y/z members), never in indexable arrays: the compiler turns
+// "if (i == a) v = arr[i]" chains into dynamically indexed loads, which pushes the whole state to local memory.
 #include "meso_internal.cuh"
 #include <cstdlib>
 #include <cstring>
-#include <cstdio>
 
 #define F_INF __int_as_float(0x7F800000)
-#define RM_THREADS 256
 #define SEL3(a, X, Y, Z) ((a) == 0 ? (X) : ((a) == 1 ? (Y) : (Z)))
 
 struct Ray {
@@ -82,42 +80,13 @@ __device__ __forceinline__ int advance_axis(float o, float d, float inv, int st,
   return e;
 }
 
-struct Scene {
-  const DVolume* v;
-  uint8_t* touch_chunk;
-  uint8_t* touch_brick;
-  unsigned* lv;              // STATS only: per-thread steps per level
-  CubeTables ct;             // CUBES only: per-octant forward cubes (meso_build_cubes)
-};
-
-// Walk state of one ray.  cs = c ^ (step >> 31): mirrored coordinates, so every aligned step is "(cs | mask) + 1".
-// All three are exact between iterations: a step out of a box bigger than a voxel re-derives the two other axes from
-// the consumed key right away (one sync site in the step section; syncing lazily, only when the walk looks finer, needs
-// the same ~35 instructions at three places of the cascade, and a warp pays for every place any of its lanes visits).
-// need: 3 = the 32^3 cell may have changed (look the distance field up), 2 = the brick changed, 1 = the 2^3 cell
-// changed, 0 = same 2^3 cell.
-struct Walk {
-  int csx, csy, csz;
-  int la; float lt;
-  int need;
-  int ci, wtag, ztag;
-  uint32_t slot;
-  unsigned long long wocc, wfull, slice, cm;
-};
-
 enum { W_CONTINUE = 0, W_HIT = 1, W_EXIT = 2 };
 
-// make the two axes other than w.la exact (true coordinates cx,cy,cz in/out)
-__device__ __forceinline__ void sync_axes(const Ray& r, const Walk& w, int& cx, int& cy, int& cz) {
-  if (w.la != 0) cx = advance_axis(r.ox, r.dx, r.ix, r.sx, 0, cx, w.lt, w.la);
-  if (w.la != 1) cy = advance_axis(r.oy, r.dy, r.iy, r.sy, 1, cy, w.lt, w.la);
-  if (w.la != 2) cz = advance_axis(r.oz, r.dz, r.iz, r.sz, 2, cz, w.lt, w.la);
-}
-
 // Places the ray at its first cell inside the grid (entry from outside included).  Returns false if it never enters.
-__device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int cx, int cy, int cz, Walk& w, unsigned& steps) {
+// (cx, cy, cz) in: floor of the origin; out: that first cell; (la, lt) = the entry crossing, la = -1 if the ray starts inside.
+__device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int& cx, int& cy, int& cz, int& la, float& lt, unsigned& steps) {
   const int nx = v.nvox[0], ny = v.nvox[1], nz = v.nvox[2];
-  w.la = -1; w.lt = 0.0f;
+  la = -1; lt = 0.0f;
   bool alive = true;
   const bool in = (unsigned)cx < (unsigned)nx && (unsigned)cy < (unsigned)ny && (unsigned)cz < (unsigned)nz;
   if (!in) {
@@ -134,164 +103,11 @@ __device__ __forceinline__ bool walk_begin(const DVolume& v, const Ray& r, int c
       cx = a == 0 ? (r.sx > 0 ? 0 : nx - 1) : advance_axis(r.ox, r.dx, r.ix, r.sx, 0, cx, ta, a);
       cy = a == 1 ? (r.sy > 0 ? 0 : ny - 1) : advance_axis(r.oy, r.dy, r.iy, r.sy, 1, cy, ta, a);
       cz = a == 2 ? (r.sz > 0 ? 0 : nz - 1) : advance_axis(r.oz, r.dz, r.iz, r.sz, 2, cz, ta, a);
-      w.la = a; w.lt = ta; steps++;
+      la = a; lt = ta; steps++;
       alive = (unsigned)cx < (unsigned)nx && (unsigned)cy < (unsigned)ny && (unsigned)cz < (unsigned)nz;
     }
   }
-  w.csx = cx ^ (r.sx >> 31); w.csy = cy ^ (r.sy >> 31); w.csz = cz ^ (r.sz >> 31);
-  w.need = 3; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0;
-  w.wocc = 0; w.wfull = 0; w.slice = 0; w.cm = 0;
   return alive;
-}
-
-// One iteration: classify the current cell from the coarsest level that changed down to the first empty level (or a
-// solid voxel), then take one step at that level.  Levels: the distance field over 32^3 cells (a step leaves the whole
-// empty cube of half-width df - 1 cells around the current cell, clamped to the grid), bricks (8^3), voxels.
-// On W_HIT (cx,cy,cz) is the exact hit voxel.
-// CUBES (opt-in, MESO_FLAG_CUBES; chosen by the step model in profiles/README.md, not yet measured on hardware): every
-// level reads the edge of the largest empty cube that STARTS at the current cell / brick / 2^3 cell and extends towards
-// the ray's octant (CubeTables) where the shipped walk reads a symmetric distance or an occupancy bit.  Same levels, same
-// single step section, bigger boxes; any empty box is a legal skip, so the records cannot change.
-template <bool STATS, bool CUBES = false>
-__device__ __forceinline__ int walk_iter(const Scene& s, const Ray& r, Walk& w, int& cx, int& cy, int& cz, unsigned& steps) {
-  const DVolume& v = *s.v;
-  const int gx = r.sx >> 31, gy = r.sy >> 31, gz = r.sz >> 31;
-  cx = w.csx ^ gx; cy = w.csy ^ gy; cz = w.csz ^ gz;
-  bool go = true;  // keep looking finer
-  int sh = 0;      // level of the step: 0 voxel, 1 2^3 cell, 3 brick, 5 distance-field cube
-  int kdf = 1;     // cells to advance at that level (> 1 only for distance-field steps)
-  if (CUBES) {
-    const int oct = (gx & 1) | (gy & 2) | (gz & 4);
-    if (w.need >= 3) {
-      const int ex = cx >> 5, ey = cy >> 5, ez = cz >> 5;
-      const int k = (int)__ldg(&s.ct.cell[(size_t)oct * (size_t)s.ct.ncells + (size_t)(ex + v.ddims[0] * (ey + v.ddims[1] * ez))]);
-      if (k > 0) { sh = 5; kdf = k; go = false; }
-      else {
-        const int ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
-        if (ci != w.ci) { w.ci = ci; w.wtag = -1; }
-        if (STATS) {
-          const int e = ((cx >> 5) & 3) + 4 * ((cy >> 5) & 3) + 16 * ((cz >> 5) & 3);
-          if ((v.cells[ci] >> e) & 1ull) s.touch_chunk[ci] = 1;
-        }
-      }
-    }
-    if (go && w.need >= 2) {
-      const int bx = (cx >> 3) & 15, by = (cy >> 3) & 15, bz = (cz >> 3) & 15;
-      const int wi = bz * 4 + (by >> 2);
-      if (wi != w.wtag) {
-        const ulonglong2 p = __ldg(&v.of[(size_t)w.ci * 64 + wi]);
-        w.wocc = p.x; w.wfull = p.y; w.wtag = wi;
-      }
-      const int bit = bx + 16 * (by & 3);
-      if (!((w.wocc >> bit) & 1ull)) {
-        sh = 3; go = false;
-        kdf = 1 + (((int)__ldg(&s.ct.brick[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]) >> (2 * oct)) & 3);
-      } else {
-        if ((w.wfull >> bit) & 1ull) return W_HIT;
-        w.slot = __ldg(&v.bptr[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
-        w.cm = __ldg(&v.pool_cm[w.slot]);
-        if (STATS) s.touch_brick[w.slot] = 1;
-        w.ztag = -1;
-      }
-    }
-    if (go && w.need >= 1) {
-      const int ce = ((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3);
-      if (!((w.cm >> ce) & 1ull)) {
-        sh = 1; go = false;
-        kdf = 1 + (((int)__ldg(&s.ct.cell2[(size_t)w.slot * 64 + ce]) >> (2 * oct)) & 3);
-      }
-    }
-  } else {
-  if (w.need >= 3) {
-    const int ex = cx >> 5, ey = cy >> 5, ez = cz >> 5;
-    const int df = (int)__ldg(&v.df[ex + v.ddims[0] * (ey + v.ddims[1] * ez)]);
-    if (df > 0) {   // the cube of half-width df - 1 cells around this cell is empty
-      sh = 5; kdf = df; go = false;
-      // Probe ahead: the cell m = c + df along the ray's octant diagonal.  If its own empty cube has half-width >= df it
-      // contains this cell too, and the box [c, c + df + df(m) - 1] (forward only) lies inside it: a ray never needs
-      // what is behind it, so rays leaving or skimming a surface take steps about twice as long for one more byte.
-      const int mx = ex + ((df ^ gx) - gx), my = ey + ((df ^ gy) - gy), mz = ez + ((df ^ gz) - gz);
-      if ((unsigned)mx < (unsigned)v.ddims[0] && (unsigned)my < (unsigned)v.ddims[1] && (unsigned)mz < (unsigned)v.ddims[2]) {
-        const int d2 = (int)__ldg(&v.df[mx + v.ddims[0] * (my + v.ddims[1] * mz)]);
-        if (d2 > df) kdf = df + d2;
-      }
-    } else {
-      const int ci = (cx >> 7) + v.dims[0] * ((cy >> 7) + v.dims[1] * (cz >> 7));
-      if (ci != w.ci) { w.ci = ci; w.wtag = -1; }
-      if (STATS) {
-        const int e = ((cx >> 5) & 3) + 4 * ((cy >> 5) & 3) + 16 * ((cz >> 5) & 3);
-        if ((v.cells[ci] >> e) & 1ull) s.touch_chunk[ci] = 1;   // exact cell occupancy (df may be stale-conservative after a carve)
-      }
-    }
-  }
-  if (go && w.need >= 2) {
-    const int bx = (cx >> 3) & 15, by = (cy >> 3) & 15, bz = (cz >> 3) & 15;
-    const int wi = bz * 4 + (by >> 2);
-    if (wi != w.wtag) {
-      const ulonglong2 p = __ldg(&v.of[(size_t)w.ci * 64 + wi]);
-      w.wocc = p.x; w.wfull = p.y; w.wtag = wi;
-    }
-    const int bit = bx + 16 * (by & 3);
-    if (!((w.wocc >> bit) & 1ull)) { sh = 3; go = false; }
-    else {
-      if ((w.wfull >> bit) & 1ull) return W_HIT;
-      w.slot = __ldg(&v.bptr[(size_t)w.ci * MESO_BLOCKS + (bx + 16 * by + 256 * bz)]);
-      w.cm = __ldg(&v.pool_cm[w.slot]);
-      if (STATS) s.touch_brick[w.slot] = 1;
-      w.ztag = -1;
-    }
-  }
-  if (go && w.need >= 1) {
-    // 2^3-voxel cells of the partial brick
-    // (a 4^3 level on top of this one was measured: 9 % fewer steps, 7 % slower -- one more divergent path per iteration)
-    if (!((w.cm >> (((cx >> 1) & 3) + 4 * ((cy >> 1) & 3) + 16 * ((cz >> 1) & 3))) & 1ull)) { sh = 1; go = false; }
-  }
-  }  // !CUBES
-  if (go) {
-    const int z = cz & 7;
-    if (z != w.ztag) { w.slice = __ldg(&v.pool[(size_t)w.slot * 8 + z]); w.ztag = z; }
-    if ((w.slice >> ((cx & 7) + 8 * (cy & 7))) & 1ull) return W_HIT;
-  }
-  // ---- one step at level sh: consume the smallest of the three pending keys (ties: lower axis first) ----
-  // mirrored coordinate after crossing: kdf cells of size 2^sh ahead, never beyond the grid end (nvox if step > 0, else 0);
-  // for the aligned levels (kdf = 1) this is (cs | mask) + 1 and the clamp never binds
-  const int nxx = min(((w.csx >> sh) + kdf) << sh, v.nvox[0] & ~gx);
-  const int nxy = min(((w.csy >> sh) + kdf) << sh, v.nvox[1] & ~gy);
-  const int nxz = min(((w.csz >> sh) + kdf) << sh, v.nvox[2] & ~gz);
-  const float tx = r.sx != 0 ? plane_t1(r.ox, r.ix, (nxx ^ gx) - gx) : F_INF;               // (n ^ g) - g = true plane index
-  const float ty = r.sy != 0 ? plane_t1(r.oy, r.iy, (nxy ^ gy) - gy) : F_INF;
-  const float tz = r.sz != 0 ? plane_t1(r.oz, r.iz, (nxz ^ gz) - gz) : F_INF;
-  int a = 0; float ta = tx;
-  if (ty < ta) { a = 1; ta = ty; }
-  if (tz < ta) { a = 2; ta = tz; }
-  if (!(ta < F_INF)) return W_EXIT;  // zero direction
-  const int olds = SEL3(a, w.csx, w.csy, w.csz);
-  const int news = SEL3(a, nxx, nxy, nxz);
-  const int ox0 = w.csx, oy0 = w.csy, oz0 = w.csz;   // CUBES: cell before the step, all axes
-  if (a == 0) w.csx = nxx; else if (a == 1) w.csy = nxy; else w.csz = nxz;
-  w.la = a; w.lt = ta; steps++;
-  if (STATS) s.lv[sh == 0 ? 0 : (sh <= 2 ? 1 : (sh == 3 ? 2 : (kdf <= 2 ? 3 : 4)))]++;
-  unsigned ucross = (unsigned)(olds ^ news);
-  w.need = (ucross >> 5) ? 3 : ((ucross >> 3) ? 2 : ((ucross >> 1) ? 1 : 0));
-  if (w.need >= 3) {
-    const int st = SEL3(a, r.sx, r.sy, r.sz);
-    const int nv = SEL3(a, v.nvox[0], v.nvox[1], v.nvox[2]);
-    if (news >= (st > 0 ? nv : 0)) return W_EXIT;   // mirrored coordinate at which the ray has left the grid
-  }
-  // the one place where the two other axes are made exact: right after every step that left a box bigger than a voxel
-  if (sh > 0) {
-    cx = w.csx ^ gx; cy = w.csy ^ gy; cz = w.csz ^ gz;
-    sync_axes(r, w, cx, cy, cz);
-    w.csx = cx ^ gx; w.csy = cy ^ gy; w.csz = cz ^ gz;
-    if (CUBES) {
-      // A forward cube of several bricks / 2^3 cells is unaligned: the two synced axes may have crossed a brick, a 32^3
-      // cell or a chunk face inside it although the stepping axis did not -- the cached chunk index, word pair and
-      // payload slot are only valid for what `need` says, so it has to look at all three axes here.
-      ucross = (unsigned)((ox0 ^ w.csx) | (oy0 ^ w.csy) | (oz0 ^ w.csz));
-      w.need = (ucross >> 5) ? 3 : ((ucross >> 3) ? 2 : ((ucross >> 1) ? 1 : 0));
-    }
-  }
-  return W_CONTINUE;
 }
 
 __device__ __forceinline__ uint32_t to_un8(float x) { return (uint32_t)__fadd_rn(__fmul_rn(x, 255.0f), 0.5f); }
@@ -320,36 +136,8 @@ __device__ __forceinline__ uint4 shade_record(const Done& dn) {
                     __float_as_uint(dn.t), r | (g << 8) | (b << 16));
 }
 
-// CTA = one 32x8 screen tile; warp = 8x4 pixels (four full 128 B lines per record store).  All primary rays of a warp
-// start together from the same eye, so the lanes stay at similar levels of the walk; when all of them are done, the lanes
-// that hit a lit-facing face trace that pixel's shadow ray, again all starting together.  Keeping phases apart matters:
-// refilling idle lanes with new pixels (v4) or letting a lane continue as its shadow ray inside the primary loop (v9)
-// both raise lane occupancy and both cost 30 % or more extra warp instructions (profiles/README.md).
-// No shared memory, no barriers: the CTA is only the unit of tile ownership.
-#define RM_KERNEL_NAME raymarch_kernel
-#define RM_EXTRA_PARAM
-#define RM_CUBES false
-#define RM_SET_CUBES(sc)
-#include "raymarch_kernel.inc"
-#undef RM_KERNEL_NAME
-#undef RM_EXTRA_PARAM
-#undef RM_CUBES
-#undef RM_SET_CUBES
-
-// the same frame through the per-octant forward cubes (MESO_FLAG_CUBES)
-#define RM_KERNEL_NAME raymarch_cubes_kernel
-#define RM_EXTRA_PARAM , CubeTables ct
-#define RM_CUBES true
-#define RM_SET_CUBES(sc) (sc).ct = ct
-#include "raymarch_kernel.inc"
-#undef RM_KERNEL_NAME
-#undef RM_EXTRA_PARAM
-#undef RM_CUBES
-#undef RM_SET_CUBES
-
-
 // =====================================================================================================================
-// v10: the same walk, written in MIRRORED SPACE with a branch-free axis sync.
+// The walk, written in MIRRORED SPACE with a branch-free axis sync.
 //
 // Mirrored space.  With g = step >> 31 (0 or -1) the walk already keeps cs = c ^ g, in which every active axis moves
 // towards +.  v10 mirrors the ray as well: om = g ? -o : o, dm = |d|, im = |1/d|.  The key of mirrored plane m is
@@ -365,7 +153,8 @@ __device__ __forceinline__ uint4 shade_record(const Done& dn) {
 // floor(x -+ 6e-8 |x|): while |o| <= 1e6 (hence t < 2e6 inside a grid of at most 65 536 voxels per axis) the two differ by
 // at most one, and testing the keys of the two planes that bound the estimated cell decides it exactly -- fixed cost, no
 // data-dependent loop, no divergent slow path.  A ray whose origin is farther out than 1e6 voxels takes the loop form for
-// its whole walk (walk10_slow).  Result identical to oracle/orc_raymarch.c either way.
+// its whole walk -- decided on the host from the eye (launch_raymarch picks the FAR instantiation; a shadow ray starts at a
+// hit point inside the grid and is never far).  Result identical to oracle/orc_raymarch.c either way.
 #define RM10_FAR 1.0e6f
 struct MRay {
   float ox, oy, oz, dx, dy, dz, ix, iy, iz;
@@ -486,13 +275,6 @@ __device__ __forceinline__ int walk10(const DVolume& v, const Scene10& s, const 
         const unsigned b12 = ((unsigned)(cx >> 3) & 15u) | (((unsigned)(cy >> 3) & 15u) << 4) | (((unsigned)(cz >> 3) & 15u) << 8);
         const int wi = (int)(b12 >> 6);
         const unsigned bit = b12 & 63u;
-#ifdef RM10_DEBUG
-        if (w.ci < 0 || w.ci >= (int)v.nchunks) {
-          printf("RM10 bad ci=%d c=(%d,%d,%d) cs=(%d,%d,%d) g=(%d,%d,%d) ux=%u steps=%u la=%d lt=%g o=(%g,%g,%g) d=(%g,%g,%g) i=(%g,%g,%g)\n", w.ci, cx, cy, cz,
-                 w.csx, w.csy, w.csz, gx, gy, gz, w.ux, steps, w.la, w.lt, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz);
-          return W_EXIT;
-        }
-#endif
         if (wi != w.wtag) {
           const ulonglong2 p = __ldg(v.of + ((unsigned)w.ci * 64u + (unsigned)wi));
           w.wocc = p.x; w.wfull = p.y; w.wtag = wi;
@@ -506,7 +288,13 @@ __device__ __forceinline__ int walk10(const DVolume& v, const Scene10& s, const 
         w.slot = __ldg(v.bptr + ((unsigned)w.ci * (unsigned)MESO_BLOCKS + b12));
         w.cm = __ldg(v.pool_cm + w.slot);
         if (STATS) s.touch_brick[w.slot] = 1;
+#ifdef RM10_PREFETCH
+        // the z-slice of the entry voxel, requested together with the cell mask (both depend on the slot only)
+        w.ztag = cz & 7;
+        w.slice = __ldg(v.pool + ((size_t)w.slot * 8 + w.ztag));
+#else
         w.ztag = -1;
+#endif
       }
       if (w.ux >= 2u) {
         const unsigned ce = ((unsigned)(cx >> 1) & 3u) | (((unsigned)(cy >> 1) & 3u) << 2) | (((unsigned)(cz >> 1) & 3u) << 4);
@@ -563,18 +351,10 @@ __device__ __forceinline__ int walk10(const DVolume& v, const Scene10& s, const 
   }
 }
 
-// the whole walk of a ray that starts farther than RM10_FAR from the grid's corner: loop-form axis sync, out of line
-template <bool STATS, int CL>
-__device__ __noinline__ int walk10_slow(const DVolume& v, const Scene10& s, const MRay& r, Walk10& w, int& cx, int& cy, int& cz, unsigned& steps) {
-  return walk10<STATS, CL, true>(v, s, r, w, cx, cy, cz, steps);
-}
-__device__ __forceinline__ bool ray_is_far(const MRay& r) { return fmaxf(fmaxf(fabsf(r.ox), fabsf(r.oy)), fabsf(r.oz)) > RM10_FAR; }
-
 // first cell of a ray (walk_begin, true space) -> mirrored walk state
 __device__ __forceinline__ bool walk10_begin(const DVolume& v, const Ray& r, int cx, int cy, int cz, Walk10& w, unsigned& steps) {
-  Walk w0;
-  const bool alive = walk_begin(v, r, cx, cy, cz, w0, steps);
-  w.csx = w0.csx; w.csy = w0.csy; w.csz = w0.csz; w.la = w0.la; w.lt = w0.lt;
+  const bool alive = walk_begin(v, r, cx, cy, cz, w.la, w.lt, steps);
+  w.csx = cx ^ (r.sx >> 31); w.csy = cy ^ (r.sy >> 31); w.csz = cz ^ (r.sz >> 31);
   w.ux = 0xFFFFFFFFu; w.ci = -1; w.wtag = -1; w.ztag = -1; w.slot = 0; w.wocc = 0; w.wfull = 0; w.slice = 0; w.cm = 0;
   return alive;
 }
@@ -607,7 +387,7 @@ __device__ __forceinline__ void scene10_octant(Scene10& sc, const CubeTables& ct
 #define RM10_THREADS 128
 #endif
 #define RM10_SPLIT (256 / RM10_THREADS)
-template <bool STATS, int CL>
+template <bool STATS, int CL, bool FAR>
 __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS)) raymarch10_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
                                                                    int rank, int world, int layout, int tiles_x, int n_tiles, int local_tile0,
                                                                    MesoHitRecord* __restrict__ out, RayStatsDev* stats,
@@ -645,13 +425,8 @@ __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS))
     mirror_ray(r, m);   // from here on only the mirrored ray is live (the true one is m with the signs put back)
     if (alive) {
       scene10_octant<CL>(sc, ct, m);
-      const bool far = ray_is_far(m);
       park_inactive(m, w);
-#ifdef RM10_NO_SLOW
-      (void)far; res = walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
-#else
-      res = far ? walk10_slow<STATS, CL>(v, sc, m, w, cx, cy, cz, steps) : walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
-#endif
+      res = walk10<STATS, CL, FAR>(v, sc, m, w, cx, cy, cz, steps);
     }
     if (res == W_HIT) {
       dn.t = w.lt; dn.cx = cx; dn.cy = cy; dn.cz = cz;
@@ -691,13 +466,8 @@ __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS))
       if (walk10_begin(v, r, dn.cx + (hit_axis == 0 ? nrm : 0), dn.cy + (hit_axis == 1 ? nrm : 0), dn.cz + (hit_axis == 2 ? nrm : 0), w, steps)) {
         MRay m; mirror_ray(r, m);
         scene10_octant<CL>(sc, ct, m);
-        const bool far = ray_is_far(m);
         park_inactive(m, w);
-#ifdef RM10_NO_SLOW
-        (void)far; res = walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
-#else
-        res = far ? walk10_slow<STATS, CL>(v, sc, m, w, cx, cy, cz, steps) : walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
-#endif
+        res = walk10<STATS, CL, false>(v, sc, m, w, cx, cy, cz, steps);
       }
       dn.shadow = res == W_HIT ? 1 : 0;
       n_shadow = 1;
@@ -759,42 +529,21 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
   const int all_local = (n_tiles - rank + world - 1) / world;
   if (local_tile_count < 0) local_tile_count = all_local - local_tile0;
   if (local_tile_count <= 0) return;
-  const size_t smem = 0;
-  // A/B switch while both walks exist: MESO_RM_KERNEL=v8 selects the round-1 kernels, anything else v10;
-  // MESO_CUBES_LEVEL = 1..3 = how many levels of the v10 walk read forward cubes under MESO_FLAG_CUBES.
-  const bool use_v8 = [] { const char* e = getenv("MESO_RM_KERNEL"); return e && strcmp(e, "v8") == 0; }();
-  const int cubes_level = [] { const char* e = getenv("MESO_CUBES_LEVEL"); const int l = e ? atoi(e) : 3; return l < 1 ? 1 : (l > 3 ? 3 : l); }();
-  if (!use_v8) {
-    const CubeTables ct = cubes ? *cubes : CubeTables{};
-    const int cl = cubes ? cubes_level : 0;
-#define RM10_LAUNCH(ST, CL)                                                                                                        \
-    raymarch10_kernel<ST, CL><<<local_tile_count * RM10_SPLIT, RM10_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, \
-                                                                                 tiles_x, n_tiles, local_tile0, d_out, d_stats,    \
-                                                                                 d_touch_chunk, d_touch_brick, ct)
-    if (d_stats) { if (cl == 0) RM10_LAUNCH(true, 0); else if (cl == 1) RM10_LAUNCH(true, 1); else if (cl == 2) RM10_LAUNCH(true, 2); else RM10_LAUNCH(true, 3); }
-    else         { if (cl == 0) RM10_LAUNCH(false, 0); else if (cl == 1) RM10_LAUNCH(false, 1); else if (cl == 2) RM10_LAUNCH(false, 2); else RM10_LAUNCH(false, 3); }
+  // `cubes` = the per-octant forward-cube tables (k_cubes.cu) when they are current, else null: the walk then reads the
+  // distance field + probe-ahead (CL = 0; streaming updates, which would have to rebuild the tables every frame).
+  // cubes_level: 1 = cell cubes, 2 = + brick cubes (default, fastest measured on B200), 3 = + 2^3-cell cubes.
+  const CubeTables ct = cubes ? *cubes : CubeTables{};
+  // an eye farther than RM10_FAR voxels from the grid's corner: loop-form axis sync for the primary rays, over the distance field
+  const bool far = fmaxf(fmaxf(fabsf(rs.o[0]), fabsf(rs.o[1])), fabsf(rs.o[2])) > RM10_FAR;
+  const int cl = (cubes && !far) ? (cubes->cell2 ? 3 : (cubes->brick ? 2 : 1)) : 0;
+#define RM10_LAUNCH(ST, CL, FR)                                                                                                    \
+  raymarch10_kernel<ST, CL, FR><<<local_tile_count * RM10_SPLIT, RM10_THREADS, 0, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, \
+                                                                               tiles_x, n_tiles, local_tile0, d_out, d_stats,    \
+                                                                               d_touch_chunk, d_touch_brick, ct)
+  if (far)          { if (d_stats) RM10_LAUNCH(true, 0, true); else RM10_LAUNCH(false, 0, true); }
+  else if (d_stats) { if (cl == 0) RM10_LAUNCH(true, 0, false); else if (cl == 1) RM10_LAUNCH(true, 1, false); else if (cl == 2) RM10_LAUNCH(true, 2, false); else RM10_LAUNCH(true, 3, false); }
+  else              { if (cl == 0) RM10_LAUNCH(false, 0, false); else if (cl == 1) RM10_LAUNCH(false, 1, false); else if (cl == 2) RM10_LAUNCH(false, 2, false); else RM10_LAUNCH(false, 3, false); }
 #undef RM10_LAUNCH
-    (*lc.launches)++;
-    return;
-  }
-  // (Dispatching the tiles in a golden-ratio permuted order, to spread the expensive silhouette tiles over the launch,
-  // was measured: no gain in the pipelined loop, 2 % slower alone -- neighbouring tiles share distance-field and brick lines.)
-  if (cubes) {
-    if (d_stats)
-      raymarch_cubes_kernel<true><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
-                                                                                     n_tiles, local_tile0, d_out, d_stats, d_touch_chunk, d_touch_brick, *cubes);
-    else
-      raymarch_cubes_kernel<false><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
-                                                                                      n_tiles, local_tile0, d_out, nullptr, nullptr, nullptr, *cubes);
-    (*lc.launches)++;
-    return;
-  }
-  if (d_stats)
-    raymarch_kernel<true><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
-                                                                             n_tiles, local_tile0, d_out, d_stats, d_touch_chunk, d_touch_brick);
-  else
-    raymarch_kernel<false><<<local_tile_count, RM_THREADS, smem, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, tiles_x,
-                                                                              n_tiles, local_tile0, d_out, nullptr, nullptr, nullptr);
   (*lc.launches)++;
 }
 

@@ -304,6 +304,8 @@ static int join_frames(MesoCtx* c) {
 }
 #define JOIN_FRAMES(c) do { const int jr__ = join_frames(c); if (jr__ != MESO_OK) return jr__; } while (0)
 
+static int build_cubes(MesoCtx* c);
+
 static int check_overflow(MesoCtx* c, const char* what) {
   int h = 0;
   CK(cudaMemcpyAsync(&h, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -325,7 +327,9 @@ int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granular
   JOIN_FRAMES(c);
   launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
   CK_LAST("voxelize");
-  return check_overflow(c, "meso_voxelize_sdf");
+  const int r = check_overflow(c, "meso_voxelize_sdf");
+  if (r != MESO_OK) return r;
+  return build_cubes(c);   // derived data of a whole-grid generation, like the distance field (enqueue only)
 }
 
 int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, const uint64_t* keys, const uint64_t* payload, int64_t n) {
@@ -364,6 +368,8 @@ int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, co
     }
     launch_volume_finalize(c->lc(), c->v);
     CK_LAST("volume upload");
+    const int rc = build_cubes(c);
+    if (rc != MESO_OK) return rc;
     CK(cudaStreamSynchronize(c->stream));
     return MESO_OK;
   };
@@ -398,6 +404,8 @@ int meso_volume_upload_blocks(MesoCtx* c, const MesoGPUChunk* chunks, int64_t n_
     }
     launch_volume_finalize(c->lc(), v);
     CK_LAST("volume upload blocks");
+    const int rc = build_cubes(c);
+    if (rc != MESO_OK) return rc;
     unsigned long long acc = 0;
     CK(cudaMemcpyAsync(&acc, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -527,44 +535,60 @@ int meso_ray_setup(const MesoGPUUniformCamera* cam, const int32_t origin_chunk[3
   return MESO_OK;
 }
 
-int meso_build_cubes(MesoCtx* c) {
-  NEED_SCENE(c);
+// Forward-cube tables for the current volume, enqueued on the context's stream.  level: 1 = cell cubes only, 2 = + brick
+// cubes (default: fastest measured), 3 = + 2^3-cell cubes (MESO_CUBES_LEVEL, a measurement knob).
+static int cubes_level() {
+  static const int level = [] { const char* e = getenv("MESO_CUBES_LEVEL"); const int l = e ? atoi(e) : 3; return l < 1 ? 1 : (l > 3 ? 3 : l); }();
+  return level;
+}
+static int build_cubes(MesoCtx* c) {
   const DVolume& v = c->v;
+  const int level = cubes_level();
   const size_t ncells = (size_t)v.ddims[0] * v.ddims[1] * v.ddims[2];
   const size_t npcells = (size_t)(v.ddims[0] + 2) * (v.ddims[1] + 2) * (v.ddims[2] + 2);
   if (!c->d_cube_cell) CK(cudaMalloc(&c->d_cube_cell, 8 * ncells));
   if (!c->d_cube_cellp) CK(cudaMalloc(&c->d_cube_cellp, 8 * npcells));
-  if (!c->d_cube_brick) CK(cudaMalloc(&c->d_cube_brick, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t)));
-  if (!c->d_cube_cell2) CK(cudaMalloc(&c->d_cube_cell2, (size_t)v.max_bricks * 64 * sizeof(uint16_t)));
+  if (level >= 2 && !c->d_cube_brick) CK(cudaMalloc(&c->d_cube_brick, (size_t)v.nchunks * MESO_BLOCKS * sizeof(uint16_t)));
+  if (level >= 3 && !c->d_cube_cell2) CK(cudaMalloc(&c->d_cube_cell2, (size_t)v.max_bricks * 64 * sizeof(uint16_t)));
   for (int i = 0; i < MESO_FRAME_RING; i++)     // frames in flight may be reading the old tables
     if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
   // Entries of payload slots that do not exist yet read as "one cell": a carve only REMOVES voxels, so every cube the
   // tables certify stays empty afterwards, and the slots it allocates (full bricks that became partial) are covered by
   // this zero fill -- the tables survive carves (like the distance field) and are rebuilt only when voxels may be added.
-  CK(cudaMemsetAsync(c->d_cube_cell2, 0, (size_t)v.max_bricks * 64 * sizeof(uint16_t), c->stream));
-  launch_build_cubes(c->lc(), v, c->d_cube_cell, c->d_cube_cellp, c->d_cube_brick, c->d_cube_cell2);
+  if (level >= 3) CK(cudaMemsetAsync(c->d_cube_cell2, 0, (size_t)v.max_bricks * 64 * sizeof(uint16_t), c->stream));
+  launch_build_cubes(c->lc(), v, c->d_cube_cell, c->d_cube_cellp, level >= 2 ? c->d_cube_brick : nullptr, level >= 3 ? c->d_cube_cell2 : nullptr);
   CK_LAST("build cubes");
   c->cubes.cell = c->d_cube_cell; c->cubes.cellp = c->d_cube_cellp; c->cubes.pd0 = v.ddims[0] + 2; c->cubes.pd01 = (v.ddims[0] + 2) * (v.ddims[1] + 2);
-  c->cubes.npcells = (int64_t)npcells; c->cubes.brick = c->d_cube_brick; c->cubes.cell2 = c->d_cube_cell2; c->cubes.ncells = (int64_t)ncells;
+  c->cubes.npcells = (int64_t)npcells; c->cubes.ncells = (int64_t)ncells;
+  c->cubes.brick = level >= 2 ? c->d_cube_brick : nullptr;
+  c->cubes.cell2 = level >= 3 ? c->d_cube_cell2 : nullptr;
   c->cubes_valid = true;
   return MESO_OK;
+}
+
+int meso_build_cubes(MesoCtx* c) {
+  NEED_SCENE(c);
+  return build_cubes(c);
 }
 
 int meso_download_cubes(MesoCtx* c, uint8_t* cell, uint16_t* brick) {
   NEED_SCENE(c);
   if (!c->cubes_valid) return fail(MESO_ERR_ARGUMENT, "meso_download_cubes: call meso_build_cubes first");
   if (cell) CK(cudaMemcpyAsync(cell, c->d_cube_cell, 8 * (size_t)c->cubes.ncells, cudaMemcpyDeviceToHost, c->stream));
+  if (brick && !c->cubes.brick) return fail(MESO_ERR_ARGUMENT, "meso_download_cubes: the brick table is not built at MESO_CUBES_LEVEL=1");
   if (brick) CK(cudaMemcpyAsync(brick, c->d_cube_brick, (size_t)c->v.nchunks * MESO_BLOCKS * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return MESO_OK;
 }
 
-// the tables a raymarch launch should use: nullptr for the shipped walk, an error if MESO_FLAG_CUBES has nothing valid to read
+// The tables a raymarch launch reads: the forward cubes whenever they are current (the default walk), nullptr -> the
+// distance-field walk when they are not (streaming updates) or MESO_FLAG_NO_CUBES asks for it; MESO_FLAG_CUBES insists.
 static int cubes_for(MesoCtx* c, uint32_t flags, const CubeTables** out) {
   *out = nullptr;
-  if (!(flags & MESO_FLAG_CUBES)) return MESO_OK;
-  if (!c->cubes_valid) return fail(MESO_ERR_ARGUMENT, "MESO_FLAG_CUBES: call meso_build_cubes after the last change of the volume");
-  *out = &c->cubes;
+  if ((flags & MESO_FLAG_CUBES) && (flags & MESO_FLAG_NO_CUBES)) return fail(MESO_ERR_ARGUMENT, "MESO_FLAG_CUBES and MESO_FLAG_NO_CUBES exclude each other");
+  if (flags & MESO_FLAG_NO_CUBES) return MESO_OK;
+  if (c->cubes_valid) { *out = &c->cubes; return MESO_OK; }
+  if (flags & MESO_FLAG_CUBES) return fail(MESO_ERR_ARGUMENT, "MESO_FLAG_CUBES: the forward-cube tables are not current (meso_build_cubes)");
   return MESO_OK;
 }
 

@@ -1,4 +1,4 @@
-"""One raymarch launch per configuration named in RM_ONE (comma list of v8, v8+cubes, v10, v10+cubesN) on the bench
+"""One raymarch launch per configuration named in RM_ONE (comma list of v10, v10+cubes; MESO_CUBES_LEVEL picks the level) on the bench
 workload, camera 0 -- the command ncu wraps (-k regex:raymarch)."""
 import os, sys
 import torch
@@ -10,14 +10,10 @@ origin, dims, params = scenes.sphere_scene(N)
 ctx = capi.Context(0)
 ctx.scene_create(origin, dims, max_bricks=(1 << 20) if N >= 4096 else (1 << 18))
 ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
-ctx.build_cubes()
 eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
 cam = camera.camera_uniform(eyes[int(os.environ.get("RM_ONE_CAM", "0"))], ctr, W, H)
 frame = torch.empty((H, W, 4), dtype=torch.int32, device="cuda")
-for name in os.environ.get("RM_ONE", "v10").split(","):
-    kern, _, cub = name.partition("+cubes")
-    os.environ["MESO_RM_KERNEL"] = kern
-    os.environ["MESO_CUBES_LEVEL"] = cub or "3"
-    ctx.raymarch_device(cam, W, H, frame.data_ptr(), shadow=True, layout=capi.LAYOUT_FRAME, flags_extra=capi.FLAG_CUBES if "+cubes" in name else 0)
+for name in os.environ.get("RM_ONE", "v10+cubes").split(","):
+    ctx.raymarch_device(cam, W, H, frame.data_ptr(), shadow=True, layout=capi.LAYOUT_FRAME, flags_extra=capi.FLAG_CUBES if "+cubes" in name else capi.FLAG_NO_CUBES)
     ctx.sync()
 ctx.close()
