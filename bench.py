@@ -273,6 +273,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barriers around the single-process group leg (no GPU spin)
     dev = torch.device("cuda", local_rank)
 
     n, width, height, desc = WORKLOADS[args.workload]
@@ -507,6 +508,61 @@ def run_ours(args):
         if host_fused:
             shm_views =[shm[i * px * 16:(i + 1) * px * 16].view(capi.HitRecord).reshape(height, width) for i in range(R)]
 
+    # N > 1, default: SLAB gather.  Rank r owns rows [r * rows, (r + 1) * rows) of every frame in flight in its own device
+    # memory, exported to all ranks over CUDA IPC; every rank's kernel stores each record straight into the owner's slab
+    # over NVLink (MESO_LAYOUT_SLABS: the all-to-all is fused into the store), and after the rendezvous every rank copies its
+    # contiguous slab into the shared host frame with ONE large DMA over its own PCIe link -- instead of 512-byte stores
+    # from N GPUs interleaved inside every 4 KB host page.  Falls back to the host-fused stores above.
+    slabs_ok = False
+    slab_rows = ((((height + capi.TILE_H - 1) // capi.TILE_H) + world - 1) // world) * capi.TILE_H
+    slab_mine, slab_ptrs = [None] * R, [[None] * world for _ in range(R)]
+    if host_fused and not args.no_slabs:
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        handles = torch.zeros((R, capi.IPC_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+        try:
+            for i in range(R):
+                slab_mine[i] = ctx.device_alloc(slab_rows * width * 16)
+                handles[i].copy_(torch.from_numpy(ctx.ipc_export(slab_mine[i])))
+        except Exception as e:
+            sys.stderr.write("bench: slab gather unavailable on rank %d (%s)\n" % (rank, e))
+            ok.zero_()
+        allh = torch.zeros((world, R, capi.IPC_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, handles)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            allh_np = allh.cpu().numpy()
+            try:
+                for i in range(R):
+                    for r in range(world):
+                        slab_ptrs[i][r] = slab_mine[i] if r == rank else ctx.ipc_open(allh_np[r, i])
+            except Exception as e:
+                sys.stderr.write("bench: slab gather unavailable on rank %d (%s)\n" % (rank, e))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        slabs_ok = int(ok.item()) == 1
+    my_row0 = rank * slab_rows
+    my_rows = max(0, min(slab_rows, height - my_row0))
+    flags2 = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(R)]
+
+    def slab_frame(k, slot, rgba8=False):
+        """One frame through the slab gather on ring slot `slot`'s stream: kernel -> rendezvous (every rank's slab is
+        complete) -> this rank's slab to the shared host frame -> rendezvous (every slab has landed)."""
+        bpp = 4 if rgba8 else 16
+        s = streams[slot]
+        ctx.set_stream(s.cuda_stream)
+        with torch.cuda.stream(s):
+            ctx.raymarch_device_slabs(cams[k % 8], width, height, slab_ptrs[slot], slab_rows, shadow=True, light=LIGHT,
+                                      flags_extra=capi.FLAG_RGBA8 if rgba8 else 0)
+            dist.all_reduce(flags[slot])
+            if my_rows > 0:
+                off = slot * px * 16 + my_row0 * width * bpp
+                ctx.download_async(shm[off:off + my_rows * width * bpp], slab_mine[slot])
+            dist.all_reduce(flags2[slot])
+            e = torch.cuda.Event()
+            e.record(s)
+        ctx.set_stream(stream.cuda_stream)
+        return e
+
     def e2e_run(nsteps, rgba8=False):
         nonlocal consumed
         if world > 1 and host_fused:
@@ -520,6 +576,9 @@ def run_ours(args):
                             consumed += int(shm[slot * px * 16]) + int(shm[slot * px * 16 + 4 * px - 1])
                         else:
                             consumed += int(shm_views[slot]["w1"][0, 0]) + int(shm_views[slot]["w1"][-1, -1])
+                if slabs_ok:
+                    pend[slot] = slab_frame(k, slot, rgba8)
+                    continue
                 s = streams[slot]
                 ctx.set_stream(s.cuda_stream)
                 with torch.cuda.stream(s):
@@ -594,7 +653,10 @@ def run_ours(args):
         e2e_rgba8 = {"value": e2e_rays / float(dt8.item()) / 1e6, "unit": "Mrays/s", "d2h_bytes_per_step": 4 * px,
                      "note": "MESO_FLAG_RGBA8 through the host-fused gather: only the colour word of every record travels"}
         # the frame the ranks assembled in host memory equals the frame one GPU renders on its own
-        ctx.raymarch_device(cams[0], width, height, shm_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+        if slabs_ok:
+            slab_frame(0, 0).synchronize()
+        else:
+            ctx.raymarch_device(cams[0], width, height, shm_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
         barrier()
         if rank == 0:
             ctx.set_partition(0, 1)
@@ -605,8 +667,18 @@ def run_ours(args):
         # BASELINE.json configs[4] on N GPUs: carve replicated on every rank, render split by tiles into the shared frame
         edit_multi = None
         if not args.no_mesh:
-            edit_multi = bench_edit_loop_multi(ctx, capi, cams, width, height, shm_views[0], shm_dptr, flags[0], stream, rank, dist, torch)
+            slab_info = dict(ptrs=slab_ptrs, mine=slab_mine, rows=slab_rows, row0=my_row0, my_rows=my_rows, shm=shm, px=px, R=R,
+                             flags2=flags2, streams=streams) if slabs_ok else None
+            edit_multi = bench_edit_loop_multi(ctx, capi, cams, width, height, shm_views[0], shm_dptr, flags[0], stream, rank, dist, torch, slabs=slab_info)
         barrier()
+        if slabs_ok:
+            for i in range(R):
+                for r in range(world):
+                    if r != rank:
+                        ctx.ipc_close(slab_ptrs[i][r])
+            dist.barrier()
+            for i in range(R):
+                ctx.device_free(slab_mine[i])
         ctx.host_unregister(shm)
         del shm_views
         shm = None
@@ -664,15 +736,20 @@ def run_ours(args):
                     "steps": e2e_steps, "rgba8": e2e_rgba8,
                     "note": ("meso_raymarch_async()/meso_frame_wait() frame ring of 4: FGPUUniformCamera from host memory (kernel parameters), records copied to pinned host memory, copy of frame k overlapping frame k+1"
                              if world == 1 else
-                             ("fused gather into host memory: one shared-memory segment registered by every rank (meso_host_register); each rank's kernel stores its tile records there over its own PCIe link, 4-byte NCCL all-reduce as the rendezvous, frames consumed on rank 0"
+                             (("slab gather: every rank's kernel stores each record into the device slab of the rank that owns its rows (peer memory over NVLink, MESO_LAYOUT_SLABS), 4-byte NCCL all-reduce as the rendezvous, then every rank copies its contiguous slab into the shared host frame with one DMA over its own PCIe link; frames consumed on rank 0"
+                               if slabs_ok else
+                               "fused gather into host memory: one shared-memory segment registered by every rank (meso_host_register); each rank's kernel stores its tile records there over its own PCIe link, 4-byte NCCL all-reduce as the rendezvous, frames consumed on rank 0")
                               if host_fused else
                               "frame gathered on rank 0 (fused p2p stores or NCCL), then copied to pinned host memory on that frame's stream, overlapping the next frame in flight")),
-                    "host_fused": host_fused, "host_fused_verified_equal_to_1gpu_frame": host_fused_verified},
+                    "host_fused": host_fused, "slab_gather": slabs_ok, "host_fused_verified_equal_to_1gpu_frame": host_fused_verified},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "raymarch10_kernel<false, 2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
-                         "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": kms, "kernel_ms_is": "isolated: one launch per CUDA-event pair, L2 flushed (256 MiB write) before each; NOT the per-step cost",
+                         "kernel_ms_in_loop": ms / args.steps, "kernel_ms_in_loop_is": "timed region / steps with %d frames in flight on alternating streams (the tail of frame k overlaps frame k+1)" % R,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture committed under profiles/ (profiles/raymarch_traffic.json names the file); not measured in this run",
+                         "algorithmic_bytes_per_launch": alg_bytes,
                          "issue": issue_roofline(ctx, world, args.workload, kms, clocks),
                          "note": "divergence/instruction-issue-bound traversal; working set is L2-resident (SURVEY.md 8d); 'issue' relates the ncu-counted warp instructions of one launch to the SMs' issue peak"},
         }
@@ -693,10 +770,25 @@ def run_ours(args):
     if world == 1 and not args.no_mesh and rank == 0:
         line["stream"] = bench_stream(ctx, capi, torch, stream)
 
+    # ---- BASELINE.json configs[0] and configs[1] at their stated sizes (1 GPU leg): Mrays/s + sampled parity vs the oracle ----
+    if world == 1 and not args.no_mesh and rank == 0 and args.workload == "cfg3":
+        line["configs"] = {name: bench_small_config(ctx, capi, scenes, torch, stream, name, args) for name in ("cfg0", "cfg1")}
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample, outputs byte-compared ----
     if world == 1 and not args.no_cpu and rank == 0:
         line["cpu_baseline"] = cpu_baseline(ctx, capi, scene, cams, width, height, args)
 
+    # ---- the same job through the single-process group API (meso_group_*: the C++ host's way in), rank 0 drives all N GPUs
+    #      while the other ranks wait on a host-side barrier ----
+    if world > 1 and not args.no_group:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                line["group_api"] = bench_group(capi, torch, scene, cams, rays_cam, width, height, world, args)
+            except Exception as e:
+                line["group_api"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        dist.barrier(group=cpu_group)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -704,6 +796,130 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     ctx.close()
     return 0
+
+
+def bench_group(capi, torch, scene, cams, rays_cam, width, height, world, args):
+    """N GPUs behind one handle in ONE process (meso_group_*, csrc/meso_group.cu): what a C++ MesoEngine host calls.  Frames
+    through the group's ring (slab gather fused into the kernels' stores, cross-device event waits, one DMA per member),
+    quads gathered to the host at prefix offsets and on member 0 in segments, the edit loop through the synchronous calls."""
+    origin, dims, params = scene
+    g = capi.Group(list(range(world)))
+    try:
+        g.scene_create(origin, dims, max_bricks=(1 << 20) if dims[0] >= 32 else (1 << 18))
+        g.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
+        g.sync()
+        RING = 4
+        hosts = [torch.empty((height, width, 4), dtype=torch.int32).pin_memory() for _ in range(RING)]
+        hosts_np = [h.numpy().view(capi.HitRecord).reshape(height, width) for h in hosts]
+        consumed = 0
+
+        def run(nsteps):
+            nonlocal consumed
+            for k in range(nsteps):
+                slot = k % RING
+                if k >= RING:
+                    g.frame_wait(slot)
+                    consumed += int(hosts_np[slot]["w1"][0, 0]) + int(hosts_np[slot]["w1"][-1, -1])
+                g.raymarch_async(cams[k % 8], width, height, hosts_np[slot], slot, shadow=True, light=LIGHT)
+            for slot in range(RING):
+                g.frame_wait(slot)
+                consumed += int(hosts_np[slot]["w1"][0, 0]) + int(hosts_np[slot]["w1"][-1, -1])
+
+        run(RING)
+        nsteps = max(8, min(args.steps, 40))
+        t0 = time.perf_counter()
+        run(nsteps)
+        dt = time.perf_counter() - t0
+        rays = sum(rays_cam[k % 8] for k in range(nsteps))
+        # the group's frame == member 0 rendering the whole frame on its own
+        got = g.raymarch(cams[0], width, height, shadow=True, light=LIGHT)
+        m0 = g.member(0)
+        m0.set_partition(0, 1)
+        ref = m0.raymarch(cams[0], width, height, shadow=True, light=LIGHT)
+        m0.set_partition(0, world)
+        out = {"e2e": {"value": rays / dt / 1e6, "unit": "Mrays/s", "steps": nsteps, "d2h_bytes_per_step": 16 * width * height,
+                       "frame_equal_to_1gpu_frame": bool(got.tobytes() == ref.tobytes())}}
+        if not args.no_mesh:
+            cap = 1 << 25
+            q, counts = g.mesh(cap)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); g.mesh(cap); ts.append(time.perf_counter() - t0)
+            out["mesh_to_host"] = {"quads": int(len(q)), "ms": min(ts) * 1e3, "per_member": [int(x) for x in counts]}
+            dq = m0.device_alloc(cap * 16)
+            n, _ = g.mesh_device(dq, cap, compact=False)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); g.mesh_device(dq, cap, compact=False); ts.append(time.perf_counter() - t0)
+            ts2 = []
+            for _ in range(3):
+                t0 = time.perf_counter(); g.mesh_device(dq, cap, compact=True); ts2.append(time.perf_counter() - t0)
+            m0.device_free(dq)
+            out["mesh_on_member0"] = {"quads": int(n), "ms_segments": min(ts) * 1e3, "ms_compacted": min(ts2) * 1e3,
+                                      "note": "wall clock of the call incl. the 8-byte count read-backs"}
+            # edit loop, synchronous group calls
+            frames = 32
+            rec = g.raymarch(cams[0], width, height, shadow=True, light=LIGHT, out=hosts_np[0])
+            t_all = time.perf_counter()
+            nd_total = 0
+            for k in range(frames):
+                r = rec[height // 2, width // 2]
+                if (int(r["w1"]) >> 20) & 1:
+                    center = [int(r["w0"]) & 0xFFFF, int(r["w0"]) >> 16, int(r["w1"]) & 0xFFFF]
+                    nd_total += g.carve_sphere(center, 24)
+                    g.remesh_dirty(1 << 16)
+                rec = g.raymarch(cams[(k + 1) % 8], width, height, shadow=True, light=LIGHT, out=hosts_np[0])
+            t_all = time.perf_counter() - t_all
+            out["edit_loop"] = {"frames": frames, "fps": frames / t_all, "ms_per_frame": t_all / frames * 1e3, "dirty_bricks_per_frame": nd_total / frames}
+        out["note"] = "one process, one handle: meso_group_create over %d devices, peer access, no NCCL; what host/Samples/SimpleVoxel --gpus N uses" % world
+        return out
+    finally:
+        g.close()
+
+
+def bench_small_config(ctx, capi, scenes, torch, stream, name, args):
+    """One of BASELINE.json's smaller raymarch configurations at its stated size: device-timed Mrays/s (kernel per frame, L2
+    flushed: these scenes fit the L2) and, unless --no-cpu, the oracle's records on sampled scanlines byte-compared."""
+    n, width, height, desc = WORKLOADS[name]
+    scene = scenes.sphere_scene(n)
+    origin, dims, params = scene
+    ctx.scene_create(origin, dims, max_bricks=1 << 18)
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
+    cams = make_cameras(scene, width, height)
+    st = [ctx.raymarch_stats(c, width, height, shadow=True, light=LIGHT) for c in cams]
+    rays = [int(s["primary"]) + int(s["shadow"]) for s in st]
+    frame = torch.empty((height, width, 4), dtype=torch.int32, device="cuda")
+    steps = 24
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(4):
+        ctx.raymarch_device(cams[k % 8], width, height, frame.data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+    for k in range(steps):
+        ctx.flush_l2()
+        ev[k][0].record(stream)
+        ctx.raymarch_device(cams[k % 8], width, height, frame.data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    out = {"workload": desc, "mrays_s": float(np.mean([rays[k % 8] for k in range(steps)])) / ms / 1e3, "ms_per_frame": ms,
+           "rays_per_frame_mean": float(np.mean(rays))}
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc
+        vol = cpu_build_volume(orc, scene)
+        rows = sample_rows(height, 8, 8)
+        mism, cpu_rays, cpu_dt = 0, 0, 0.0
+        nthreads = orc.hw_threads()
+        for k in (0, 3, 6):
+            t0 = time.perf_counter()
+            r, rec = cpu_step(orc, vol, cams[k], width, height, rows, nthreads)
+            cpu_dt += time.perf_counter() - t0
+            cpu_rays += r
+            gpu = ctx.raymarch(cams[k], width, height, shadow=True, light=LIGHT)
+            mism += int((gpu[rows].view(np.uint32).reshape(-1, 4) != rec[rows].view(np.uint32).reshape(-1, 4)).any(axis=1).sum())
+        out["parity_mismatches_on_sampled_rows"] = mism
+        out["cpu_mrays_s"] = cpu_rays / cpu_dt / 1e6
+        out["cpu_sample"] = "3 cameras x 64 scanlines x %d px, oracle on %d threads" % (width, nthreads)
+    return out
 
 
 def bench_edit_loop(ctx, capi, cams, width, height, frames=48):
@@ -737,54 +953,109 @@ def bench_edit_loop(ctx, capi, cams, width, height, frames=48):
             "note": "carve r=24 voxels at the centre-pixel hit, re-mesh dirty bricks + neighbours, re-render 3840x2160 to host memory (synchronous API)"}
 
 
-def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, flag, stream, rank, dist, torch, frames=48):
-    """The edit loop on N GPUs: every rank reads the centre-pixel hit of the last frame from the shared host frame, carves
-    the same sphere into its replica of the volume (replicated compute), rank 0 re-meshes the dirty bricks, and the next 4K
-    frame is rendered split by tiles, every rank's kernel storing its records into the shared host frame.  One rendezvous
-    per frame (the next carve needs the frame), wall clock between two barriers."""
+def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, flag, stream, rank, dist, torch, frames=48, slabs=None):
+    """The edit loop on N GPUs.  Every rank reads the centre-pixel hit of the last frame, carves the same sphere into its
+    replica of the volume (replicated compute), re-meshes ITS SHARE of the dirty bricks (sharded by key hash) and renders its
+    tiles of the next 4K frame.  With the slab gather the loop is pipelined: the only thing frame k+1's carve needs from
+    frame k is one 16-byte record, read from the owning rank's slab right behind the kernels' rendezvous, so the slab-to-host
+    DMAs of frame k run behind the carve, re-mesh and traversal of frame k+1 (two slab sets alternate).  Wall clock between
+    two barriers, every frame's records in host memory at the end."""
     dist.barrier()
     torch.cuda.synchronize()
-
-    def render(k):
-        ctx.raymarch_device(cams[k % 8], width, height, frame_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
-        with torch.cuda.stream(stream):
-            dist.all_reduce(flag)
-        stream.synchronize()
-
-    render(0)
+    py, pxl = height // 2, width // 2
+    pick = np.zeros(1, dtype=capi.HitRecord)
     t_carve = t_mesh = t_render = 0.0
     dirty_total = quads_total = 0
+
+    if slabs is None:
+        def render(k):
+            ctx.raymarch_device(cams[k % 8], width, height, frame_dptr, shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+            with torch.cuda.stream(stream):
+                dist.all_reduce(flag)
+            stream.synchronize()
+            return frame[py, pxl]
+        finish = lambda: None
+    else:
+        R, rows, px = slabs["R"], slabs["rows"], slabs["px"]
+        owner = py // rows
+        copy_streams = [torch.cuda.Stream() for _ in range(2)]
+        dma_done = [None, None]
+
+        def render(k):
+            slot = k % 2
+            if dma_done[slot] is not None:
+                dma_done[slot].synchronize()          # this slab set's previous frame has left for the host
+            ctx.raymarch_device_slabs(cams[k % 8], width, height, slabs["ptrs"][slot], rows, shadow=True, light=LIGHT)
+            with torch.cuda.stream(stream):
+                # this rank's DMA of the PREVIOUS frame (other slab set) is ordered before the rendezvous, so that the
+                # rendezvous also tells every rank that all slabs of that set have left: the frame after this one may then
+                # overwrite them (other ranks' kernels store into this rank's slab)
+                if dma_done[1 - slot] is not None:
+                    stream.wait_event(dma_done[1 - slot])
+                dist.all_reduce(flag)                 # every rank's kernel is done: all slabs of this frame are complete
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            # the pick: one record from the owning rank's slab (peer memory), on the main stream
+            ctx.download(pick, slabs["ptrs"][slot][owner] + ((py - owner * rows) * width + pxl) * 16, 16)
+            # the frame itself leaves on a copy stream, behind the next frame's work
+            cs = copy_streams[slot]
+            cs.wait_event(ev)
+            if slabs["my_rows"] > 0:
+                off = slot * px * 16 + slabs["row0"] * width * 16
+                ctx.set_stream(cs.cuda_stream)
+                ctx.download_async(slabs["shm"][off:off + slabs["my_rows"] * width * 16], slabs["mine"][slot])
+                ctx.set_stream(stream.cuda_stream)
+            e = torch.cuda.Event()
+            e.record(cs)
+            dma_done[slot] = e
+            return pick[0]
+
+        def finish():
+            for e in dma_done:
+                if e is not None:
+                    e.synchronize()
+
+    r = render(0)
     t_all = time.perf_counter()
     for k in range(frames):
-        r = frame[height // 2, width // 2]
         if (int(r["w1"]) >> 20) & 1:
             center = [int(r["w0"]) & 0xFFFF, int(r["w0"]) >> 16, int(r["w1"]) & 0xFFFF]
             t0 = time.perf_counter()
             nd = ctx.carve_sphere(center, 24)
             t1 = time.perf_counter()
-            if rank == 0:
-                quads, keys = ctx.remesh_dirty(1 << 16, 1 << 13)
-                quads_total += len(quads)
+            quads, keys = ctx.remesh_dirty(1 << 16, 1 << 13)     # this rank's share of the dirty bricks (+ neighbours)
+            quads_total += len(quads)
             t2 = time.perf_counter()
             t_carve += t1 - t0; t_mesh += t2 - t1
             dirty_total += nd
         t0 = time.perf_counter()
-        render(k + 1)
+        r = render(k + 1)
         t_render += time.perf_counter() - t0
+    finish()
     t_all = time.perf_counter() - t_all
     dist.barrier()
+    qt = torch.tensor([quads_total], dtype=torch.int64, device="cuda")
+    dist.all_reduce(qt)
     return {"frames": frames, "fps": frames / t_all, "ms_per_frame": t_all / frames * 1e3, "ms_carve": t_carve / frames * 1e3,
             "ms_remesh_dirty": t_mesh / frames * 1e3, "ms_render_to_host": t_render / frames * 1e3,
-            "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": quads_total / frames,
-            "note": "rank 0's clock; carve r=24 voxels at the centre-pixel hit on every rank's replica, dirty bricks re-meshed on rank 0, 3840x2160 re-rendered by all ranks into the shared host frame (host-fused gather), one rendezvous per frame"}
+            "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": int(qt.item()) / frames,
+            "pipelined": slabs is not None,
+            "note": "rank 0's clock; carve r=24 voxels at the centre-pixel hit on every rank's replica, dirty bricks re-meshed sharded over the ranks by key hash, 3840x2160 re-rendered by all ranks"
+                    + (" through the slab gather: the next carve waits only for the 16-byte pick behind the kernels' rendezvous, the slab-to-host DMAs of frame k overlap frame k+1"
+                       if slabs is not None else " into the shared host frame (host-fused stores), one rendezvous per frame")}
 
 
 def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels, steps=8):
-    """Meshing on N GPUs with a fused quad gather: chunk c belongs to rank c % world; rank 0 owns the quad list and its
-    8-byte counter (exported over CUDA IPC); every rank's mesh kernel reserves slots with a system-scope atomicAdd on the
-    counter and stores its 16 B quads into the list over NVLink.  The scene is the resident raymarch scene.  Returns None
-    if IPC is unavailable.  Time = CUDA events on every rank around kernel + rendezvous, max over ranks."""
+    """Meshing on N GPUs: chunk c belongs to rank c % world (replicated volume), quads gathered on rank 0.
+
+    Default gather = SEGMENTS: rank 0 owns the list (exported over CUDA IPC); rank r's mesh kernel writes its quads straight
+    into segment r = [r * cap / N, ...) of it over NVLink while it is meshing, reserving slots on a counter in its OWN
+    memory (no cross-GPU atomic, no second pass); the ranks' 8-byte counts are all-gathered.  The result is the list a
+    renderer draws from (N ranges); `compact_ms` is what closing the gaps on rank 0 costs when one contiguous list is wanted.
+    Also timed: the round-1 form (one shared counter, system-scope atomics over NVLink) and the per-GPU lists without any
+    gather.  Time = CUDA events on every rank around kernel + rendezvous, max over ranks.  Returns None without IPC."""
     cap = 1 << 25
+    seg = cap // world
     # every rank runs the same collectives whatever fails where
     hq = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
     hc = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
@@ -821,85 +1092,84 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
                     ctx.device_free(p)
         return None
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    mine = torch.zeros(1, dtype=torch.int64, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
 
-    def one():
+    def timed(body):
+        with torch.cuda.stream(stream):
+            dist.all_reduce(flag)            # start together
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            body()
+            b.record(stream)
+        stream.synchronize()
+        return a.elapsed_time(b)
+
+    def avg(body):
+        timed(body)
+        ts = [timed(body) for _ in range(steps)]
+        t = torch.tensor([sum(ts) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # (1) segments: kernel writes into rank 0's list at this rank's segment, count stays local; rendezvous = the all-gather
+    def seg_body():
+        ctx.mesh_device(qptr + rank * seg * 16, seg, want_count=False)
+        ctx.mesh_count_device(mine.data_ptr())                 # 8-byte count -> device tensor (stream-ordered, no host wait)
+        dist.all_gather_into_tensor(counts, mine)              # behind it every rank's quads are in the list
+    ms_seg = avg(seg_body)
+    seg_counts = [int(x) for x in counts.cpu()]
+    got = None
+    if rank == 0:
+        parts = []
+        for r in range(world):
+            part = np.zeros((seg_counts[r], 4), dtype=np.uint32)
+            if seg_counts[r]:
+                ctx.download(part, qptr + r * seg * 16, seg_counts[r] * 16)
+            parts.append(part)
+        got = np.concatenate(parts, axis=0)
+    # what closing the gaps costs (rank 0, device-local copies on its own stream)
+    compact_ms = None
+    if rank == 0:
+        def compact():
+            at = seg_counts[0]
+            for r in range(1, world):
+                n, src, dst = seg_counts[r], r * seg, at
+                done = 0
+                while done < n and src > dst:
+                    stepn = min(n - done, src - dst)       # chunks no longer than the gap never overlap their source
+                    ctx.device_copy(qptr + (dst + done) * 16, qptr + (src + done) * 16, stepn * 16)
+                    done += stepn
+                at += n
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a, b in ev:
+            ctx.mesh_device(qptr, seg, want_count=False)        # restore segment 0..: contents irrelevant for the timing
+            a.record(stream); compact(); b.record(stream)
+        stream.synchronize()
+        compact_ms = min(a.elapsed_time(b) for a, b in ev)
+    dist.barrier()
+
+    # (2) round 1's form: one shared counter on rank 0, system-scope atomics over NVLink
+    def shared_body():
+        ctx.mesh_device_shared(qptr, cptr, cap)
+        dist.all_reduce(flag)
+    def shared_timed():
         with torch.cuda.stream(stream):
             if rank == 0:
                 ctx.device_memset(cptr, 0, 8)
-            dist.all_reduce(flag)            # nobody starts before the counter is zero
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            ctx.mesh_device_shared(qptr, cptr, cap)
-            dist.all_reduce(flag)            # behind it every rank's quads are in the list
-            b.record(stream)
-        stream.synchronize()
-        return a.elapsed_time(b)
-
-    one()
-    ts = [one() for _ in range(steps)]
-    t = torch.tensor([sum(ts) / steps], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-
-    # the same partition with the lists left where they are made (one list per GPU, no gather): what the meshing itself costs
-    local = torch.empty(((cap // world) + (1 << 20), 4), dtype=torch.int32, device=dev)
-
-    def one_sharded():
-        with torch.cuda.stream(stream):
-            dist.all_reduce(flag)
-            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            ctx.mesh_device(local.data_ptr(), local.shape[0], want_count=False)
-            b.record(stream)
-        stream.synchronize()
-        return a.elapsed_time(b)
-
-    one_sharded()
-    tl = [one_sharded() for _ in range(steps)]
-    t_sh = torch.tensor([sum(tl) / steps], dtype=torch.float64, device=dev)
+        return timed(shared_body)
+    shared_timed()
+    ts = [shared_timed() for _ in range(max(2, steps // 2))]
+    t_sh = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
     dist.all_reduce(t_sh, op=dist.ReduceOp.MAX)
 
-    # Opt-in (MESO_BENCH_PREFIX_GATHER=1; written after the round's GPU budget was spent, not yet measured): the gather
-    # DESIGN.md section 8 item 5 proposes for N >= 4 -- every rank meshes into its own list, the counts are all-gathered,
-    # and each rank sends its list in ONE bulk copy (meso_device_copy over NVLink) into rank 0's list at its prefix
-    # offset: one reservation per rank instead of one per warp.  Runs after the fused leg, so the list rank 0 verifies
-    # below is the one this leg assembled.
-    prefix = None
-    if os.environ.get("MESO_BENCH_PREFIX_GATHER") == "1":
-        counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        mine = torch.zeros(1, dtype=torch.int64, device=dev)
-
-        def one_prefix():
-            with torch.cuda.stream(stream):
-                dist.all_reduce(flag)
-                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                nloc = ctx.mesh_device(local.data_ptr(), local.shape[0])      # reads its 8-byte count back
-                mine.fill_(nloc)
-                dist.all_gather_into_tensor(counts, mine)
-                c = counts.cpu()
-                off = int(c[:rank].sum())
-                if off + nloc > cap:
-                    raise RuntimeError("prefix gather: quad list capacity exceeded")
-                ctx.device_copy(qptr + off * 16, local.data_ptr(), nloc * 16)
-                dist.all_reduce(flag)        # behind it every rank's list has landed
-                b.record(stream)
-            stream.synchronize()
-            return a.elapsed_time(b), int(c.sum())
-
-        one_prefix()
-        tp = [one_prefix() for _ in range(steps)]
-        t_px = torch.tensor([sum(x[0] for x in tp) / steps], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_px, op=dist.ReduceOp.MAX)
-        prefix = {"ms": float(t_px.item()), "quads": tp[-1][1],
-                  "note": "per-rank lists + all-gather of counts + one bulk NVLink copy per rank at prefix offsets into rank 0's list"}
+    # (3) the same partition with the lists left where they are made (one list per GPU, no gather)
+    local = torch.empty((seg + (1 << 20), 4), dtype=torch.int32, device=dev)
+    ms_local = avg(lambda: ctx.mesh_device(local.data_ptr(), local.shape[0], want_count=False))
     del local
+
     out = None
     if rank == 0:
-        cnt = np.zeros(1, dtype=np.uint64)
-        ctx.download(cnt, cptr)
-        nq = int(cnt[0])
-        got = np.zeros((nq, 4), dtype=np.uint32)
-        ctx.download(got, qptr, nq * 16)
         # the same mesh on one GPU, compared through an order-independent fingerprint (the list order is scheduling-dependent)
         ctx.set_partition(0, 1)
         ref_t = torch.empty((cap, 4), dtype=torch.int32, device=dev)
@@ -907,15 +1177,13 @@ def bench_mesh_multi(ctx, capi, torch, dist, dev, rank, world, stream, n_voxels,
         ref = ref_t[:nref].cpu().numpy().view(np.uint32)
         ctx.set_partition(rank, world)
         fp = lambda q: (int(q.shape[0]), [int(x) for x in q.astype(np.uint64).sum(axis=0)], [int(x) for x in np.bitwise_xor.reduce(q, axis=0)])
-        ms = float(t.item())
-        ms_sh = float(t_sh.item())
-        out = {"scene_voxels": n_voxels, "quads": nq, "ms": ms, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms * 1e-3),
-               "equal_to_1gpu_mesh": bool(fp(got) == fp(ref)),
-               "sharded_lists": {"ms": ms_sh, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms_sh * 1e-3),
+        nq = int(got.shape[0])
+        out = {"scene_voxels": n_voxels, "quads": nq, "ms": ms_seg, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms_seg * 1e-3),
+               "equal_to_1gpu_mesh": bool(fp(got) == fp(ref)), "segment_counts": seg_counts, "compact_ms": compact_ms,
+               "shared_counter": {"ms": float(t_sh.item()), "note": "round-1 form: one counter on rank 0, a system-scope atomicAdd per warp over NVLink"},
+               "sharded_lists": {"ms": ms_local, "meshed_voxels_per_s": float(n_voxels) ** 3 / (ms_local * 1e-3),
                                  "note": "same partition, every rank keeps its own quad list (no gather): max over ranks of the mesh kernels"},
-               "note": "chunk c -> rank c % N; fused quad gather into rank 0's list over NVLink (system-scope atomicAdd per warp, 16 B stores); fingerprint = (count, column sums, column xors)"}
-        if prefix is not None:
-            out["prefix_gather"] = prefix
+               "note": "chunk c -> rank c % N; segmented gather: every rank's mesh kernel stores its quads into its own segment of rank 0's list over NVLink (local counter, 16 B stores), counts all-gathered; fingerprint = (count, column sums, column xors)"}
         del ref_t
     dist.barrier()
     if rank != 0:
@@ -991,6 +1259,23 @@ def bench_mesh(ctx, capi, scenes, torch, stream, args, dev, n_work=1024):
         alg = 64.0 * len(keys) + 1024.0 * int(np.prod(dims)) + 16.0 * nq + 4
         out[name] = {"meshed_voxels_per_s": n ** 3 / (ms * 1e-3), "ms": ms, "quads": int(nq), "populated_bricks": populated,
                      "partial_bricks": int(len(keys)), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9}
+        if name == "terrain_1024_blocks" and not args.no_cpu:
+            # BASELINE.json configs[2], CPU beside GPU: the oracle meshes the very same volume on all host threads; the two
+            # quad lists are compared in full after the canonical sort (bit-exact), not sampled
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import orc
+            occ_f, full_f, keys_f, payload_f = ctx.volume_download()
+            vol = orc.Volume(origin, dims).import_(occ_f, full_f, keys_f, payload_f)
+            nthreads = orc.hw_threads()
+            vol.mesh(nthreads)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); ref_q = vol.mesh(nthreads); ts.append(time.perf_counter() - t0)
+            got_q = quads[:nq].cpu().numpy().view(np.uint32).reshape(-1, 4).copy().view(orc.Quad).reshape(-1)
+            equal = bool(len(ref_q) == nq and orc.sort_quads(got_q).tobytes() == orc.sort_quads(ref_q).tobytes())
+            out[name]["cpu_baseline"] = {"ms": min(ts) * 1e3, "meshed_voxels_per_s": n ** 3 / min(ts), "cores": nthreads, "kind": "port",
+                                         "quad_lists_bit_exact_after_canonical_sort": equal,
+                                         "note": "oracle/orc_mesh.c (count pass + emit pass) on the same volume, all host threads"}
         del quads
     return out
 
@@ -1039,6 +1324,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="frame ring depth of the timed loop (reference: kNumBufferedFrames = 4)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame gather (p2p falls back to nccl if IPC is unavailable)")
+    ap.add_argument("--no-group", action="store_true", help="N > 1: skip the single-process group-API leg")
+    ap.add_argument("--no-slabs", action="store_true", help="N > 1 e2e: host-fused 512-byte stores instead of the slab gather")
     ap.add_argument("--no-host-fused", action="store_true", help="N > 1 e2e: gather on rank 0 and copy instead of storing straight into shared host memory")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmeso_b200.so")
-SOURCES = ["meso_capi.cu", "k_voxelize.cu", "k_occupancy.cu", "k_raymarch.cu", "k_mesh.cu", "k_carve.cu", "k_resident.cu", "k_cubes.cu"]
+SOURCES = ["meso_capi.cu", "k_voxelize.cu", "k_occupancy.cu", "k_raymarch.cu", "k_mesh.cu", "k_carve.cu", "k_resident.cu", "k_cubes.cu", "meso_group.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

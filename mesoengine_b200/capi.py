@@ -35,7 +35,7 @@ StreamStats = np.dtype([("generated", "<u4"), ("missing", "<u4"), ("candidates",
 SDF_SPHERE, SDF_TERRAIN = 0, 1
 GRAN_BLOCK, GRAN_VOXEL = 0, 1
 FLAG_SHADOW, FLAG_RGBA8, FLAG_CUBES, FLAG_NO_CUBES = 1, 2, 4, 8
-LAYOUT_FRAME, LAYOUT_TILES = 0, 1
+LAYOUT_FRAME, LAYOUT_TILES, LAYOUT_SLABS = 0, 1, 2
 TILE_W, TILE_H = 32, 8
 
 # every symbol include/meso_cuda.h declares (tests/test_abi.py checks the header against this and the .so)
@@ -51,7 +51,10 @@ SYMBOLS = [
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
-    "meso_device_copy", "meso_build_cubes", "meso_download_cubes", "meso_volume_upload_blocks",
+    "meso_device_copy", "meso_build_cubes", "meso_download_cubes", "meso_volume_upload_blocks", "meso_raymarch_device_slabs", "meso_mesh_count_device",
+    "meso_group_create", "meso_group_destroy", "meso_group_size", "meso_group_ctx", "meso_group_sync", "meso_group_scene_create",
+    "meso_group_voxelize_sdf", "meso_group_volume_upload_blocks", "meso_group_carve_sphere", "meso_group_raymarch",
+    "meso_group_raymarch_async", "meso_group_frame_wait", "meso_group_mesh", "meso_group_mesh_device", "meso_group_remesh_dirty",
 ]
 IPC_HANDLE_BYTES = 64
 UPLOAD_MERGE = 1
@@ -72,6 +75,8 @@ def load():
     lib.meso_launch_count.restype = C.c_int64
     lib.meso_launch_count.argtypes = [C.c_void_p]
     lib.meso_device_sm_count.argtypes = [C.c_void_p]
+    lib.meso_group_ctx.restype = C.c_void_p
+    lib.meso_group_ctx.argtypes = [C.c_void_p, C.c_int]
     return lib
 
 
@@ -265,6 +270,13 @@ class Context:
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
                                      C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
 
+    def raymarch_device_slabs(self, cam, width, height, slab_ptrs, rows_per_slab, shadow=True, light=(0.3, 0.5, 0.8), flags_extra=0):
+        """MESO_LAYOUT_SLABS: slab_ptrs[k] = device address (own or peer) of rows [k * rows_per_slab, ...) of the frame."""
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        arr = (C.c_void_p * len(slab_ptrs))(*[C.c_void_p(int(p)) for p in slab_ptrs])
+        _ck(lib.meso_raymarch_device_slabs(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra),
+                                           _p(l), arr, C.c_int(len(slab_ptrs)), C.c_int(rows_per_slab)))
+
     def raymarch_stats(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), cubes=None):
         st = np.zeros(1, dtype=RayStats)
         l = np.ascontiguousarray(light, dtype=np.float32)
@@ -288,6 +300,10 @@ class Context:
         n = C.c_int64(0)
         _ck(lib.meso_mesh_device(self.h, C.c_void_p(d_quads), C.c_int64(cap), C.byref(n) if want_count else None))
         return n.value
+
+    def mesh_count_device(self, d_count_out):
+        """8-byte count of the last mesh_device -> device buffer, stream-ordered (no host wait)."""
+        _ck(lib.meso_mesh_count_device(self.h, C.c_void_p(int(d_count_out))))
 
     def mesh_device_shared(self, d_quads, d_counter, cap):
         """Fused quad gather: append this rank's quads to a list (and 8-byte counter) that may live in a peer GPU."""
@@ -412,3 +428,92 @@ class Context:
         """device -> host (numpy array or raw host address), synchronous on the context's stream."""
         n = host_array.nbytes if nbytes is None else nbytes
         _ck(lib.meso_download(self.h, _p(host_array), C.c_void_p(dptr), C.c_size_t(n)))
+
+
+class Group:
+    """N GPUs of one box behind one handle (meso_group_*): member r renders tiles t % N == r and meshes chunks c % N == r of
+    a replicated volume.  `devices` may name the same GPU more than once."""
+
+    def __init__(self, devices):
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _ck(lib.meso_group_create(devs, C.c_int(len(devices)), C.byref(h)))
+        self.h = h
+        self.n = len(devices)
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib.meso_group_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def member(self, rank):
+        """A Context view of member `rank` (owned by the group: do not close it)."""
+        c = Context.__new__(Context)
+        c.h = None
+        p = lib.meso_group_ctx(self.h, C.c_int(rank))
+        if not p:
+            raise MesoError("meso_group_ctx: rank out of range")
+        c.h = C.c_void_p(p)
+        c.origin, c.dims, c.nchunks = self.origin, self.dims, self.nchunks
+        c.close = lambda: None
+        return c
+
+    def sync(self):
+        _ck(lib.meso_group_sync(self.h))
+
+    def scene_create(self, origin_chunk, dims_chunks, max_bricks, cfg=None):
+        cfg = default_scene_config() if cfg is None else cfg
+        o = np.ascontiguousarray(origin_chunk, dtype=np.int32)
+        d = np.ascontiguousarray(dims_chunks, dtype=np.int32)
+        _ck(lib.meso_group_scene_create(self.h, _p(cfg), _p(o), _p(d), C.c_uint32(max_bricks)))
+        self.origin, self.dims, self.nchunks = tuple(int(x) for x in o), tuple(int(x) for x in d), int(np.prod(d))
+
+    def voxelize_sdf(self, kind, params, granularity):
+        p = np.ascontiguousarray(params if params is not None else [0, 0, 0, 0], dtype=np.float64)
+        _ck(lib.meso_group_voxelize_sdf(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
+
+    def carve_sphere(self, center, radius):
+        c = np.ascontiguousarray(center, dtype=np.int32)
+        n = C.c_int64(0)
+        _ck(lib.meso_group_carve_sphere(self.h, _p(c), C.c_int32(radius), C.byref(n)))
+        return n.value
+
+    def _flags(self, shadow, rgba8, cubes):
+        return (FLAG_SHADOW if shadow else 0) | (FLAG_RGBA8 if rgba8 else 0) | Context._cubes_flag(cubes)
+
+    def raymarch(self, cam, width, height, shadow=True, light=(0.3, 0.5, 0.8), out=None, rgba8=False, cubes=None):
+        rec = out if out is not None else (np.zeros((height, width), dtype=np.uint32) if rgba8 else np.zeros((height, width), dtype=HitRecord))
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        _ck(lib.meso_group_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(self._flags(shadow, rgba8, cubes)), _p(l), _p(rec)))
+        return rec
+
+    def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False, cubes=None):
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        _ck(lib.meso_group_raymarch_async(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(self._flags(shadow, rgba8, cubes)), _p(l), _p(out),
+                                          C.c_int(slot)))
+
+    def frame_wait(self, slot):
+        _ck(lib.meso_group_frame_wait(self.h, C.c_int(slot)))
+
+    def mesh(self, cap):
+        """-> (quads concatenated in member order, per-member counts)"""
+        q = np.zeros(max(cap, 1), dtype=Quad)
+        n = C.c_int64(0)
+        counts = np.zeros(self.n, dtype=np.int64)
+        _ck(lib.meso_group_mesh(self.h, _p(q), C.c_int64(cap), C.byref(n), _p(counts)))
+        return q[: n.value], counts
+
+    def mesh_device(self, d_quads, cap, compact=True):
+        n = C.c_int64(0)
+        counts = np.zeros(self.n, dtype=np.int64)
+        _ck(lib.meso_group_mesh_device(self.h, C.c_void_p(int(d_quads)), C.c_int64(cap), C.byref(n), _p(counts), C.c_int(1 if compact else 0)))
+        return n.value, counts
+
+    def remesh_dirty(self, cap):
+        q = np.zeros(max(cap, 1), dtype=Quad)
+        n = C.c_int64(0)
+        _ck(lib.meso_group_remesh_dirty(self.h, _p(q), C.c_int64(cap), C.byref(n)))
+        return q[: n.value]

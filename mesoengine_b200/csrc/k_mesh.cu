@@ -137,7 +137,8 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
 // full rounds, the non-empty ones (typically 6..12 of 48) are queued in shared memory, and the greedy merge runs over the
 // queue densely: one round of busy lanes instead of three rounds of mostly idle ones.
 __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
-                                                          uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
+                                                          uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
+                                                          int shard_rank, int shard_world) {
   __shared__ uint64_t s_e[8][2][6][8];
   __shared__ uint64_t s_img[8][96];
   __shared__ uint8_t s_meta[8][96];
@@ -166,8 +167,11 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
   for (int64_t pair =(int64_t)blockIdx.x * 8 + warp; pair < n_pairs; pair += (int64_t)gridDim.x * 8) {
   __syncwarp();
   const int64_t item = pair * 2 + half;
-  const bool valid = item < (int64_t)n_work;
+  bool valid = item < (int64_t)n_work;
   const uint64_t key = valid ? work[item] : 0ull;
+  // key lists (dirty re-mesh) are sharded over the ranks by a hash of the key: the list order is scheduling-dependent and
+  // differs between the replicas, the key set does not
+  if (shard_world > 1 && (int)(((key * 0x9E3779B97F4A7C15ull) >> 40) % (unsigned)shard_world) != shard_rank) valid = false;
   const int64_t c = (int64_t)(key >> 12); const int b = (int)(key & 4095);
   const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
   const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
@@ -285,15 +289,15 @@ void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uin
   if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   const int64_t n = v.nchunks * MESO_WORDS;
   mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, d_work, d_work_count);
-  mesh_bricks_kernel<<<lc.sm_count * 8, 256, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count);
+  mesh_bricks_kernel<<<lc.sm_count * 8, 256, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
   (*lc.launches) += 2;
 }
 
 void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
-                      int64_t cap, unsigned long long* d_quad_count) {
+                      int64_t cap, unsigned long long* d_quad_count, int rank, int world) {
   cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   if (n_keys == 0) return;
   const unsigned grid = (unsigned)min((int64_t)lc.sm_count * 8, ((int64_t)n_keys + 7) / 8);
-  mesh_bricks_kernel<<<grid, 256, 0, lc.stream>>>(v, d_keys, nullptr, n_keys, d_quads, cap, d_quad_count);
+  mesh_bricks_kernel<<<grid, 256, 0, lc.stream>>>(v, d_keys, nullptr, n_keys, d_quads, cap, d_quad_count, rank, world);
   (*lc.launches)++;
 }

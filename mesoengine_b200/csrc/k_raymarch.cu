@@ -288,13 +288,7 @@ __device__ __forceinline__ int walk10(const DVolume& v, const Scene10& s, const 
         w.slot = __ldg(v.bptr + ((unsigned)w.ci * (unsigned)MESO_BLOCKS + b12));
         w.cm = __ldg(v.pool_cm + w.slot);
         if (STATS) s.touch_brick[w.slot] = 1;
-#ifdef RM10_PREFETCH
-        // the z-slice of the entry voxel, requested together with the cell mask (both depend on the slot only)
-        w.ztag = cz & 7;
-        w.slice = __ldg(v.pool + ((size_t)w.slot * 8 + w.ztag));
-#else
         w.ztag = -1;
-#endif
       }
       if (w.ux >= 2u) {
         const unsigned ce = ((unsigned)(cx >> 1) & 3u) | (((unsigned)(cy >> 1) & 3u) << 2) | (((unsigned)(cz >> 1) & 3u) << 4);
@@ -390,7 +384,7 @@ __device__ __forceinline__ void scene10_octant(Scene10& sc, const CubeTables& ct
 template <bool STATS, int CL, bool FAR>
 __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS)) raymarch10_kernel(DVolume v, MesoRaySetup rs, int width, int height, uint32_t flags,
                                                                    int rank, int world, int layout, int tiles_x, int n_tiles, int local_tile0,
-                                                                   MesoHitRecord* __restrict__ out, RayStatsDev* stats,
+                                                                   FrameMap fm, RayStatsDev* stats,
                                                                    uint8_t* touch_chunk, uint8_t* touch_brick, CubeTables ct) {
   const int warp = (threadIdx.x >> 5) + (blockIdx.x % RM10_SPLIT) * (RM10_THREADS / 32), lane = threadIdx.x & 31;
   const int local_tile = local_tile0 + blockIdx.x / RM10_SPLIT;
@@ -475,8 +469,17 @@ __global__ void __launch_bounds__(RM10_THREADS, RM10_MINB *(256 / RM10_THREADS))
   }
 
   if (valid) {
-    const size_t dst = layout == MESO_LAYOUT_FRAME ? (size_t)py * width + px
-                                                   : (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
+    // MESO_LAYOUT_SLABS: the frame is cut into horizontal slabs of rows_per_slab scanlines, slab k living in fm.slab[k] --
+    // another GPU's memory over NVLink for the rows this rank does not own (the all-to-all of the slab gather, fused into
+    // the store: every record is written once, to where it will be copied to the host from)
+    void* out = fm.slab[0];
+    size_t dst;
+    if (layout == MESO_LAYOUT_SLABS) {
+      const int k = py / fm.rows_per_slab;
+      out = fm.slab[k];
+      dst = (size_t)(py - k * fm.rows_per_slab) * width + px;
+    } else if (layout == MESO_LAYOUT_FRAME) dst = (size_t)py * width + px;
+    else dst = (size_t)local_tile * (MESO_TILE_W * MESO_TILE_H) + ty * MESO_TILE_W + tx;
     const uint4 rec = shade_record(dn);
     if (flags & MESO_FLAG_RGBA8) reinterpret_cast<uint32_t*>(out)[dst] = rec.w;
     else reinterpret_cast<uint4*>(out)[dst] = rec;
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(256) compose_tiles_kernel(const uint4* __restr
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick, int local_tile0, int local_tile_count, const CubeTables* cubes) {
+                     uint8_t* d_touch_brick, int local_tile0, int local_tile_count, const CubeTables* cubes, const FrameMap* slabs) {
   const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
   const int n_tiles = tiles_x * tiles_y;
   const int all_local = (n_tiles - rank + world - 1) / world;
@@ -533,12 +536,14 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
   // distance field + probe-ahead (CL = 0; streaming updates, which would have to rebuild the tables every frame).
   // cubes_level: 1 = cell cubes, 2 = + brick cubes (default, fastest measured on B200), 3 = + 2^3-cell cubes.
   const CubeTables ct = cubes ? *cubes : CubeTables{};
+  FrameMap fm{};
+  if (slabs) fm = *slabs; else { fm.slab[0] = d_out; fm.rows_per_slab = 1 << 30; fm.n_slabs = 1; }
   // an eye farther than RM10_FAR voxels from the grid's corner: loop-form axis sync for the primary rays, over the distance field
   const bool far = fmaxf(fmaxf(fabsf(rs.o[0]), fabsf(rs.o[1])), fabsf(rs.o[2])) > RM10_FAR;
   const int cl = (cubes && !far) ? (cubes->cell2 ? 3 : (cubes->brick ? 2 : 1)) : 0;
 #define RM10_LAUNCH(ST, CL, FR)                                                                                                    \
   raymarch10_kernel<ST, CL, FR><<<local_tile_count * RM10_SPLIT, RM10_THREADS, 0, lc.stream>>>(v, rs, width, height, flags, rank, world, layout, \
-                                                                               tiles_x, n_tiles, local_tile0, d_out, d_stats,    \
+                                                                               tiles_x, n_tiles, local_tile0, fm, d_stats,       \
                                                                                d_touch_chunk, d_touch_brick, ct)
   if (far)          { if (d_stats) RM10_LAUNCH(true, 0, true); else RM10_LAUNCH(false, 0, true); }
   else if (d_stats) { if (cl == 0) RM10_LAUNCH(true, 0, false); else if (cl == 1) RM10_LAUNCH(true, 1, false); else if (cl == 2) RM10_LAUNCH(true, 2, false); else RM10_LAUNCH(true, 3, false); }

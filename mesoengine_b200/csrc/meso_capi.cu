@@ -8,101 +8,12 @@
 #include <vector>
 #include <algorithm>
 
-#include "meso_internal.cuh"
+#include "meso_ctx.cuh"
 
 static thread_local std::string g_err;
 
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-#define CK(call)                                                                                         \
-  do {                                                                                                   \
-    cudaError_t e__ = (call);                                                                            \
-    if (e__ != cudaSuccess) {                                                                            \
-      (void)cudaGetLastError(); /* reported here: do not let it surface again in a later CK_LAST */      \
-      return fail(MESO_ERR_RUNTIME, std::string(#call) + ": " + cudaGetErrorString(e__));                \
-    }                                                                                                    \
-  } while (0)
-#define CK_LAST(what)                                                                                    \
-  do {                                                                                                   \
-    cudaError_t e__ = cudaGetLastError();                                                                \
-    if (e__ != cudaSuccess) return fail(MESO_ERR_RUNTIME, std::string(what) + ": " + cudaGetErrorString(e__)); \
-  } while (0)
-
-struct MesoCtx {
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
-  int rank = 0, world = 1;
-  int64_t launches = 0;
-  bool has_scene = false;
-  MesoGPUUniformSceneConfig cfg{};
-  DVolume v{};
-  // K2
-  MesoGPUChunk* d_table = nullptr;
-  uint32_t* d_counts = nullptr;
-  uint32_t* d_offsets = nullptr;
-  uint64_t* d_total = nullptr;
-  MesoGPUBlock* d_inst = nullptr;
-  int64_t cap_inst = 0;
-  int64_t n_inst = 0;
-  // K4
-  MesoHitRecord* d_frame = nullptr;
-  size_t frame_px = 0;
-  RayStatsDev* d_stats = nullptr;
-  uint8_t* d_touch_chunk = nullptr;
-  uint8_t* d_touch_brick = nullptr;
-  // K3
-  uint64_t* d_work = nullptr;
-  int64_t cap_work = 0;
-  uint32_t* d_work_count = nullptr;
-  unsigned long long* d_quad_count = nullptr;
-  MesoQuad* d_quads = nullptr;
-  int64_t cap_quads = 0;
-  // K5
-  uint64_t* d_dirty = nullptr;
-  uint32_t* d_dirty_count = nullptr;
-  uint32_t cap_dirty = 0;
-  uint32_t n_dirty = 0;
-  uint64_t* d_keys = nullptr;
-  uint32_t* d_keys_count = nullptr;
-  uint32_t* d_mark = nullptr;
-  int* d_overflow = nullptr;
-  // K6
-  uint64_t* d_sel_keys = nullptr;         // candidate keys (scratch), sel_cap entries
-  MesoChunkCandidate* d_sel_out = nullptr;  // sorted candidates, sel_cap entries
-  int64_t sel_cap = 0;
-  uint32_t* d_sel_count = nullptr;
-  uint32_t* d_loaded = nullptr;           // bit per chunk slot (scene-sized)
-  uint32_t* d_stream_list = nullptr;      // generation list of the current update
-  uint32_t stream_list_cap = 0;
-  uint32_t* d_stream_stats = nullptr;     // 4 words
-  bool streaming = false;
-  int stream_kind = 0, stream_gran = 0;
-  double stream_params[4] = {0, 0, 0, 0};
-  // forward cubes (MESO_FLAG_CUBES)
-  uint8_t* d_cube_cell = nullptr;
-  uint8_t* d_cube_cellp = nullptr;
-  uint16_t* d_cube_brick = nullptr;
-  uint16_t* d_cube_cell2 = nullptr;
-  CubeTables cubes{};
-  bool cubes_valid = false;
-  // misc
-  uint32_t* d_flush = nullptr;
-  size_t flush_words = 0;
-  uint32_t* d_tmp_count = nullptr;
-  cudaStream_t copy_stream = nullptr;       // D2H of finished bands overlaps the next band's kernel (meso_raymarch)
-  cudaEvent_t band_done[16] = {nullptr};
-  cudaStream_t band_stream[2] = {nullptr, nullptr};
-  cudaEvent_t band_fork = nullptr;
-  // frame ring (meso_raymarch_async): the reference's kNumBufferedFrames
-  MesoHitRecord* d_ring[MESO_FRAME_RING] = {nullptr};
-  size_t ring_px = 0;
-  bool ring_busy[MESO_FRAME_RING] = {false};
-  cudaEvent_t ring_traced[MESO_FRAME_RING] = {nullptr};
-  cudaEvent_t ring_copied[MESO_FRAME_RING] = {nullptr};
-
-  LaunchCtx lc() { return LaunchCtx{stream, sm_count, &launches}; }
-};
+int meso_fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int fail(int code, const std::string& msg) { return meso_fail(code, msg); }
 
 extern "C" {
 
@@ -287,26 +198,19 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   return MESO_OK;
 }
 
-#define NEED_SCENE(c)                                                               \
-  do {                                                                              \
-    if (!(c)) return fail(MESO_ERR_ARGUMENT, "null context");                       \
-    if (!(c)->has_scene) return fail(MESO_ERR_ARGUMENT, "no scene: call meso_scene_create first"); \
-    CK(cudaSetDevice((c)->device));                                                 \
-  } while (0)
-
 // Frames started with meso_raymarch_async are traced on the band streams and may still be reading the volume when the
 // call returns.  Every entry point that rewrites the volume in place orders its work on the context's stream behind the
 // traversal (not the host copy) of the frames still in flight; with no frame in flight this does nothing.
-static int join_frames(MesoCtx* c) {
+int meso_join_frames(MesoCtx* c) {
   for (int i = 0; i < MESO_FRAME_RING; i++)
     if (c->ring_busy[i]) CK(cudaStreamWaitEvent(c->stream, c->ring_traced[i], 0));
   return MESO_OK;
 }
-#define JOIN_FRAMES(c) do { const int jr__ = join_frames(c); if (jr__ != MESO_OK) return jr__; } while (0)
+#define JOIN_FRAMES(c) do { const int jr__ = meso_join_frames(c); if (jr__ != MESO_OK) return jr__; } while (0)
 
 static int build_cubes(MesoCtx* c);
 
-static int check_overflow(MesoCtx* c, const char* what) {
+int meso_overflow_finish(MesoCtx* c, const char* what) {
   int h = 0;
   CK(cudaMemcpyAsync(&h, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -317,7 +221,7 @@ static int check_overflow(MesoCtx* c, const char* what) {
   return MESO_OK;
 }
 
-int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granularity) {
+int meso_voxelize_enqueue(MesoCtx* c, int kind, const double params[4], int granularity) {
   NEED_SCENE(c);
   if (kind != MESO_SDF_SPHERE && kind != MESO_SDF_TERRAIN) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown sdf kind");
   if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown granularity");
@@ -327,9 +231,15 @@ int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granular
   JOIN_FRAMES(c);
   launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
   CK_LAST("voxelize");
-  const int r = check_overflow(c, "meso_voxelize_sdf");
-  if (r != MESO_OK) return r;
   return build_cubes(c);   // derived data of a whole-grid generation, like the distance field (enqueue only)
+}
+
+int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granularity) {
+  const int r = meso_voxelize_enqueue(c, kind, params, granularity);
+  if (r != MESO_OK) return r;
+  const int ro = meso_overflow_finish(c, "meso_voxelize_sdf");
+  if (ro != MESO_OK) c->cubes_valid = false;   // bricks were dropped: whatever the tables say is about another volume
+  return ro;
 }
 
 int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, const uint64_t* keys, const uint64_t* payload, int64_t n) {
@@ -583,7 +493,7 @@ int meso_download_cubes(MesoCtx* c, uint8_t* cell, uint16_t* brick) {
 
 // The tables a raymarch launch reads: the forward cubes whenever they are current (the default walk), nullptr -> the
 // distance-field walk when they are not (streaming updates) or MESO_FLAG_NO_CUBES asks for it; MESO_FLAG_CUBES insists.
-static int cubes_for(MesoCtx* c, uint32_t flags, const CubeTables** out) {
+int meso_cubes_for(MesoCtx* c, uint32_t flags, const CubeTables** out) {
   *out = nullptr;
   if ((flags & MESO_FLAG_CUBES) && (flags & MESO_FLAG_NO_CUBES)) return fail(MESO_ERR_ARGUMENT, "MESO_FLAG_CUBES and MESO_FLAG_NO_CUBES exclude each other");
   if (flags & MESO_FLAG_NO_CUBES) return MESO_OK;
@@ -609,11 +519,35 @@ int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width,
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
   const CubeTables* cubes = nullptr;
-  r = cubes_for(c, flags, &cubes);
+  r = meso_cubes_for(c, flags, &cubes);
   if (r != MESO_OK) return r;
   launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, layout, (MesoHitRecord*)d_records, nullptr, nullptr, nullptr,
                   0, -1, cubes);
   CK_LAST("raymarch");
+  return MESO_OK;
+}
+
+int meso_raymarch_device_slabs(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3],
+                               void* const* d_slabs, int n_slabs, int rows_per_slab) {
+  NEED_SCENE(c);
+  if (!cam || !d_slabs || width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_device_slabs: bad argument");
+  if (n_slabs < 1 || n_slabs > MESO_MAX_SLABS) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_device_slabs: n_slabs out of range [1, MESO_MAX_SLABS]");
+  if (rows_per_slab <= 0 || rows_per_slab % MESO_TILE_H != 0) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_device_slabs: rows_per_slab must be a positive multiple of MESO_TILE_H");
+  if ((int64_t)rows_per_slab * n_slabs < height) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_device_slabs: the slabs do not cover the frame");
+  FrameMap fm{};
+  for (int i = 0; i < n_slabs; i++) {
+    if (!d_slabs[i]) return fail(MESO_ERR_ARGUMENT, "meso_raymarch_device_slabs: null slab pointer");
+    fm.slab[i] = d_slabs[i];
+  }
+  fm.rows_per_slab = rows_per_slab; fm.n_slabs = n_slabs;
+  MesoRaySetup rs;
+  int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
+  if (r != MESO_OK) return r;
+  const CubeTables* cubes = nullptr;
+  r = meso_cubes_for(c, flags, &cubes);
+  if (r != MESO_OK) return r;
+  launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_SLABS, nullptr, nullptr, nullptr, nullptr, 0, -1, cubes, &fm);
+  CK_LAST("raymarch (slabs)");
   return MESO_OK;
 }
 
@@ -641,7 +575,7 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
   r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
   const CubeTables* cubes = nullptr;
-  r = cubes_for(c, flags, &cubes);
+  r = meso_cubes_for(c, flags, &cubes);
   if (r != MESO_OK) return r;
   const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W, tiles_y = (height + MESO_TILE_H - 1) / MESO_TILE_H;
   int bands = tiles_y >= 64 ? 4 : (tiles_y >= 16 ? 2 : 1);   // measured on B200 at 4K: 1 -> 5.6 ms, 4 -> 4.0 ms, 16 -> 5.7 ms
@@ -687,7 +621,7 @@ int meso_raymarch_async(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   int r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
   if (r != MESO_OK) return r;
   const CubeTables* cubes = nullptr;
-  r = cubes_for(c, flags, &cubes);
+  r = meso_cubes_for(c, flags, &cubes);
   if (r != MESO_OK) return r;
   // Frames of the ring alternate between the two band streams so that the tail of frame k (a few tiles with grazing
   // rays) overlaps the body of frame k+1; each is ordered after whatever the caller enqueued on the context's stream.
@@ -729,7 +663,7 @@ int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   CK(cudaMemsetAsync(c->d_touch_chunk, 0, (size_t)c->v.nchunks, c->stream));
   CK(cudaMemsetAsync(c->d_touch_brick, 0, c->v.max_bricks, c->stream));
   const CubeTables* cubes = nullptr;
-  r = cubes_for(c, flags, &cubes);
+  r = meso_cubes_for(c, flags, &cubes);
   if (r != MESO_OK) return r;
   launch_raymarch(c->lc(), c->v, rs, width, height, flags, c->rank, c->world, MESO_LAYOUT_FRAME, c->d_frame, c->d_stats, c->d_touch_chunk, c->d_touch_brick,
                   0, -1, cubes);
@@ -766,7 +700,7 @@ int meso_compose_tiles_device(MesoCtx* c, const void* d_tiles, int world, int wi
   return MESO_OK;
 }
 
-static int ensure_mesh_buffers(MesoCtx* c) {
+int meso_ensure_mesh_buffers(MesoCtx* c) {
   if (!c->d_work) {
     // worst case: every block of this rank's chunks
     c->cap_work = c->v.nchunks * MESO_BLOCKS;
@@ -778,7 +712,7 @@ static int ensure_mesh_buffers(MesoCtx* c) {
 int meso_mesh_device(MesoCtx* c, void* d_quads, int64_t cap, int64_t* n_quads) {
   NEED_SCENE(c);
   if (cap < 0 || (cap > 0 && !d_quads)) return fail(MESO_ERR_ARGUMENT, "meso_mesh_device: bad argument");
-  int r = ensure_mesh_buffers(c);
+  int r = meso_ensure_mesh_buffers(c);
   if (r != MESO_OK) return r;
   launch_mesh(c->lc(), c->v, c->rank, c->world, c->d_work, c->d_work_count, (MesoQuad*)d_quads, cap, c->d_quad_count);
   CK_LAST("mesh");
@@ -791,10 +725,17 @@ int meso_mesh_device(MesoCtx* c, void* d_quads, int64_t cap, int64_t* n_quads) {
   return MESO_OK;
 }
 
+int meso_mesh_count_device(MesoCtx* c, void* d_count_out) {
+  NEED_SCENE(c);
+  if (!d_count_out) return fail(MESO_ERR_ARGUMENT, "meso_mesh_count_device: null argument");
+  CK(cudaMemcpyAsync(d_count_out, c->d_quad_count, 8, cudaMemcpyDeviceToDevice, c->stream));
+  return MESO_OK;
+}
+
 int meso_mesh_device_shared(MesoCtx* c, void* d_quads, void* d_counter, int64_t cap) {
   NEED_SCENE(c);
   if (cap <= 0 || !d_quads || !d_counter) return fail(MESO_ERR_ARGUMENT, "meso_mesh_device_shared: bad argument");
-  int r = ensure_mesh_buffers(c);
+  int r = meso_ensure_mesh_buffers(c);
   if (r != MESO_OK) return r;
   launch_mesh(c->lc(), c->v, c->rank, c->world, c->d_work, c->d_work_count, (MesoQuad*)d_quads, cap, (unsigned long long*)d_counter,
               /*reset_count=*/false);
@@ -820,20 +761,28 @@ int meso_mesh(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads) {
   return MESO_OK;
 }
 
-int meso_carve_sphere(MesoCtx* c, const int32_t center[3], int32_t radius, int64_t* n_dirty) {
+int meso_carve_enqueue(MesoCtx* c, const int32_t center[3], int32_t radius) {
   NEED_SCENE(c);
   if (!center || radius < 0 || radius > 30000) return fail(MESO_ERR_ARGUMENT, "meso_carve_sphere: bad argument");
   JOIN_FRAMES(c);
   launch_carve(c->lc(), c->v, center, radius, c->d_dirty, c->cap_dirty, c->d_dirty_count, c->d_overflow);
   CK_LAST("carve");
+  return MESO_OK;
+}
+int meso_carve_finish(MesoCtx* c, int64_t* n_dirty) {
+  NEED_SCENE(c);
   uint32_t n = 0;
   CK(cudaMemcpyAsync(&n, c->d_dirty_count, 4, cudaMemcpyDeviceToHost, c->stream));
-  int r = check_overflow(c, "meso_carve_sphere");
+  int r = meso_overflow_finish(c, "meso_carve_sphere");
   if (r != MESO_OK) return r;
   if (n > c->cap_dirty) return fail(MESO_ERR_RUNTIME, "meso_carve_sphere: dirty list overflow");
   c->n_dirty = n;
   if (n_dirty) *n_dirty = n;
   return MESO_OK;
+}
+int meso_carve_sphere(MesoCtx* c, const int32_t center[3], int32_t radius, int64_t* n_dirty) {
+  const int r = meso_carve_enqueue(c, center, radius);
+  return r != MESO_OK ? r : meso_carve_finish(c, n_dirty);
 }
 
 int meso_download_dirty(MesoCtx* c, uint64_t* keys, int64_t cap) {
@@ -867,7 +816,7 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
     CK(cudaMalloc(&c->d_quads, (size_t)cap * sizeof(MesoQuad)));
     c->cap_quads = cap;
   }
-  launch_mesh_list(c->lc(), c->v, c->d_keys, nk, c->d_quads, cap, c->d_quad_count);
+  launch_mesh_list(c->lc(), c->v, c->d_keys, nk, c->d_quads, cap, c->d_quad_count, c->rank, c->world);   // sharded by key hash over the partition
   CK_LAST("remesh");
   unsigned long long n = 0;
   CK(cudaMemcpyAsync(&n, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1040,7 +989,7 @@ int meso_stream_update(MesoCtx* c, const int32_t cam[3], const float forward[3],
   r = meso_stream_stats(c, &s);
   if (r != MESO_OK) return r;
   if (stats) *stats = s;
-  return check_overflow(c, "meso_stream_update");
+  return meso_overflow_finish(c, "meso_stream_update");
 }
 
 int meso_stream_loaded(MesoCtx* c, uint32_t* host_words, int64_t n_words) {

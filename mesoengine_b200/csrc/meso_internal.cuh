@@ -59,6 +59,13 @@ struct CubeTables {
   int64_t ncells;
 };
 
+// MESO_LAYOUT_SLABS: where the rows of the frame live (meso_raymarch_device_slabs); slab k = rows [k * rows_per_slab, ...)
+struct FrameMap {
+  void* slab[MESO_MAX_SLABS];
+  int rows_per_slab;
+  int n_slabs;
+};
+
 struct RayStatsDev {
   unsigned long long primary, shadow, hits, steps;
   unsigned long long steps_primary, warp_slots_primary, warp_slots_shadow;
@@ -89,7 +96,8 @@ void launch_scatter_blocks(const LaunchCtx& lc, const DVolume& v, const MesoGPUC
 
 void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& rs, int width, int height, uint32_t flags,
                      int rank, int world, int layout, MesoHitRecord* d_out, RayStatsDev* d_stats, uint8_t* d_touch_chunk,
-                     uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1, const CubeTables* cubes = nullptr);
+                     uint8_t* d_touch_brick, int local_tile0 = 0, int local_tile_count = -1, const CubeTables* cubes = nullptr,
+                     const FrameMap* slabs = nullptr);
 // k_cubes.cu: (re)build the three tables for the current volume
 void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint8_t* d_cellp, uint16_t* d_brick, uint16_t* d_cell2);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
@@ -97,7 +105,7 @@ void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count = true);
 void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
-                      int64_t cap, unsigned long long* d_quad_count);
+                      int64_t cap, unsigned long long* d_quad_count, int rank = 0, int world = 1);
 
 void launch_carve(const LaunchCtx& lc, const DVolume& v, const int32_t center[3], int32_t radius, uint64_t* d_dirty,
                   uint32_t cap_dirty, uint32_t* d_dirty_count, int* d_overflow);

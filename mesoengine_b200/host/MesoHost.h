@@ -316,12 +316,16 @@ class FChunkManage {
     ThreadCount = ThreadCount_ ? ThreadCount_ : std::max(hc > 2 ? hc - 2 : 1u, 1u);
     bDirty = true;
   }
+  // N GPUs: the volume is replicated on every member of the group; Ctx_ is then member 0, which also runs K2.
+  void SetGroup(MesoGroup* Group_) { Group = Group_; }
   void Initialize(MesoCtx* Ctx_, const FVoxelSceneConfig& VoxelSceneConfig, FGeneratorDesc Generator_, ivec3 WindowOrigin_, ivec3 WindowDims_,
                   bool bStreaming_ = false) {
     Ctx = Ctx_; Generator = Generator_; WindowOrigin = WindowOrigin_; WindowDims = WindowDims_; bStreaming = bStreaming_;
+    if (Group && bStreaming) throw std::runtime_error("FChunkManage: streaming generation runs on one context (no group)");
     const FGPUUniformSceneConfig cfg{VoxelSceneConfig.BlockSize, (uint32_t)VoxelSceneConfig.BlockResolution, VoxelSceneConfig.GetChunkSize(), (uint32_t)VoxelSceneConfig.ChunkResolution};
     const int32_t o[3] = {WindowOrigin.x, WindowOrigin.y, WindowOrigin.z}, d[3] = {WindowDims.x, WindowDims.y, WindowDims.z};
-    Check(meso_scene_create(Ctx, &cfg, o, d, VoxelSceneConfig.MaxVolumeCount), "meso_scene_create");
+    if (Group) Check(meso_group_scene_create(Group, &cfg, o, d, VoxelSceneConfig.MaxVolumeCount), "meso_group_scene_create");
+    else Check(meso_scene_create(Ctx, &cfg, o, d, VoxelSceneConfig.MaxVolumeCount), "meso_scene_create");
     ChunkPool.MaxBlockCount = VoxelSceneConfig.MaxBlockCount;
     ChunkPool.ChunkCount = (int64_t)d[0] * d[1] * d[2];
     if (bStreaming) Check(meso_stream_begin(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_stream_begin");
@@ -364,7 +368,8 @@ class FChunkManage {
       bDirty = false;
       return;
     }
-    Check(meso_voxelize_sdf(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_voxelize_sdf");
+    if (Group) Check(meso_group_voxelize_sdf(Group, Generator.Kind, Generator.Params, Generator.Granularity), "meso_group_voxelize_sdf");
+    else Check(meso_voxelize_sdf(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_voxelize_sdf");
     Check(meso_build_occupancy(Ctx, FrameStamp, &ChunkPool.CurrentBlockCount), "meso_build_occupancy");
     bDirty = false;
   }
@@ -404,9 +409,11 @@ class FChunkManage {
     for (const auto& p : Parts) total += p.size();
     Blocks.reserve(total);
     for (const auto& p : Parts) Blocks.insert(Blocks.end(), p.begin(), p.end());
-    Check(meso_volume_upload_blocks(Ctx, Table.data(), n, Blocks.data(), (int64_t)Blocks.size(), 0u, &DebugUploadedBlockNum), "meso_volume_upload_blocks");
+    if (Group) Check(meso_group_volume_upload_blocks(Group, Table.data(), n, Blocks.data(), (int64_t)Blocks.size(), 0u, &DebugUploadedBlockNum), "meso_group_volume_upload_blocks");
+    else Check(meso_volume_upload_blocks(Ctx, Table.data(), n, Blocks.data(), (int64_t)Blocks.size(), 0u, &DebugUploadedBlockNum), "meso_volume_upload_blocks");
   }
   MesoCtx* Ctx = nullptr;
+  MesoGroup* Group = nullptr;
   FGeneratorDesc Generator;
   GeneratorType HostGenerator;
   uint32_t ThreadCount = 1;
@@ -421,6 +428,7 @@ struct VoxelInstanceInitialConfig {
   bool bReverseZ = true;
   uint32_t kNumBufferedFrames = 4;
   int Device = 0;
+  std::vector<int> Devices;                       // more than one entry: the frame is split over these GPUs (meso_group_*)
   FVoxelSceneConfig VoxelSceneConfig;
 };
 
@@ -429,6 +437,7 @@ struct VoxelInstanceInitialConfig {
 class VoxelWindowsInstance {
  public:
   MesoCtx* Context = nullptr;                     // stands where std::unique_ptr<lvk::IContext> LVKContext stood
+  MesoGroup* Group = nullptr;                     // InitialConfig.Devices.size() > 1: N GPUs behind one handle; Context = member 0
   int WindowsWidth = 0, WindowsHeight = 0;
   bool bLVKReverseZ = true;
   uint32_t LVKNumBufferedFrames = 3;
@@ -439,13 +448,17 @@ class VoxelWindowsInstance {
   std::vector<MesoHitRecord> OffscreenRecords;    // stands where TEXOffscreenColor stood (16 B records instead of RGBA8)
   uint32_t RenderGlobalFrameIndex = 0, RenderFrameIndex = 0;
 
-  virtual ~VoxelWindowsInstance() { if (Context) meso_ctx_destroy(Context); }
+  virtual ~VoxelWindowsInstance() {
+    if (Group) meso_group_destroy(Group);         // owns its members, Context included
+    else if (Context) meso_ctx_destroy(Context);
+  }
   virtual void Initialize(const VoxelInstanceInitialConfig& InitialConfig) {
     bLVKReverseZ = InitialConfig.bReverseZ; LVKNumBufferedFrames = InitialConfig.kNumBufferedFrames;
     WindowsWidth = InitialConfig.WindowsWidth; WindowsHeight = InitialConfig.WindowsHeight;
     VoxelSceneConfig = InitialConfig.VoxelSceneConfig;
     InitializeCameraAndScene(InitialConfig);
     Device = InitialConfig.Device;
+    Devices = InitialConfig.Devices;
     InitializeContext();
     InitializeBegin();
     CreateWindowsFrameBuffer();
@@ -459,7 +472,12 @@ class VoxelWindowsInstance {
                    InitialConfig.VoxelSceneConfig.GetChunkSize(), (uint32_t)InitialConfig.VoxelSceneConfig.ChunkResolution};
   }
   virtual void InitializeContext() {               // lvk::createVulkanContextWithSwapchain -> meso_ctx_create
-    Check(meso_ctx_create(Device, &Context), "meso_ctx_create");
+    if (Devices.size() > 1) {
+      Check(meso_group_create(Devices.data(), (int)Devices.size(), &Group), "meso_group_create");
+      Context = meso_group_ctx(Group, 0);
+    } else {
+      Check(meso_ctx_create(Devices.empty() ? Device : Devices[0], &Context), "meso_ctx_create");
+    }
     UBOCamera.assign(LVKNumBufferedFrames, FGPUUniformCamera{});
   }
   virtual void InitializeBegin() {}
@@ -480,6 +498,7 @@ class VoxelWindowsInstance {
   virtual void WhenCameraUpdate() {}
  protected:
   int Device = 0;
+  std::vector<int> Devices;
 };
 
 }  // namespace meso

@@ -3,12 +3,15 @@
 // instanced draw of Render() (cmdBindVertexBuffer / cmdPushConstants / cmdDrawIndexed(8, MaxBlockCount),
 // SimpleVoxel.cpp:352-398) is one call: meso_raymarch().
 //
-//   SimpleVoxel [--stream | --cpu-generator] [frames] [width height] [eye x y z] [target x y z] [out.bin]
+//   SimpleVoxel [--stream | --cpu-generator | --gpus N] [frames] [width height] [eye x y z] [target x y z] [out.bin]
+// --gpus N: the frame is split over GPUs 0..N-1 behind one MesoGroup (replicated volume, slab gather into host memory);
+//           N may exceed the number of devices in the box (members then share GPUs: device r % count).
 // --cpu-generator: the generator is the reference's std::function callback (SimpleVoxel.cpp:263-267) run on host worker
 // threads; its FChunk.Blocks reach the device as FGPUChunk / FGPUBlock records (meso_volume_upload_blocks).
 // --stream: the reference's loading loop -- chunks are generated as the view asks for them (FChunkManage::UpdateChunks +
 // UpdateLoadingQueue, at most MaxUnsyncedLoadChunkCount per frame), not all at once.
 // Prints an FNV-1a checksum of the last frame's records (tests/test_gpu_host_sample.py compares it with the Python path).
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +32,7 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
     VoxelWindowsInstance::InitializeBegin();
     FGeneratorDesc Generator;   // FGeneratorHelper::GenerateSphere, the generator SimpleVoxel.cpp:263-267 wires in
     // the 8^3 chunks around the reference sphere (centre (100,0,0), radius 50 blocks)
+    ChunkManager.SetGroup(Group);
     ChunkManager.Initialize(Context, VoxelSceneConfig, Generator, ivec3{2, -4, -4}, ivec3{8, 8, 8}, bStream);
     if (bCpuGenerator) {
       auto GeneratorInstance = [](ivec3 StartLocation, float BlockSize, unsigned char ChunkResolution, uint32_t MipmapLevel) {
@@ -46,8 +50,12 @@ class SimpleVoxelWindowsInstance : public VoxelWindowsInstance {
   void Render() override {
     const auto t0 = std::chrono::steady_clock::now();
     const float Light[3] = {0.3f, 0.5f, 0.8f};
-    Check(meso_raymarch(Context, &UBOCamera[RenderFrameIndex], WindowsWidth, WindowsHeight, MESO_FLAG_SHADOW, Light, OffscreenRecords.data()),
-          "meso_raymarch");
+    if (Group)
+      Check(meso_group_raymarch(Group, &UBOCamera[RenderFrameIndex], WindowsWidth, WindowsHeight, MESO_FLAG_SHADOW, Light, OffscreenRecords.data()),
+            "meso_group_raymarch");
+    else
+      Check(meso_raymarch(Context, &UBOCamera[RenderFrameIndex], WindowsWidth, WindowsHeight, MESO_FLAG_SHADOW, Light, OffscreenRecords.data()),
+            "meso_raymarch");
     RenderMs += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
 };
@@ -56,8 +64,15 @@ int main(int argc, char* argv[]) {
   bool stream = false, cpu_generator = false;
   if (argc > 1 && std::strcmp(argv[1], "--stream") == 0) { stream = true; argc--; argv++; }
   else if (argc > 1 && std::strcmp(argv[1], "--cpu-generator") == 0) { cpu_generator = true; argc--; argv++; }
+  int gpus = 1;
+  if (argc > 2 && std::strcmp(argv[1], "--gpus") == 0) { gpus = std::max(1, std::atoi(argv[2])); argc -= 2; argv += 2; }
   const uint32_t frames = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 4;
   VoxelInstanceInitialConfig cfg;
+  if (gpus > 1) {
+    int count = 1;
+    if (const char* e = std::getenv("MESO_SAMPLE_DEVICE_COUNT")) count = std::max(1, std::atoi(e));   // set by the caller (no CUDA headers here)
+    for (int r = 0; r < gpus; r++) cfg.Devices.push_back(r % count);
+  }
   if (argc > 3) { cfg.WindowsWidth = std::atoi(argv[2]); cfg.WindowsHeight = std::atoi(argv[3]); }
   vec3 eye{5.0f, 2.0f, 2.0f}, target{100.0f, 0.0f, 0.0f};   // the reference start position, turned towards the sphere
   if (argc > 9) {

@@ -88,3 +88,23 @@ def test_cpp_sample_cpu_generator_callback_equals_device_generator(tmp_path):
         assert "blocks=201936" in log, log
         frames[mode] = np.fromfile(out, dtype=capi.HitRecord).reshape(h, w)
     assert frames["--cpu-generator"].tobytes() == frames[None].tobytes()
+
+
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_cpp_sample_on_a_group_of_gpus_equals_one_gpu(gpus, tmp_path):
+    """--gpus N: the C++ host renders through meso_group_* (replicated volume, slab gather into host memory).  Members share
+    devices when the box has fewer GPUs than N.  Same frame as one GPU."""
+    import torch
+    from mesoengine_b200 import capi
+    subprocess.check_call(["make", "-C", os.path.dirname(EXE), "CXX=g++"])
+    w, h = 320, 180
+    eye, target = (20.5, -61.25, 33.0), (100.0, 0.0, 0.0)
+    env = dict(os.environ, MESO_SAMPLE_DEVICE_COUNT=str(torch.cuda.device_count()))
+    frames = {}
+    for mode in (["--gpus", str(gpus)], []):
+        out = tmp_path / ("frame%d.bin" % len(mode))
+        args = [EXE] + mode + ["2", str(w), str(h)] + [repr(float(v)) for v in eye + target] + [str(out)]
+        log = subprocess.check_output(args, text=True, env=env)
+        assert "blocks=201936" in log, log
+        frames[len(mode)] = np.fromfile(out, dtype=capi.HitRecord).reshape(h, w)
+    assert frames[2].tobytes() == frames[0].tobytes()

@@ -2,7 +2,7 @@
 
 What these tests pin: (1) frames through the cubes are byte-identical to the oracle's (any certified-empty box is a legal skip, so
 a wrong table shows up as a wrong record); (2) the kernel takes the steps the oracle's step model takes with the same cubes
-(directional cells cap 32, brick cubes <= 4, aligned 2^3 cells) within 0.2 % -- the kernel does not look the cell table
+(directional cells cap 32, brick cubes <= 4, 2^3-cell cubes <= 4) within 0.2 % -- the kernel does not look the cell table
 up again while a ray stays inside one 32^3 cell, the model does at every step, so a few steps differ in kind; (3) the tables survive carves (which only remove voxels) and are invalidated by every call that may add
 voxels."""
 import os
@@ -77,7 +77,7 @@ def test_cube_tables_equal_the_cpu_tables(ctx, orc, scene):
 def test_cubes_steps_match_the_step_model(ctx, orc):
     origin, dims, params = scenes.sphere_scene(256)
     vol = _scene(ctx, orc, orc.SDF_SPHERE, origin, dims, params, orc.GRAN_VOXEL)
-    orc.step_model(vol, df_shift=5, df_cap=32, probe=False, directional=True, brick_cap=4, cell2=1)
+    orc.step_model(vol, df_shift=5, df_cap=32, probe=False, directional=True, brick_cap=4, cell2=4)
     w, h = 160, 96
     eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
     for eye in eyes[:4]:
