@@ -498,9 +498,9 @@ class Group:
     def frame_wait(self, slot):
         _ck(lib.meso_group_frame_wait(self.h, C.c_int(slot)))
 
-    def mesh(self, cap):
-        """-> (quads concatenated in member order, per-member counts)"""
-        q = np.zeros(max(cap, 1), dtype=Quad)
+    def mesh(self, cap, out=None):
+        """-> (quads concatenated in member order, per-member counts); out: optional (pinned) Quad buffer of >= cap records"""
+        q = out if out is not None else np.zeros(max(cap, 1), dtype=Quad)
         n = C.c_int64(0)
         counts = np.zeros(self.n, dtype=np.int64)
         _ck(lib.meso_group_mesh(self.h, _p(q), C.c_int64(cap), C.byref(n), _p(counts)))

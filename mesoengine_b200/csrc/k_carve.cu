@@ -5,6 +5,7 @@
 // Mapping: 8 lanes per brick (one z-slice each), 4 bricks per warp; full bricks that become partial take a payload
 // slot from the same bump allocator the voxeliser uses.
 #include "meso_internal.cuh"
+#include <algorithm>
 
 struct CarveBox { int lo[3]; int hi[3]; int c[3]; int radius; };
 
@@ -131,6 +132,22 @@ void launch_expand_dirty(const LaunchCtx& lc, const DVolume& v, const uint64_t* 
   const uint32_t bound = (uint32_t)(nt < (int64_t)cap ? nt : (int64_t)cap);
   clear_marks_kernel<<<(bound + 255) / 256, 256, 0, lc.stream>>>(d_keys, d_count, cap, d_mark);
   (*lc.launches) += 2;
+}
+
+// Small device -> host reads (counters, a picked record, a few thousand quads) go through a kernel that stores into mapped
+// pinned host memory instead of cudaMemcpyAsync: a copy command queues behind whatever large DMA is in flight on the same
+// copy engine (a 66 MB slab on its way to the host delayed a 4-byte count by 2 ms in the N-GPU edit loop); stores do not.
+__global__ void __launch_bounds__(256) peek_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes) {
+  const size_t words = bytes >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+  if (blockIdx.x == 0 && threadIdx.x < (bytes & 3)) dst[(words << 2) + threadIdx.x] = src[(words << 2) + threadIdx.x];
+}
+void launch_peek(const LaunchCtx& lc, void* d_dst_mapped, const void* d_src, size_t bytes) {
+  if (bytes == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((bytes / 4 + 255) / 256 + 1, (size_t)lc.sm_count * 4);
+  peek_kernel<<<grid, 256, 0, lc.stream>>>((unsigned char*)d_dst_mapped, (const unsigned char*)d_src, bytes);
+  (*lc.launches)++;
 }
 
 void launch_flush(const LaunchCtx& lc, uint32_t* d_scratch, size_t n_words) {

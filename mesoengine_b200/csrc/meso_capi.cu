@@ -59,6 +59,23 @@ static int ctx_init(MesoCtx* c) {
   }
   CK(cudaMalloc(&c->d_overflow, sizeof(int)));
   CK(cudaMemset(c->d_overflow, 0, sizeof(int)));
+  CK(cudaHostAlloc(&c->h_stage, MESO_STAGE_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
+  CK(cudaHostGetDevicePointer((void**)&c->d_stage, c->h_stage, 0));
+  return MESO_OK;
+}
+
+int meso_small_read(MesoCtx* c, void* host_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return MESO_OK;
+  CK(cudaSetDevice(c->device));   // a kernel launch needs the stream's device current (a group drives several from one thread)
+  if (bytes > MESO_STAGE_BYTES || ((uintptr_t)d_src & 3)) {
+    CK(cudaMemcpyAsync(host_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MESO_OK;
+  }
+  launch_peek(c->lc(), c->d_stage, d_src, bytes);
+  CK_LAST("small read");
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(host_dst, c->h_stage, bytes);
   return MESO_OK;
 }
 
@@ -88,6 +105,7 @@ int meso_ctx_destroy(MesoCtx* c) {
   cudaStreamSynchronize(c->stream);
   free_scene(c);
   cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow);
+  if (c->h_stage) cudaFreeHost(c->h_stage);
   cudaFree(c->d_sel_keys); cudaFree(c->d_sel_out); cudaFree(c->d_sel_count);
   for (int i = 0; i < 16; i++) if (c->band_done[i]) cudaEventDestroy(c->band_done[i]);
   cudaStreamDestroy(c->copy_stream);
@@ -212,8 +230,8 @@ static int build_cubes(MesoCtx* c);
 
 int meso_overflow_finish(MesoCtx* c, const char* what) {
   int h = 0;
-  CK(cudaMemcpyAsync(&h, c->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  const int rr = meso_small_read(c, &h, c->d_overflow, sizeof(int));
+  if (rr != MESO_OK) return rr;
   if (h) {
     cudaMemsetAsync(c->d_overflow, 0, sizeof(int), c->stream);
     return fail(MESO_ERR_RUNTIME, std::string(what) + ": brick payload pool exhausted (raise max_bricks in meso_scene_create)");
@@ -380,8 +398,7 @@ int meso_build_occupancy(MesoCtx* c, uint32_t stamp, int64_t* n_instances) {
   launch_occupancy_count(c->lc(), c->v, stamp, c->d_table, c->d_counts, c->d_offsets, c->d_total);
   CK_LAST("occupancy count");
   uint64_t total = 0;
-  CK(cudaMemcpyAsync(&total, c->d_total, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  { const int rr = meso_small_read(c, &total, c->d_total, 8); if (rr != MESO_OK) return rr; }
   if ((int64_t)total > c->cap_inst) {
     cudaFree(c->d_inst); c->d_inst = nullptr;
     c->cap_inst = (int64_t)total + (int64_t)total / 8;   // a little headroom for edits
@@ -718,8 +735,8 @@ int meso_mesh_device(MesoCtx* c, void* d_quads, int64_t cap, int64_t* n_quads) {
   CK_LAST("mesh");
   if (n_quads) {
     unsigned long long n = 0;
-    CK(cudaMemcpyAsync(&n, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    const int rr = meso_small_read(c, &n, c->d_quad_count, 8);
+    if (rr != MESO_OK) return rr;
     *n_quads = (int64_t)n;
   }
   return MESO_OK;
@@ -772,8 +789,9 @@ int meso_carve_enqueue(MesoCtx* c, const int32_t center[3], int32_t radius) {
 int meso_carve_finish(MesoCtx* c, int64_t* n_dirty) {
   NEED_SCENE(c);
   uint32_t n = 0;
-  CK(cudaMemcpyAsync(&n, c->d_dirty_count, 4, cudaMemcpyDeviceToHost, c->stream));
-  int r = meso_overflow_finish(c, "meso_carve_sphere");
+  int r = meso_small_read(c, &n, c->d_dirty_count, 4);
+  if (r != MESO_OK) return r;
+  r = meso_overflow_finish(c, "meso_carve_sphere");
   if (r != MESO_OK) return r;
   if (n > c->cap_dirty) return fail(MESO_ERR_RUNTIME, "meso_carve_sphere: dirty list overflow");
   c->n_dirty = n;
@@ -800,8 +818,7 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
   launch_expand_dirty(c->lc(), c->v, c->d_dirty, c->n_dirty, c->d_keys, c->cap_dirty, c->d_keys_count, c->d_mark);
   CK_LAST("expand dirty");
   uint32_t nk = 0;
-  CK(cudaMemcpyAsync(&nk, c->d_keys_count, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  { const int rr = meso_small_read(c, &nk, c->d_keys_count, 4); if (rr != MESO_OK) return rr; }
   if (nk > c->cap_dirty) {
     cudaMemsetAsync(c->d_mark, 0, (((size_t)c->v.nchunks * MESO_BLOCKS + 31) / 32) * 4, c->stream);
     return fail(MESO_ERR_RUNTIME, "meso_remesh_dirty: key list overflow");
@@ -809,7 +826,7 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
   if (n_keys) *n_keys = nk;
   if (host_keys) {
     if (cap_keys < (int64_t)nk) return fail(MESO_ERR_ARGUMENT, "meso_remesh_dirty: cap_keys too small");
-    if (nk) CK(cudaMemcpyAsync(host_keys, c->d_keys, (size_t)nk * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (nk) { const int rr = meso_small_read(c, host_keys, c->d_keys, (size_t)nk * 8); if (rr != MESO_OK) return rr; }
   }
   if (cap > c->cap_quads) {
     cudaFree(c->d_quads); c->d_quads = nullptr; c->cap_quads = 0;
@@ -819,14 +836,10 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
   launch_mesh_list(c->lc(), c->v, c->d_keys, nk, c->d_quads, cap, c->d_quad_count, c->rank, c->world);   // sharded by key hash over the partition
   CK_LAST("remesh");
   unsigned long long n = 0;
-  CK(cudaMemcpyAsync(&n, c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  { const int rr = meso_small_read(c, &n, c->d_quad_count, 8); if (rr != MESO_OK) return rr; }
   *n_quads = (int64_t)n;
   const int64_t m = std::min<int64_t>((int64_t)n, cap);
-  if (m > 0 && host) {
-    CK(cudaMemcpyAsync(host, c->d_quads, (size_t)m * sizeof(MesoQuad), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-  }
+  if (m > 0 && host) return meso_small_read(c, host, c->d_quads, (size_t)m * sizeof(MesoQuad));
   return MESO_OK;
 }
 
@@ -1070,9 +1083,7 @@ int meso_ipc_close(MesoCtx* c, void* peer) {
 int meso_download(MesoCtx* c, void* host_dst, const void* dptr, size_t bytes) {
   if (!c || !host_dst || !dptr) return fail(MESO_ERR_ARGUMENT, "meso_download: bad argument");
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpyAsync(host_dst, dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  return MESO_OK;
+  return meso_small_read(c, host_dst, dptr, bytes);   // small reads never queue behind a DMA in flight
 }
 
 int meso_download_async(MesoCtx* c, void* host_dst, const void* dptr, size_t bytes) {

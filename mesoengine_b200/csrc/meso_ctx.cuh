@@ -82,6 +82,9 @@ struct MesoCtx {
   uint32_t* d_flush = nullptr;
   size_t flush_words = 0;
   uint32_t* d_tmp_count = nullptr;
+  unsigned char* h_stage = nullptr;         // pinned + mapped staging for small device -> host reads (meso_small_read)
+  unsigned char* d_stage = nullptr;         // its device alias
+
   cudaStream_t copy_stream = nullptr;       // D2H of finished bands overlaps the next band's kernel (meso_raymarch)
   cudaEvent_t band_done[16] = {nullptr};
   cudaStream_t band_stream[2] = {nullptr, nullptr};
@@ -113,4 +116,8 @@ int meso_overflow_finish(MesoCtx* c, const char* what);                 // waits
 int meso_carve_enqueue(MesoCtx* c, const int32_t center[3], int32_t radius);
 int meso_carve_finish(MesoCtx* c, int64_t* n_dirty);
 int meso_ensure_mesh_buffers(MesoCtx* c);
+#define MESO_STAGE_BYTES (1u << 20)
+// device -> host, synchronous on the context's stream; up to MESO_STAGE_BYTES through a kernel + mapped staging (never
+// queued behind a DMA in flight), larger reads through cudaMemcpyAsync
+int meso_small_read(MesoCtx* c, void* host_dst, const void* d_src, size_t bytes);
 }

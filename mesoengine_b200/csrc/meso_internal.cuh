@@ -112,6 +112,7 @@ void launch_carve(const LaunchCtx& lc, const DVolume& v, const int32_t center[3]
 void launch_expand_dirty(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_dirty, uint32_t n_dirty, uint64_t* d_keys,
                          uint32_t cap, uint32_t* d_count, uint32_t* d_mark);
 void launch_flush(const LaunchCtx& lc, uint32_t* d_scratch, size_t n_words);
+void launch_peek(const LaunchCtx& lc, void* d_dst_mapped, const void* d_src, size_t bytes);   // src 4-byte aligned
 
 // K6 (k_resident.cu, k_voxelize.cu)
 int64_t resident_max_candidates(const MesoViewConfig& vc);
