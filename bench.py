@@ -286,7 +286,7 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
     # frames in flight: the reference keeps kNumBufferedFrames = 4 per-frame buffers (Samples/SimpleVoxel.cpp:15); consecutive
     # frames go to alternating streams / frame buffers so the long tail of one frame (a few grazing rays) overlaps the next
-    R = max(1, min(4, args.frames_in_flight))
+    R = max(1, min(8, args.frames_in_flight))
     streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(R - 1)]
     ctx.scene_create(origin, dims, max_bricks=(1 << 20) if n >= 4096 else (1 << 18))
     t_build = time.perf_counter()
@@ -348,6 +348,13 @@ def run_ours(args):
                         ctx.device_free(frame_owner_ptrs[i])
             frame_ptrs = [None] * R
             frame_owner_ptrs = [None] * R
+    # rendezvous of the frame loops: arrival words (signal / wait kernels over peer memory, no collective) unless --rendezvous nccl
+    arrival = None
+    if world > 1:
+        arrival = ArrivalWords(ctx, capi, torch, dist, dev, rank, world)
+        if not arrival.ok or args.rendezvous == "nccl":
+            arrival.close(dist)
+            arrival = None
     if world == 1 or gather != "p2p":
         frames = [torch.empty((height, width, 4), dtype=torch.int32, device=dev) for _ in range(R)]
     if world > 1 and gather != "p2p":
@@ -364,6 +371,13 @@ def run_ours(args):
         with torch.cuda.stream(s):
             if world == 1:
                 ctx.raymarch_device(cam, width, height, frames[slot].data_ptr(), shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+            elif gather == "p2p" and arrival is not None:
+                # word `slot` of rank 0: every rank adds 1 behind its kernel (stream order); rank 0's stream waits for all of them
+                ctx.raymarch_device(cam, width, height, frame_ptrs[slot], shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
+                ctx.signal_device([arrival.words[0] + 4 * slot])
+                arrival.gen[slot] += world
+                if rank == 0:
+                    ctx.wait_device(arrival.words[0] + 4 * slot, arrival.gen[slot])
             elif gather == "p2p":
                 ctx.raymarch_device(cam, width, height, frame_ptrs[slot], shadow=True, light=LIGHT, layout=capi.LAYOUT_FRAME)
                 dist.all_reduce(flags[slot])   # stream-ordered 4-byte rendezvous: when it completes on rank 0 every tile has landed
@@ -388,27 +402,34 @@ def run_ours(args):
     # ---- timed region: exactly K steps between two barrier + synchronize points, CUDA events on the launching streams.
     # R frames in flight; every step writes its own 132.7 MB frame buffer (R of them cycled) and re-reads ~12 MB of scene,
     # so the per-step footprint exceeds the 126 MB L2 on its own -- no artificial flush inside the region. ----
-    launches0 = ctx.launch_count()
-    ctx.flush_l2()
-    barrier()
-    ev_start = torch.cuda.Event(enable_timing=True)
-    ev_start.record(stream)
-    for s in streams[1:]:
-        s.wait_event(ev_start)
-    for k in range(args.steps):
-        step(k, k % R)
-    ev_end = []
-    for s in streams:
-        e = torch.cuda.Event(enable_timing=True)
-        e.record(s)
-        ev_end.append(e)
-    barrier()
-    launches = ctx.launch_count() - launches0 - 1  # minus the one flush before the region
-    ms = max(ev_start.elapsed_time(e) for e in ev_end)
-    total_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    ms = float(total_ms.item())
+    # The region is run `--regions` times (default 5), each one exactly K steps between two barrier + synchronize points; the
+    # line reports the MEDIAN region (at 8 GPUs a 20-step region is 4 ms: one region alone is noise-sensitive), all of them
+    # are listed in config.regions_ms.
+    region_ms = []
+    launches = 0
+    for reg in range(max(1, args.regions)):
+        launches0 = ctx.launch_count()
+        ctx.flush_l2()
+        barrier()
+        ev_start = torch.cuda.Event(enable_timing=True)
+        ev_start.record(stream)
+        for s in streams[1:]:
+            s.wait_event(ev_start)
+        for k in range(args.steps):
+            step(k, k % R)
+        ev_end = []
+        for s in streams:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(s)
+            ev_end.append(e)
+        barrier()
+        launches = ctx.launch_count() - launches0 - 1  # minus the one flush before the region
+        ms_r = max(ev_start.elapsed_time(e) for e in ev_end)
+        total_ms = torch.tensor([ms_r], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        region_ms.append(float(total_ms.item()))
+    ms = float(np.median(region_ms))
     rays_total = sum(rays_cam[k % 8] for k in range(args.steps))
     value = rays_total / (ms * 1e-3) / 1e6
 
@@ -551,13 +572,28 @@ def run_ours(args):
         s = streams[slot]
         ctx.set_stream(s.cuda_stream)
         with torch.cuda.stream(s):
-            ctx.raymarch_device_slabs(cams[k % 8], width, height, slab_ptrs[slot], slab_rows, shadow=True, light=LIGHT,
-                                      flags_extra=capi.FLAG_RGBA8 if rgba8 else 0)
-            dist.all_reduce(flags[slot])
-            if my_rows > 0:
-                off = slot * px * 16 + my_row0 * width * bpp
-                ctx.download_async(shm[off:off + my_rows * width * bpp], slab_mine[slot])
-            dist.all_reduce(flags2[slot])
+            off = slot * px * 16 + my_row0 * width * bpp
+            if arrival is not None:
+                # words 8 + slot: "kernels done" (all-to-all: every rank's slab receives rows from every rank);
+                # words 16 + slot: "slab has reached the host" (all-to-all: the next frame on this slot overwrites peers' slabs)
+                ia, ib = 8 + slot, 16 + slot
+                ctx.raymarch_device_slabs(cams[k % 8], width, height, slab_ptrs[slot], slab_rows, shadow=True, light=LIGHT,
+                                          flags_extra=capi.FLAG_RGBA8 if rgba8 else 0)
+                ctx.signal_device(arrival.all_ranks(ia))
+                arrival.gen[ia] += world
+                ctx.wait_device(arrival.mine + 4 * ia, arrival.gen[ia])
+                if my_rows > 0:
+                    ctx.download_async(shm[off:off + my_rows * width * bpp], slab_mine[slot])
+                ctx.signal_device(arrival.all_ranks(ib))
+                arrival.gen[ib] += world
+                ctx.wait_device(arrival.mine + 4 * ib, arrival.gen[ib])
+            else:
+                ctx.raymarch_device_slabs(cams[k % 8], width, height, slab_ptrs[slot], slab_rows, shadow=True, light=LIGHT,
+                                          flags_extra=capi.FLAG_RGBA8 if rgba8 else 0)
+                dist.all_reduce(flags[slot])
+                if my_rows > 0:
+                    ctx.download_async(shm[off:off + my_rows * width * bpp], slab_mine[slot])
+                dist.all_reduce(flags2[slot])
             e = torch.cuda.Event()
             e.record(s)
         ctx.set_stream(stream.cuda_stream)
@@ -668,8 +704,14 @@ def run_ours(args):
         edit_multi = None
         if not args.no_mesh:
             slab_info = dict(ptrs=slab_ptrs, mine=slab_mine, rows=slab_rows, row0=my_row0, my_rows=my_rows, shm=shm, px=px, R=R,
-                             flags2=flags2, streams=streams) if slabs_ok else None
+                             flags2=flags2, streams=streams, arrival=arrival, world=world) if slabs_ok else None
             edit_multi = bench_edit_loop_multi(ctx, capi, cams, width, height, shm_views[0], shm_dptr, flags[0], stream, rank, dist, torch, slabs=slab_info)
+            if slabs_ok:
+                # the same loop delivering the image as RGBA8 (the reference's TEXOffscreenColor format): the records stay on the
+                # devices for the pick, their colour words are packed and copied -- 33 MB instead of 133 MB per frame into the host
+                e8 = bench_edit_loop_multi(ctx, capi, cams, width, height, shm_views[0], shm_dptr, flags[0], stream, rank, dist, torch, slabs=slab_info, rgba8=True)
+                if edit_multi is not None and e8 is not None:
+                    edit_multi["rgba8"] = {k: e8[k] for k in ("fps", "ms_per_frame", "ms_carve", "ms_remesh_dirty", "ms_render_to_host", "host_bytes_per_frame")}
         barrier()
         if slabs_ok:
             for i in range(R):
@@ -725,10 +767,10 @@ def run_ours(args):
                        "resolution": [width, height], "rays_per_frame_mean": rays_total / args.steps,
                        "partition": ("single GPU, row-major frame" if world == 1 else
                                      ("32x8 screen tiles, tile %% %d == rank; " % world) +
-                                     ("fused gather: every rank's kernel stores its records into rank 0's frame over NVLink peer memory, 4-byte NCCL all-reduce as the rendezvous"
+                                     ("fused gather: every rank's kernel stores its records into rank 0's frame over NVLink peer memory; rendezvous = " + ("an arrival word on rank 0 that every rank increments behind its kernel (one-thread signal kernel, system-scope atomic over NVLink), waited for on rank 0's stream: no collective in the frame loop" if arrival is not None else "4-byte NCCL all-reduce")
                                       if gather == "p2p" else "NCCL all_gather of packed tile records + compose kernel")),
                        "cache": "no flush inside the timed region: every step writes its own 132.7 MB frame (%d frame buffers cycled) and re-reads the scene, a per-step footprint above the 126 MB L2; the kernel-alone roofline loop flushes L2 (256 MiB write) between launches" % R,
-                       "frames_in_flight": R,
+                       "frames_in_flight": R, "regions_ms": region_ms, "regions_note": "each region = exactly `steps` steps between barrier + synchronize points, max over ranks; value / ms_per_step are the median region",
                        "gather": gather, "gather_verified_equal_to_1gpu_frame": gather_verified,
                        "scene_build_s": t_build,
                        "walk": "mirrored-space stateless DDA over per-octant forward cubes (32^3 cells, bricks), built with the volume"},
@@ -790,6 +832,11 @@ def run_ours(args):
                 line["group_api"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
         dist.barrier(group=cpu_group)
     if world > 1:
+        if arrival is not None:
+            timed_out = ctx.wait_timed_out()
+            if rank == 0:
+                line["config"]["rendezvous_wait_timed_out"] = timed_out
+            arrival.close(dist)
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
@@ -881,6 +928,55 @@ def bench_group(capi, torch, scene, cams, rays_cam, width, height, world, args):
         g.close()
 
 
+class ArrivalWords:
+    """32-bit arrival words in every rank's device memory, opened by all ranks over CUDA IPC: the rendezvous of the N-GPU
+    frame loops without a collective.  words[r] = base device address of rank r's block of `n` words (own or peer mapping).
+    Every rank runs the same collectives here whatever fails where; .ok tells whether all ranks succeeded."""
+
+    def __init__(self, ctx, capi, torch, dist, dev, rank, world, n=32):
+        self.ctx, self.rank, self.world, self.n = ctx, rank, world, n
+        self.words = [None] * world
+        self.mine = None
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        h = torch.zeros(capi.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        try:
+            self.mine = ctx.device_alloc(4 * n)
+            ctx.device_memset(self.mine, 0, 4 * n)
+            ctx.sync()
+            h.copy_(torch.from_numpy(ctx.ipc_export(self.mine)))
+        except Exception as e:
+            sys.stderr.write("bench: arrival words unavailable on rank %d (%s)\n" % (rank, e))
+            ok.zero_()
+        allh = torch.zeros((world, capi.IPC_HANDLE_BYTES), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, h)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            hs = allh.cpu().numpy()
+            try:
+                for r in range(world):
+                    self.words[r] = self.mine if r == rank else ctx.ipc_open(hs[r])
+            except Exception as e:
+                sys.stderr.write("bench: arrival words unavailable on rank %d (%s)\n" % (rank, e))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        self.ok = int(ok.item()) == 1
+        self.gen = [0] * n          # launches signalled so far per word index (identical on every rank)
+
+    def all_ranks(self, i):
+        return [w + 4 * i for w in self.words]
+
+    def close(self, dist):
+        for r in range(self.world):
+            if r != self.rank and self.words[r] is not None:
+                try:
+                    self.ctx.ipc_close(self.words[r])
+                except Exception:
+                    pass
+        dist.barrier()
+        if self.mine is not None:
+            self.ctx.device_free(self.mine)
+
+
 def bench_small_config(ctx, capi, scenes, torch, stream, name, args):
     """One of BASELINE.json's smaller raymarch configurations at its stated size: device-timed Mrays/s (kernel per frame, L2
     flushed: these scenes fit the L2) and, unless --no-cpu, the oracle's records on sampled scanlines byte-compared."""
@@ -957,7 +1053,7 @@ def bench_edit_loop(ctx, capi, cams, width, height, frames=48):
             "note": "carve r=24 voxels at the centre-pixel hit, re-mesh dirty bricks + neighbours, re-render 3840x2160 to host memory (synchronous API)"}
 
 
-def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, flag, stream, rank, dist, torch, frames=48, slabs=None):
+def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, flag, stream, rank, dist, torch, frames=48, slabs=None, rgba8=False):
     """The edit loop on N GPUs.  Every rank reads the centre-pixel hit of the last frame, carves the same sphere into its
     replica of the volume (replicated compute), re-meshes ITS SHARE of the dirty bricks (sharded by key hash) and renders its
     tiles of the next 4K frame.  With the slab gather the loop is pipelined: the only thing frame k+1's carve needs from
@@ -984,31 +1080,58 @@ def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, fla
         owner = py // rows
         copy_streams = [torch.cuda.Stream() for _ in range(2)]
         dma_done = [None, None]
+        # rgba8: the records stay in the slabs (the pick needs them), only their colour words are packed and sent to the host
+        packed = [torch.empty((max(slabs["my_rows"], 1), width), dtype=torch.int32, device="cuda") for _ in range(2)] if rgba8 else None
 
         def render(k):
             slot = k % 2
             if dma_done[slot] is not None:
                 dma_done[slot].synchronize()          # this slab set's previous frame has left for the host
-            ctx.raymarch_device_slabs(cams[k % 8], width, height, slabs["ptrs"][slot], rows, shadow=True, light=LIGHT)
-            with torch.cuda.stream(stream):
-                # this rank's DMA of the PREVIOUS frame (other slab set) is ordered before the rendezvous, so that the
-                # rendezvous also tells every rank that all slabs of that set have left: the frame after this one may then
-                # overwrite them (other ranks' kernels store into this rank's slab)
-                if dma_done[1 - slot] is not None:
-                    stream.wait_event(dma_done[1 - slot])
-                dist.all_reduce(flag)                 # every rank's kernel is done: all slabs of this frame are complete
-                ev = torch.cuda.Event()
-                ev.record(stream)
+            arr = slabs.get("arrival")
+            if arr is not None:
+                ia, ib = 24 + slot, 26 + slot
+                # every rank's copy of the frame that used this slab set two frames ago has left for the host (the kernels of
+                # this frame store into peers' slabs): wait for all ranks' "slab has reached the host" signals of that frame
+                if arr.gen[ib] > 0:
+                    ctx.wait_device(arr.mine + 4 * ib, arr.gen[ib])
+                ctx.raymarch_device_slabs(cams[k % 8], width, height, slabs["ptrs"][slot], rows, shadow=True, light=LIGHT)
+                ctx.signal_device(arr.all_ranks(ia))
+                arr.gen[ia] += slabs["world"]
+                ctx.wait_device(arr.mine + 4 * ia, arr.gen[ia])      # every rank's kernel is done: all slabs of this frame are complete
+                with torch.cuda.stream(stream):
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+            else:
+                ctx.raymarch_device_slabs(cams[k % 8], width, height, slabs["ptrs"][slot], rows, shadow=True, light=LIGHT)
+                with torch.cuda.stream(stream):
+                    # this rank's DMA of the PREVIOUS frame (other slab set) is ordered before the rendezvous, so that the
+                    # rendezvous also tells every rank that all slabs of that set have left: the frame after this one may then
+                    # overwrite them (other ranks' kernels store into this rank's slab)
+                    if dma_done[1 - slot] is not None:
+                        stream.wait_event(dma_done[1 - slot])
+                    dist.all_reduce(flag)                 # every rank's kernel is done: all slabs of this frame are complete
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
             # the pick: one record from the owning rank's slab (peer memory), on the main stream
             ctx.download(pick, slabs["ptrs"][slot][owner] + ((py - owner * rows) * width + pxl) * 16, 16)
             # the frame itself leaves on a copy stream, behind the next frame's work
             cs = copy_streams[slot]
             cs.wait_event(ev)
             if slabs["my_rows"] > 0:
-                off = slot * px * 16 + slabs["row0"] * width * 16
                 ctx.set_stream(cs.cuda_stream)
-                ctx.download_async(slabs["shm"][off:off + slabs["my_rows"] * width * 16], slabs["mine"][slot])
+                if rgba8:
+                    off = slot * px * 16 + slabs["row0"] * width * 4
+                    ctx.pack_rgba8_device(slabs["mine"][slot], slabs["my_rows"] * width, packed[slot].data_ptr())
+                    ctx.download_async(slabs["shm"][off:off + slabs["my_rows"] * width * 4], packed[slot].data_ptr())
+                else:
+                    off = slot * px * 16 + slabs["row0"] * width * 16
+                    ctx.download_async(slabs["shm"][off:off + slabs["my_rows"] * width * 16], slabs["mine"][slot])
                 ctx.set_stream(stream.cuda_stream)
+            if arr is not None:
+                ctx.set_stream(cs.cuda_stream)
+                ctx.signal_device(arr.all_ranks(26 + slot))          # "my slab of this frame has reached the host", to every rank
+                ctx.set_stream(stream.cuda_stream)
+                arr.gen[26 + slot] += slabs["world"]
             e = torch.cuda.Event()
             e.record(cs)
             dma_done[slot] = e
@@ -1043,7 +1166,7 @@ def bench_edit_loop_multi(ctx, capi, cams, width, height, frame, frame_dptr, fla
     return {"frames": frames, "fps": frames / t_all, "ms_per_frame": t_all / frames * 1e3, "ms_carve": t_carve / frames * 1e3,
             "ms_remesh_dirty": t_mesh / frames * 1e3, "ms_render_to_host": t_render / frames * 1e3,
             "dirty_bricks_per_frame": dirty_total / frames, "quads_per_frame": int(qt.item()) / frames,
-            "pipelined": slabs is not None,
+            "pipelined": slabs is not None, "host_bytes_per_frame": (4 if rgba8 else 16) * width * height,
             "note": "rank 0's clock; carve r=24 voxels at the centre-pixel hit on every rank's replica, dirty bricks re-meshed sharded over the ranks by key hash, 3840x2160 re-rendered by all ranks"
                     + (" through the slab gather: the next carve waits only for the 16-byte pick behind the kernels' rendezvous, the slab-to-host DMAs of frame k overlap frame k+1"
                        if slabs is not None else " into the shared host frame (host-fused stores), one rendezvous per frame")}
@@ -1324,10 +1447,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--regions", type=int, default=5, help="number of K-step timed regions; the median is reported")
     ap.add_argument("--no-mesh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="frame ring depth of the timed loop (reference: kNumBufferedFrames = 4)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="multi-GPU frame gather (p2p falls back to nccl if IPC is unavailable)")
+    ap.add_argument("--rendezvous", default="arrival", choices=["arrival", "nccl"], help="N > 1 frame loops: arrival words over peer memory, or NCCL all-reduce")
     ap.add_argument("--no-group", action="store_true", help="N > 1: skip the single-process group-API leg")
     ap.add_argument("--no-slabs", action="store_true", help="N > 1 e2e: host-fused 512-byte stores instead of the slab gather")
     ap.add_argument("--no-host-fused", action="store_true", help="N > 1 e2e: gather on rank 0 and copy instead of storing straight into shared host memory")

@@ -51,7 +51,8 @@ SYMBOLS = [
     "meso_select_view_chunks", "meso_chunk_importance", "meso_baked_direction", "meso_stream_begin", "meso_stream_update",
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
-    "meso_device_copy", "meso_build_cubes", "meso_download_cubes", "meso_volume_upload_blocks", "meso_raymarch_device_slabs", "meso_mesh_count_device",
+    "meso_device_copy", "meso_build_cubes", "meso_download_cubes", "meso_volume_upload_blocks", "meso_raymarch_device_slabs", "meso_mesh_count_device", "meso_stream_recentre", "meso_pool_stats", "meso_block_importance",
+    "meso_signal_device", "meso_present_rgba8", "meso_pack_rgba8_device", "meso_wait_device", "meso_wait_timed_out",
     "meso_group_create", "meso_group_destroy", "meso_group_size", "meso_group_ctx", "meso_group_sync", "meso_group_scene_create",
     "meso_group_voxelize_sdf", "meso_group_volume_upload_blocks", "meso_group_carve_sphere", "meso_group_raymarch",
     "meso_group_raymarch_async", "meso_group_frame_wait", "meso_group_mesh", "meso_group_mesh_device", "meso_group_remesh_dirty",
@@ -256,6 +257,16 @@ class Context:
         _ck(lib.meso_raymarch(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(flags), _p(l), _p(rec)))
         return rec
 
+    def present_rgba8(self, cam, width, height, rect=None, shadow=True, light=(0.3, 0.5, 0.8)):
+        """Tightly packed RGBA8 of the range rect = (x, y, w, h) (None = whole frame): the data of IContext::upload(TextureHandle, ...)."""
+        x, y, w, h = rect if rect is not None else (0, 0, width, height)
+        out = np.zeros((h, w), dtype=np.uint32)
+        l = np.ascontiguousarray(light, dtype=np.float32)
+        rg = np.array([x, y, w, h], dtype=np.uint32)
+        _ck(lib.meso_present_rgba8(self.h, _p(cam), C.c_int(width), C.c_int(height), C.c_uint32(FLAG_SHADOW if shadow else 0), _p(l),
+                                   _p(rg) if rect is not None else None, _p(out)))
+        return out
+
     def raymarch_async(self, cam, width, height, out, slot, shadow=True, light=(0.3, 0.5, 0.8), rgba8=False, cubes=None):
         """Frame-ring call: enqueue frame + copy into `out` (pinned numpy array); pair with frame_wait(slot)."""
         l = np.ascontiguousarray(light, dtype=np.float32)
@@ -269,6 +280,44 @@ class Context:
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
                                      C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
+
+    def pack_rgba8_device(self, d_records, n, d_rgba8):
+        _ck(lib.meso_pack_rgba8_device(self.h, C.c_void_p(int(d_records)), C.c_int64(n), C.c_void_p(int(d_rgba8))))
+
+    def signal_device(self, words):
+        arr = (C.c_void_p * len(words))(*[C.c_void_p(int(p)) for p in words])
+        _ck(lib.meso_signal_device(self.h, arr, C.c_int(len(words))))
+
+    def wait_device(self, d_word, target):
+        _ck(lib.meso_wait_device(self.h, C.c_void_p(int(d_word)), C.c_uint32(target & 0xFFFFFFFF)))
+
+    def wait_timed_out(self):
+        v = C.c_int(0)
+        _ck(lib.meso_wait_timed_out(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def stream_recentre(self, camera_chunk):
+        """Moving window: the grid follows the camera; returns the origin's displacement in chunks."""
+        cc = np.ascontiguousarray(camera_chunk, dtype=np.int32)
+        moved = np.zeros(3, dtype=np.int32)
+        _ck(lib.meso_stream_recentre(self.h, _p(cc), _p(moved)))
+        if self.origin is not None:
+            self.origin = tuple(int(o) + int(m) for o, m in zip(self.origin, moved))
+        return tuple(int(m) for m in moved)
+
+    def pool_stats(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _ck(lib.meso_pool_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def block_importance(self, camera_chunk, forward, chunk_locations, block_locations, chunk_resolution=16):
+        cc = np.ascontiguousarray(camera_chunk, dtype=np.int32)
+        f = np.ascontiguousarray(forward, dtype=np.float32)
+        cl = np.ascontiguousarray(chunk_locations, dtype=np.int32).reshape(-1, 3)
+        bl = np.ascontiguousarray(block_locations, dtype=np.uint8).reshape(-1, 3)
+        out = np.zeros(len(cl), dtype=np.float32)
+        _ck(lib.meso_block_importance(self.h, _p(cc), _p(f), _p(cl), _p(bl), C.c_int64(len(cl)), C.c_uint32(chunk_resolution), _p(out)))
+        return out
 
     def raymarch_device_slabs(self, cam, width, height, slab_ptrs, rows_per_slab, shadow=True, light=(0.3, 0.5, 0.8), flags_extra=0):
         """MESO_LAYOUT_SLABS: slab_ptrs[k] = device address (own or peer) of rows [k * rows_per_slab, ...) of the frame."""

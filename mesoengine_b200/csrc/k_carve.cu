@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) carve_kernel(DVolume v, CarveBox box, uin
     // reports the overflow -- the volume stays consistent (no occ && !full brick without a payload).
     bool ok = true;
     if (was_full && any) {
-      slot = atomicAdd(v.pool_count, 1u);
-      if (slot >= v.max_bricks) { atomicSub(v.pool_count, 1u); *overflow = 1; slot = 0xFFFFFFFFu; ok = false; }
+      slot = alloc_payload_slot(v);
+      if (slot >= v.max_bricks) { release_bump(v); *overflow = 1; slot = 0xFFFFFFFFu; ok = false; }
     }
     if (ok) {
       const uint32_t di = atomicAdd(dirty_count, 1u);
@@ -147,6 +147,33 @@ void launch_peek(const LaunchCtx& lc, void* d_dst_mapped, const void* d_src, siz
   if (bytes == 0) return;
   const unsigned grid = (unsigned)std::min<size_t>((bytes / 4 + 255) / 256 + 1, (size_t)lc.sm_count * 4);
   peek_kernel<<<grid, 256, 0, lc.stream>>>((unsigned char*)d_dst_mapped, (const unsigned char*)d_src, bytes);
+  (*lc.launches)++;
+}
+
+// Stream-ordered rendezvous between GPUs without a collective: a signal adds one to a word (usually a peer's), a wait spins
+// on a word in this GPU's memory until it reaches `target`.  The wait is bounded (about 2 s): a peer that never arrives sets
+// the timeout flag instead of hanging the device.
+__global__ void signal_kernel(SignalTargets t) {
+  __threadfence_system();
+  for (int i = 0; i < t.n; i++) atomicAdd_system(t.word[i], 1u);
+}
+__global__ void wait_kernel(const unsigned* word, unsigned target, int* timeout_flag) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+    if ((int)(v - target) >= 0) break;
+    if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1; break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+void launch_signal(const LaunchCtx& lc, const SignalTargets& t) {
+  signal_kernel<<<1, 1, 0, lc.stream>>>(t);
+  (*lc.launches)++;
+}
+void launch_wait(const LaunchCtx& lc, const unsigned* d_word, unsigned target, int* d_timeout_flag) {
+  wait_kernel<<<1, 1, 0, lc.stream>>>(d_word, target, d_timeout_flag);
   (*lc.launches)++;
 }
 

@@ -25,6 +25,7 @@
 #include "meso_internal.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #define F_INF __int_as_float(0x7F800000)
 #define SEL3(a, X, Y, Z) ((a) == 0 ? (X) : ((a) == 1 ? (Y) : (Z)))
@@ -549,6 +550,18 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
   else if (d_stats) { if (cl == 0) RM10_LAUNCH(true, 0, false); else if (cl == 1) RM10_LAUNCH(true, 1, false); else if (cl == 2) RM10_LAUNCH(true, 2, false); else RM10_LAUNCH(true, 3, false); }
   else              { if (cl == 0) RM10_LAUNCH(false, 0, false); else if (cl == 1) RM10_LAUNCH(false, 1, false); else if (cl == 2) RM10_LAUNCH(false, 2, false); else RM10_LAUNCH(false, 3, false); }
 #undef RM10_LAUNCH
+  (*lc.launches)++;
+}
+
+// colour words of n records, packed: what travels to the host when only the image is wanted but the records stay useful on
+// the device (picking); 16 B read + 4 B written per pixel
+__global__ void __launch_bounds__(256) pack_rgba8_kernel(const uint4* __restrict__ rec, size_t n, uint32_t* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = rec[i].w;
+}
+void launch_pack_rgba8(const LaunchCtx& lc, const MesoHitRecord* d_records, size_t n, uint32_t* d_out) {
+  if (n == 0) return;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)lc.sm_count * 16);
+  pack_rgba8_kernel<<<grid, 256, 0, lc.stream>>>(reinterpret_cast<const uint4*>(d_records), n, d_out);
   (*lc.launches)++;
 }
 

@@ -203,6 +203,95 @@ void launch_select_view(const LaunchCtx& lc, const float fwd[3], const MesoViewC
   (*lc.launches) += 2;
 }
 
+// FImportanceComputeInfo::CalculateBlockImportance (ChunkManagerHelper.h:50-70), restated literally including its dead near
+// branch: the int offset is compared with `-2 * ChunkResolution`, ChunkResolution being uint32_t, so both sides convert to
+// unsigned and no value satisfies `u >= 4294967264 && u <= 32`.  Far branch: the chunk formula with Far = 64 * ChunkResolution.
+__global__ void block_importance_kernel(const int32_t* __restrict__ chunk_loc, const uint8_t* __restrict__ block_loc, int64_t n, int cx, int cy, int cz,
+                                        float fx, float fy, float fz, uint32_t res, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = (int)res;
+  const int x = (chunk_loc[3 * i] - cx) * r + block_loc[3 * i], y = (chunk_loc[3 * i + 1] - cy) * r + block_loc[3 * i + 1],
+            z = (chunk_loc[3 * i + 2] - cz) * r + block_loc[3 * i + 2];
+  const uint32_t lo = (uint32_t)(-2) * res, hi = 2u * res;
+  const bool near_ = ((uint32_t)x >= lo && (uint32_t)x <= hi) && ((uint32_t)y >= lo && (uint32_t)y <= hi) && ((uint32_t)z >= lo && (uint32_t)z <= hi);
+  if (near_) { out[i] = 1.0e6f; return; }
+  const float ox = (float)x, oy = (float)y, oz = (float)z;
+  const float d2 = dot3(ox, oy, oz, ox, oy, oz);
+  const float inv = 1.0f / sqrtf(d2);
+  const float dist = sqrtf(d2);
+  const float angle = std_max((std_max(0.0f, dot3(ox * inv, oy * inv, oz * inv, fx, fy, fz)) - 0.5f) * 2.0f, 0.75f);
+  const float distance = std_max(0.25f, 64.0f * (float)res - dist);
+  out[i] = angle * distance;
+}
+void launch_block_importance(const LaunchCtx& lc, const int32_t* d_chunk_loc, const uint8_t* d_block_loc, int64_t n, const int32_t cam[3], const float fwd[3],
+                             uint32_t chunk_resolution, float* d_out) {
+  if (n <= 0) return;
+  block_importance_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(d_chunk_loc, d_block_loc, n, cam[0], cam[1], cam[2], fwd[0], fwd[1], fwd[2],
+                                                                               chunk_resolution, d_out);
+  (*lc.launches)++;
+}
+
+// ---- moving window (FChunkPool's eviction, ChunkPool.h:447-622, in the form a dense window needs) --------------------------
+// The window follows the camera: origin' = origin + delta.  Chunks that leave it are evicted -- their payload slots go on
+// the free stack and are handed out again before any new slot (alloc_payload_slot) -- chunks that stay keep their data at
+// their new slot (slot = position relative to the origin), chunks that enter start empty and not generated; the next
+// meso_stream_update generates them in priority order like any other missing chunk.
+__global__ void __launch_bounds__(256) evict_chunks_kernel(DVolume v, int dx, int dy, int dz) {
+  const int64_t c = blockIdx.x;     // old slot
+  const int x = (int)(c % v.dims[0]), y = (int)((c / v.dims[0]) % v.dims[1]), z = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
+  const int nx = x - dx, ny = y - dy, nz = z - dz;   // position in the new window
+  if ((unsigned)nx < (unsigned)v.dims[0] && (unsigned)ny < (unsigned)v.dims[1] && (unsigned)nz < (unsigned)v.dims[2]) return;   // stays
+  for (int w = threadIdx.x; w < 64; w += blockDim.x) {
+    uint64_t part = v.occ[c * 64 + w] & ~v.full[c * 64 + w];
+    while (part) {
+      const int bit = __ffsll((long long)part) - 1;
+      part &= part - 1;
+      const uint32_t slot = v.bptr[c * MESO_BLOCKS + w * 64 + bit];
+      if (slot < v.max_bricks) v.pool_free[atomicAdd(v.pool_free_count, 1)] = slot;
+    }
+  }
+}
+// dst[new slot] = src[new slot + delta] for the chunks that stay, `fill` words for those that enter; W 32-bit words per chunk
+__global__ void __launch_bounds__(256) shift_chunks_kernel(DVolume v, int dx, int dy, int dz, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                           int words_per_chunk, uint32_t fill) {
+  const int64_t n = blockIdx.x;     // new slot
+  const int x = (int)(n % v.dims[0]), y = (int)((n / v.dims[0]) % v.dims[1]), z = (int)(n / ((int64_t)v.dims[0] * v.dims[1]));
+  const int ox = x + dx, oy = y + dy, oz = z + dz;   // where it was
+  const bool stays = (unsigned)ox < (unsigned)v.dims[0] && (unsigned)oy < (unsigned)v.dims[1] && (unsigned)oz < (unsigned)v.dims[2];
+  const int64_t o = stays ? (int64_t)ox + (int64_t)v.dims[0] * ((int64_t)oy + (int64_t)v.dims[1] * oz) : 0;
+  const uint4 f4 = make_uint4(fill, fill, fill, fill);
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + o * words_per_chunk);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + n * words_per_chunk);
+  for (int i = threadIdx.x; i < words_per_chunk / 4; i += blockDim.x) d4[i] = stays ? s4[i] : f4;
+}
+__global__ void shift_loaded_kernel(DVolume v, int dx, int dy, int dz, const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= v.nchunks) return;
+  const int x = (int)(n % v.dims[0]), y = (int)((n / v.dims[0]) % v.dims[1]), z = (int)(n / ((int64_t)v.dims[0] * v.dims[1]));
+  const int ox = x + dx, oy = y + dy, oz = z + dz;
+  if (!((unsigned)ox < (unsigned)v.dims[0] && (unsigned)oy < (unsigned)v.dims[1] && (unsigned)oz < (unsigned)v.dims[2])) return;
+  const int64_t o = (int64_t)ox + (int64_t)v.dims[0] * ((int64_t)oy + (int64_t)v.dims[1] * oz);
+  if ((src[o >> 5] >> (o & 31)) & 1u) atomicOr(&dst[n >> 5], 1u << (n & 31));
+}
+// d_scratch: nchunks * 16 KiB (the largest per-chunk array, bptr).  v.origin is updated (host copy of the descriptor).
+void launch_window_shift(const LaunchCtx& lc, DVolume& v, const int delta[3], uint32_t* d_loaded, void* d_scratch) {
+  const unsigned nc = (unsigned)v.nchunks;
+  evict_chunks_kernel<<<nc, 64, 0, lc.stream>>>(v, delta[0], delta[1], delta[2]);
+  struct Arr { void* p; int words; uint32_t fill; };
+  const Arr arrs[4] = {{v.occ, 128, 0u}, {v.full, 128, 0u}, {v.mips, 384, 0u}, {v.bptr, MESO_BLOCKS, 0xFFFFFFFFu}};
+  for (const Arr& a : arrs) {
+    shift_chunks_kernel<<<nc, 256, 0, lc.stream>>>(v, delta[0], delta[1], delta[2], (const uint32_t*)a.p, (uint32_t*)d_scratch, a.words, a.fill);
+    cudaMemcpyAsync(a.p, d_scratch, (size_t)nc * a.words * 4, cudaMemcpyDeviceToDevice, lc.stream);
+  }
+  cudaMemsetAsync(d_scratch, 0, (size_t)v.chunk_words * 4, lc.stream);
+  shift_loaded_kernel<<<(nc + 255) / 256, 256, 0, lc.stream>>>(v, delta[0], delta[1], delta[2], d_loaded, (uint32_t*)d_scratch);
+  cudaMemcpyAsync(d_loaded, d_scratch, (size_t)v.chunk_words * 4, cudaMemcpyDeviceToDevice, lc.stream);
+  (*lc.launches) += 6;
+  for (int i = 0; i < 3; i++) v.origin[i] += delta[i];
+  launch_volume_finalize(lc, v);   // of / cells / chunk and region bits / distance field of the shifted window
+}
+
 void launch_chunk_importance(const LaunchCtx& lc, const int32_t* d_loc, int64_t n, const int32_t cam[3], const float fwd[3], float* d_out) {
   if (n <= 0) return;
   chunk_importance_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(d_loc, n, cam[0], cam[1], cam[2], fwd[0], fwd[1], fwd[2], d_out);

@@ -262,14 +262,14 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
     bool keep = any;
     if (any && !all) {
       uint32_t slot = 0;
-      if (lane == 0) slot = atomicAdd(v.pool_count, 1u);
+      if (lane == 0) slot = alloc_payload_slot(v);
       slot = __shfl_sync(0xffffffffu, slot, 0);
       if (slot < v.max_bricks) {
         if (q == 0) v.pool[(size_t)slot * 8 + vz] = s;
         if (lane == 0) v.bptr[c * MESO_BLOCKS + bi] = slot;
       } else {
         keep = false;
-        if (lane == 0) { atomicSub(v.pool_count, 1u); *overflow = 1; }
+        if (lane == 0) { release_bump(v); *overflow = 1; }
       }
     }
     if (lane == 0) {
@@ -488,6 +488,7 @@ void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const doub
   for (int i = 0; i < 4; i++) sp.p[i] = params ? params[i] : 0.0;
   cudaMemsetAsync(v.bptr, 0xFF, sizeof(uint32_t) * MESO_BLOCKS * (size_t)v.nchunks, lc.stream);
   cudaMemsetAsync(v.pool_count, 0, sizeof(uint32_t), lc.stream);
+  cudaMemsetAsync(v.pool_free_count, 0, sizeof(int), lc.stream);
   const unsigned grid = (unsigned)(v.nchunks * 64);
   if (granularity == MESO_GRAN_VOXEL) {
     launch_voxelize_words(lc, v, kind, sp, g_overflow, nullptr, nullptr, v.nchunks);

@@ -59,6 +59,7 @@ static int ctx_init(MesoCtx* c) {
   }
   CK(cudaMalloc(&c->d_overflow, sizeof(int)));
   CK(cudaMemset(c->d_overflow, 0, sizeof(int)));
+  CK(cudaMalloc(&c->d_timeout, sizeof(int))); CK(cudaMemset(c->d_timeout, 0, sizeof(int)));
   CK(cudaHostAlloc(&c->h_stage, MESO_STAGE_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
   CK(cudaHostGetDevicePointer((void**)&c->d_stage, c->h_stage, 0));
   return MESO_OK;
@@ -82,7 +83,7 @@ int meso_small_read(MesoCtx* c, void* host_dst, const void* d_src, size_t bytes)
 static void free_scene(MesoCtx* c) {
   DVolume& v = c->v;
   cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.cells); cudaFree(v.region_any); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
-  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count); cudaFree(v.df); cudaFree(v.df_tmp); cudaFree(v.pool_cm); cudaFree(v.words); cudaFree(v.n_words);
+  cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count); cudaFree(v.pool_free); cudaFree(v.pool_free_count); cudaFree(c->d_shift_scratch); c->d_shift_scratch = nullptr; cudaFree(v.df); cudaFree(v.df_tmp); cudaFree(v.pool_cm); cudaFree(v.words); cudaFree(v.n_words);
   cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
@@ -106,6 +107,7 @@ int meso_ctx_destroy(MesoCtx* c) {
   free_scene(c);
   cudaFree(c->d_flush); cudaFree(c->d_tmp_count); cudaFree(c->d_overflow);
   if (c->h_stage) cudaFreeHost(c->h_stage);
+  cudaFree(c->d_timeout);
   cudaFree(c->d_sel_keys); cudaFree(c->d_sel_out); cudaFree(c->d_sel_count);
   for (int i = 0; i < 16; i++) if (c->band_done[i]) cudaEventDestroy(c->band_done[i]);
   cudaStreamDestroy(c->copy_stream);
@@ -194,6 +196,8 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   CK(cudaMalloc(&v.words, nc * 64 * 4)); CK(cudaMalloc(&v.n_words, 4));
   CK(cudaMalloc(&v.chunk_any, (size_t)v.chunk_words * 4)); CK(cudaMalloc(&v.chunk_full, (size_t)v.chunk_words * 4));
   CK(cudaMalloc(&v.pool_count, 4));
+  CK(cudaMalloc(&v.pool_free, (size_t)max_bricks * 4)); CK(cudaMalloc(&v.pool_free_count, 4));
+  CK(cudaMemsetAsync(v.pool_free_count, 0, 4, c->stream));
   CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
   CK(cudaMemsetAsync(v.mips, 0, nc * 3 * 64 * 8, c->stream));
   CK(cudaMemsetAsync(v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
@@ -288,6 +292,7 @@ int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, co
     CK(cudaMemsetAsync(c->v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
     const uint32_t n32 = (uint32_t)n;
     CK(cudaMemcpyAsync(c->v.pool_count, &n32, 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->v.pool_free_count, 0, 4, c->stream));
     if (n > 0) {
       CK(cudaMalloc(&d_k, (size_t)n * 8)); CK(cudaMalloc(&d_p, (size_t)n * 64));
       CK(cudaMemcpyAsync(d_k, keys, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
@@ -322,6 +327,7 @@ int meso_volume_upload_blocks(MesoCtx* c, const MesoGPUChunk* chunks, int64_t n_
       CK(cudaMemsetAsync(v.occ, 0, nc * 64 * 8, c->stream)); CK(cudaMemsetAsync(v.full, 0, nc * 64 * 8, c->stream));
       CK(cudaMemsetAsync(v.bptr, 0xFF, nc * MESO_BLOCKS * 4, c->stream));
       CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
+      CK(cudaMemsetAsync(v.pool_free_count, 0, 4, c->stream));
     }
     CK(cudaMemsetAsync(c->d_quad_count, 0, 8, c->stream));   // borrowed as the accepted-block counter
     if (n_blocks > 0 && n_chunks > 0) {
@@ -544,6 +550,36 @@ int meso_raymarch_device(MesoCtx* c, const MesoGPUUniformCamera* cam, int width,
   return MESO_OK;
 }
 
+int meso_signal_device(MesoCtx* c, void* const* d_words, int n) {
+  if (!c || !d_words || n < 1 || n > MESO_MAX_SLABS) return fail(MESO_ERR_ARGUMENT, "meso_signal_device: bad argument");
+  CK(cudaSetDevice(c->device));
+  SignalTargets t{};
+  for (int i = 0; i < n; i++) {
+    if (!d_words[i]) return fail(MESO_ERR_ARGUMENT, "meso_signal_device: null word");
+    t.word[i] = (unsigned*)d_words[i];
+  }
+  t.n = n;
+  launch_signal(c->lc(), t);
+  CK_LAST("signal");
+  return MESO_OK;
+}
+int meso_wait_device(MesoCtx* c, const void* d_word, uint32_t target) {
+  if (!c || !d_word) return fail(MESO_ERR_ARGUMENT, "meso_wait_device: bad argument");
+  CK(cudaSetDevice(c->device));
+  launch_wait(c->lc(), (const unsigned*)d_word, target, c->d_timeout);
+  CK_LAST("wait");
+  return MESO_OK;
+}
+int meso_wait_timed_out(MesoCtx* c, int* out) {
+  if (!c || !out) return fail(MESO_ERR_ARGUMENT, "meso_wait_timed_out: bad argument");
+  int h = 0;
+  const int r = meso_small_read(c, &h, c->d_timeout, sizeof(int));
+  if (r != MESO_OK) return r;
+  *out = h;
+  if (h) CK(cudaMemsetAsync(c->d_timeout, 0, sizeof(int), c->stream));
+  return MESO_OK;
+}
+
 int meso_raymarch_device_slabs(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3],
                                void* const* d_slabs, int n_slabs, int rows_per_slab) {
   NEED_SCENE(c);
@@ -618,6 +654,38 @@ int meso_raymarch(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int he
                        cudaMemcpyDeviceToHost, c->copy_stream));
   }
   CK(cudaStreamSynchronize(c->copy_stream));   // every band kernel precedes its copy, so this covers both band streams
+  return MESO_OK;
+}
+
+// The present path: the frame as tightly packed RGBA8 for a texture range, i.e. exactly the `data` that
+// lvk::IContext::upload(TextureHandle, const TextureRangeDesc&, const void* data[]) (LVK.h:830) takes for TEXOffscreenColor.
+int meso_present_rgba8(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, int height, uint32_t flags, const float light[3],
+                       const MesoTextureRange* range, void* host_pixels) {
+  NEED_SCENE(c);
+  if (!cam || !host_pixels) return fail(MESO_ERR_ARGUMENT, "meso_present_rgba8: null argument");
+  if (width <= 0 || height <= 0 || width > 65536 || height > 65536) return fail(MESO_ERR_ARGUMENT, "meso_present_rgba8: bad size");
+  MesoTextureRange full{0u, 0u, (uint32_t)width, (uint32_t)height};
+  const MesoTextureRange rg = range ? *range : full;
+  if (rg.width == 0 || rg.height == 0 || (uint64_t)rg.x + rg.width > (uint64_t)width || (uint64_t)rg.y + rg.height > (uint64_t)height)
+    return fail(MESO_ERR_ARGUMENT, "meso_present_rgba8: range outside the frame");
+  const size_t px = (size_t)width * height;
+  int r = ensure_frame(c, px);
+  if (r != MESO_OK) return r;
+  MesoRaySetup rs;
+  r = meso_ray_setup(cam, c->v.origin, width, height, light, &rs);
+  if (r != MESO_OK) return r;
+  const CubeTables* cubes = nullptr;
+  r = meso_cubes_for(c, flags, &cubes);
+  if (r != MESO_OK) return r;
+  // only the tile rows the range touches are traced (tiles are numbered row-major: a band of rows is one index range)
+  const int tiles_x = (width + MESO_TILE_W - 1) / MESO_TILE_W;
+  const int ty0 = (int)rg.y / MESO_TILE_H, ty1 = ((int)(rg.y + rg.height) + MESO_TILE_H - 1) / MESO_TILE_H;
+  launch_raymarch(c->lc(), c->v, rs, width, height, (flags | MESO_FLAG_RGBA8) & ~0u, 0, 1, MESO_LAYOUT_FRAME, c->d_frame, nullptr, nullptr, nullptr,
+                  ty0 * tiles_x, (ty1 - ty0) * tiles_x, cubes);
+  CK_LAST("present");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(c->d_frame) + (size_t)rg.y * width + rg.x;
+  CK(cudaMemcpy2DAsync(host_pixels, (size_t)rg.width * 4, src, (size_t)width * 4, (size_t)rg.width * 4, rg.height, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return MESO_OK;
 }
 
@@ -699,6 +767,14 @@ int meso_raymarch_stats(MesoCtx* c, const MesoGPUUniformCamera* cam, int width, 
   for (uint8_t x : tb) out->touched_bricks += x;
   // DESIGN.md "algorithmic bytes": chunk any/full bit grids once + 1024 B of block masks per touched chunk + 68 B per touched brick
   out->u_bytes = 2 * (uint64_t)((c->v.nchunks + 7) / 8) + 1024 * out->touched_chunks + 68 * out->touched_bricks;
+  return MESO_OK;
+}
+
+int meso_pack_rgba8_device(MesoCtx* c, const void* d_records, int64_t n, void* d_rgba8) {
+  if (!c || n < 0 || (n > 0 && (!d_records || !d_rgba8))) return fail(MESO_ERR_ARGUMENT, "meso_pack_rgba8_device: bad argument");
+  CK(cudaSetDevice(c->device));
+  launch_pack_rgba8(c->lc(), (const MesoHitRecord*)d_records, (size_t)n, (uint32_t*)d_rgba8);
+  CK_LAST("pack rgba8");
   return MESO_OK;
 }
 
@@ -952,6 +1028,7 @@ int meso_stream_begin(MesoCtx* c, int kind, const double params[4], int granular
   CK(cudaMemsetAsync(v.chunk_full, 0, (size_t)v.chunk_words * 4, c->stream));
   CK(cudaMemsetAsync(v.region_any, 0, (size_t)v.region_words * 4, c->stream));
   CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
+  CK(cudaMemsetAsync(v.pool_free_count, 0, 4, c->stream));
   CK(cudaMemsetAsync(v.df, MESO_DF_K + 1, nc * 64, c->stream));
   CK(cudaMemsetAsync(c->d_loaded, 0, (size_t)v.chunk_words * 4, c->stream));
   CK(cudaMemsetAsync(c->d_stream_stats, 0, 16, c->stream));
@@ -983,6 +1060,60 @@ int meso_stream_update_async(MesoCtx* c, const int32_t cam[3], const float forwa
   launch_voxelize_list(c->lc(), c->v, c->stream_kind, c->stream_params, c->stream_gran, c->d_overflow, c->d_stream_list, c->d_stream_stats, max_new);
   CK_LAST("stream update");
   return MESO_OK;
+}
+
+// The window follows the camera (FChunkPool's eviction in the form a dense window needs, ChunkPool.h:447-622): the new
+// origin puts camera_chunk at the window's centre chunk; chunks that leave are evicted and their payload slots recycled,
+// chunks that stay are moved to their new slot, chunks that enter are marked not generated.
+int meso_stream_recentre(MesoCtx* c, const int32_t camera_chunk[3], int32_t moved[3]) {
+  NEED_SCENE(c);
+  if (!c->streaming) return fail(MESO_ERR_ARGUMENT, "meso_stream_recentre: call meso_stream_begin first");
+  if (!camera_chunk) return fail(MESO_ERR_ARGUMENT, "meso_stream_recentre: camera_chunk is null");
+  DVolume& v = c->v;
+  int delta[3];
+  bool any = false;
+  for (int i = 0; i < 3; i++) { delta[i] = (camera_chunk[i] - v.dims[i] / 2) - v.origin[i]; any |= delta[i] != 0; }
+  if (moved) for (int i = 0; i < 3; i++) moved[i] = delta[i];
+  if (!any) return MESO_OK;
+  if (!c->d_shift_scratch) CK(cudaMalloc(&c->d_shift_scratch, (size_t)v.nchunks * MESO_BLOCKS * 4));
+  c->cubes_valid = false;
+  JOIN_FRAMES(c);
+  launch_window_shift(c->lc(), v, delta, c->d_loaded, c->d_shift_scratch);
+  CK_LAST("stream recentre");
+  return MESO_OK;
+}
+
+int meso_pool_stats(MesoCtx* c, int64_t* slots_handed_out, int64_t* slots_free) {
+  NEED_SCENE(c);
+  uint32_t hw = 0; int fr = 0;
+  int r = meso_small_read(c, &hw, c->v.pool_count, 4);
+  if (r != MESO_OK) return r;
+  r = meso_small_read(c, &fr, c->v.pool_free_count, 4);
+  if (r != MESO_OK) return r;
+  if (slots_handed_out) *slots_handed_out = hw;
+  if (slots_free) *slots_free = fr;
+  return MESO_OK;
+}
+
+int meso_block_importance(MesoCtx* c, const int32_t cam[3], const float forward[3], const int32_t* chunk_locations, const uint8_t* block_locations,
+                          int64_t n, uint32_t chunk_resolution, float* host_out) {
+  if (!c || !cam || !forward || n < 0 || (n > 0 && (!chunk_locations || !block_locations || !host_out))) return fail(MESO_ERR_ARGUMENT, "meso_block_importance: bad argument");
+  if (n == 0) return MESO_OK;
+  CK(cudaSetDevice(c->device));
+  int32_t* d_loc = nullptr; uint8_t* d_blk = nullptr; float* d_out = nullptr;
+  auto body = [&]() -> int {
+    CK(cudaMalloc(&d_loc, (size_t)n * 12)); CK(cudaMalloc(&d_blk, (size_t)n * 3)); CK(cudaMalloc(&d_out, (size_t)n * 4));
+    CK(cudaMemcpyAsync(d_loc, chunk_locations, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_blk, block_locations, (size_t)n * 3, cudaMemcpyHostToDevice, c->stream));
+    launch_block_importance(c->lc(), d_loc, d_blk, n, cam, forward, chunk_resolution, d_out);
+    CK_LAST("block importance");
+    CK(cudaMemcpyAsync(host_out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MESO_OK;
+  };
+  const int r = body();
+  cudaFree(d_loc); cudaFree(d_blk); cudaFree(d_out);
+  return r;
 }
 
 int meso_stream_stats(MesoCtx* c, MesoStreamStats* stats) {

@@ -68,6 +68,8 @@ struct MesoCtx {
   uint32_t* d_stream_list = nullptr;      // generation list of the current update
   uint32_t stream_list_cap = 0;
   uint32_t* d_stream_stats = nullptr;     // 4 words
+  int* d_timeout = nullptr;               // set by a wait that gave up
+  void* d_shift_scratch = nullptr;        // moving window: nchunks * 16 KiB, allocated by the first meso_stream_recentre
   bool streaming = false;
   int stream_kind = 0, stream_gran = 0;
   double stream_params[4] = {0, 0, 0, 0};

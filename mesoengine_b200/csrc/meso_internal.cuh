@@ -40,7 +40,9 @@ struct DVolume {
   int ddims[3];         // cells per axis = dims * 4
   int rdims[3];         // regions per axis = ceil(dims / 4)
   int region_words;
-  uint32_t* pool_count; // device counter: payload slots in use
+  uint32_t* pool_count; // device counter: payload slots handed out so far (high-water mark; slot indices are < this)
+  uint32_t* pool_free;  // max_bricks: stack of payload slots returned by evicted chunks (moving window), reused before the bump allocator
+  int* pool_free_count; // entries on that stack
   uint32_t max_bricks;
   int chunk_words;      // number of u32 words in chunk_any / chunk_full
 };
@@ -100,6 +102,7 @@ void launch_raymarch(const LaunchCtx& lc, const DVolume& v, const MesoRaySetup& 
                      const FrameMap* slabs = nullptr);
 // k_cubes.cu: (re)build the three tables for the current volume
 void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, uint8_t* d_cellp, uint16_t* d_brick, uint16_t* d_cell2);
+void launch_pack_rgba8(const LaunchCtx& lc, const MesoHitRecord* d_records, size_t n, uint32_t* d_out);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
@@ -112,7 +115,15 @@ void launch_carve(const LaunchCtx& lc, const DVolume& v, const int32_t center[3]
 void launch_expand_dirty(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_dirty, uint32_t n_dirty, uint64_t* d_keys,
                          uint32_t cap, uint32_t* d_count, uint32_t* d_mark);
 void launch_flush(const LaunchCtx& lc, uint32_t* d_scratch, size_t n_words);
+struct SignalTargets { unsigned* word[MESO_MAX_SLABS]; int n; };
+void launch_signal(const LaunchCtx& lc, const SignalTargets& t);
+void launch_wait(const LaunchCtx& lc, const unsigned* d_word, unsigned target, int* d_timeout_flag);
 void launch_peek(const LaunchCtx& lc, void* d_dst_mapped, const void* d_src, size_t bytes);   // src 4-byte aligned
+
+// moving window (k_resident.cu): evict what leaves, shift what stays, see meso_stream_recentre
+void launch_window_shift(const LaunchCtx& lc, DVolume& v, const int delta[3], uint32_t* d_loaded, void* d_scratch);
+void launch_block_importance(const LaunchCtx& lc, const int32_t* d_chunk_loc, const uint8_t* d_block_loc, int64_t n, const int32_t cam[3], const float fwd[3],
+                             uint32_t chunk_resolution, float* d_out);
 
 // K6 (k_resident.cu, k_voxelize.cu)
 int64_t resident_max_candidates(const MesoViewConfig& vc);
@@ -129,3 +140,14 @@ __device__ __forceinline__ int64_t chunk_index(const DVolume& v, int cx, int cy,
   return (int64_t)cx + (int64_t)v.dims[0] * ((int64_t)cy + (int64_t)v.dims[1] * (int64_t)cz);
 }
 __device__ __forceinline__ int block_bit(int x, int y, int z) { return x + 16 * y + 256 * z; }
+
+// A payload slot for a brick that just became partial: a slot an evicted chunk gave back if there is one, else the next
+// unused one.  The result may be >= max_bricks (pool exhausted): the caller drops the brick and calls release_bump().
+// Pushes onto the free stack happen in their own kernel (evict_chunks_kernel), never concurrently with this.
+__device__ __forceinline__ uint32_t alloc_payload_slot(const DVolume& v) {
+  const int n = atomicSub(v.pool_free_count, 1);
+  if (n > 0) return v.pool_free[n - 1];
+  atomicAdd(v.pool_free_count, 1);
+  return atomicAdd(v.pool_count, 1u);
+}
+__device__ __forceinline__ void release_bump(const DVolume& v) { atomicSub(v.pool_count, 1u); }

@@ -376,6 +376,7 @@ def probe(b):
     r["chunk_importance_cam"], r["chunk_importance_fwd"], r["chunk_importance_loc"] = cams, fw, cams + offs
     r["chunk_importance"] = np.array([b.chunk_importance(c, f, l) for c, f, l in zip(cams, fw, cams + offs)], dtype=np.float32)
     blocks = rng.integers(0, 16, (1500, 3)).astype(np.uint8)
+    r["block_importance_chunk"], r["block_importance_block"] = (cams + offs // 8).astype(np.int32), blocks    # inputs, for the GPU test
     r["block_importance"] = np.array([b.block_importance(c, f, c + o, bl) for c, f, o, bl in zip(cams, fw, offs // 8, blocks)], dtype=np.float32)
 
     for i, v in enumerate(VIEWS):

@@ -566,3 +566,21 @@ def test_pool_overflow_leaves_a_consistent_volume(ctx, capi, orc):
     assert ctx.raymarch(cam, 96, 60, shadow=True).tobytes() == ref.tobytes()
     q = ctx.mesh(1 << 20)
     assert orc.sort_quads(q).tobytes() == orc.sort_quads(vol.mesh()).tobytes()
+
+
+def test_present_rgba8_texture_ranges(ctx, capi, orc):
+    """meso_present_rgba8: the colour words of the records, tightly packed for a TextureRangeDesc-style range (whole frame, a
+    ragged interior rectangle, a single pixel, the last row); ranges outside the frame are rejected."""
+    origin, dims, params = scenes.sphere_scene(256)
+    ctx.scene_create(origin, dims, 1 << 16)
+    ctx.voxelize_sdf(capi.SDF_SPHERE, params, capi.GRAN_VOXEL)
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    w, h = 331, 187
+    cam = orc.camera_uniform(eyes[4], ctr, width=w, height=h)
+    rec = ctx.raymarch(cam, w, h, shadow=True)
+    assert np.array_equal(ctx.present_rgba8(cam, w, h), rec["rgba"])
+    for (x, y, rw, rh) in ((37, 21, 200, 100), (150, 90, 1, 1), (0, h - 1, w, 1), (w - 5, 0, 5, h)):
+        got = ctx.present_rgba8(cam, w, h, rect=(x, y, rw, rh))
+        assert got.shape == (rh, rw) and np.array_equal(got, rec["rgba"][y:y + rh, x:x + rw])
+    with pytest.raises(capi.MesoError):
+        ctx.present_rgba8(cam, w, h, rect=(w - 4, 0, 5, 5))

@@ -3,6 +3,8 @@ oracle/orc_resident.c and the oracle voxeliser."""
 import numpy as np
 import pytest
 
+import scenes
+
 pytestmark = pytest.mark.gpu
 
 
@@ -189,3 +191,76 @@ def test_stream_errors(ctx, capi):
         ctx.select_view_chunks((0, 0, 1), capi.view_config(0, 0, 120.0, 0))
     with pytest.raises(capi.MesoError):
         ctx.select_view_chunks((0, 0, 1), capi.view_config(4, 2, 120.0, 7))
+
+
+def test_block_importance(ctx, orc):
+    """CalculateBlockImportance on the device == the oracle's literal restatement (dead near branch included)."""
+    rng = np.random.default_rng(5)
+    cam = (3, -2, 5)
+    chunks = (rng.integers(-6, 7, size=(3000, 3)) + np.array(cam)).astype(np.int32)
+    chunks[:300] = np.array(cam) + rng.integers(-1, 2, size=(300, 3))       # where a live near branch would have fired
+    blocks = rng.integers(0, 16, size=(3000, 3)).astype(np.uint8)
+    fwd = (0.3, -0.8, 0.52)
+    got = ctx.block_importance(cam, fwd, chunks, blocks)
+    want = np.array([orc.block_importance(cam, fwd, c, b) for c, b in zip(chunks, blocks)], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert not (got == 1.0e6).any()                                          # the reference's near branch is dead code
+
+
+@pytest.mark.parametrize("gran", ["block", "voxel"])
+def test_moving_window_follows_the_camera(ctx, capi, orc, gran):
+    """meso_stream_recentre: the window follows the camera over three window widths (and back diagonally).  After every
+    move + update the resident volume equals a fresh voxelisation of the window where it now is -- chunks that stayed were
+    moved, not regenerated (the generated count says so), chunks that left were evicted and their payload slots reused
+    (the pool's high-water mark stays bounded), chunks that entered were generated by the next update."""
+    g = capi.GRAN_BLOCK if gran == "block" else capi.GRAN_VOXEL
+    og = orc.GRAN_BLOCK if gran == "block" else orc.GRAN_VOXEL
+    dims = (5, 3, 3)
+    cam = [2, 0, 1]
+    ctx.scene_create((0, -1, 0), dims, 1 << 18)
+    ctx.stream_begin(capi.SDF_TERRAIN, None, g)
+    view = capi.view_config(8, 8, 120.0, 1)           # radius covers the whole window: everything in it is desired
+    nchunks = int(np.prod(dims))
+
+    def fill():
+        total = 0
+        for _ in range(8):
+            st = ctx.stream_update(cam, (0.0, 0.0, 1.0), 64, view)
+            total += int(st["generated"])
+            if st["missing"] == 0:
+                break
+        return total
+
+    def check():
+        origin = tuple(c - d // 2 for c, d in zip(cam, dims))
+        assert tuple(ctx.origin) == origin
+        vol = orc.Volume(origin, dims).voxelize(orc.SDF_TERRAIN, None, granularity=og, sin_mode=orc.SIN_PORTABLE)
+        occ, full, keys, payload = ctx.volume_download()
+        assert np.array_equal(occ, vol.occ()) and np.array_equal(full, vol.full())
+        k2, p2 = vol.export_partial()
+        assert np.array_equal(keys, k2) and np.array_equal(payload, p2)
+        return vol, origin
+
+    ctx.stream_recentre(cam)                          # the window is already centred on the camera: nothing moves
+    assert fill() <= nchunks
+    vol, origin = check()
+    partial_max = len(vol.export_partial()[0])
+    moves = [(1, 0, 0)] * 15 + [(-2, 1, 1), (-3, -1, -1), (0, 0, 2), (-5, 0, 0)]     # 15 = three window widths along x
+    for mv in moves:
+        cam = [c + m for c, m in zip(cam, mv)]
+        assert ctx.stream_recentre(cam) == mv
+        entered = nchunks - int(np.prod([max(0, d - abs(m)) for d, m in zip(dims, mv)]))
+        assert fill() == entered                      # only what entered was generated; what stayed was moved
+        vol, origin = check()
+        partial_max = max(partial_max, len(vol.export_partial()[0]))
+    handed_out, free = ctx.pool_stats()
+    if gran == "voxel":
+        assert partial_max > 0 and handed_out <= 2 * partial_max, (handed_out, free, partial_max)   # slots of evicted chunks were reused
+    # the frame through the moved window == the oracle's frame of the same region
+    w, h = 128, 72
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    camu = orc.camera_uniform(eyes[1], ctr, width=w, height=h)
+    ref = vol.raymarch(orc.ray_setup(camu, origin, w, h), w, h, shadow=True)
+    assert ctx.raymarch(camu, w, h, shadow=True).tobytes() == ref.tobytes()
+    q = ctx.mesh(1 << 22)
+    assert np.array_equal(orc.sort_quads(q.copy()), orc.sort_quads(vol.mesh()))

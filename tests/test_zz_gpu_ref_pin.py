@@ -87,3 +87,13 @@ def test_chunk_importance_on_gpu_equals_reference(ctx):
     for g in range(0, len(want), 50):
         got = ctx.chunk_importance(cam[g], fwd[g], loc[g:g + 50])
         assert np.array_equal(got.view(np.uint32), want[g:g + 50].view(np.uint32)), g
+
+
+def test_block_importance_on_gpu_equals_reference(ctx):
+    """FImportanceComputeInfo::CalculateBlockImportance as the reference build ran it (tests/golden/ref_build.npz) against
+    the device kernel, bit for bit -- including the dead near branch the reference's unsigned comparison produces."""
+    cam, fwd = GOLD["chunk_importance_cam"], GOLD["chunk_importance_fwd"]
+    chunk, block, want = GOLD["block_importance_chunk"], GOLD["block_importance_block"], GOLD["block_importance"]
+    for g in range(0, len(want), 50):      # 30 cameras x 50 blocks
+        got = ctx.block_importance(cam[g], fwd[g], chunk[g:g + 50], block[g:g + 50])
+        assert np.array_equal(got.view(np.uint32), want[g:g + 50].view(np.uint32))
