@@ -82,6 +82,19 @@ typedef struct {
   uint64_t level_steps[5];
 } MesoRayStats;
 
+/* Runtimes/Shader/GPUStructures.h:86-92: the instance record of the reference's chunk-wireframe debug pass (48 B) */
+typedef struct { float Position[3]; int32_t ChunkLocation[3]; float Scale; float Rotation[4]; float Marker; } MesoGPUSimpleInstanceData;
+/* The counters of FChunkManage::RenderManagerInfo (Runtimes/Voxel/Chunk/ChunkManager.h:466-489) */
+typedef struct {
+  uint32_t VisibleChunk;          /* DebugVisibleChunkNum: size of the desired set of the last update                       */
+  uint32_t LoadedChunk;           /* ChunkPool.CurrentDebugDrawInstanceCount: resident chunks (with blocks or empty)        */
+  uint32_t LoadedChunkWithBlocks; /* of which FChunk (the rest are FEmptyChunk)                                             */
+  uint32_t NewlyAddedVisibleChunk;/* DebugNewVisibleChunkNum: chunks generated by the last update                           */
+  uint32_t MissingChunk;          /* desired chunks inside the window still not generated                                   */
+  uint32_t PayloadSlotsHandedOut, PayloadSlotsFree;   /* brick payload pool (no reference counterpart)                      */
+  int64_t LoadedBlock;            /* ChunkPool.CurrentBlockCount: instances emitted by the last meso_build_occupancy        */
+} MesoDebugStats;
+
 /* K6.  FChunkManageHelper::FTempChunkDataType = std::pair<float, ivec3> (ChunkManagerHelper.h:76): 16 B. */
 typedef struct { float Importance; int32_t Offset[3]; } MesoChunkCandidate;
 /* The view fields of FVoxelSceneConfig (VoxelSceneConfig.h:34-35,40; defaults 24, 6, 120).  Mode 0 =
@@ -145,6 +158,13 @@ MESO_API int meso_scene_create(MesoCtx* ctx, const MesoGPUUniformSceneConfig* cf
  * the grid.  params = sphere centre xyz + radius in world units (reference: 100,0,0,50); ignored for terrain.
  * Terrain uses the portable fp64 sin; host-generated volumes go through meso_volume_upload. */
 MESO_API int meso_voxelize_sdf(MesoCtx* ctx, int kind, const double params[4], int granularity);
+
+/* The generator plug-in's fourth argument (GeneratorType = FChunk(ivec3, float, unsigned char, uint32_t MipmapLevel),
+ * ChunkManager.h:61; passed down at :167,233,291 and ignored by both reference generators): level of detail of the
+ * generation.  Block granularity, one SDF sample per (2^MipmapLevel)^3 blocks taken at the group's minimum-corner block
+ * (MipmapLevel 0 = meso_voxelize_sdf(..., MESO_GRAN_BLOCK); 4 = one sample per chunk).  The definition is this library's
+ * ("parity unpinned by reference; bit-exact vs repo oracle"). */
+MESO_API int meso_voxelize_sdf_lod(MesoCtx* ctx, int kind, const double params[4], uint32_t mipmap_level);
 
 /* ---- volume upload / download ---------------------------------------------------------------------------
  * Replaces FChunkPool::UploadChunk/UploadBlock (ChunkPool.h:662-679: whole-buffer lvk::IContext::upload, LVK.h:822)
@@ -319,6 +339,14 @@ MESO_API int meso_block_importance(MesoCtx* ctx, const int32_t camera_chunk[3], 
                                    const uint8_t* block_locations, int64_t n, uint32_t chunk_resolution, float* host_out);
 /* Bit per chunk slot of the window: generated (EChunkState != absent in ChunksLookupTable).  words = ceil(nchunks / 32). */
 MESO_API int meso_stream_loaded(MesoCtx* ctx, uint32_t* host_words, int64_t n_words);
+
+/* ---- debug visualisation parity ------------------------------------------------------------------
+ * The data behind the reference's operator feedback: one FGPUSimpleInstanceData per resident chunk (what
+ * FChunkManage::DrawDebugVisibleChunk draws an octahedron for, Runtimes/Voxel/Chunk/ChunkManager.h:402-428, records built at
+ * ChunkPool.h:550-561, coloured by Marker in ShaderWireFrame.h:18-22) in FIVec3Comparator order of ChunkLocation, and the
+ * counters of RenderManagerInfo (ChunkManager.h:466-489).  Drawing them stays with the engine. */
+MESO_API int meso_debug_chunk_instances(MesoCtx* ctx, MesoGPUSimpleInstanceData* host_out, int64_t cap, int64_t* count);
+MESO_API int meso_debug_stats(MesoCtx* ctx, MesoDebugStats* out);
 
 /* ---- peer memory (one process per GPU) -------------------------------------------------------------------------
  * Fused gather: every rank's raymarch kernel stores its tile records straight into the frame buffer of the gathering

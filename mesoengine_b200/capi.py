@@ -15,6 +15,9 @@ SO_PATH = os.environ.get("MESO_SO") or os.path.join(_HERE, "libmeso_b200.so")
 
 GPUBlock = np.dtype([("ChunkIndex", "<u4"), ("BlockLocation", "u1", (4,)), ("BlockFrameStamp", "<u4")])
 GPUChunk = np.dtype([("ChunkLocation", "<i4", (3,)), ("ChunkFrameStamp", "<u4")])
+SimpleInstanceData = np.dtype([("Position", "<f4", (3,)), ("ChunkLocation", "<i4", (3,)), ("Scale", "<f4"), ("Rotation", "<f4", (4,)), ("Marker", "<f4")])
+DebugStats = np.dtype([("VisibleChunk", "<u4"), ("LoadedChunk", "<u4"), ("LoadedChunkWithBlocks", "<u4"), ("NewlyAddedVisibleChunk", "<u4"),
+                       ("MissingChunk", "<u4"), ("PayloadSlotsHandedOut", "<u4"), ("PayloadSlotsFree", "<u4"), ("_pad", "<u4"), ("LoadedBlock", "<i8")])
 HitRecord = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("t", "<f4"), ("rgba", "<u4")])
 Quad = np.dtype([("w0", "<u4"), ("w1", "<u4"), ("w2", "<u4"), ("w3", "<u4")])
 Camera = np.dtype([("Projection", "<f4", (16,)), ("View", "<f4", (16,)), ("CameraChunkLocation", "<i4", (4,)),
@@ -52,7 +55,7 @@ SYMBOLS = [
     "meso_stream_update_async", "meso_stream_stats", "meso_stream_loaded",
     "meso_host_register", "meso_host_unregister", "meso_mesh_device_shared", "meso_device_memset",
     "meso_device_copy", "meso_build_cubes", "meso_download_cubes", "meso_volume_upload_blocks", "meso_raymarch_device_slabs", "meso_mesh_count_device", "meso_stream_recentre", "meso_pool_stats", "meso_block_importance",
-    "meso_signal_device", "meso_present_rgba8", "meso_pack_rgba8_device", "meso_wait_device", "meso_wait_timed_out",
+    "meso_signal_device", "meso_present_rgba8", "meso_pack_rgba8_device", "meso_debug_chunk_instances", "meso_debug_stats", "meso_voxelize_sdf_lod", "meso_wait_device", "meso_wait_timed_out",
     "meso_group_create", "meso_group_destroy", "meso_group_size", "meso_group_ctx", "meso_group_sync", "meso_group_scene_create",
     "meso_group_voxelize_sdf", "meso_group_volume_upload_blocks", "meso_group_carve_sphere", "meso_group_raymarch",
     "meso_group_raymarch_async", "meso_group_frame_wait", "meso_group_mesh", "meso_group_mesh_device", "meso_group_remesh_dirty",
@@ -190,6 +193,10 @@ class Context:
             p[: len(params)] = np.asarray(params, dtype=np.float64)
         _ck(lib.meso_voxelize_sdf(self.h, C.c_int(kind), _p(p), C.c_int(granularity)))
 
+    def voxelize_sdf_lod(self, kind, params, mipmap_level):
+        p = np.ascontiguousarray(params if params is not None else [0, 0, 0, 0], dtype=np.float64)
+        _ck(lib.meso_voxelize_sdf_lod(self.h, C.c_int(kind), _p(p), C.c_uint32(mipmap_level)))
+
     def volume_upload(self, occ, full, keys, payload):
         occ = np.ascontiguousarray(occ, dtype=np.uint64)
         full = np.ascontiguousarray(full, dtype=np.uint64)
@@ -280,6 +287,17 @@ class Context:
         l = np.ascontiguousarray(light, dtype=np.float32)
         _ck(lib.meso_raymarch_device(self.h, _p(cam), C.c_int(width), C.c_int(height),
                                      C.c_uint32((FLAG_SHADOW if shadow else 0) | flags_extra), _p(l), C.c_void_p(d_records), C.c_int(layout)))
+
+    def debug_chunk_instances(self):
+        out = np.zeros(max(self.nchunks, 1), dtype=SimpleInstanceData)
+        n = C.c_int64(0)
+        _ck(lib.meso_debug_chunk_instances(self.h, _p(out), C.c_int64(len(out)), C.byref(n)))
+        return out[: n.value]
+
+    def debug_stats(self):
+        st = np.zeros(1, dtype=DebugStats)
+        _ck(lib.meso_debug_stats(self.h, _p(st)))
+        return st[0]
 
     def pack_rgba8_device(self, d_records, n, d_rgba8):
         _ck(lib.meso_pack_rgba8_device(self.h, C.c_void_p(int(d_records)), C.c_int64(n), C.c_void_p(int(d_rgba8))))

@@ -232,6 +232,40 @@ void launch_block_importance(const LaunchCtx& lc, const int32_t* d_chunk_loc, co
   (*lc.launches)++;
 }
 
+// ---- debug visualisation data (ChunkPool.h:550-561, ShaderWireFrame.h:18-22) ------------------------------------------------
+// One FGPUSimpleInstanceData per resident chunk -- what the reference's chunk-wireframe pass draws an octahedron for:
+// Position = (ChunkSize,)*3, ChunkLocation, Scale = ChunkSize * 0.1, Rotation = identity quaternion, Marker = 1 for a chunk
+// with blocks (FChunk) and 0 for an empty one (FEmptyChunk).  loaded == null: every chunk of the window is resident.
+__global__ void __launch_bounds__(256) debug_instances_kernel(DVolume v, const uint32_t* __restrict__ loaded, float chunk_size,
+                                                              MesoGPUSimpleInstanceData* __restrict__ out, int64_t cap, uint32_t* count) {
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  bool ok = c < v.nchunks && (!loaded || ((loaded[c >> 5] >> (c & 31)) & 1u));
+  const unsigned m = __ballot_sync(0xffffffffu, ok);
+  if (m == 0u) return;
+  const int lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (!ok) return;
+  const int64_t idx = (int64_t)base + __popc(m & ((1u << lane) - 1u));
+  if (idx >= cap) return;
+  MesoGPUSimpleInstanceData r;
+  r.Position[0] = r.Position[1] = r.Position[2] = chunk_size;
+  r.ChunkLocation[0] = v.origin[0] + (int)(c % v.dims[0]);
+  r.ChunkLocation[1] = v.origin[1] + (int)((c / v.dims[0]) % v.dims[1]);
+  r.ChunkLocation[2] = v.origin[2] + (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
+  r.Scale = chunk_size * 0.1f;
+  r.Rotation[0] = 1.0f; r.Rotation[1] = r.Rotation[2] = r.Rotation[3] = 0.0f;
+  r.Marker = ((v.chunk_any[c >> 5] >> (c & 31)) & 1u) ? 1.0f : 0.0f;
+  out[idx] = r;
+}
+void launch_debug_instances(const LaunchCtx& lc, const DVolume& v, const uint32_t* d_loaded, float chunk_size, MesoGPUSimpleInstanceData* d_out,
+                            int64_t cap, uint32_t* d_count) {
+  cudaMemsetAsync(d_count, 0, sizeof(uint32_t), lc.stream);
+  debug_instances_kernel<<<(unsigned)((v.nchunks + 255) / 256), 256, 0, lc.stream>>>(v, d_loaded, chunk_size, d_out, cap, d_count);
+  (*lc.launches)++;
+}
+
 // ---- moving window (FChunkPool's eviction, ChunkPool.h:447-622, in the form a dense window needs) --------------------------
 // The window follows the camera: origin' = origin + delta.  Chunks that leave it are evicted -- their payload slots go on
 // the free stack and are handed out again before any new slot (alloc_payload_slot) -- chunks that stay keep their data at

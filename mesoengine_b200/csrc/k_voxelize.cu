@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(256) voxelize_voxel_kernel(DVolume v, SdfParam
 }
 
 // Block-granular (reference semantics, GeneratorHelper.h:120-150): one sample at the block min corner; brick all-ones.
+// mip > 0 (the generator plug-in's MipmapLevel, ChunkManager.h:61): one sample per (2^mip)^3 blocks, at the group's minimum corner.
 template <int KIND>
 __global__ void __launch_bounds__(64) voxelize_block_kernel(DVolume v, SdfParams sp, const uint32_t* __restrict__ list,
-                                                            const uint32_t* __restrict__ list_n) {
+                                                            const uint32_t* __restrict__ list_n, int mip) {
   int64_t c = blockIdx.x >> 6;
   if (list) {
     if (c >= (int64_t)*list_n) return;
@@ -298,7 +299,8 @@ __global__ void __launch_bounds__(64) voxelize_block_kernel(DVolume v, SdfParams
   const int64_t word_global = c * 64 + W;
   const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
   const int bi = W * 64 + threadIdx.x;
-  const int X = bi & 15, Y = (bi >> 4) & 15, Z = bi >> 8;
+  const int gm = ~((1 << mip) - 1);
+  const int X = (bi & 15) & gm, Y = ((bi >> 4) & 15) & gm, Z = (bi >> 8) & gm;
   const double px = (double)(v.origin[0] + cx) * 1.0 * 16.0 + (double)X * 1.0;
   const double py = (double)(v.origin[1] + cy) * 1.0 * 16.0 + (double)Y * 1.0;
   const double pz = (double)(v.origin[2] + cz) * 1.0 * 16.0 + (double)Z * 1.0;
@@ -483,7 +485,7 @@ static void launch_voxelize_words(const LaunchCtx& lc, const DVolume& v, int kin
   (*lc.launches)++;
 }
 
-void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* g_overflow) {
+void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* g_overflow, int mip) {
   SdfParams sp;
   for (int i = 0; i < 4; i++) sp.p[i] = params ? params[i] : 0.0;
   cudaMemsetAsync(v.bptr, 0xFF, sizeof(uint32_t) * MESO_BLOCKS * (size_t)v.nchunks, lc.stream);
@@ -493,8 +495,8 @@ void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const doub
   if (granularity == MESO_GRAN_VOXEL) {
     launch_voxelize_words(lc, v, kind, sp, g_overflow, nullptr, nullptr, v.nchunks);
   } else {
-    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp, nullptr, nullptr);
-    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp, nullptr, nullptr);
+    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp, nullptr, nullptr, mip);
+    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp, nullptr, nullptr, mip);
   }
   (*lc.launches)++;
   launch_volume_finalize(lc, v);
@@ -511,8 +513,8 @@ void launch_voxelize_list(const LaunchCtx& lc, const DVolume& v, int kind, const
   if (granularity == MESO_GRAN_VOXEL) {
     launch_voxelize_words(lc, v, kind, sp, g_overflow, d_list, d_n, (int64_t)max_n);
   } else {
-    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp, d_list, d_n);
-    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp, d_list, d_n);
+    if (kind == MESO_SDF_SPHERE) voxelize_block_kernel<MESO_SDF_SPHERE><<<grid, 64, 0, lc.stream>>>(v, sp, d_list, d_n, 0);
+    else voxelize_block_kernel<MESO_SDF_TERRAIN><<<grid, 64, 0, lc.stream>>>(v, sp, d_list, d_n, 0);
   }
   finalize_list_kernel<<<(max_n + 7) / 8, 256, 0, lc.stream>>>(v, d_list, d_n);
   (*lc.launches) += 2;

@@ -243,7 +243,9 @@ int meso_overflow_finish(MesoCtx* c, const char* what) {
   return MESO_OK;
 }
 
-int meso_voxelize_enqueue(MesoCtx* c, int kind, const double params[4], int granularity) {
+static int voxelize_enqueue_lod(MesoCtx* c, int kind, const double params[4], int granularity, int mip);
+int meso_voxelize_enqueue(MesoCtx* c, int kind, const double params[4], int granularity) { return voxelize_enqueue_lod(c, kind, params, granularity, 0); }
+static int voxelize_enqueue_lod(MesoCtx* c, int kind, const double params[4], int granularity, int mip) {
   NEED_SCENE(c);
   if (kind != MESO_SDF_SPHERE && kind != MESO_SDF_TERRAIN) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown sdf kind");
   if (granularity != MESO_GRAN_BLOCK && granularity != MESO_GRAN_VOXEL) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf: unknown granularity");
@@ -251,7 +253,7 @@ int meso_voxelize_enqueue(MesoCtx* c, int kind, const double params[4], int gran
   c->streaming = false;  // the whole grid is regenerated: a stream in progress ends (meso_stream_begin starts a new one)
   c->cubes_valid = false;
   JOIN_FRAMES(c);
-  launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow);
+  launch_voxelize(c->lc(), c->v, kind, params, granularity, c->d_overflow, mip);
   CK_LAST("voxelize");
   return build_cubes(c);   // derived data of a whole-grid generation, like the distance field (enqueue only)
 }
@@ -262,6 +264,13 @@ int meso_voxelize_sdf(MesoCtx* c, int kind, const double params[4], int granular
   const int ro = meso_overflow_finish(c, "meso_voxelize_sdf");
   if (ro != MESO_OK) c->cubes_valid = false;   // bricks were dropped: whatever the tables say is about another volume
   return ro;
+}
+
+int meso_voxelize_sdf_lod(MesoCtx* c, int kind, const double params[4], uint32_t mipmap_level) {
+  if (mipmap_level > 4) return fail(MESO_ERR_ARGUMENT, "meso_voxelize_sdf_lod: MipmapLevel out of range [0,4] (16 blocks per chunk axis)");
+  const int r = voxelize_enqueue_lod(c, kind, params, MESO_GRAN_BLOCK, (int)mipmap_level);
+  if (r != MESO_OK) return r;
+  return meso_overflow_finish(c, "meso_voxelize_sdf_lod");
 }
 
 int meso_volume_upload(MesoCtx* c, const uint64_t* occ, const uint64_t* full, const uint64_t* keys, const uint64_t* payload, int64_t n) {
@@ -1114,6 +1123,70 @@ int meso_block_importance(MesoCtx* c, const int32_t cam[3], const float forward[
   const int r = body();
   cudaFree(d_loc); cudaFree(d_blk); cudaFree(d_out);
   return r;
+}
+
+int meso_debug_chunk_instances(MesoCtx* c, MesoGPUSimpleInstanceData* host_out, int64_t cap, int64_t* count) {
+  NEED_SCENE(c);
+  if (!count || cap < 0 || (cap > 0 && !host_out)) return fail(MESO_ERR_ARGUMENT, "meso_debug_chunk_instances: bad argument");
+  MesoGPUSimpleInstanceData* d_out = nullptr;
+  const int64_t n_alloc = std::max<int64_t>(std::min<int64_t>(cap, c->v.nchunks), 1);
+  auto body = [&]() -> int {
+    CK(cudaMalloc(&d_out, (size_t)n_alloc * sizeof(MesoGPUSimpleInstanceData)));
+    launch_debug_instances(c->lc(), c->v, c->streaming ? c->d_loaded : nullptr, c->cfg.ChunkSize, d_out, std::min<int64_t>(cap, c->v.nchunks), c->d_tmp_count);
+    CK_LAST("debug instances");
+    uint32_t n = 0;
+    int r = meso_small_read(c, &n, c->d_tmp_count, 4);
+    if (r != MESO_OK) return r;
+    *count = n;
+    const int64_t m = std::min<int64_t>(n, std::min<int64_t>(cap, c->v.nchunks));
+    if (m > 0) {
+      CK(cudaMemcpyAsync(host_out, d_out, (size_t)m * sizeof(MesoGPUSimpleInstanceData), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      // canonical order: FIVec3Comparator (Helper/Comparator.h:15-23), x then y then z
+      std::sort(host_out, host_out + m, [](const MesoGPUSimpleInstanceData& a, const MesoGPUSimpleInstanceData& b) {
+        if (a.ChunkLocation[0] != b.ChunkLocation[0]) return a.ChunkLocation[0] < b.ChunkLocation[0];
+        if (a.ChunkLocation[1] != b.ChunkLocation[1]) return a.ChunkLocation[1] < b.ChunkLocation[1];
+        return a.ChunkLocation[2] < b.ChunkLocation[2];
+      });
+    }
+    return MESO_OK;
+  };
+  const int r = body();
+  cudaFree(d_out);
+  return r;
+}
+
+int meso_debug_stats(MesoCtx* c, MesoDebugStats* out) {
+  NEED_SCENE(c);
+  if (!out) return fail(MESO_ERR_ARGUMENT, "meso_debug_stats: null argument");
+  memset(out, 0, sizeof(*out));
+  const DVolume& v = c->v;
+  std::vector<uint32_t> any((size_t)v.chunk_words), loaded((size_t)v.chunk_words, 0xFFFFFFFFu);
+  int r = meso_small_read(c, any.data(), v.chunk_any, (size_t)v.chunk_words * 4);
+  if (r != MESO_OK) return r;
+  if (c->streaming) {
+    r = meso_small_read(c, loaded.data(), c->d_loaded, (size_t)v.chunk_words * 4);
+    if (r != MESO_OK) return r;
+    uint32_t h[4];
+    r = meso_small_read(c, h, c->d_stream_stats, 16);
+    if (r != MESO_OK) return r;
+    out->NewlyAddedVisibleChunk = h[0]; out->MissingChunk = h[1]; out->VisibleChunk = h[2];
+  } else {
+    out->VisibleChunk = (uint32_t)v.nchunks;
+  }
+  for (int64_t i = 0; i < v.nchunks; i++) {
+    const uint32_t l = (loaded[(size_t)(i >> 5)] >> (i & 31)) & 1u;
+    out->LoadedChunk += l;
+    out->LoadedChunkWithBlocks += l & ((any[(size_t)(i >> 5)] >> (i & 31)) & 1u);
+  }
+  uint32_t hw = 0; int fr = 0;
+  r = meso_small_read(c, &hw, v.pool_count, 4);
+  if (r != MESO_OK) return r;
+  r = meso_small_read(c, &fr, v.pool_free_count, 4);
+  if (r != MESO_OK) return r;
+  out->PayloadSlotsHandedOut = hw; out->PayloadSlotsFree = (uint32_t)std::max(fr, 0);
+  out->LoadedBlock = c->n_inst;
+  return MESO_OK;
 }
 
 int meso_stream_stats(MesoCtx* c, MesoStreamStats* stats) {

@@ -81,7 +81,7 @@ struct LaunchCtx {
   int64_t* launches;
 };
 
-void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* d_overflow);
+void launch_voxelize(const LaunchCtx& lc, const DVolume& v, int kind, const double params[4], int granularity, int* d_overflow, int mip = 0);
 void launch_volume_finalize(const LaunchCtx& lc, const DVolume& v, bool rebuild_df = true);  // derived data: of, cells, chunk/region bits, df
 void launch_df_build(const LaunchCtx& lc, const DVolume& v);
 void launch_coarse_masks(const LaunchCtx& lc, const DVolume& v);
@@ -120,6 +120,8 @@ void launch_signal(const LaunchCtx& lc, const SignalTargets& t);
 void launch_wait(const LaunchCtx& lc, const unsigned* d_word, unsigned target, int* d_timeout_flag);
 void launch_peek(const LaunchCtx& lc, void* d_dst_mapped, const void* d_src, size_t bytes);   // src 4-byte aligned
 
+void launch_debug_instances(const LaunchCtx& lc, const DVolume& v, const uint32_t* d_loaded, float chunk_size, MesoGPUSimpleInstanceData* d_out,
+                            int64_t cap, uint32_t* d_count);
 // moving window (k_resident.cu): evict what leaves, shift what stays, see meso_stream_recentre
 void launch_window_shift(const LaunchCtx& lc, DVolume& v, const int delta[3], uint32_t* d_loaded, void* d_scratch);
 void launch_block_importance(const LaunchCtx& lc, const int32_t* d_chunk_loc, const uint8_t* d_block_loc, int64_t n, const int32_t cam[3], const float fwd[3],

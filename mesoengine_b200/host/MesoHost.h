@@ -257,6 +257,7 @@ struct FGeneratorDesc {
   int Kind = MESO_SDF_SPHERE;                       // FGeneratorHelper::GenerateSphere / TestGenerator
   double Params[4] = {100.0, 0.0, 0.0, 50.0};       // GeneratorHelper.h:134
   int Granularity = MESO_GRAN_BLOCK;                // reference: one sample per block
+  uint32_t MipmapLevel = 0;                         // the plug-in's fourth argument (ChunkManager.h:61): (2^level)^3 blocks per sample
 };
 
 // FImportanceComputeInfo / FChunkManageHelper (ChunkManagerHelper.h:22-198) over the C ABI (K6 runs on the device).
@@ -369,6 +370,8 @@ class FChunkManage {
       return;
     }
     if (Group) Check(meso_group_voxelize_sdf(Group, Generator.Kind, Generator.Params, Generator.Granularity), "meso_group_voxelize_sdf");
+    else if (Generator.MipmapLevel > 0 && Generator.Granularity == MESO_GRAN_BLOCK)
+      Check(meso_voxelize_sdf_lod(Ctx, Generator.Kind, Generator.Params, Generator.MipmapLevel), "meso_voxelize_sdf_lod");
     else Check(meso_voxelize_sdf(Ctx, Generator.Kind, Generator.Params, Generator.Granularity), "meso_voxelize_sdf");
     Check(meso_build_occupancy(Ctx, FrameStamp, &ChunkPool.CurrentBlockCount), "meso_build_occupancy");
     bDirty = false;
@@ -388,7 +391,7 @@ class FChunkManage {
         for (int64_t i = t; i < n; i += nt) {
           const ivec3 loc{WindowOrigin.x + (int32_t)(i % WindowDims.x), WindowOrigin.y + (int32_t)((i / WindowDims.x) % WindowDims.y),
                           WindowOrigin.z + (int32_t)(i / ((int64_t)WindowDims.x * WindowDims.y))};
-          FChunk c = HostGenerator(loc, VoxelSceneConfig.BlockSize, VoxelSceneConfig.ChunkResolution, 0u);
+          FChunk c = HostGenerator(loc, VoxelSceneConfig.BlockSize, VoxelSceneConfig.ChunkResolution, Generator.MipmapLevel);
           c.ChunkLocation = loc;   // "just make sure" (ChunkManager.h:167)
           FGPUChunk rec;
           if (c.Blocks.empty()) { rec.ChunkLocation[0] = rec.ChunkLocation[1] = rec.ChunkLocation[2] = INT_MAX; rec.ChunkFrameStamp = 0; }

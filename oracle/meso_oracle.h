@@ -114,6 +114,8 @@ OrcVolume* orc_volume_create(const int32_t origin_chunk[3], const int32_t dims_c
 void orc_volume_destroy(OrcVolume*);
 void orc_volume_voxelize(OrcVolume*, int kind, const double params[4], int granularity, int sin_mode, int nthreads);
 /* fast = 1: exact hierarchical classification for the sphere (see orc_volume.c); identical output, used at 4096^3. */
+/* block granularity with the generator's MipmapLevel argument: one sample per (2^mip)^3 blocks (mip 0..4) */
+void orc_volume_voxelize_lod(OrcVolume*, int kind, const double params[4], int sin_mode, int nthreads, int mip);
 void orc_volume_voxelize_ex(OrcVolume*, int kind, const double params[4], int granularity, int sin_mode, int nthreads, int fast);
 int64_t orc_volume_num_chunks(const OrcVolume*);
 const uint64_t* orc_volume_occ(const OrcVolume*);   /* nchunks*64 words */

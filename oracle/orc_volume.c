@@ -88,7 +88,7 @@ static void set_brick(OrcVolume* v, int64_t c, int b, const uint64_t s[8]) {
   pthread_mutex_unlock(&v->lock);
 }
 
-typedef struct { OrcVolume* v; int kind; const double* params; int gran; int sin_mode; int fast; } VoxArg;
+typedef struct { OrcVolume* v; int kind; const double* params; int gran; int sin_mode; int fast; int mip; } VoxArg;
 
 /* Sphere fast path (ORC_FAST=1 in orc_volume_voxelize_ex).  The fp64 sphere SDF sqrt((dx*dx + dy*dy) + dz*dz) - r is
  * monotone non-decreasing in each of |dx|, |dy|, |dz| separately (every rounding step is monotone), so over an
@@ -128,7 +128,18 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
       uint8_t xyz[3 * ORC_BLOCKS];
       int n = orc_generate_chunk(a->kind, a->params, a->sin_mode, loc, 1.0f, ORC_CR, xyz);
       uint64_t ones[8]; for (int z = 0; z < 8; z++) ones[z] = ~0ull;
-      for (int i = 0; i < n; i++) set_brick(v, c, orc_bidx(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), ones);
+      if (a->mip <= 0) {
+        for (int i = 0; i < n; i++) set_brick(v, c, orc_bidx(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]), ones);
+      } else {
+        /* MipmapLevel m (the generator plug-in's fourth argument, ChunkManager.h:61; the reference's generators ignore it --
+         * this definition is ours): one sample per (2^m)^3 blocks, taken at the group's minimum-corner block, i.e. block
+         * (X, Y, Z) is solid iff the reference generator makes block (X & ~(2^m - 1), ...) solid. */
+        uint8_t solid[ORC_BLOCKS]; memset(solid, 0, sizeof solid);
+        for (int i = 0; i < n; i++) solid[orc_bidx(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2])] = 1;
+        const int mask = ~((1 << a->mip) - 1);
+        for (int X = 0; X < ORC_CR; X++) for (int Y = 0; Y < ORC_CR; Y++) for (int Z = 0; Z < ORC_CR; Z++)
+          if (solid[orc_bidx(X & mask, Y & mask, Z & mask)]) set_brick(v, c, orc_bidx(X, Y, Z), ones);
+      }
     } else {
       double cs[3]; for (int k = 0; k < 3; k++) cs[k] = (double)loc[k] * BlockSize * (double)ORC_CR;
       int X = (int)(item % ORC_CR);
@@ -156,9 +167,14 @@ static void vox_range(void* ctx, int64_t b, int64_t e, int tid) {
     }
   }
 }
+void orc_volume_voxelize_lod(OrcVolume* v, int kind, const double params[4], int sin_mode, int nthreads, int mip) {
+  clear_volume(v);
+  VoxArg a = {v, kind, params, ORC_GRAN_BLOCK, sin_mode, 0, mip < 0 ? 0 : (mip > 4 ? 4 : mip)};
+  orc_parallel_for(v->nchunks, nthreads, 1, vox_range, &a);
+}
 void orc_volume_voxelize_ex(OrcVolume* v, int kind, const double params[4], int gran, int sin_mode, int nthreads, int fast) {
   clear_volume(v);
-  VoxArg a = {v, kind, params, gran, sin_mode, fast};
+  VoxArg a = {v, kind, params, gran, sin_mode, fast, 0};
   orc_parallel_for(gran == ORC_GRAN_BLOCK ? v->nchunks : v->nchunks * ORC_CR, nthreads, 1, vox_range, &a);
 }
 void orc_volume_voxelize(OrcVolume* v, int kind, const double params[4], int gran, int sin_mode, int nthreads) {

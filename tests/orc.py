@@ -221,6 +221,11 @@ class Volume:
                                    C.c_int(nthreads or hw_threads()), C.c_int(1 if fast else 0))
         return self
 
+    def voxelize_lod(self, kind, params=None, mip=0, sin_mode=SIN_PORTABLE, nthreads=None):
+        self._params = _d4(params)
+        lib.orc_volume_voxelize_lod(self.h, C.c_int(kind), _p(self._params), C.c_int(sin_mode), C.c_int(nthreads or hw_threads()), C.c_int(mip))
+        return self
+
     def occ(self):
         ptr = lib.orc_volume_occ(self.h)
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(self.nchunks, 64)).copy()

@@ -584,3 +584,32 @@ def test_present_rgba8_texture_ranges(ctx, capi, orc):
         assert got.shape == (rh, rw) and np.array_equal(got, rec["rgba"][y:y + rh, x:x + rw])
     with pytest.raises(capi.MesoError):
         ctx.present_rgba8(cam, w, h, rect=(w - 4, 0, 5, 5))
+
+
+@pytest.mark.parametrize("kind", ["sphere", "terrain"])
+def test_generator_lod_mipmap_level(ctx, capi, orc, kind):
+    """MipmapLevel of the generator plug-in: one sample per (2^m)^3 blocks.  Level 0 == the plain block generator; every
+    level == the oracle's; a coarser level never has more distinct block groups than a finer one."""
+    if kind == "sphere":
+        origin, dims, k, ok, params = (2, -4, -4), (8, 8, 8), capi.SDF_SPHERE, orc.SDF_SPHERE, orc.REF_SPHERE
+    else:
+        origin, dims, k, ok, params = (0, -2, 0), (3, 4, 3), capi.SDF_TERRAIN, orc.SDF_TERRAIN, None
+    ctx.scene_create(origin, dims, 1 << 10)
+    ctx.voxelize_sdf(k, params, capi.GRAN_BLOCK)
+    occ0 = ctx.volume_download()[0]
+    for m in range(5):
+        ctx.voxelize_sdf_lod(k, params, m)
+        occ, full, keys, _ = ctx.volume_download()
+        vol = orc.Volume(origin, dims).voxelize_lod(ok, params, mip=m)
+        assert np.array_equal(occ, vol.occ()) and np.array_equal(full, vol.full()) and len(keys) == 0
+        if m == 0:
+            assert np.array_equal(occ, occ0)
+    with pytest.raises(capi.MesoError):
+        ctx.voxelize_sdf_lod(k, params, 5)
+    # the coarse volume renders and meshes like any other
+    ctx.voxelize_sdf_lod(k, params, 2)
+    vol = orc.Volume(origin, dims).voxelize_lod(ok, params, mip=2)
+    eyes, ctr = scenes.orbit_eyes(origin, dims, 8)
+    cam = orc.camera_uniform(eyes[1], ctr, width=128, height=72)
+    assert ctx.raymarch(cam, 128, 72, shadow=True).tobytes() == vol.raymarch(orc.ray_setup(cam, origin, 128, 72), 128, 72, shadow=True).tobytes()
+    assert orc.sort_quads(ctx.mesh(1 << 20)).tobytes() == orc.sort_quads(vol.mesh()).tobytes()

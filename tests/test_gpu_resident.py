@@ -264,3 +264,37 @@ def test_moving_window_follows_the_camera(ctx, capi, orc, gran):
     assert ctx.raymarch(camu, w, h, shadow=True).tobytes() == ref.tobytes()
     q = ctx.mesh(1 << 22)
     assert np.array_equal(orc.sort_quads(q.copy()), orc.sort_quads(vol.mesh()))
+
+
+def test_debug_instances_and_counters(ctx, capi, orc):
+    """Debug visualisation parity: one FGPUSimpleInstanceData per resident chunk (Marker 1 = has blocks, 0 = empty chunk) in
+    FIVec3Comparator order, and RenderManagerInfo's counters, for a static window and while streaming."""
+    assert capi.SimpleInstanceData.itemsize == 48 and capi.DebugStats.itemsize == 40
+    origin, dims = (0, -2, 0), (3, 4, 2)
+    ctx.scene_create(origin, dims, 1 << 12)
+    ctx.voxelize_sdf(capi.SDF_TERRAIN, None, capi.GRAN_BLOCK)
+    n_inst = ctx.build_occupancy(stamp=2)
+    occ, _, _, _ = ctx.volume_download()
+    inst = ctx.debug_chunk_instances()
+    locs = sorted((origin[0] + x, origin[1] + y, origin[2] + z) for z in range(dims[2]) for y in range(dims[1]) for x in range(dims[0]))
+    assert [tuple(int(v) for v in r["ChunkLocation"]) for r in inst] == locs
+    for r in inst:
+        x, y, z = (int(r["ChunkLocation"][i]) - origin[i] for i in range(3))
+        has = bool(occ[x + dims[0] * (y + dims[1] * z)].any())
+        assert float(r["Marker"]) == (1.0 if has else 0.0)
+        assert tuple(r["Position"]) == (16.0, 16.0, 16.0) and float(r["Scale"]) == np.float32(1.6) and tuple(r["Rotation"]) == (1.0, 0.0, 0.0, 0.0)
+    st = ctx.debug_stats()
+    assert int(st["LoadedChunk"]) == 24 and int(st["LoadedChunkWithBlocks"]) == int(sum(bool(o.any()) for o in occ)) and int(st["LoadedBlock"]) == n_inst
+    # streaming: only generated chunks are resident
+    ctx.stream_begin(capi.SDF_TERRAIN, None, capi.GRAN_BLOCK)
+    view = capi.view_config(8, 8, 120.0, 1)
+    s1 = ctx.stream_update((1, 0, 1), (0.0, 0.0, 1.0), 5, view)
+    st = ctx.debug_stats()
+    assert int(st["LoadedChunk"]) == 5 and int(st["NewlyAddedVisibleChunk"]) == 5 and int(st["MissingChunk"]) == int(s1["missing"]) == 19
+    assert int(st["VisibleChunk"]) == int(s1["candidates"])
+    loaded = ctx.stream_loaded(24)
+    inst = ctx.debug_chunk_instances()
+    assert len(inst) == 5
+    for r in inst:
+        x, y, z = (int(r["ChunkLocation"][i]) - origin[i] for i in range(3))
+        assert loaded[x + dims[0] * (y + dims[1] * z)]
