@@ -7,11 +7,10 @@
 //
 // Pass A (worklist): one thread per 64-brick occupancy word; occupied bricks that are not buried (full with six full
 // neighbours, decided with word-wide shifts) are compacted with a warp prefix sum + one atomic per warp.
-// Pass B (mesh): one warp per brick.  Lanes 0..6 resolve the seven bricks involved, then lanes 0..7 own one z-slice
-// each (64 voxels as a u64, every slice an independent 8 B load) and build the six exposed-face slice masks with
-// shifts against the neighbour slices; the 48 (direction, layer) 8x8 images are then merged greedily by 48
-// lane-tasks, counted, prefix-summed across the warp, and written behind one atomicAdd.
-// HBM-bound integer work: 64 B per populated brick + 16 B per quad (+ neighbour slices, mostly L2 hits).
+// Pass B (mesh): one THREAD per (brick, axis), 32 bricks and one axis per warp pass: the brick's eight z-slices in registers, the eight planes
+// along the axis formed from them, the facing plane of the two neighbours, sixteen (direction, layer) 8x8 images merged
+// greedily; quads staged per warp in shared memory and written behind one reservation per batch.
+// HBM-bound integer work on paper: 64 B per populated brick + 16 B per quad (+ neighbour slices, mostly L1 / L2 hits).
 #include "meso_internal.cuh"
 
 // full word w of chunk (cx,cy,cz), zeros outside the grid
@@ -73,43 +72,15 @@ __device__ __forceinline__ uint32_t gather_col(uint64_t e, int x) {  // bits (x 
   return (uint32_t)((((e >> x) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
 }
 
-// Greedy merge of one 8x8 image (row v = byte v).  EMIT=false counts only.
-template <bool EMIT>
-__device__ __forceinline__ int greedy_image(uint64_t img, int dir, int layer, int ox, int oy, int oz, MesoQuad* out, int64_t pos, int64_t cap) {
-  int n = 0;
-  const int ax = dir >> 1;
-#pragma unroll 1
-  for (int vv = 0; vv < 8; vv++) {
-    uint32_t row = (uint32_t)(img >> (8 * vv)) & 0xFFu;
-    while (row) {
-      const int u0 = __ffs(row) - 1;
-      const int w = __ffs(~(row >> u0)) - 1;
-      const uint32_t m = ((1u << w) - 1u) << u0;
-      int h = 1;
-      while (vv + h < 8 && (((uint32_t)(img >> (8 * (vv + h))) & m) == m)) { img &= ~((uint64_t)m << (8 * (vv + h))); h++; }
-      row &= ~m;
-      if (EMIT) {
-        int x, y, z;
-        if (ax == 0) { x = layer; y = u0; z = vv; } else if (ax == 1) { x = u0; y = layer; z = vv; } else { x = u0; y = vv; z = layer; }
-        if (pos + n < cap) {
-          uint4 q;
-          q.x = (uint32_t)(ox + x) | ((uint32_t)(oy + y) << 16);
-          q.y = (uint32_t)(oz + z) | ((uint32_t)dir << 16) | ((uint32_t)w << 24);
-          q.z = (uint32_t)h; q.w = 0u;
-          reinterpret_cast<uint4*>(out)[pos + n] = q;
-        }
-      }
-      n++;
-    }
-  }
-  return n;
-}
+#ifndef MQ_CAP
+#define MQ_CAP 320    // quads a warp can stage in shared memory (32 bricks x one axis of a smooth surface yield ~230)
+#endif
+#define MQ_FLUSH (MQ_CAP / 2)  // staged quads are written out once this many have accumulated (and at the end of the warp's work)
 
-#define MQ_CAP 224   // quads a warp can stage in shared memory (a smooth surface brick yields ~20)
-#define MQ_FLUSH 128 // staged quads are written out once this many have accumulated (and at the end of the warp's work)
-
-// Same greedy merge, staging the quads in shared memory; slots come from a shared-memory atomic counter.
-__device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count) {
+// Greedy merge of one 8x8 image, quads staged in shared memory (slot = shared atomic); what does not fit goes straight to
+// the global list (rare: a warp's ten bricks yield more than MQ_CAP quads between two flushes).
+__device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count,
+                                             MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
   const int ax = dir >> 1;
 #pragma unroll 1
   for (int vv = 0; vv < 8; vv++) {
@@ -123,33 +94,134 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
       row &= ~m;
       int x, y, z;
       if (ax == 0) { x = layer; y = u0; z = vv; } else if (ax == 1) { x = u0; y = layer; z = vv; } else { x = u0; y = vv; z = layer; }
+      const uint4 q = make_uint4((uint32_t)(ox + x) | ((uint32_t)(oy + y) << 16), (uint32_t)(oz + z) | ((uint32_t)dir << 16) | ((uint32_t)w << 24),
+                                 (uint32_t)h, 0u);
       const int idx = atomicAdd(count, 1);
-      if (idx < MQ_CAP)
-        stage[idx] = make_uint4((uint32_t)(ox + x) | ((uint32_t)(oy + y) << 16), (uint32_t)(oz + z) | ((uint32_t)dir << 16) | ((uint32_t)w << 24),
-                                (uint32_t)h, 0u);
+      if (idx < MQ_CAP) stage[idx] = q;
+      else {
+        const unsigned long long g = atomicAdd_system(quad_count, 1ull);
+        if ((int64_t)g < cap) reinterpret_cast<uint4*>(quads)[g] = q;
+      }
     }
+    if (vv == 7 || (img >> (8 * (vv + 1))) == 0ull) break;   // nothing left in the rows below
+  }
+}
+
+// state of a brick: 0 absent / outside the grid, 1 full, 2 partial (slot = its payload)
+__device__ __forceinline__ int brick_state(const DVolume& v, int bx, int by, int bz, uint32_t& slot) {
+  if ((unsigned)bx >= (unsigned)(v.dims[0] * 16) || (unsigned)by >= (unsigned)(v.dims[1] * 16) || (unsigned)bz >= (unsigned)(v.dims[2] * 16)) return 0;
+  const int64_t nc = chunk_index(v, bx >> 4, by >> 4, bz >> 4);
+  const int nb = block_bit(bx & 15, by & 15, bz & 15);
+  const ulonglong2 p = __ldg(&v.of[nc * 64 + (nb >> 6)]);
+  if (!((p.x >> (nb & 63)) & 1ull)) return 0;
+  if ((p.y >> (nb & 63)) & 1ull) return 1;
+  slot = __ldg(&v.bptr[nc * MESO_BLOCKS + nb]);
+  return 2;
+}
+__device__ __forceinline__ void load_slices(const DVolume& v, uint32_t slot, uint64_t s[8]) {
+  const ulonglong2* p = reinterpret_cast<const ulonglong2*>(v.pool + (size_t)slot * 8);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const ulonglong2 q = __ldg(p + i); s[2 * i] = q.x; s[2 * i + 1] = q.y; }
+}
+// plane `l` of the brick along `axis`, as the 8x8 image the oracle defines for that axis:
+//   axis 0 (x = l): row z, bit y;   axis 1 (y = l): row z, bit x;   axis 2 (z = l): row y, bit x (the slice itself)
+template <int AXIS>
+__device__ __forceinline__ uint64_t axis_plane(const uint64_t s[8], int l) {
+  if (AXIS == 2) {   // select chain, not s[l]: a dynamically indexed register array would live in local memory
+    const uint64_t a = (l & 1) ? s[1] : s[0], b = (l & 1) ? s[3] : s[2], c = (l & 1) ? s[5] : s[4], d = (l & 1) ? s[7] : s[6];
+    const uint64_t ab = (l & 2) ? b : a, cd = (l & 2) ? d : c;
+    return (l & 4) ? cd : ab;
+  }
+  uint64_t p = 0;
+#pragma unroll
+  for (int z = 0; z < 8; z++) {
+    const uint32_t row = AXIS == 0 ? gather_col(s[z], l) : ((uint32_t)(s[z] >> (8 * l)) & 0xFFu);
+    p |= (uint64_t)row << (8 * z);
+  }
+  return p;
+}
+// the plane of a neighbouring brick that faces this one: its layer 7 (the neighbour on the minus side) or 0 (plus side)
+template <int AXIS>
+__device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, int by, int bz, int layer) {
+  uint32_t slot = 0;
+  const int st = brick_state(v, bx, by, bz, slot);
+  if (st == 0) return 0ull;
+  if (st == 1) return ~0ull;
+  if (AXIS == 2) return __ldg(&v.pool[(size_t)slot * 8 + layer]);
+  uint64_t s[8];
+  load_slices(v, slot, s);
+  return axis_plane<AXIS>(s, layer);
+}
+
+#define MB_THREADS 128   // 4 warps per CTA: 20 KB of staged quads + 16 KB of queued images in static shared memory
+#define MB_WARPS (MB_THREADS / 32)
+#ifndef MI_CAP
+#define MI_CAP 256       // (direction, layer) images a warp can queue per pass (32 bricks x one axis: typically 100-200 non-empty)
+#endif
+#ifndef MB_MINB
+#define MB_MINB 6
+#endif
+
+// Phase 1 of a warp pass: the sixteen (direction, layer) exposed-face images of one brick along AXIS; the non-empty ones go
+// into the warp's queue as {image, origin | direction | layer} (a full queue merges the image on the spot).
+template <int AXIS>
+__device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, int bx, int by, int bz, ulonglong2* queue, int* qn, uint4* stage, int* count,
+                                                  MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
+  uint32_t slot = 0;
+  const int st = valid ? brick_state(v, bx, by, bz, slot) : 0;
+  if (st == 0) return;
+  uint64_t s[8];
+  if (st == 2) load_slices(v, slot, s);
+  else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = ~0ull;
+  }
+  const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7);
+  const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0);
+  const uint64_t org = (uint64_t)(uint32_t)(bx * 8) | ((uint64_t)(uint32_t)(by * 8) << 16) | ((uint64_t)(uint32_t)(bz * 8) << 32);
+  uint64_t prev = nbm, cur = s[0];
+  if (AXIS != 2 && st == 2) cur = axis_plane<AXIS>(s, 0);
+#pragma unroll 1
+  for (int l = 0; l < 8; l++) {
+    uint64_t next = nbp;
+    if (l < 7) {
+      next = AXIS == 2 ? axis_plane<2>(s, l + 1) : cur;      // full bricks: every plane equals the first
+      if (AXIS != 2 && st == 2) next = axis_plane<AXIS>(s, l + 1);
+    }
+    const uint64_t em = cur & ~prev, ep = cur & ~next;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      const uint64_t img = side ? ep : em;
+      if (img) {
+        const int dir = 2 * AXIS + side;
+        const int idx = atomicAdd(qn, 1);
+        if (idx < MI_CAP) queue[idx] = make_ulonglong2(img, org | ((uint64_t)dir << 48) | ((uint64_t)l << 52));
+        else greedy_stage(img, dir, l, bx * 8, by * 8, bz * 8, stage, count, quads, cap, quad_count);
+      }
+    }
+    prev = cur; cur = next;
   }
 }
 
 // Persistent, grid-stride over the work list (count read from device memory: no host round trip between the passes).
-// A warp takes TWO bricks per iteration, one per half-warp, through the slice phase (lanes 0..6 of each half resolve the
-// seven bricks involved, lanes 0..7 own one z-slice each).  The 2 x 48 (direction, layer) images are then built in three
-// full rounds, the non-empty ones (typically 6..12 of 48) are queued in shared memory, and the greedy merge runs over the
-// queue densely: one round of busy lanes instead of three rounds of mostly idle ones.
-__global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
-                                                          uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
-                                                          int shard_rank, int shard_world) {
-  __shared__ uint64_t s_e[8][2][6][8];
-  __shared__ uint64_t s_img[8][96];
-  __shared__ uint8_t s_meta[8][96];
-  __shared__ int s_org[8][2][3];
-  __shared__ uint4 s_q[8][MQ_CAP];
-  __shared__ int s_n[8];
+// A warp pass = 32 bricks x one axis.  Phase 1, one THREAD per brick: the brick's eight z-slices in registers, the eight
+// planes along the axis formed from them (the slices themselves for z, byte / column gathers for y / x), the facing plane of
+// the two neighbours, sixteen exposed-face images; the non-empty ones are queued in shared memory.  Phase 2: the lanes take the
+// queued images round-robin and merge them greedily -- the merge loops run over a dense queue instead of every lane waiting
+// for the lane with the busiest (direction, layer).  Quads are staged per warp and leave in batches behind one reservation.
+// (Round 1's warp-per-two-bricks form spent 55 % of its instructions building slices and images cooperatively and ran the
+// greedy loops at 2-6 active lanes, profiles/r2_mesh_bricks_sass_hot.txt; one thread per (brick, axis) WITHOUT the queue ran
+// them at 4.)
+__global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
+                                                                    uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
+                                                                    int shard_rank, int shard_world) {
+  __shared__ uint4 s_q[MB_WARPS][MQ_CAP];
+  __shared__ ulonglong2 s_img[MB_WARPS][MI_CAP];
+  __shared__ int s_n[MB_WARPS], s_in[MB_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, hl = lane & 15;
   const uint32_t n_work = work_count_ptr ? *work_count_ptr : work_count_imm;
-  const int64_t n_pairs = ((int64_t)n_work + 1) >> 1;
-  if (lane == 0) s_n[warp] = 0;
+  const int64_t n_groups = (((int64_t)n_work + 31) / 32) * 3;     // (32 bricks, axis)
+  if (lane == 0) { s_n[warp] = 0; s_in[warp] = 0; }
   __syncwarp();
   // write the first `count` staged quads behind one reservation and empty the staging area
   auto flush = [&](int count) {
@@ -164,123 +236,34 @@ __global__ void __launch_bounds__(256) mesh_bricks_kernel(DVolume v, const uint6
     if (lane == 0) s_n[warp] = 0;
     __syncwarp();
   };
-  for (int64_t pair =(int64_t)blockIdx.x * 8 + warp; pair < n_pairs; pair += (int64_t)gridDim.x * 8) {
-  __syncwarp();
-  const int64_t item = pair * 2 + half;
-  bool valid = item < (int64_t)n_work;
-  const uint64_t key = valid ? work[item] : 0ull;
-  // key lists (dirty re-mesh) are sharded over the ranks by a hash of the key: the list order is scheduling-dependent and
-  // differs between the replicas, the key set does not
-  if (shard_world > 1 && (int)(((key * 0x9E3779B97F4A7C15ull) >> 40) % (unsigned)shard_world) != shard_rank) valid = false;
-  const int64_t c = (int64_t)(key >> 12); const int b = (int)(key & 4095);
-  const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
-  const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
-  if (hl == 0) { s_org[warp][half][0] = bx * 8; s_org[warp][half][1] = by * 8; s_org[warp][half][2] = bz * 8; }
-
-  const int z = hl & 7;
-  // Step 1: lanes 0..6 of each half resolve the seven bricks involved (self, -x, +x, -y, +y, -z, +z) in parallel: one
-  // 16 B {occ,full} load each, then the payload slot of the partial ones.  state: 0 empty / outside, 1 full, 2 partial.
-  int st = 0; uint32_t slot = 0;
-  if (valid && hl < 7) {
-    const int nx = bx + (hl == 1 ? -1 : (hl == 2 ? 1 : 0));
-    const int ny = by + (hl == 3 ? -1 : (hl == 4 ? 1 : 0));
-    const int nz = bz + (hl == 5 ? -1 : (hl == 6 ? 1 : 0));
-    if ((unsigned)nx < (unsigned)(v.dims[0] * 16) && (unsigned)ny < (unsigned)(v.dims[1] * 16) && (unsigned)nz < (unsigned)(v.dims[2] * 16)) {
-      const int64_t nc = chunk_index(v, nx >> 4, ny >> 4, nz >> 4);
-      const int nb = block_bit(nx & 15, ny & 15, nz & 15);
-      const ulonglong2 p = __ldg(&v.of[nc * 64 + (nb >> 6)]);
-      if ((p.x >> (nb & 63)) & 1ull) {
-        if ((p.y >> (nb & 63)) & 1ull) st = 1;
-        else { st = 2; slot = __ldg(&v.bptr[nc * MESO_BLOCKS + nb]); }
-      }
+  for (int64_t grp = (int64_t)blockIdx.x * MB_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * MB_WARPS) {
+    const int axis = (int)(grp % 3);
+    const int64_t item = (grp / 3) * 32 + lane;
+    bool valid = item < (int64_t)n_work;
+    const uint64_t key = valid ? work[item] : 0ull;
+    // key lists (dirty re-mesh) are sharded over the ranks by a hash of the key: the list order is scheduling-dependent and
+    // differs between the replicas, the key set does not
+    if (shard_world > 1 && (int)(((key * 0x9E3779B97F4A7C15ull) >> 40) % (unsigned)shard_world) != shard_rank) valid = false;
+    const int64_t c = (int64_t)(key >> 12); const int b = (int)(key & 4095);
+    const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
+    const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
+    if (axis == 0) queue_axis_images<0>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    __syncwarp();
+    const int ni = min(s_in[warp], MI_CAP);
+    for (int i = lane; i < ni; i += 32) {
+      const ulonglong2 e = s_img[warp][i];
+      greedy_stage(e.x, (int)((e.y >> 48) & 7), (int)((e.y >> 52) & 7), (int)(e.y & 0xFFFF), (int)((e.y >> 16) & 0xFFFF), (int)((e.y >> 32) & 0xFFFF),
+                   s_q[warp], &s_n[warp], quads, cap, quad_count);
     }
-  }
-  // Step 2: every slice needed is one independent 8 B load (lanes 0..7 of the half: slice z of self and of the four
-  // lateral neighbours; lane 0 / 7: the facing slice of the -z / +z neighbour).
-  auto slice_of = [&](int which, int zz) -> uint64_t {
-    const int s_st = __shfl_sync(0xffffffffu, st, (lane & 16) | which);
-    const uint32_t s_slot = __shfl_sync(0xffffffffu, slot, (lane & 16) | which);
-    if (s_st == 2 && hl < 8) return __ldg(&v.pool[(size_t)s_slot * 8 + zz]);
-    return s_st == 1 ? ~0ull : 0ull;
-  };
-  uint64_t s = slice_of(0, z);   // every lane takes part in the shuffles
-  if (hl >= 8) s = 0ull;
-  const uint64_t xm = slice_of(1, z), xp = slice_of(2, z), ym = slice_of(3, z), yp = slice_of(4, z);
-  const uint64_t nzm = slice_of(5, 7), nzp = slice_of(6, 0);
-  const uint64_t s_dn = __shfl_up_sync(0xffffffffu, s, 1), s_up = __shfl_down_sync(0xffffffffu, s, 1);
-  if (hl < 8) {
-    const uint64_t C0 = 0x0101010101010101ull;
-    const uint64_t n_xm = ((s << 1) & ~C0) | ((xm >> 7) & C0);
-    const uint64_t n_xp = ((s >> 1) & ~(C0 << 7)) | ((xp & C0) << 7);
-    const uint64_t n_ym = (s << 8) | (ym >> 56);
-    const uint64_t n_yp = (s >> 8) | (yp << 56);
-    const uint64_t n_zm = z > 0 ? s_dn : nzm;
-    const uint64_t n_zp = z < 7 ? s_up : nzp;
-    s_e[warp][half][0][z] = s & ~n_xm; s_e[warp][half][1][z] = s & ~n_xp;
-    s_e[warp][half][2][z] = s & ~n_ym; s_e[warp][half][3][z] = s & ~n_yp;
-    s_e[warp][half][4][z] = s & ~n_zm; s_e[warp][half][5][z] = s & ~n_zp;
+    __syncwarp();
+    if (lane == 0) s_in[warp] = 0;
+    if (s_n[warp] >= MQ_FLUSH) flush(min(s_n[warp], MQ_CAP));
+    __syncwarp();
   }
   __syncwarp();
-  // 2 x 48 (dir, layer) images over 32 lanes in three full rounds; the non-empty ones are queued (order irrelevant)
-  int ni = 0;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    const int task = lane + 32 * k;
-    const int h = task >= 48 ? 1 : 0;
-    const int t48 = task - 48 * h;
-    const int dir = t48 >> 3, l = t48 & 7;
-    uint64_t im = 0;
-    if (dir >= 4) im = s_e[warp][h][dir][l];
-    else {
-#pragma unroll
-      for (int zz = 0; zz < 8; zz++) {
-        const uint64_t e = s_e[warp][h][dir][zz];
-        const uint32_t row = dir < 2 ? gather_col(e, l) : ((uint32_t)(e >> (8 * l)) & 0xFFu);
-        im |= (uint64_t)row << (8 * zz);
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, im != 0ull);
-    if (im) {
-      const int idx = ni + __popc(bal & ((1u << lane) - 1u));
-      s_img[warp][idx] = im;
-      s_meta[warp][idx] = (uint8_t)(dir | (l << 3) | (h << 6));
-    }
-    ni += __popc(bal);
-  }
-  __syncwarp();
-  if (ni == 0) continue;
-  // Fast path: greedy passes over the queue stage the quads of both bricks in shared memory (slot = shared atomic, order
-  // is irrelevant).  Staged quads accumulate over several iterations and leave in batches of >= MQ_FLUSH: one
-  // (system-scope) atomicAdd and one coalesced copy of 16 B records per batch -- the reservation is a round trip over
-  // NVLink when the list lives in a peer GPU.
-  int before = s_n[warp];
-  if (before >= MQ_FLUSH) { flush(before); before = 0; }
-  for (int i = lane; i < ni; i += 32) {
-    const int m = s_meta[warp][i], h = m >> 6;
-    greedy_stage(s_img[warp][i], m & 7, (m >> 3) & 7, s_org[warp][h][0], s_org[warp][h][1], s_org[warp][h][2], s_q[warp], &s_n[warp]);
-  }
-  __syncwarp();
-  if (s_n[warp] <= MQ_CAP) continue;
-  // Rare: more quads than the staging area holds -> write out what earlier iterations staged, then count, prefix and emit
-  // this pair's quads straight to global memory.
-  flush(before);
-  int cnt = 0;
-  for (int i = lane; i < ni; i += 32) cnt += greedy_image<false>(s_img[warp][i], 0, 0, 0, 0, 0, nullptr, 0, 0);
-  int incl = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  unsigned long long base = 0;
-  if (lane == 0) base = atomicAdd_system(quad_count, (unsigned long long)total);
-  base = __shfl_sync(0xffffffffu, base, 0);
-  int64_t pos = (int64_t)base + incl - cnt;
-  for (int i = lane; i < ni; i += 32) {
-    const int m = s_meta[warp][i], h = m >> 6;
-    pos += greedy_image<true>(s_img[warp][i], m & 7, (m >> 3) & 7, s_org[warp][h][0], s_org[warp][h][1], s_org[warp][h][2], quads, pos, cap);
-  }
-}
-  __syncwarp();
-  flush(s_n[warp]);
+  flush(min(s_n[warp], MQ_CAP));
 }
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
@@ -289,7 +272,7 @@ void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uin
   if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   const int64_t n = v.nchunks * MESO_WORDS;
   mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, d_work, d_work_count);
-  mesh_bricks_kernel<<<lc.sm_count * 8, 256, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
+  mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
   (*lc.launches) += 2;
 }
 
@@ -297,7 +280,8 @@ void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_k
                       int64_t cap, unsigned long long* d_quad_count, int rank, int world) {
   cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   if (n_keys == 0) return;
-  const unsigned grid = (unsigned)min((int64_t)lc.sm_count * 8, ((int64_t)n_keys + 7) / 8);
-  mesh_bricks_kernel<<<grid, 256, 0, lc.stream>>>(v, d_keys, nullptr, n_keys, d_quads, cap, d_quad_count, rank, world);
+  const int64_t passes = (((int64_t)n_keys + 31) / 32) * 3;
+  const unsigned grid = (unsigned)min((int64_t)lc.sm_count * 12, (passes + MB_WARPS - 1) / MB_WARPS);
+  mesh_bricks_kernel<<<grid, MB_THREADS, 0, lc.stream>>>(v, d_keys, nullptr, n_keys, d_quads, cap, d_quad_count, rank, world);
   (*lc.launches)++;
 }
