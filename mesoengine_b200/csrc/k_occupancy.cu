@@ -87,41 +87,46 @@ __global__ void __launch_bounds__(64) occupancy_mips_kernel(DVolume v, uint32_t 
   }
 }
 
-// exclusive scan of per-chunk counts: a single CTA, 32 consecutive counts per thread (one pass covers 32 768 chunks)
-#define SCAN_PER_THREAD 32
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* __restrict__ counts, uint32_t* offsets, int64_t n, uint64_t* total) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
+// exclusive scan of per-chunk counts in three small launches: 1024 counts per CTA (local exclusive offsets + the CTA's
+// total), one CTA scanning the totals (up to 1024 of them: 2^20 chunks), and the add.  (A single 1024-thread CTA walking all
+// counts took 38 us at 32 768 chunks -- a fifth of K2.)
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t x, uint32_t* s_warp, uint32_t& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < n; base += 1024 * SCAN_PER_THREAD) {
-    const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_PER_THREAD;
-    uint32_t loc[SCAN_PER_THREAD];
-    uint32_t x = 0;
+  uint32_t incl = x;
 #pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; k++) { loc[k] = (i0 + k < n) ? counts[i0 + k] : 0u; x += loc[k]; }
-    uint32_t incl = x;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t wv = s_warp[lane];
+    uint32_t wi = wv;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t wv = s_warp[lane], wi = wv;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
-      s_warp[lane] = wi - wv;  // exclusive
-    }
-    __syncthreads();
-    const uint32_t carry = s_carry;
-    uint32_t run = carry + s_warp[warp] + incl - x;
-#pragma unroll
-    for (int k = 0; k < SCAN_PER_THREAD; k++) { if (i0 + k < n) offsets[i0 + k] = run; run += loc[k]; }
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + incl;
-    __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+    s_warp[lane] = wi - wv;                    // exclusive per warp
+    if (lane == 31) s_warp[32] = wi;           // CTA total
   }
-  if (threadIdx.x == 0) *total = s_carry;
+  __syncthreads();
+  total = s_warp[32];
+  return s_warp[warp] + incl - x;
+}
+__global__ void __launch_bounds__(1024) scan_local_kernel(const uint32_t* __restrict__ counts, uint32_t* offsets, int64_t n, uint32_t* block_totals) {
+  __shared__ uint32_t s_warp[33];
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  uint32_t total;
+  const uint32_t ex = block_exclusive_scan_1024(i < n ? counts[i] : 0u, s_warp, total);
+  if (i < n) offsets[i] = ex;
+  if (threadIdx.x == 0) block_totals[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) scan_totals_kernel(uint32_t* block_totals, int nblocks, uint64_t* total_out) {
+  __shared__ uint32_t s_warp[33];
+  uint32_t total;
+  const uint32_t ex = block_exclusive_scan_1024((int)threadIdx.x < nblocks ? block_totals[threadIdx.x] : 0u, s_warp, total);
+  if ((int)threadIdx.x < nblocks) block_totals[threadIdx.x] = ex;
+  if (threadIdx.x == 0) *total_out = total;
+}
+__global__ void __launch_bounds__(1024) scan_add_kernel(uint32_t* offsets, int64_t n, const uint32_t* __restrict__ block_totals) {
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  if (i < n && blockIdx.x > 0) offsets[i] += block_totals[blockIdx.x];
 }
 
 // One CTA (256 threads) per chunk.  Thread t <-> column (X = t>>4, Y = t&15), i.e. thread order is the reference's
@@ -133,7 +138,8 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(DVolume v, uint32_t
   const int64_t c = blockIdx.x;
   const uint32_t total = counts[c];
   if (total == 0) return;
-  extern __shared__ uint32_t s_rec[];   // 3 words per record, up to 4096 records
+  __shared__ uint16_t s_xyz[MESO_BLOCKS];   // X | Y << 4 | Z << 8 of the emitted blocks, at their rank (8 KB: eight CTAs per SM;
+                                            // staging the 12-byte records themselves took 48 KB and capped occupancy at four)
   __shared__ uint64_t cull[64];
   __shared__ uint32_t s_warp[8];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -155,17 +161,19 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(DVolume v, uint32_t
   while (col) {
     const int Z = __ffs(col) - 1;
     col &= col - 1;
-    s_rec[r * 3 + 0] = (uint32_t)c;                                                           // ChunkIndex (+ thread offset 0)
-    s_rec[r * 3 + 1] = (uint32_t)X | ((uint32_t)Y << 8) | ((uint32_t)Z << 16) | (255u << 24);  // u8vec4(x,y,z,255)
-    s_rec[r * 3 + 2] = stamp;
-    r++;
+    s_xyz[r++] = (uint16_t)(X | (Y << 4) | (Z << 8));
   }
   __syncthreads();
   const int64_t first = (int64_t)offsets[c];
   const int64_t room = cap - first;
   const uint32_t words = (uint32_t)(room <= 0 ? 0 : (room < (int64_t)total ? room : (int64_t)total)) * 3u;
   uint32_t* out = reinterpret_cast<uint32_t*>(inst) + first * 3;
-  for (uint32_t i = t; i < words; i += 256) out[i] = s_rec[i];
+  // one contiguous, coalesced run of 32-bit words; word i belongs to record i / 3: {ChunkIndex, u8vec4(x, y, z, 255), stamp}
+  for (uint32_t i = t; i < words; i += 256) {
+    const uint32_t rec = i / 3u, part = i - 3u * rec;
+    const uint32_t q = s_xyz[rec];
+    out[i] = part == 0 ? (uint32_t)c : (part == 1 ? ((q & 15u) | (((q >> 4) & 15u) << 8) | ((q >> 8) << 16) | (255u << 24)) : stamp);
+  }
 }
 
 // The reference's own upload records (FChunkPool::UploadChunk / UploadBlock, ChunkPool.h:662-679) scattered into the block
@@ -206,17 +214,17 @@ void launch_scatter_blocks(const LaunchCtx& lc, const DVolume& v, const MesoGPUC
 
 // pass 1: mips + per-chunk instance counts + exclusive scan (d_total = number of instances)
 void launch_occupancy_count(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, MesoGPUChunk* d_table, uint32_t* d_counts,
-                            uint32_t* d_offsets, uint64_t* d_total) {
+                            uint32_t* d_offsets, uint64_t* d_total, uint32_t* d_block_totals) {
   occupancy_mips_kernel<<<(unsigned)v.nchunks, 64, 0, lc.stream>>>(v, stamp, d_table, d_counts);
-  scan_counts_kernel<<<1, 1024, 0, lc.stream>>>(d_counts, d_offsets, v.nchunks, d_total);
-  (*lc.launches) += 2;
+  const int nblocks = (int)((v.nchunks + 1023) / 1024);      // <= 1024: meso_scene_create caps the grid at 2^20 chunks
+  scan_local_kernel<<<nblocks, 1024, 0, lc.stream>>>(d_counts, d_offsets, v.nchunks, d_block_totals);
+  scan_totals_kernel<<<1, 1024, 0, lc.stream>>>(d_block_totals, nblocks, d_total);
+  scan_add_kernel<<<nblocks, 1024, 0, lc.stream>>>(d_offsets, v.nchunks, d_block_totals);
+  (*lc.launches) += 4;
 }
 // pass 2: compacted FGPUBlock list in generator order
 void launch_occupancy_emit(const LaunchCtx& lc, const DVolume& v, uint32_t stamp, const uint32_t* d_counts, const uint32_t* d_offsets,
                            MesoGPUBlock* d_inst, int64_t cap_inst) {
-  const int smem = MESO_BLOCKS * 12;
-  // function attributes are per device: set it on every launch (a host-side table write), not once per process
-  cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  emit_instances_kernel<<<(unsigned)v.nchunks, 256, smem, lc.stream>>>(v, stamp, d_counts, d_offsets, d_inst, cap_inst);
+  emit_instances_kernel<<<(unsigned)v.nchunks, 256, 0, lc.stream>>>(v, stamp, d_counts, d_offsets, d_inst, cap_inst);
   (*lc.launches) += 1;
 }

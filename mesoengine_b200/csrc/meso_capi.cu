@@ -84,7 +84,8 @@ static void free_scene(MesoCtx* c) {
   DVolume& v = c->v;
   cudaFree(v.occ); cudaFree(v.full); cudaFree(v.of); cudaFree(v.cells); cudaFree(v.region_any); cudaFree(v.mips); cudaFree(v.bptr); cudaFree(v.pool);
   cudaFree(v.chunk_any); cudaFree(v.chunk_full); cudaFree(v.pool_count); cudaFree(v.pool_free); cudaFree(v.pool_free_count); cudaFree(c->d_shift_scratch); c->d_shift_scratch = nullptr; cudaFree(v.df); cudaFree(v.df_tmp); cudaFree(v.pool_cm); cudaFree(v.words); cudaFree(v.n_words);
-  cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_inst);
+  cudaFree(c->d_table); cudaFree(c->d_counts); cudaFree(c->d_offsets); cudaFree(c->d_total); cudaFree(c->d_block_totals); cudaFree(c->d_inst);
+  c->d_block_totals = nullptr;
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
   cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
@@ -206,6 +207,7 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   CK(cudaMemsetAsync(v.pool_count, 0, 4, c->stream));
   CK(cudaMalloc(&c->d_table, nc * sizeof(MesoGPUChunk)));
   CK(cudaMalloc(&c->d_counts, nc * 4)); CK(cudaMalloc(&c->d_offsets, nc * 4)); CK(cudaMalloc(&c->d_total, 8));
+  CK(cudaMalloc(&c->d_block_totals, 1024 * 4));
   CK(cudaMalloc(&c->d_stats, sizeof(RayStatsDev)));
   CK(cudaMalloc(&c->d_touch_chunk, nc)); CK(cudaMalloc(&c->d_touch_brick, max_bricks));
   CK(cudaMalloc(&c->d_work_count, 4)); CK(cudaMalloc(&c->d_quad_count, 8));
@@ -410,7 +412,7 @@ int meso_volume_download(MesoCtx* c, uint64_t* occ, uint64_t* full, uint64_t* ke
 int meso_build_occupancy(MesoCtx* c, uint32_t stamp, int64_t* n_instances) {
   NEED_SCENE(c);
   // pass 1 on the device (mips, per-chunk counts, scan); the 8-byte total sizes the instance buffer, then pass 2 emits
-  launch_occupancy_count(c->lc(), c->v, stamp, c->d_table, c->d_counts, c->d_offsets, c->d_total);
+  launch_occupancy_count(c->lc(), c->v, stamp, c->d_table, c->d_counts, c->d_offsets, c->d_total, c->d_block_totals);
   CK_LAST("occupancy count");
   uint64_t total = 0;
   { const int rr = meso_small_read(c, &total, c->d_total, 8); if (rr != MESO_OK) return rr; }

@@ -34,6 +34,7 @@ struct MesoCtx {
   uint32_t* d_counts = nullptr;
   uint32_t* d_offsets = nullptr;
   uint64_t* d_total = nullptr;
+  uint32_t* d_block_totals = nullptr;   // scan scratch: one word per 1024 chunks
   MesoGPUBlock* d_inst = nullptr;
   int64_t cap_inst = 0;
   int64_t n_inst = 0;
