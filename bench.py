@@ -65,8 +65,13 @@ def issue_roofline(ctx, world, workload, kernel_ms, clocks):
         return None
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
     peak = ctx.sm_count() * 4 * mhz * 1e6
-    return {"warp_instructions_per_launch": w, "peak_warp_instructions_per_s": peak, "achieved_per_s": w / (kernel_ms * 1e-3),
-            "frac": w / (kernel_ms * 1e-3) / peak, "source": "profiles/raymarch_traffic.json (ncu capture of the shipped kernel)"}
+    out = {"warp_instructions_per_launch": w, "peak_warp_instructions_per_s": peak, "achieved_per_s": w / (kernel_ms * 1e-3),
+           "frac": w / (kernel_ms * 1e-3) / peak, "source": "profiles/raymarch_traffic.json (ncu capture of the shipped kernel)"}
+    ti, lanes, rays = (load_traffic(workload, workload + k) for k in ("_thread_instructions", "_active_threads_per_instruction", "_rays_in_capture"))
+    if ti and rays:
+        out["thread_instructions_per_ray"] = ti / rays          # round 1: ~3 500
+        out["active_threads_per_instruction"] = lanes
+    return out
 
 
 class ClockSampler:

@@ -123,6 +123,36 @@ __device__ __forceinline__ void load_slices(const DVolume& v, uint32_t slot, uin
 #pragma unroll
   for (int i = 0; i < 4; i++) { const ulonglong2 q = __ldg(p + i); s[2 * i] = q.x; s[2 * i + 1] = q.y; }
 }
+// ---- bulk asynchronous copy (TMA engine, non-tensor form) of brick payloads into shared memory, completion on an mbarrier ----
+// MEASURED AND OFF (MB_BULK = 1 builds it; tools/build_variant.sh): staging the 64-byte payloads of a pass with one
+// cp.async.bulk per lane + an mbarrier wait + LDS reads is correct (parity green) and slower than four LDG.128 per lane --
+// 0.79 vs 0.57 ms at 4096^3 (8 KB more shared memory per CTA = 5 instead of 6 CTAs per SM, a 4-way bank conflict on the
+// read-back, and nothing to hide: the merge loops bound the kernel, not the payload latency).  profiles/README.md.
+#ifndef MB_BULK
+#define MB_BULK 0
+#endif
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 64 bytes (one brick payload) global -> shared, counted against the mbarrier's transaction bytes
+__device__ __forceinline__ void bulk_load_64(void* dst_smem, const void* src_gmem, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(smem_u32(bar)) : "memory");
+}
+
 // plane `l` of the brick along `axis`, as the 8x8 image the oracle defines for that axis:
 //   axis 0 (x = l): row z, bit y;   axis 1 (y = l): row z, bit x;   axis 2 (z = l): row y, bit x (the slice itself)
 template <int AXIS>
@@ -166,9 +196,39 @@ __device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, in
 // into the warp's queue as {image, origin | direction | layer} (a full queue merges the image on the spot).
 template <int AXIS>
 __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, int bx, int by, int bz, ulonglong2* queue, int* qn, uint4* stage, int* count,
-                                                  MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
+                                                  MesoQuad* quads, int64_t cap, unsigned long long* quad_count, uint64_t* pay, uint64_t* bar, uint32_t& phase) {
   uint32_t slot = 0;
   const int st = valid ? brick_state(v, bx, by, bz, slot) : 0;
+#if MB_BULK
+  // The payloads of the pass's partial bricks travel global -> shared as bulk asynchronous copies (64 B each, the TMA engine's
+  // non-tensor form) while the lanes resolve their neighbours; one mbarrier per warp counts the bytes.
+  const unsigned partial = __ballot_sync(0xffffffffu, st == 2);
+  if (partial) {
+    if ((threadIdx.x & 31) == 0) mbar_expect_tx(bar, 64u * (uint32_t)__popc(partial));
+    __syncwarp();
+    if (st == 2) bulk_load_64(pay + (threadIdx.x & 31) * 8, v.pool + (size_t)slot * 8, bar);
+  }
+  uint64_t nbm = 0, nbp = 0;
+  if (st != 0) {
+    nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7);
+    nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0);
+  }
+  uint64_t s[8];
+  if (partial) {
+    mbar_wait(bar, phase & 1u);
+    phase++;
+  }
+  if (st == 2) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pay + (threadIdx.x & 31) * 8);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const ulonglong2 q = p[i]; s[2 * i] = q.x; s[2 * i + 1] = q.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = ~0ull;
+  }
+  __syncwarp();     // every lane has its slices in registers: the staging area may be overwritten by the next pass
+  if (st == 0) return;
+#else
   if (st == 0) return;
   uint64_t s[8];
   if (st == 2) load_slices(v, slot, s);
@@ -178,6 +238,7 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
   }
   const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7);
   const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0);
+#endif
   const uint64_t org = (uint64_t)(uint32_t)(bx * 8) | ((uint64_t)(uint32_t)(by * 8) << 16) | ((uint64_t)(uint32_t)(bz * 8) << 32);
   uint64_t prev = nbm, cur = s[0];
   if (AXIS != 2 && st == 2) cur = axis_plane<AXIS>(s, 0);
@@ -218,10 +279,20 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
   __shared__ uint4 s_q[MB_WARPS][MQ_CAP];
   __shared__ ulonglong2 s_img[MB_WARPS][MI_CAP];
   __shared__ int s_n[MB_WARPS], s_in[MB_WARPS];
+#if MB_BULK
+  __shared__ __align__(16) uint64_t s_pay[MB_WARPS][32 * 8];   // one pass's brick payloads, 64 B per lane (bulk-copy destination)
+  __shared__ __align__(8) uint64_t s_bar[MB_WARPS];            // one mbarrier per warp
+#else
+  uint64_t (*s_pay)[1] = nullptr; uint64_t* s_bar = nullptr;   // unused
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_work = work_count_ptr ? *work_count_ptr : work_count_imm;
   const int64_t n_groups = (((int64_t)n_work + 31) / 32) * 3;     // (32 bricks, axis)
+  uint32_t phase = 0;
   if (lane == 0) { s_n[warp] = 0; s_in[warp] = 0; }
+#if MB_BULK
+  if (lane == 0) mbar_init(&s_bar[warp], 1u);
+#endif
   __syncwarp();
   // write the first `count` staged quads behind one reservation and empty the staging area
   auto flush = [&](int count) {
@@ -247,9 +318,9 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     const int64_t c = (int64_t)(key >> 12); const int b = (int)(key & 4095);
     const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
     const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
-    if (axis == 0) queue_axis_images<0>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
-    else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
-    else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    if (axis == 0) queue_axis_images<0>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
+    else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
+    else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     __syncwarp();
     const int ni = min(s_in[warp], MI_CAP);
     for (int i = lane; i < ni; i += 32) {
