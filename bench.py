@@ -570,6 +570,45 @@ def run_ours(args):
     my_rows = max(0, min(slab_rows, height - my_row0))
     flags2 = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(R)]
 
+    # The timed loop again with the frame left DISTRIBUTED (device only, no copy to the host): every rank ends up with its
+    # rows of the frame instead of rank 0 receiving (N-1)/N of 132.7 MB per frame.  Shows how much of `value` at large N is
+    # rank 0's NVLink ingress rather than tracing (reported as config.distributed_slabs, not the headline).
+    distributed = None
+    if slabs_ok and arrival is not None:
+        def slab_step(k):
+            slot = k % R
+            s = streams[slot]
+            ctx.set_stream(s.cuda_stream)
+            ctx.raymarch_device_slabs(cams[k % 8], width, height, slab_ptrs[slot], slab_rows, shadow=True, light=LIGHT)
+            ctx.signal_device(arrival.all_ranks(28 + slot % 4))
+            arrival.gen[28 + slot % 4] += world
+            ctx.wait_device(arrival.mine + 4 * (28 + slot % 4), arrival.gen[28 + slot % 4])
+            ctx.set_stream(stream.cuda_stream)
+        for k in range(args.warmup):
+            slab_step(k)
+        regs = []
+        for _ in range(3):
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for s in streams[1:]:
+                s.wait_event(e0)
+            for k in range(args.steps):
+                slab_step(k)
+            ends = []
+            for s in streams:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(s)
+                ends.append(e)
+            barrier()
+            t = torch.tensor([max(e0.elapsed_time(e) for e in ends)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            regs.append(float(t.item()))
+        dms = float(np.median(regs)) / args.steps
+        distributed = {"ms_per_step": dms, "mrays_s": rays_total / args.steps / dms / 1e3,
+                       "rank0_ingress_gbs_in_the_gathered_loop": 16.0 * px * (world - 1) / world / (ms / args.steps * 1e-3) / 1e9,
+                       "note": "same kernels and ring, MESO_LAYOUT_SLABS: every rank keeps rows [r*H/N, (r+1)*H/N) of the frame (all-to-all over NVLink, arrival words), nothing is gathered on one GPU"}
+
     def slab_frame(k, slot, rgba8=False):
         """One frame through the slab gather on ring slot `slot`'s stream: kernel -> rendezvous (every rank's slab is
         complete) -> this rank's slab to the shared host frame -> rendezvous (every slab has landed)."""
@@ -775,7 +814,7 @@ def run_ours(args):
                                      ("fused gather: every rank's kernel stores its records into rank 0's frame over NVLink peer memory; rendezvous = " + ("an arrival word on rank 0 that every rank increments behind its kernel (one-thread signal kernel, system-scope atomic over NVLink), waited for on rank 0's stream: no collective in the frame loop" if arrival is not None else "4-byte NCCL all-reduce")
                                       if gather == "p2p" else "NCCL all_gather of packed tile records + compose kernel")),
                        "cache": "no flush inside the timed region: every step writes its own 132.7 MB frame (%d frame buffers cycled) and re-reads the scene, a per-step footprint above the 126 MB L2; the kernel-alone roofline loop flushes L2 (256 MiB write) between launches" % R,
-                       "frames_in_flight": R, "regions_ms": region_ms, "regions_note": "each region = exactly `steps` steps between barrier + synchronize points, max over ranks; value / ms_per_step are the median region",
+                       "frames_in_flight": R, "distributed_slabs": distributed, "regions_ms": region_ms, "regions_note": "each region = exactly `steps` steps between barrier + synchronize points, max over ranks; value / ms_per_step are the median region",
                        "gather": gather, "gather_verified_equal_to_1gpu_frame": gather_verified,
                        "scene_build_s": t_build,
                        "walk": "mirrored-space stateless DDA over per-octant forward cubes (32^3 cells, bricks), built with the volume"},
