@@ -131,6 +131,9 @@ __device__ __forceinline__ void load_slices(const DVolume& v, uint32_t slot, uin
 #ifndef MB_BULK
 #define MB_BULK 0
 #endif
+#ifndef MB_BULK_STORE
+#define MB_BULK_STORE 1
+#endif
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -276,7 +279,7 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
 __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
                                                                     uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
                                                                     int shard_rank, int shard_world) {
-  __shared__ uint4 s_q[MB_WARPS][MQ_CAP];
+  __shared__ __align__(128) uint4 s_q[MB_WARPS][MQ_CAP];
   __shared__ ulonglong2 s_img[MB_WARPS][MI_CAP];
   __shared__ int s_n[MB_WARPS], s_in[MB_WARPS];
 #if MB_BULK
@@ -297,11 +300,30 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
   // write the first `count` staged quads behind one reservation and empty the staging area
   auto flush = [&](int count) {
     if (count > 0) {
+#if MB_BULK_STORE
+      // the staged batch leaves shared memory as ONE bulk asynchronous store (TMA engine, non-tensor form): lane 0 reserves,
+      // makes the lanes' generic-proxy writes visible to the async proxy, issues the copy and waits until the source has
+      // been read (the staging area is reused right away)
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned long long sbase = atomicAdd_system(quad_count, (unsigned long long)count);   // system scope: the counter may live in a peer GPU
+        const long long room = (long long)cap - (long long)sbase;
+        const int n = room <= 0 ? 0 : (room < count ? (int)room : count);
+        if (n > 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(reinterpret_cast<uint4*>(quads) + sbase), "r"(smem_u32(&s_q[warp][0])), "r"(n * 16) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+      }
+#else
       unsigned long long sbase = 0;
       if (lane == 0) sbase = atomicAdd_system(quad_count, (unsigned long long)count);   // system scope: the counter may live in a peer GPU
       sbase = __shfl_sync(0xffffffffu, sbase, 0);
       for (int i = lane; i < count; i += 32)
         if ((int64_t)sbase + i < cap) reinterpret_cast<uint4*>(quads)[sbase + i] = s_q[warp][i];
+#endif
     }
     __syncwarp();
     if (lane == 0) s_n[warp] = 0;
