@@ -470,7 +470,7 @@ def check_grid_against_golden(gold, prefix, chunks, origin, dims, occ, mips123, 
 
 # ---- the reference's voxel shaders, executed (oracle/ref_glsl_driver.cpp) ---------------------------------------------
 DRAW_GOLDEN = os.path.join(_ROOT, "tests", "golden", "ref_draw.npz")
-DRAW_W, DRAW_H, DRAW_EYES, DRAW_STAMP = 96, 54, (0, 2, 5), 5
+DRAW_W, DRAW_H, DRAW_EYES, DRAW_STAMP = 256, 144, (0, 2, 5), 5
 
 
 def draw_scene(orc):

@@ -160,7 +160,7 @@ def test_restated_draw_and_dda_match_the_executed_reference_shaders(orc, eye_idx
             assert int(u["face"][py, px]) == face
             d8 = [(int(rec["rgba"][py, px]) >> (8 * c)) & 0xFF for c in range(4)]
             assert all(abs(a - e) <= 1 for a, e in zip(d8, r8)), (px, py, d8, r8)                  # (D) colour ~ (R) colour
-    assert checked > 1500 and skipped < 0.08 * w * h, (checked, skipped)
+    assert checked > 15000 and skipped < 0.03 * w * h, (checked, skipped)
 
 
 @pytest.mark.parametrize("eye_idx", refprobe.DRAW_EYES)

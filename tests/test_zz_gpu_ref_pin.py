@@ -62,7 +62,7 @@ def test_raymarch_on_gpu_against_the_executed_reference_shaders(ctx, eye_idx):
     cam = np.frombuffer(DRAW[f"eye{eye_idx}_camera"].tobytes(), dtype=capi.Camera).copy()
     rec = ctx.raymarch(cam, refprobe.DRAW_W, refprobe.DRAW_H, shadow=False)
     hits, misses, skipped = refprobe.check_records_against_ref_draw(DRAW, eye_idx, rec, origin)
-    assert hits > 2000 and misses > 1500 and skipped < 0.15 * rec.size, (hits, misses, skipped)
+    assert hits > 15000 and misses > 12000 and skipped < 0.03 * rec.size, (hits, misses, skipped)   # 256 x 144: 1.2-1.6 % of the pixels lie within 1e-3 of a face edge
 
 
 @pytest.mark.parametrize("i,mode", [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (0, 1), (1, 1)])
