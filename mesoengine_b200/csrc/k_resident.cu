@@ -40,7 +40,8 @@ __device__ __forceinline__ float chunk_importance(int x, int y, int z, float fx,
   return angle * distance;
 }
 
-__global__ void __launch_bounds__(256) select_view_kernel(ViewParams p, uint64_t* __restrict__ keys, uint32_t* count) {
+#define SEL_BUCKETS 4096   // top 12 bits of the key (sign, exponent and three mantissa bits of the inverted importance)
+__global__ void __launch_bounds__(256) select_view_kernel(ViewParams p, uint64_t* __restrict__ keys, uint32_t* count, uint32_t* hist) {
   const int side = 2 * p.F + 1;
   const int64_t total = (int64_t)side * side * side;
   const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -79,23 +80,67 @@ __global__ void __launch_bounds__(256) select_view_kernel(ViewParams p, uint64_t
   uint32_t base = 0;
   if (lane == __ffs(m) - 1) base = atomicAdd(count, (uint32_t)__popc(m));
   base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (ok) keys[base + __popc(m & ((1u << lane) - 1u))] = ((uint64_t)(0xFFFFFFFFu - __float_as_uint(imp)) << 32) | (uint64_t)(uint32_t)idx;
+  if (ok) {
+    const uint64_t key = ((uint64_t)(0xFFFFFFFFu - __float_as_uint(imp)) << 32) | (uint64_t)(uint32_t)idx;
+    keys[base + __popc(m & ((1u << lane) - 1u))] = key;
+    atomicAdd(&hist[key >> 52], 1u);
+  }
 }
 
-// Rank sort: 32 keys per CTA, 8 lanes per key.  The grid is sized for the worst case; CTAs past *count exit.
-__global__ void __launch_bounds__(256) rank_sort_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ count,
-                                                        MesoChunkCandidate* __restrict__ out, int64_t cap, int F) {
+// Sorting ~20 k 64-bit keys: a counting pass on the key's top 12 bits (histogram filled by the select kernel, one-CTA scan,
+// scatter into bucket order) followed by a rank sort INSIDE each bucket, 8 lanes per key -- every key counts the keys of its
+// bucket below it.  The importances spread over ~70 buckets, so this does ~2 % of the comparisons of ranking against all
+// keys (round 1: 400 M comparisons, 158 us -- the second-largest kernel of a stream update); still no passes over the data
+// that depend on its size class, and the output is the exact ascending key order.
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(uint32_t* hist /* SEL_BUCKETS + 1 */, uint32_t* cursor) {
+  __shared__ uint32_t s_warp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t v[4], x = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { v[k] = hist[threadIdx.x * 4 + k]; x += v[k]; cursor[threadIdx.x * 4 + k] = 0u; }
+  uint32_t incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t wv = s_warp[lane];
+    uint32_t wi = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += y; }
+    s_warp[lane] = wi - wv;
+  }
+  __syncthreads();
+  uint32_t run = s_warp[warp] + incl - x;
+#pragma unroll
+  for (int k = 0; k < 4; k++) { hist[threadIdx.x * 4 + k] = run; run += v[k]; }
+  if (threadIdx.x == 1023) hist[SEL_BUCKETS] = run;
+}
+__global__ void __launch_bounds__(256) bucket_scatter_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ count,
+                                                             const uint32_t* __restrict__ off, uint32_t* cursor, uint64_t* __restrict__ keys2) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= *count) return;
+  const uint64_t k = keys[i];
+  const uint32_t b = (uint32_t)(k >> 52);
+  keys2[off[b] + atomicAdd(&cursor[b], 1u)] = k;
+}
+// 32 keys per CTA, 8 lanes per key.  The grid is sized for the worst case; CTAs past *count exit.
+__global__ void __launch_bounds__(256) rank_sort_kernel(const uint64_t* __restrict__ keys2, const uint32_t* __restrict__ count,
+                                                        const uint32_t* __restrict__ off, MesoChunkCandidate* __restrict__ out, int64_t cap, int F) {
   const uint32_t n = *count;
   if (blockIdx.x * 32u >= n) return;
   const uint32_t k = blockIdx.x * 32u + (threadIdx.x >> 3);
   const uint32_t sub = threadIdx.x & 7;
-  const uint64_t my = (k < n) ? keys[k] : ~0ull;
+  const uint64_t my = (k < n) ? keys2[k] : ~0ull;
+  const uint32_t b = (uint32_t)(my >> 52);
+  const uint32_t lo = (k < n) ? off[b] : 0u, hi = (k < n) ? off[b + 1] : 0u;
   uint32_t rank = 0;
 #pragma unroll 4
-  for (uint32_t j = sub; j < n; j += 8) rank += (__ldg(keys + j) < my) ? 1u : 0u;
+  for (uint32_t j = lo + sub; j < hi; j += 8) rank += (__ldg(keys2 + j) < my) ? 1u : 0u;
   rank += __shfl_xor_sync(0xffffffffu, rank, 1);
   rank += __shfl_xor_sync(0xffffffffu, rank, 2);
   rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+  rank += lo;
   if (sub == 0 && k < n && (int64_t)rank < cap) {
     const int side = 2 * F + 1;
     const uint32_t idx = (uint32_t)my;
@@ -192,15 +237,23 @@ int64_t resident_max_candidates(const MesoViewConfig& vc) {
   return side * side * side;
 }
 
-// keys: scratch for resident_max_candidates() u64; d_count: one u32; d_out: cap candidates, sorted
+// d_keys: scratch of resident_sort_scratch_bytes(): keys | keys in bucket order | bucket offsets | bucket cursors;
+// d_count: one u32; d_out: cap candidates, sorted
+size_t resident_sort_scratch_bytes(const MesoViewConfig& vc) { return (size_t)resident_max_candidates(vc) * 16 + (size_t)(2 * SEL_BUCKETS + 8) * 4; }
 void launch_select_view(const LaunchCtx& lc, const float fwd[3], const MesoViewConfig& vc, uint64_t* d_keys, uint32_t* d_count,
                         MesoChunkCandidate* d_out, int64_t cap) {
   const ViewParams p = make_params(fwd, vc);
   const int64_t total = resident_max_candidates(vc);
+  uint64_t* keys2 = d_keys + total;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(keys2 + total);
+  uint32_t* cursor = hist + SEL_BUCKETS + 4;
   cudaMemsetAsync(d_count, 0, sizeof(uint32_t), lc.stream);
-  select_view_kernel<<<(unsigned)((total + 255) / 256), 256, 0, lc.stream>>>(p, d_keys, d_count);
-  rank_sort_kernel<<<(unsigned)((total + 31) / 32), 256, 0, lc.stream>>>(d_keys, d_count, d_out, cap, p.F);
-  (*lc.launches) += 2;
+  cudaMemsetAsync(hist, 0, (SEL_BUCKETS + 1) * sizeof(uint32_t), lc.stream);
+  select_view_kernel<<<(unsigned)((total + 255) / 256), 256, 0, lc.stream>>>(p, d_keys, d_count, hist);
+  bucket_scan_kernel<<<1, 1024, 0, lc.stream>>>(hist, cursor);
+  bucket_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, lc.stream>>>(d_keys, d_count, hist, cursor, keys2);
+  rank_sort_kernel<<<(unsigned)((total + 31) / 32), 256, 0, lc.stream>>>(keys2, d_count, hist, d_out, cap, p.F);
+  (*lc.launches) += 4;
 }
 
 // FImportanceComputeInfo::CalculateBlockImportance (ChunkManagerHelper.h:50-70), restated literally including its dead near

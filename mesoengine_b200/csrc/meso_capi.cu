@@ -944,7 +944,7 @@ static int ensure_select_buffers(MesoCtx* c, const MesoViewConfig& vc) {
   if (need > c->sel_cap) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_sel_keys); cudaFree(c->d_sel_out); c->d_sel_keys = nullptr; c->d_sel_out = nullptr; c->sel_cap = 0;
-    CK(cudaMalloc(&c->d_sel_keys, (size_t)need * 8));
+    CK(cudaMalloc(&c->d_sel_keys, resident_sort_scratch_bytes(vc)));
     CK(cudaMalloc(&c->d_sel_out, (size_t)need * sizeof(MesoChunkCandidate)));
     c->sel_cap = need;
   }

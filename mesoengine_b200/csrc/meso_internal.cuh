@@ -129,6 +129,7 @@ void launch_block_importance(const LaunchCtx& lc, const int32_t* d_chunk_loc, co
 
 // K6 (k_resident.cu, k_voxelize.cu)
 int64_t resident_max_candidates(const MesoViewConfig& vc);
+size_t resident_sort_scratch_bytes(const MesoViewConfig& vc);
 void launch_select_view(const LaunchCtx& lc, const float fwd[3], const MesoViewConfig& vc, uint64_t* d_keys, uint32_t* d_count,
                         MesoChunkCandidate* d_out, int64_t cap);
 void launch_chunk_importance(const LaunchCtx& lc, const int32_t* d_loc, int64_t n, const int32_t cam[3], const float fwd[3], float* d_out);
