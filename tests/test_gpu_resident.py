@@ -245,7 +245,9 @@ def test_moving_window_follows_the_camera(ctx, capi, orc, gran):
     assert fill() <= nchunks
     vol, origin = check()
     partial_max = len(vol.export_partial()[0])
-    moves = [(1, 0, 0)] * 15 + [(-2, 1, 1), (-3, -1, -1), (0, 0, 2), (-5, 0, 0)]     # 15 = three window widths along x
+    # block granularity: 15 = three window widths along x; voxel granularity (the oracle voxelises every window afresh on the
+    # CPU, ~8 s each): one window width, then the same diagonal / multi-chunk / full-width jumps
+    moves = [(1, 0, 0)] * (15 if gran == "block" else 5) + [(-2, 1, 1), (-3, -1, -1), (0, 0, 2), (-5, 0, 0)]
     for mv in moves:
         cam = [c + m for c, m in zip(cam, mv)]
         assert ctx.stream_recentre(cam) == mv
