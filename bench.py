@@ -1428,8 +1428,14 @@ def bench_mesh(ctx, capi, scenes, torch, stream, args, dev, n_work=1024):
         occ, full, keys, _ = ctx.volume_download()
         populated = int(np.unpackbits(occ.view(np.uint8)).sum())
         alg = 64.0 * len(keys) + 1024.0 * int(np.prod(dims)) + 16.0 * nq + 4
+        # second merge level (oracle/orc_mesh.c): faces of full bricks towards absent bricks, merged per chunk -- how many quads
+        # they became and how many 8x8 brick faces (one quad each before this level existed) those quads cover
+        q1 = quads[:nq, 1]
+        lvl = ((q1 >> 19) & 1) == 1
+        brick_faces = int((((q1[lvl] >> 27) & 0x1F).to(torch.int64) * (quads[:nq, 2][lvl] >> 3).to(torch.int64)).sum().item())
         out[name] = {"meshed_voxels_per_s": n ** 3 / (ms * 1e-3), "ms": ms, "quads": int(nq), "populated_bricks": populated,
-                     "partial_bricks": int(len(keys)), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9}
+                     "partial_bricks": int(len(keys)), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
+                     "brick_level": {"quads": int(lvl.sum().item()), "brick_faces_covered": brick_faces}}
         if name == "terrain_1024_blocks" and not args.no_cpu:
             # BASELINE.json configs[2], CPU beside GPU: the oracle meshes the very same volume on all host threads; the two
             # quad lists are compared in full after the canonical sort (bit-exact), not sampled

@@ -61,7 +61,10 @@ typedef struct { float BlockSize; uint32_t BlockResolution; float ChunkSize; uin
  * face: 0 -X, 1 +X, 2 -Y, 3 +Y, 4 -Z, 5 +Z, 6 = eye inside a solid voxel, 7 = miss.
  * miss = {0xFFFFFFFF, 0x0007FFFF, +inf, 0xFF000000} (clear colour (0,0,0,1): Samples/SimpleVoxel.cpp:315). */
 typedef struct { uint32_t w0, w1; float t; uint32_t rgba; } MesoHitRecord;
-/* w0 = x | y<<16 ; w1 = z | face<<16 | w<<24 ; w2 = h ; w3 = 0 (reserved: material). */
+/* w0 = x | y<<16 ; w1 = z | face<<16 | level<<19 | w<<24 ; w2 = h ; w3 = 0 (reserved: material).  (x,y,z) = minimum-corner
+ * voxel of the quad, w along u, h along v with (u,v) = (y,z) / (x,z) / (x,y) for X / Y / Z faces.  level 0: voxel-level quad
+ * inside one brick (w, h <= 8); level 1: brick-level quad -- whole faces of full bricks towards absent bricks, merged inside one
+ * chunk (w, h multiples of 8, <= 128). */
 typedef struct { uint32_t w0, w1, w2, w3; } MesoQuad;
 /* Host-derived ray setup (meso_ray_setup); 80 B, passed to the kernel by value. */
 typedef struct {
@@ -274,8 +277,9 @@ MESO_API int64_t meso_tiles_per_rank(int width, int height, int world);
 
 /* ---- K3: face cull + greedy merge -------------------------------------------------------------------------
  * The north-star form of the reference's "mesher" (hidden-block cull + instance compaction, ChunkPool.h:381-445):
- * exposed faces of every occupied brick merged greedily into quads.  Order of the output list is unspecified;
- * compare after a canonical sort. */
+ * exposed faces of every occupied brick merged greedily into quads -- voxel faces inside each brick, and the faces of full
+ * bricks towards absent ones across each chunk (the block-granular scenes of the reference are made of those only: a flat
+ * chunk face is one quad).  Order of the output list is unspecified; compare after a canonical sort. */
 MESO_API int meso_mesh(MesoCtx* ctx, MesoQuad* host_quads, int64_t cap, int64_t* n_quads);
 MESO_API int meso_mesh_device(MesoCtx* ctx, void* d_quads, int64_t cap, int64_t* n_quads /* host, written after sync */);
 /* The 8-byte quad count of the last meso_mesh_device on this context, copied device -> device into d_count_out (int64) on
@@ -290,7 +294,9 @@ MESO_API int meso_mesh_device_shared(MesoCtx* ctx, void* d_quads, void* d_counte
 /* ---- K5: edit --------------------------------------------------------------------------------------------- */
 MESO_API int meso_carve_sphere(MesoCtx* ctx, const int32_t center[3], int32_t radius, int64_t* n_dirty);
 MESO_API int meso_download_dirty(MesoCtx* ctx, uint64_t* keys, int64_t cap);
-/* Re-mesh only the bricks of the last carve's dirty list and their six neighbours. */
+/* Re-mesh only the bricks of the last carve's dirty list and their six neighbours (host_keys: those bricks, chunk*4096+block).
+ * Returned: the voxel-level quads of the listed bricks and the brick-level quads of every chunk that holds one of them -- the
+ * caller replaces exactly those (a quad's brick and chunk follow from its corner). */
 MESO_API int meso_remesh_dirty(MesoCtx* ctx, MesoQuad* host_quads, int64_t cap, int64_t* n_quads, uint64_t* host_keys,
                                int64_t cap_keys, int64_t* n_keys);
 

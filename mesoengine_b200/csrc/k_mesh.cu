@@ -5,49 +5,89 @@
 // Neither quads nor a face-neighbour test exist in the reference: the definition is oracle/orc_mesh.c
 // ("parity unpinned by reference; bit-exact vs repo oracle" after the canonical sort).
 //
-// Pass A (worklist): one thread per 64-brick occupancy word; occupied bricks that are not buried (full with six full
-// neighbours, decided with word-wide shifts) are compacted with a warp prefix sum + one atomic per warp.
+// Two levels (definition: oracle/orc_mesh.c).  Voxel level: the exposed voxel faces of a brick, merged inside the brick (passes A
+// and B below).  Brick level: the face of a FULL brick towards an ABSENT brick is not a voxel-level face; those faces are merged
+// per chunk, direction and brick layer over 16x16-brick images (pass C) -- the block-granular scenes of the reference consist of
+// nothing else, and a flat chunk face is one quad instead of 256.
+//
+// Pass A (worklist): one thread per 64-brick occupancy word; partial bricks, and full bricks with at least one PARTIAL
+// neighbour (decided with word-wide shifts), are compacted with a warp prefix sum + one atomic per warp.
 // Pass B (mesh): one THREAD per (brick, axis), 32 bricks and one axis per warp pass: the brick's eight z-slices in registers, the eight planes
 // along the axis formed from them, the facing plane of the two neighbours, sixteen (direction, layer) 8x8 images merged
 // greedily; quads staged per warp in shared memory and written behind one reservation per batch.
 // HBM-bound integer work on paper: 64 B per populated brick + 16 B per quad (+ neighbour slices, mostly L1 / L2 hits).
 #include "meso_internal.cuh"
 
-// full word w of chunk (cx,cy,cz), zeros outside the grid
-__device__ __forceinline__ uint64_t full_word(const DVolume& v, int cx, int cy, int cz, int w) {
-  if ((unsigned)cx >= (unsigned)v.dims[0] || (unsigned)cy >= (unsigned)v.dims[1] || (unsigned)cz >= (unsigned)v.dims[2]) return 0ull;
-  return __ldg(&v.full[chunk_index(v, cx, cy, cz) * 64 + w]);
+// chunk index -> coordinates in 32-bit arithmetic (a 64-bit division per thread costs more than the loads it guards)
+__device__ __forceinline__ void chunk_coords(const DVolume& v, int64_t c, int& cx, int& cy, int& cz) {
+  const uint32_t u = (uint32_t)c, dx = (uint32_t)v.dims[0], dy = (uint32_t)v.dims[1];
+  const uint32_t q = u / dx;
+  cx = (int)(u - q * dx); cz = (int)(q / dy); cy = (int)(q - (uint32_t)cz * dy);
+}
+// {occupancy, full} word w of chunk (cx,cy,cz), zeros outside the grid
+__device__ __forceinline__ ulonglong2 of_word(const DVolume& v, int cx, int cy, int cz, int w) {
+  if ((unsigned)cx >= (unsigned)v.dims[0] || (unsigned)cy >= (unsigned)v.dims[1] || (unsigned)cz >= (unsigned)v.dims[2]) return make_ulonglong2(0ull, 0ull);
+  return __ldg(&v.of[chunk_index(v, cx, cy, cz) * 64 + w]);
+}
+__device__ __forceinline__ uint64_t partial_of(const ulonglong2 p) { return p.x & ~p.y; }
+
+// The six neighbour words of 64-brick word w (= z*4 + y/4, four 16-bit x-rows) of chunk c, each brick's neighbour moved onto
+// the brick's own bit: m[2a] = minus side, m[2a+1] = plus side of axis a.  F picks the bit plane: occupancy, full or partial.
+template <class F>
+__device__ __forceinline__ void neighbour_words(const DVolume& v, int64_t c, int w, F pick, uint64_t m[6]) {
+  int cx, cy, cz;
+  chunk_coords(v, c, cx, cy, cz);
+  const int z = w >> 2, yq = w & 3;
+  const ulonglong2* own = v.of + c * 64;
+  const uint64_t X0 = 0x0001000100010001ull, X15 = 0x8000800080008000ull;
+  const uint64_t me = pick(__ldg(own + w));
+  m[0] = ((me << 1) & ~X0) | ((pick(of_word(v, cx - 1, cy, cz, w)) >> 15) & X0);
+  m[1] = ((me >> 1) & ~X15) | ((pick(of_word(v, cx + 1, cy, cz, w)) << 15) & X15);
+  const uint64_t ym_src = pick(yq > 0 ? __ldg(own + w - 1) : of_word(v, cx, cy - 1, cz, z * 4 + 3));
+  const uint64_t yp_src = pick(yq < 3 ? __ldg(own + w + 1) : of_word(v, cx, cy + 1, cz, z * 4 + 0));
+  m[2] = (me << 16) | (ym_src >> 48);
+  m[3] = (me >> 16) | (yp_src << 48);
+  m[4] = pick(z > 0 ? __ldg(own + w - 4) : of_word(v, cx, cy, cz - 1, 15 * 4 + yq));
+  m[5] = pick(z < 15 ? __ldg(own + w + 4) : of_word(v, cx, cy, cz + 1, 0 * 4 + yq));
 }
 
-// Pass A, one thread per 64-brick occupancy word (word = z*4 + y/4, four 16-bit x-rows): bricks that are full and
-// have six full neighbours are buried (no exposed face); the six neighbour masks come from shifted full-words of this
-// and the adjacent words / chunks.  Survivors are appended to the work list (warp prefix + one atomic per warp).
-__global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank, int world, uint64_t* work, uint32_t* work_count) {
+__device__ __forceinline__ uint32_t chunk_hash_rank(uint64_t c, int world) { return (uint32_t)(((c * 0x9E3779B97F4A7C15ull) >> 40) % (unsigned)world); }
+__device__ __forceinline__ bool chunk_wholly_full(const DVolume& v, int cx, int cy, int cz) {
+  if ((unsigned)cx >= (unsigned)v.dims[0] || (unsigned)cy >= (unsigned)v.dims[1] || (unsigned)cz >= (unsigned)v.dims[2]) return false;
+  const int64_t ci = chunk_index(v, cx, cy, cz);
+  return (__ldg(&v.chunk_full[ci >> 5]) >> (ci & 31)) & 1u;
+}
+
+// false: the chunk cannot own a face of either level -- not this rank's, no brick, or wholly full inside wholly full neighbours
+__device__ __forceinline__ bool chunk_may_have_faces(const DVolume& v, int64_t c, bool by_hash, int rank, int world) {
+  if (by_hash ? (world > 1 && (int)chunk_hash_rank((uint64_t)c, world) != rank) : (world > 1 && ((uint32_t)c % (uint32_t)world) != (uint32_t)rank)) return false;
+  if (!((__ldg(&v.chunk_any[c >> 5]) >> (c & 31)) & 1u)) return false;
+  int cx, cy, cz;
+  chunk_coords(v, c, cx, cy, cz);
+  return !(chunk_wholly_full(v, cx, cy, cz) && chunk_wholly_full(v, cx - 1, cy, cz) && chunk_wholly_full(v, cx + 1, cy, cz) && chunk_wholly_full(v, cx, cy - 1, cz) &&
+           chunk_wholly_full(v, cx, cy + 1, cz) && chunk_wholly_full(v, cx, cy, cz - 1) && chunk_wholly_full(v, cx, cy, cz + 1));
+}
+
+// Pass A, one thread per 64-brick word: a full brick has voxel-level faces only towards PARTIAL neighbours (towards a full one
+// the face is hidden, towards an absent one it belongs to the brick level).  Survivors are appended to the work list (warp
+// prefix + one atomic per warp).
+__global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank, int world, uint64_t* work, uint32_t* work_count, uint32_t* chunk_list,
+                                                            uint32_t* chunk_count) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t todo = 0;
   int64_t c = 0; int w = 0;
   if (t < v.nchunks * MESO_WORDS) {
     c = t >> 6; w = (int)(t & 63);
-    if ((c % world) == rank) {
-      const uint64_t O = __ldg(&v.occ[t]);
-      if (O) {
-        const uint64_t F = __ldg(&v.full[t]);
-        uint64_t buried = 0;
-        if (F) {
-          const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
-          const int z = w >> 2, yq = w & 3;
-          const uint64_t X0 = 0x0001000100010001ull, X15 = 0x8000800080008000ull;
-          const uint64_t fxm = ((F << 1) & ~X0) | ((full_word(v, cx - 1, cy, cz, w) >> 15) & X0);
-          const uint64_t fxp = ((F >> 1) & ~X15) | ((full_word(v, cx + 1, cy, cz, w) << 15) & X15);
-          const uint64_t ym_src = yq > 0 ? __ldg(&v.full[t - 1]) : full_word(v, cx, cy - 1, cz, z * 4 + 3);
-          const uint64_t yp_src = yq < 3 ? __ldg(&v.full[t + 1]) : full_word(v, cx, cy + 1, cz, z * 4 + 0);
-          const uint64_t fym = (F << 16) | (ym_src >> 48);
-          const uint64_t fyp = (F >> 16) | (yp_src << 48);
-          const uint64_t fzm = z > 0 ? __ldg(&v.full[t - 4]) : full_word(v, cx, cy, cz - 1, 15 * 4 + yq);
-          const uint64_t fzp = z < 15 ? __ldg(&v.full[t + 4]) : full_word(v, cx, cy, cz + 1, 0 * 4 + yq);
-          buried = F & fxm & fxp & fym & fyp & fzm & fzp;
+    if (chunk_may_have_faces(v, c, false, rank, world)) {    // whole chunks are dismissed by their chunk bits before a word is read
+      if (w == 0) chunk_list[atomicAdd(chunk_count, 1u)] = (uint32_t)c;     // pass C's work list: the chunks that get this far
+      const ulonglong2 P = __ldg(&v.of[t]);
+      if (P.x) {
+        todo = P.x & ~P.y;
+        if (P.y) {
+          uint64_t pn[6];
+          neighbour_words(v, c, w, [](const ulonglong2 p) { return partial_of(p); }, pn);
+          todo |= P.y & (pn[0] | pn[1] | pn[2] | pn[3] | pn[4] | pn[5]);
         }
-        todo = O & ~buried;
       }
     }
   }
@@ -174,11 +214,13 @@ __device__ __forceinline__ uint64_t axis_plane(const uint64_t s[8], int l) {
   return p;
 }
 // the plane of a neighbouring brick that faces this one: its layer 7 (the neighbour on the minus side) or 0 (plus side)
+// (`absent`: what an absent neighbour counts as -- empty for a partial brick, covered for a full one, whose face towards it
+// belongs to the brick level)
 template <int AXIS>
-__device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, int by, int bz, int layer) {
+__device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, int by, int bz, int layer, uint64_t absent) {
   uint32_t slot = 0;
   const int st = brick_state(v, bx, by, bz, slot);
-  if (st == 0) return 0ull;
+  if (st == 0) return absent;
   if (st == 1) return ~0ull;
   if (AXIS == 2) return __ldg(&v.pool[(size_t)slot * 8 + layer]);
   uint64_t s[8];
@@ -213,8 +255,8 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
   }
   uint64_t nbm = 0, nbp = 0;
   if (st != 0) {
-    nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7);
-    nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0);
+    nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, st == 1 ? ~0ull : 0ull);
+    nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, st == 1 ? ~0ull : 0ull);
   }
   uint64_t s[8];
   if (partial) {
@@ -239,8 +281,8 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = ~0ull;
   }
-  const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7);
-  const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0);
+  const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, st == 1 ? ~0ull : 0ull);
+  const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, st == 1 ? ~0ull : 0ull);
 #endif
   const uint64_t org = (uint64_t)(uint32_t)(bx * 8) | ((uint64_t)(uint32_t)(by * 8) << 16) | ((uint64_t)(uint32_t)(bz * 8) << 32);
   uint64_t prev = nbm, cur = s[0];
@@ -359,22 +401,166 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
   flush(min(s_n[warp], MQ_CAP));
 }
 
-void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
+// ---- pass C: brick level -------------------------------------------------------------------------------------------------------
+// One warp per chunk.  Chunks without bricks, without full bricks, or wholly full with six wholly full neighbours (the bulk of a
+// solid's interior; one bit per chunk each) are dismissed first.  Otherwise, per axis, the lanes form the chunk's 4096-bit images
+// "full brick whose neighbour on the minus / plus side is absent" in the native word layout (two words per lane, the neighbour's
+// occupancy moved onto the brick's bit: in-chunk words from shared memory, the facing words of the adjacent chunk only where a
+// full brick touches the border) and leave them in shared memory; then lane = (side, brick layer) gathers its 16 rows x 16 bits
+// and merges them greedily.  Chunks come from all of the volume (c % world == rank) or from a list (re-mesh; sharded over the
+// ranks by a hash of the chunk index).  Streaming integer work: 1 KB of {occupancy, full} words per chunk that gets that far.
+#define CF_WARPS 4
+#define CF_STAGE 96
+__global__ void __launch_bounds__(CF_WARPS * 32) mesh_chunk_faces_kernel(DVolume v, const uint32_t* __restrict__ chunk_list, const uint32_t* __restrict__ chunk_count_ptr,
+                                                                           int shard_rank, int shard_world, MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
+  __shared__ uint64_t s_o[CF_WARPS][64];
+  __shared__ uint64_t s_e[CF_WARPS][2][64];
+  __shared__ uint16_t s_rows[CF_WARPS][32][16 + 2];   // +2: lanes start in different banks
+  __shared__ uint4 s_q[CF_WARPS][CF_STAGE];
+  __shared__ int s_n[CF_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_chunks = (int64_t)*chunk_count_ptr;
+  if (lane == 0) s_n[warp] = 0;
+  __syncwarp();
+  for (int64_t item = (int64_t)blockIdx.x * CF_WARPS + warp; item < n_chunks; item += (int64_t)gridDim.x * CF_WARPS) {
+    const int64_t c = (int64_t)chunk_list[item];
+    if (shard_world > 1 && !chunk_may_have_faces(v, c, true, shard_rank, shard_world)) continue;
+    int cx, cy, cz;
+    chunk_coords(v, c, cx, cy, cz);
+    const ulonglong2 P0 = __ldg(&v.of[c * 64 + lane]), P1 = __ldg(&v.of[c * 64 + lane + 32]);
+    if (!__any_sync(0xffffffffu, (P0.y | P1.y) != 0ull)) continue;     // no full brick
+    __syncwarp();
+    s_o[warp][lane] = P0.x; s_o[warp][lane + 32] = P1.x;
+    __syncwarp();
+#pragma unroll 1
+    for (int axis = 0; axis < 3; axis++) {
+      uint64_t any = 0;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int w = lane + 32 * k, z = w >> 2, yq = w & 3;
+        const uint64_t F = k ? P1.y : P0.y, me = k ? P1.x : P0.x;
+        uint64_t em = 0, ep = 0;
+        if (F) {
+          uint64_t om, op;
+          if (axis == 0) {
+            const uint64_t X0 = 0x0001000100010001ull, X15 = 0x8000800080008000ull;
+            om = (me << 1) & ~X0; op = (me >> 1) & ~X15;
+            if (F & X0) om |= (of_word(v, cx - 1, cy, cz, w).x >> 15) & X0;
+            if (F & X15) op |= (of_word(v, cx + 1, cy, cz, w).x << 15) & X15;
+          } else if (axis == 1) {
+            om = (me << 16) | ((yq > 0 ? s_o[warp][w - 1] : of_word(v, cx, cy - 1, cz, z * 4 + 3).x) >> 48);
+            op = (me >> 16) | ((yq < 3 ? s_o[warp][w + 1] : of_word(v, cx, cy + 1, cz, z * 4 + 0).x) << 48);
+          } else {
+            om = z > 0 ? s_o[warp][w - 4] : of_word(v, cx, cy, cz - 1, 15 * 4 + yq).x;
+            op = z < 15 ? s_o[warp][w + 4] : of_word(v, cx, cy, cz + 1, 0 * 4 + yq).x;
+          }
+          em = F & ~om; ep = F & ~op;
+        }
+        s_e[warp][0][w] = em; s_e[warp][1][w] = ep;
+        any |= em | ep;
+      }
+      if (!__any_sync(0xffffffffu, any != 0ull)) continue;     // warp-uniform: no full brick of this chunk faces an absent one along this axis
+      __syncwarp();
+      const int side = lane >> 4, L = lane & 15;
+      const uint64_t* e = s_e[warp][side];
+      uint16_t* r = s_rows[warp][lane];
+      uint32_t nonzero = 0;
+      for (int vv = 0; vv < 16; vv++) {
+        uint32_t row;
+        if (axis == 2) row = (uint32_t)(e[L * 4 + (vv >> 2)] >> (16 * (vv & 3))) & 0xFFFFu;            // layer z: row y, bit x
+        else if (axis == 1) row = (uint32_t)(e[vv * 4 + (L >> 2)] >> (16 * (L & 3))) & 0xFFFFu;        // layer y: row z, bit x
+        else {                                                                                         // layer x: row z, bit y
+          row = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint64_t t = (e[vv * 4 + q] >> L) & 0x0001000100010001ull;
+            row |= (uint32_t)((t & 1ull) | ((t >> 15) & 2ull) | ((t >> 30) & 4ull) | ((t >> 45) & 8ull)) << (4 * q);
+          }
+        }
+        r[vv] = (uint16_t)row; nonzero |= row;
+      }
+      if (nonzero) {
+        const int dir = 2 * axis + side;
+        const int lv = L * 8 + (side ? 7 : 0);     // the voxel layer that carries the face
+        for (int vv = 0; vv < 16; vv++) {
+          uint32_t row = r[vv];
+          while (row) {
+            const int u0 = __ffs(row) - 1;
+            const int w = __ffs(~(row >> u0)) - 1;
+            const uint32_t m = ((1u << w) - 1u) << u0;
+            int h = 1;
+            while (vv + h < 16 && ((uint32_t)r[vv + h] & m) == m) { r[vv + h] = (uint16_t)(r[vv + h] & ~m); h++; }
+            row &= ~m;
+            int x, y, z;
+            if (axis == 0) { x = lv; y = u0 * 8; z = vv * 8; } else if (axis == 1) { x = u0 * 8; y = lv; z = vv * 8; } else { x = u0 * 8; y = vv * 8; z = lv; }
+            const uint4 q = make_uint4((uint32_t)(cx * 128 + x) | ((uint32_t)(cy * 128 + y) << 16),
+                                       (uint32_t)(cz * 128 + z) | ((uint32_t)dir << 16) | (1u << 19) | ((uint32_t)(w * 8) << 24), (uint32_t)(h * 8), 0u);
+            const int idx = atomicAdd(&s_n[warp], 1);
+            if (idx < CF_STAGE) s_q[warp][idx] = q;
+            else {
+              const unsigned long long g = atomicAdd_system(quad_count, 1ull);
+              if ((int64_t)g < cap) reinterpret_cast<uint4*>(quads)[g] = q;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      const int count = min(s_n[warp], CF_STAGE);
+      if (count > 0) {
+        unsigned long long sbase = 0;
+        if (lane == 0) sbase = atomicAdd_system(quad_count, (unsigned long long)count);   // system scope: the counter may live in a peer GPU
+        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        for (int i = lane; i < count; i += 32)
+          if ((int64_t)sbase + i < cap) reinterpret_cast<uint4*>(quads)[sbase + i] = s_q[warp][i];
+      }
+      __syncwarp();
+      if (lane == 0) s_n[warp] = 0;
+      __syncwarp();
+    }
+  }
+}
+
+// chunks that hold a listed brick, de-duplicated through a bit per chunk (mark: zero on entry, zero again after clear_chunk_marks)
+__global__ void __launch_bounds__(256) mark_chunks_kernel(const uint64_t* __restrict__ keys, uint32_t n_keys, uint32_t* mark, uint32_t* chunk_list, uint32_t* chunk_count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_keys) return;
+  const uint32_t c = (uint32_t)(keys[i] >> 12);
+  if (i > 0 && (uint32_t)(keys[i - 1] >> 12) == c) return;   // cheap filter: runs of keys of one chunk
+  const uint32_t old = atomicOr(&mark[c >> 5], 1u << (c & 31));
+  if (old & (1u << (c & 31))) return;
+  chunk_list[atomicAdd(chunk_count, 1u)] = c;
+}
+__global__ void clear_chunk_marks_kernel(const uint32_t* __restrict__ chunk_list, const uint32_t* __restrict__ chunk_count, uint32_t* mark) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *chunk_count) atomicAnd(&mark[chunk_list[i] >> 5], ~(1u << (chunk_list[i] & 31)));
+}
+
+void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, const MeshScratch& ms,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count) {
-  cudaMemsetAsync(d_work_count, 0, sizeof(uint32_t), lc.stream);
+  cudaMemsetAsync(ms.work_count, 0, sizeof(uint32_t), lc.stream);
+  cudaMemsetAsync(ms.chunk_count, 0, sizeof(uint32_t), lc.stream);
   if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   const int64_t n = v.nchunks * MESO_WORDS;
-  mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, d_work, d_work_count);
-  mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, d_work, d_work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
-  (*lc.launches) += 2;
+  mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, ms.work, ms.work_count, ms.chunk_list, ms.chunk_count);
+  mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, ms.work, ms.work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
+  const int64_t groups = (v.nchunks + CF_WARPS - 1) / CF_WARPS;
+  mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, groups), CF_WARPS * 32, 0, lc.stream>>>(v, ms.chunk_list, ms.chunk_count, 0, 1, d_quads, cap, d_quad_count);
+  (*lc.launches) += 3;
 }
 
 void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
-                      int64_t cap, unsigned long long* d_quad_count, int rank, int world) {
+                      int64_t cap, unsigned long long* d_quad_count, const MeshScratch& ms, int rank, int world) {
   cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   if (n_keys == 0) return;
   const int64_t passes = (((int64_t)n_keys + 31) / 32) * 3;
   const unsigned grid = (unsigned)min((int64_t)lc.sm_count * 12, (passes + MB_WARPS - 1) / MB_WARPS);
   mesh_bricks_kernel<<<grid, MB_THREADS, 0, lc.stream>>>(v, d_keys, nullptr, n_keys, d_quads, cap, d_quad_count, rank, world);
-  (*lc.launches)++;
+  // the brick-level quads of every chunk that holds a listed brick
+  cudaMemsetAsync(ms.chunk_count, 0, sizeof(uint32_t), lc.stream);
+  mark_chunks_kernel<<<(n_keys + 255) / 256, 256, 0, lc.stream>>>(d_keys, n_keys, ms.chunk_mark, ms.chunk_list, ms.chunk_count);
+  const int64_t bound = min((int64_t)n_keys, v.nchunks);      // the list cannot be longer than either
+  mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, (bound + CF_WARPS - 1) / CF_WARPS), CF_WARPS * 32, 0, lc.stream>>>(
+      v, ms.chunk_list, ms.chunk_count, rank, world, d_quads, cap, d_quad_count);
+  clear_chunk_marks_kernel<<<(unsigned)((bound + 255) / 256), 256, 0, lc.stream>>>(ms.chunk_list, ms.chunk_count, ms.chunk_mark);
+  (*lc.launches) += 4;
 }

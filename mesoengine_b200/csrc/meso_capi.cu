@@ -89,6 +89,7 @@ static void free_scene(MesoCtx* c) {
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
   cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
+  cudaFree(c->d_chunk_mark); cudaFree(c->d_chunk_list); cudaFree(c->d_chunk_count); c->d_chunk_mark = nullptr; c->d_chunk_list = nullptr; c->d_chunk_count = nullptr;
   cudaFree(c->d_loaded); cudaFree(c->d_stream_list); cudaFree(c->d_stream_stats);
   cudaFree(c->d_cube_cell); cudaFree(c->d_cube_cellp); cudaFree(c->d_cube_brick); cudaFree(c->d_cube_cell2);
   c->d_cube_cell = nullptr; c->d_cube_cellp = nullptr; c->d_cube_brick = nullptr; c->d_cube_cell2 = nullptr; c->cubes = CubeTables{}; c->cubes_valid = false;
@@ -216,6 +217,8 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   CK(cudaMalloc(&c->d_keys, (size_t)c->cap_dirty * 8)); CK(cudaMalloc(&c->d_keys_count, 4));
   const size_t mark_words = (nc * MESO_BLOCKS + 31) / 32;
   CK(cudaMalloc(&c->d_mark, mark_words * 4)); CK(cudaMemsetAsync(c->d_mark, 0, mark_words * 4, c->stream));
+  CK(cudaMalloc(&c->d_chunk_mark, ((nc + 31) / 32) * 4)); CK(cudaMemsetAsync(c->d_chunk_mark, 0, ((nc + 31) / 32) * 4, c->stream));
+  CK(cudaMalloc(&c->d_chunk_list, nc * 4)); CK(cudaMalloc(&c->d_chunk_count, 4));
   c->cap_inst = 0; c->n_inst = 0; c->n_dirty = 0;
   c->has_scene = true;
   CK(cudaStreamSynchronize(c->stream));
@@ -818,7 +821,7 @@ int meso_mesh_device(MesoCtx* c, void* d_quads, int64_t cap, int64_t* n_quads) {
   if (cap < 0 || (cap > 0 && !d_quads)) return fail(MESO_ERR_ARGUMENT, "meso_mesh_device: bad argument");
   int r = meso_ensure_mesh_buffers(c);
   if (r != MESO_OK) return r;
-  launch_mesh(c->lc(), c->v, c->rank, c->world, c->d_work, c->d_work_count, (MesoQuad*)d_quads, cap, c->d_quad_count);
+  launch_mesh(c->lc(), c->v, c->rank, c->world, c->mesh_scratch(), (MesoQuad*)d_quads, cap, c->d_quad_count);
   CK_LAST("mesh");
   if (n_quads) {
     unsigned long long n = 0;
@@ -841,7 +844,7 @@ int meso_mesh_device_shared(MesoCtx* c, void* d_quads, void* d_counter, int64_t 
   if (cap <= 0 || !d_quads || !d_counter) return fail(MESO_ERR_ARGUMENT, "meso_mesh_device_shared: bad argument");
   int r = meso_ensure_mesh_buffers(c);
   if (r != MESO_OK) return r;
-  launch_mesh(c->lc(), c->v, c->rank, c->world, c->d_work, c->d_work_count, (MesoQuad*)d_quads, cap, (unsigned long long*)d_counter,
+  launch_mesh(c->lc(), c->v, c->rank, c->world, c->mesh_scratch(), (MesoQuad*)d_quads, cap, (unsigned long long*)d_counter,
               /*reset_count=*/false);
   CK_LAST("mesh (shared list)");
   return MESO_OK;
@@ -920,7 +923,8 @@ int meso_remesh_dirty(MesoCtx* c, MesoQuad* host, int64_t cap, int64_t* n_quads,
     CK(cudaMalloc(&c->d_quads, (size_t)cap * sizeof(MesoQuad)));
     c->cap_quads = cap;
   }
-  launch_mesh_list(c->lc(), c->v, c->d_keys, nk, c->d_quads, cap, c->d_quad_count, c->rank, c->world);   // sharded by key hash over the partition
+  // voxel-level quads of the listed bricks + brick-level quads of the chunks that hold them; sharded by key / chunk hash over the partition
+  launch_mesh_list(c->lc(), c->v, c->d_keys, nk, c->d_quads, cap, c->d_quad_count, c->mesh_scratch(), c->rank, c->world);
   CK_LAST("remesh");
   unsigned long long n = 0;
   { const int rr = meso_small_read(c, &n, c->d_quad_count, 8); if (rr != MESO_OK) return rr; }

@@ -282,7 +282,7 @@ int meso_group_mesh(MesoGroup* g, MesoQuad* host_quads, int64_t cap, int64_t* n_
     }
     const int rc = meso_ensure_mesh_buffers(c);
     if (rc != MESO_OK) return rc;
-    launch_mesh(c->lc(), c->v, r, g->n, c->d_work, c->d_work_count, c->d_quads, cap, c->d_quad_count);
+    launch_mesh(c->lc(), c->v, r, g->n, c->mesh_scratch(), c->d_quads, cap, c->d_quad_count);
     CK_LAST("group mesh");
     CK(cudaMemcpyAsync(&g->h_counts[r], c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
   }
@@ -323,7 +323,7 @@ int meso_group_mesh_device(MesoGroup* g, void* d_quads_on_member0, int64_t cap, 
     NEED_SCENE(c);
     const int rc = meso_ensure_mesh_buffers(c);
     if (rc != MESO_OK) return rc;
-    launch_mesh(c->lc(), c->v, r, g->n, c->d_work, c->d_work_count, reinterpret_cast<MesoQuad*>(d_quads_on_member0) + (size_t)r * seg, seg, c->d_quad_count);
+    launch_mesh(c->lc(), c->v, r, g->n, c->mesh_scratch(), reinterpret_cast<MesoQuad*>(d_quads_on_member0) + (size_t)r * seg, seg, c->d_quad_count);
     CK_LAST("group mesh (device list)");
     CK(cudaMemcpyAsync(&g->h_counts[r], c->d_quad_count, 8, cudaMemcpyDeviceToHost, c->stream));
   }

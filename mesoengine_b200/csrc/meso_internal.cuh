@@ -105,10 +105,13 @@ void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, 
 void launch_pack_rgba8(const LaunchCtx& lc, const MesoHitRecord* d_records, size_t n, uint32_t* d_out);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
-void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, uint64_t* d_work, uint32_t* d_work_count,
+// scratch of the mesh passes: brick work list (room for every brick of the rank's chunks) + its counter; chunk list (nchunks
+// entries) + its counter; one bit per chunk, all-zero between calls (re-mesh: chunks that hold a listed brick)
+struct MeshScratch { uint64_t* work; uint32_t* work_count; uint32_t* chunk_list; uint32_t* chunk_count; uint32_t* chunk_mark; };
+void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, const MeshScratch& ms,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count = true);
 void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
-                      int64_t cap, unsigned long long* d_quad_count, int rank = 0, int world = 1);
+                      int64_t cap, unsigned long long* d_quad_count, const MeshScratch& ms, int rank = 0, int world = 1);
 
 void launch_carve(const LaunchCtx& lc, const DVolume& v, const int32_t center[3], int32_t radius, uint64_t* d_dirty,
                   uint32_t cap_dirty, uint32_t* d_dirty_count, int* d_overflow);

@@ -54,9 +54,10 @@ typedef struct { float BlockSize; uint32_t BlockResolution; float ChunkSize; uin
  * (x,y,z) = hit voxel in grid voxel coordinates; face: 0 -X, 1 +X, 2 -Y, 3 +Y, 4 -Z, 5 +Z,
  * 6 = ray started inside a solid voxel, 7 = miss.  Miss = {0xFFFFFFFF, 0x0007FFFF, +inf, 0xFF000000}. */
 typedef struct { uint32_t w0, w1; float t; uint32_t rgba; } OrcHitRecord;
-/* 16 B per quad.  w0 = x | y<<16 ; w1 = z | face<<16 | w<<24 ; w2 = h ; w3 = 0 (material, reserved).
+/* 16 B per quad.  w0 = x | y<<16 ; w1 = z | face<<16 | level<<19 | w<<24 ; w2 = h ; w3 = 0 (material, reserved).
  * (x,y,z) = minimum-corner voxel of the quad in grid voxel coordinates; w along u, h along v where
- * (u,v) = (y,z) for X faces, (x,z) for Y faces, (x,y) for Z faces. */
+ * (u,v) = (y,z) for X faces, (x,z) for Y faces, (x,y) for Z faces.  level 0: voxel-level quad inside one brick
+ * (w,h <= 8); level 1: brick-level quad of whole full-brick faces inside one chunk (w,h multiples of 8, <= 128). */
 typedef struct { uint32_t w0, w1, w2, w3; } OrcQuad;
 
 /* Ray setup derived on the HOST from FGPUUniformCamera (DESIGN.md "ray setup").  Same 80-byte
@@ -155,8 +156,10 @@ void orc_triplanar_faces(int octant, int faces_out[3]);
 
 /* ---- K3: face cull + greedy merge --------------------------------------------------------- */
 int64_t orc_mesh(const OrcVolume*, int nthreads, OrcQuad* quads, int64_t cap);
-/* Mesh only listed bricks (keys = chunk*4096+block). */
+/* Voxel-level quads of the listed bricks only (keys = chunk*4096+block). */
 int64_t orc_mesh_bricks(const OrcVolume*, const uint64_t* keys, int64_t n, OrcQuad* quads, int64_t cap);
+/* Brick-level quads of the listed chunks only. */
+int64_t orc_mesh_chunk_faces(const OrcVolume*, const int64_t* chunks, int64_t n, OrcQuad* quads, int64_t cap);
 /* Number of exposed unit faces (re-expansion property check). */
 int64_t orc_count_exposed_faces(const OrcVolume*);
 void orc_sort_quads(OrcQuad* q, int64_t n);

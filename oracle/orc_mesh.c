@@ -8,8 +8,19 @@
  * (neighbour bricks/chunks consulted; outside the grid = empty).  Greedy merge per image, fixed order:
  *   for v = 0..7: while row[v] != 0: u0 = lowest set bit; w = length of the run of ones starting at u0;
  *                 h = 1 + number of following rows that contain the whole run (each cleared as it is taken).
- * Quads never cross brick boundaries (w,h <= 8).  Emission order is (brick, dir, layer, v, u0); comparisons use
- * the canonical sort of orc_sort_quads (lexicographic on (w3,w2,w1,w0) as unsigned -- cf. Comparator.h:15-23).
+ * These VOXEL-LEVEL quads never cross brick boundaries (w,h <= 8): the brick is the unit of the dirty re-mesh.
+ *
+ * Second level, over whole bricks (the block-granular scenes of the reference are made of nothing else): the face of a
+ * FULL brick towards an ABSENT brick (unoccupied, or outside the grid) is left out of the voxel level and merged per chunk
+ * instead.  For each chunk, direction and brick layer along the axis (16 of them) the image is 16 rows x 16 bits of such
+ * faces, (u,v) as above in brick units, merged greedily in the same fixed order; a quad covers wb x hb bricks and is
+ * recorded in voxel units (corner = the voxel layer carrying the face, w = 8 wb <= 128, h = 8 hb) with bit 19 of w1 set.
+ * Brick-level quads never cross chunk boundaries: the chunk is their unit of re-meshing (a re-mesh of listed bricks
+ * returns the voxel-level quads of those bricks and the brick-level quads of every chunk that holds one of them).
+ * A flat 16 x 16-brick chunk face is therefore 1 quad, not 256.
+ *
+ * Emission order is unspecified; comparisons use the canonical sort of orc_sort_quads (lexicographic on (w3,w2,w1,w0)
+ * as unsigned -- cf. Comparator.h:15-23).
  */
 #include "orc_internal.h"
 
@@ -44,6 +55,20 @@ static void face_rows(const OrcVolume* v, int64_t bx, int64_t by, int64_t bz, co
   }
 }
 
+/* 0 absent (or outside the grid), 1 full, 2 partial -- from the occupancy / full bits, not from the payload */
+static int brick_state(const OrcVolume* v, int64_t bx, int64_t by, int64_t bz) {
+  if (bx < 0 || by < 0 || bz < 0 || bx >= (int64_t)v->dims[0] * ORC_CR || by >= (int64_t)v->dims[1] * ORC_CR || bz >= (int64_t)v->dims[2] * ORC_CR) return 0;
+  int64_t c = orc_cidx(v, (int)(bx >> 4), (int)(by >> 4), (int)(bz >> 4));
+  int b = orc_bidx((int)(bx & 15), (int)(by & 15), (int)(bz & 15));
+  if (!orc_getbit(v->occ + c * ORC_WORDS, b)) return 0;
+  return orc_getbit(v->full + c * ORC_WORDS, b) ? 1 : 2;
+}
+static const int DIR_STEP[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+/* the face of brick (bx,by,bz) towards `dir` belongs to the brick level */
+static int brick_level_face(const OrcVolume* v, int64_t bx, int64_t by, int64_t bz, int dir) {
+  return brick_state(v, bx, by, bz) == 1 && brick_state(v, bx + DIR_STEP[dir][0], by + DIR_STEP[dir][1], bz + DIR_STEP[dir][2]) == 0;
+}
+
 static int64_t mesh_brick(const OrcVolume* v, int64_t bx, int64_t by, int64_t bz, OrcQuad* out, int64_t cap, int64_t n, int64_t* faces) {
   uint64_t s[8];
   orc_brick_slices(v, bx, by, bz, s);
@@ -53,9 +78,11 @@ static int64_t mesh_brick(const OrcVolume* v, int64_t bx, int64_t by, int64_t bz
   face_rows(v, bx, by, bz, s, rows);
   for (int dir = 0; dir < 6; dir++) {
     int ax = dir >> 1;
+    const int lifted = brick_level_face(v, bx, by, bz, dir);   /* layer 0 (minus side) / 7 (plus side) goes to the brick level */
     for (int l = 0; l < 8; l++) {
       uint8_t* r = rows[dir][l];
       if (faces) for (int q = 0; q < 8; q++) *faces += __builtin_popcount(r[q]);
+      if (lifted && l == ((dir & 1) ? 7 : 0)) continue;
       for (int vv = 0; vv < 8; vv++) {
         while (r[vv]) {
           int u0 = __builtin_ctz(r[vv]);
@@ -76,6 +103,54 @@ static int64_t mesh_brick(const OrcVolume* v, int64_t bx, int64_t by, int64_t bz
       }
     }
   }
+  return n;
+}
+
+/* brick-level quads of one chunk */
+static int64_t mesh_chunk_faces(const OrcVolume* v, int64_t c, OrcQuad* out, int64_t cap, int64_t n) {
+  int cx = (int)(c % v->dims[0]), cy = (int)((c / v->dims[0]) % v->dims[1]), cz = (int)(c / ((int64_t)v->dims[0] * v->dims[1]));
+  uint64_t any_full = 0;
+  for (int w = 0; w < ORC_WORDS; w++) any_full |= v->full[c * ORC_WORDS + w];
+  if (!any_full) return n;
+  for (int dir = 0; dir < 6; dir++) {
+    int ax = dir >> 1;
+    for (int l = 0; l < 16; l++) {
+      uint16_t r[16];
+      for (int vv = 0; vv < 16; vv++) {
+        r[vv] = 0;
+        for (int u = 0; u < 16; u++) {
+          int x, y, z;
+          if (ax == 0) { x = l; y = u; z = vv; } else if (ax == 1) { x = u; y = l; z = vv; } else { x = u; y = vv; z = l; }
+          if (brick_level_face(v, cx * 16 + x, cy * 16 + y, cz * 16 + z, dir)) r[vv] |= (uint16_t)(1u << u);
+        }
+      }
+      for (int vv = 0; vv < 16; vv++) {
+        while (r[vv]) {
+          int u0 = __builtin_ctz(r[vv]);
+          int w = __builtin_ctz(~((unsigned)r[vv] >> u0));
+          uint16_t m = (uint16_t)(((1u << w) - 1u) << u0);
+          int h = 1;
+          while (vv + h < 16 && (r[vv + h] & m) == m) { r[vv + h] &= (uint16_t)~m; h++; }
+          r[vv] &= (uint16_t)~m;
+          int lv = l * 8 + ((dir & 1) ? 7 : 0);   /* the voxel layer that carries the face */
+          int x, y, z;
+          if (ax == 0) { x = lv; y = u0 * 8; z = vv * 8; } else if (ax == 1) { x = u0 * 8; y = lv; z = vv * 8; } else { x = u0 * 8; y = vv * 8; z = lv; }
+          if (out && n < cap) {
+            out[n].w0 = (uint32_t)(cx * 128 + x) | ((uint32_t)(cy * 128 + y) << 16);
+            out[n].w1 = (uint32_t)(cz * 128 + z) | ((uint32_t)dir << 16) | (1u << 19) | ((uint32_t)(w * 8) << 24);
+            out[n].w2 = (uint32_t)(h * 8); out[n].w3 = 0;
+          }
+          n++;
+        }
+      }
+    }
+  }
+  return n;
+}
+
+int64_t orc_mesh_chunk_faces(const OrcVolume* v, const int64_t* chunks, int64_t nc, OrcQuad* quads, int64_t cap) {
+  int64_t n = 0;
+  for (int64_t i = 0; i < nc; i++) n = mesh_chunk_faces(v, chunks[i], quads, cap, n);
   return n;
 }
 
@@ -101,6 +176,7 @@ static void mesh_range(void* ctx, int64_t b, int64_t e, int tid) {
     for (int bb = 0; bb < ORC_BLOCKS; bb++)
       if (orc_getbit(v->occ + c * ORC_WORDS, bb))
         n = mesh_brick(v, cx * 16 + (bb & 15), cy * 16 + ((bb >> 4) & 15), cz * 16 + (bb >> 8), NULL, 0, n, &faces);
+    n = mesh_chunk_faces(v, c, NULL, 0, n);
     a->counts[c] = n;
     if (!a->count_only && n > 0) {
       a->bufs[c] = (OrcQuad*)malloc(sizeof(OrcQuad) * (size_t)n);
@@ -108,6 +184,7 @@ static void mesh_range(void* ctx, int64_t b, int64_t e, int tid) {
       for (int bb = 0; bb < ORC_BLOCKS; bb++)
         if (orc_getbit(v->occ + c * ORC_WORDS, bb))
           m = mesh_brick(v, cx * 16 + (bb & 15), cy * 16 + ((bb >> 4) & 15), cz * 16 + (bb >> 8), a->bufs[c], n, m, NULL);
+      mesh_chunk_faces(v, c, a->bufs[c], n, m);
     }
   }
   pthread_mutex_lock(&a->mu); a->faces += faces; pthread_mutex_unlock(&a->mu);

@@ -78,7 +78,7 @@ lib.orc_volume_num_chunks.restype = C.c_int64
 lib.orc_volume_occ.restype = C.c_void_p
 lib.orc_volume_full.restype = C.c_void_p
 for _n in ("orc_volume_num_partial", "orc_volume_export_partial", "orc_volume_count_voxels", "orc_volume_build_occupancy",
-           "orc_mesh", "orc_mesh_bricks", "orc_count_exposed_faces", "orc_carve_sphere"):
+           "orc_mesh", "orc_mesh_bricks", "orc_mesh_chunk_faces", "orc_count_exposed_faces", "orc_carve_sphere"):
     getattr(lib, _n).restype = C.c_int64
 
 
@@ -300,6 +300,21 @@ class Volume:
         q = np.zeros(max(n, 1), dtype=Quad)
         lib.orc_mesh_bricks(self.h, _p(keys), C.c_int64(len(keys)), _p(q), C.c_int64(n))
         return q[:n]
+
+    def mesh_chunk_faces(self, chunks):
+        """Brick-level quads (full-brick faces towards absent bricks, merged per chunk) of the listed chunks."""
+        chunks = np.ascontiguousarray(chunks, dtype=np.int64)
+        n = int(lib.orc_mesh_chunk_faces(self.h, _p(chunks), C.c_int64(len(chunks)), None, C.c_int64(0)))
+        q = np.zeros(max(n, 1), dtype=Quad)
+        lib.orc_mesh_chunk_faces(self.h, _p(chunks), C.c_int64(len(chunks)), _p(q), C.c_int64(n))
+        return q[:n]
+
+    def remesh(self, keys):
+        """What a re-mesh of the listed bricks returns: their voxel-level quads and the brick-level quads of every chunk that
+        holds one of them."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        chunks = np.unique(keys >> np.uint64(12)).astype(np.int64)
+        return np.concatenate([self.mesh_bricks(keys), self.mesh_chunk_faces(chunks)])
 
     def count_exposed_faces(self):
         return int(lib.orc_count_exposed_faces(self.h))

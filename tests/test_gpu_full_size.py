@@ -118,4 +118,4 @@ def test_carve_4096_idempotent_and_local(big, orc):
     assert nd > 0 and np.array_equal(dirty, ref)
     assert ctx.carve_sphere(center, 48) == 0          # idempotent
     quads, keys = ctx.remesh_dirty(1 << 22, 1 << 20)
-    assert orc.sort_quads(quads).tobytes() == orc.sort_quads(vol.mesh_bricks(np.sort(keys))).tobytes()
+    assert orc.sort_quads(quads).tobytes() == orc.sort_quads(vol.remesh(np.sort(keys))).tobytes()

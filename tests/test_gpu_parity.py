@@ -406,6 +406,63 @@ def test_mesh_worst_case_bricks(ctx, orc):
     _compare_frames(ctx, orc, vol, _cams(orc, origin, dims, 160, 96)[:3], 160, 96)
 
 
+def test_mesh_brick_level(ctx, orc):
+    """The second merge level: faces of full bricks towards absent bricks, merged per chunk.  A flat slab (one quad per chunk
+    face), a 3-D checkerboard of full bricks (2048 bricks x 6 unmergeable faces per chunk: the pass's staging area overflows),
+    and a random full / partial / absent mix across chunk borders and the grid border."""
+    origin, dims = (0, 0, 0), (2, 2, 1)
+    nch = 4
+    rng = np.random.default_rng(5)
+    occ = np.zeros((nch, 64), dtype=np.uint64); full = np.zeros((nch, 64), dtype=np.uint64)
+    keys, payload = [], []
+    # chunk 0: a slab of 16 x 16 x 2 full bricks; chunk 1: checkerboard of full bricks; chunks 2, 3: random mix
+    for z in (3, 4):
+        occ[0, z * 4:z * 4 + 4] = ~np.uint64(0); full[0, z * 4:z * 4 + 4] = ~np.uint64(0)
+    for b in range(4096):
+        if ((b & 15) + ((b >> 4) & 15) + (b >> 8)) & 1:
+            occ[1, b >> 6] |= np.uint64(1) << np.uint64(b & 63); full[1, b >> 6] |= np.uint64(1) << np.uint64(b & 63)
+    for c in (2, 3):
+        kind = rng.integers(0, 4, size=4096)             # 0,1 absent / 2 full / 3 partial
+        for b in np.nonzero(kind >= 2)[0]:
+            b = int(b)
+            occ[c, b >> 6] |= np.uint64(1) << np.uint64(b & 63)
+            if kind[b] == 2:
+                full[c, b >> 6] |= np.uint64(1) << np.uint64(b & 63)
+            else:
+                keys.append(c * 4096 + b)
+                payload.append(rng.integers(1, 2 ** 63, size=8, dtype=np.int64).astype(np.uint64) if rng.integers(0, 2) else np.array([0, 0, 0, 1 << 27, 0, 0, 0, 0], dtype=np.uint64))
+    keys = np.array(keys, dtype=np.uint64); payload = np.stack(payload)
+    vol = orc.Volume(origin, dims).import_(occ, full, keys, payload)
+    ctx.scene_create(origin, dims, 1 << 13)
+    ctx.volume_upload(occ, full, keys, payload)
+    ref = vol.mesh()
+    got = ctx.mesh(len(ref) + 64)
+    assert orc.sort_quads(got).tobytes() == orc.sort_quads(ref).tobytes()
+    level = (got["w1"] >> 19) & 1
+    cx = (got["w0"] & 0xFFFF) >> 7; cy = (got["w0"] >> 16) >> 7
+    in0 = (cx == 0) & (cy == 0)
+    # the slab: its two 128 x 128 faces are one quad each (its +x / +y sides touch chunks 1 and 2 and merge less)
+    big = got[in0 & (level == 1) & (((got["w1"] >> 24) & 0xFF) == 128) & (got["w2"] == 128)]
+    assert len(big) == 2 and sorted(((big["w1"] >> 16) & 7).tolist()) == [4, 5]
+    area = int((((got["w1"] >> 24) & 0xFF).astype(np.int64) * got["w2"].astype(np.int64)).sum())
+    assert area == vol.count_exposed_faces()
+    # the partition over ranks covers both levels
+    parts = []
+    for r in range(3):
+        ctx.set_partition(r, 3)
+        parts.append(ctx.mesh(len(ref) + 64))
+    ctx.set_partition(0, 1)
+    assert orc.sort_quads(np.concatenate(parts)).tobytes() == orc.sort_quads(ref).tobytes()
+    # edits: a carve through the slab and the checkerboard turns full bricks partial / absent; the re-mesh returns both levels
+    for center, radius in (((100, 100, 40), 30), ((200, 60, 64), 45), ((128, 128, 64), 20)):
+        nd = ctx.carve_sphere(center, radius)
+        assert np.array_equal(ctx.download_dirty(nd), vol.carve_sphere(center, radius))
+        quads, rkeys = ctx.remesh_dirty(1 << 20, 1 << 20)
+        assert orc.sort_quads(quads).tobytes() == orc.sort_quads(vol.remesh(np.sort(rkeys))).tobytes()
+    ref = vol.mesh()
+    assert orc.sort_quads(ctx.mesh(len(ref) + 64)).tobytes() == orc.sort_quads(ref).tobytes()
+
+
 def test_mesh_partition_union(ctx, orc):
     """Brick ranges over 'ranks' (chunk % world): the union of the per-rank quad lists is the 1-GPU list."""
     origin, dims, params = scenes.sphere_scene(256)
@@ -457,7 +514,7 @@ def test_carve_and_remesh(ctx, orc):
         _assert_volume_equal(ctx, vol)
         quads, keys = ctx.remesh_dirty(1 << 20, 1 << 20)
         keys = np.sort(keys)
-        ref_q = vol.mesh_bricks(keys)
+        ref_q = vol.remesh(keys)      # voxel-level quads of the bricks + brick-level quads of the chunks that hold them
         assert orc.sort_quads(quads).tobytes() == orc.sort_quads(ref_q).tobytes()
     # after the edits a full re-mesh and a frame still agree with the oracle
     ref = vol.mesh()

@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
     for c in partition.rank_chunks(vol.nchunks, rank, world):
         bits = np.unpackbits(occ[c].view(np.uint8), bitorder="little")
         keys += [int(c) * 4096 + int(b) for b in np.nonzero(bits)[0]]
-    quads = vol.mesh_bricks(np.array(keys, dtype=np.uint64)).view(np.uint32).reshape(-1, 4)
+    mine_chunks = np.array(list(partition.rank_chunks(vol.nchunks, rank, world)), dtype=np.int64)
+    quads = np.concatenate([vol.mesh_bricks(np.array(keys, dtype=np.uint64)), vol.mesh_chunk_faces(mine_chunks)]).view(np.uint32).reshape(-1, 4)
     counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(counts, torch.tensor([len(quads)], dtype=torch.int64))
     counts = [int(c.item()) for c in counts]

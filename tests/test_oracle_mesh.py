@@ -73,7 +73,16 @@ def test_quads_reexpand_to_exposed_faces(orc, case):
     assert area == len(faces)            # quads never overlap
     assert faces == exp                  # and cover exactly the exposed faces
     assert vol.count_exposed_faces() == len(exp)
-    assert np.all(((quads["w1"] >> 24) & 0xFF) <= 8) and np.all(quads["w2"] <= 8) and np.all(quads["w3"] == 0)
+    level = (quads["w1"] >> 19) & 1
+    wq, hq = (quads["w1"] >> 24) & 0xFF, quads["w2"]
+    assert np.all(quads["w3"] == 0) and np.all((quads["w1"] >> 20) & 0xF == 0)
+    assert np.all(wq[level == 0] <= 8) and np.all(hq[level == 0] <= 8)                   # voxel level: inside one brick
+    assert np.all(wq[level == 1] % 8 == 0) and np.all(hq[level == 1] % 8 == 0)           # brick level: whole bricks ...
+    assert np.all(wq[level == 1] <= 128) and np.all(hq[level == 1] <= 128)               # ... inside one chunk
+    if case == "terrain_block":
+        assert np.all(level == 1)        # a block-granular scene has only full bricks: everything merges at the brick level
+    if case == "sphere_voxel":
+        assert np.any(level == 0)
     # greedy merge really merges: far fewer quads than unit faces on these shapes
     assert len(quads) < len(exp)
     # canonical sort is idempotent and a permutation
@@ -90,8 +99,38 @@ def test_mesh_bricks_is_a_partition_of_mesh(orc):
         bits = np.unpackbits(occ[c].view(np.uint8), bitorder="little")
         keys += [c * 4096 + int(b) for b in np.nonzero(bits)[0]]
     a = orc.sort_quads(vol.mesh())
-    b = orc.sort_quads(vol.mesh_bricks(np.array(keys, dtype=np.uint64)))
+    b = orc.sort_quads(np.concatenate([vol.mesh_bricks(np.array(keys, dtype=np.uint64)), vol.mesh_chunk_faces(np.arange(vol.nchunks))]))
     assert a.tobytes() == b.tobytes()
+    assert orc.sort_quads(vol.remesh(np.array(keys, dtype=np.uint64))).tobytes() == a.tobytes()
+
+
+def test_brick_level_merge_of_flat_faces(orc):
+    """A slab of 16 x 16 x 2 full bricks in one chunk: two 128 x 128 quads and four 128 x 16 ones -- not 256 + 256 + 4 x 32
+    brick faces.  With a partial brick on top of one of them that brick's top face drops back to the voxel level."""
+    dims = (1, 1, 1)
+    occ = np.zeros((1, 64), dtype=np.uint64); full = np.zeros((1, 64), dtype=np.uint64)
+    for z in (3, 4):
+        occ[0, z * 4:z * 4 + 4] = ~np.uint64(0); full[0, z * 4:z * 4 + 4] = ~np.uint64(0)
+    vol = orc.Volume((0, 0, 0), dims).import_(occ, full, np.zeros(0, np.uint64), np.zeros((0, 8), np.uint64))
+    q = vol.mesh()
+    assert len(q) == 6 and np.all((q["w1"] >> 19) & 1 == 1)
+    area = (((q["w1"] >> 24) & 0xFF).astype(np.int64) * q["w2"]).sum()
+    assert area == vol.count_exposed_faces() == 2 * 128 * 128 + 4 * 128 * 16
+    top = q[((q["w1"] >> 16) & 7) == 5][0]
+    assert (top["w0"], top["w1"] & 0xFFFF, (top["w1"] >> 24) & 0xFF, top["w2"]) == (0, 4 * 8 + 7, 128, 128)
+    # a partial brick (one voxel) above brick (5, 6, 4)
+    b = 5 + 16 * 6 + 256 * 5
+    occ[0, b >> 6] |= np.uint64(1) << np.uint64(b & 63)
+    pay = np.zeros((1, 8), np.uint64); pay[0, 0] = 1
+    vol2 = orc.Volume((0, 0, 0), dims).import_(occ, full, np.array([b], np.uint64), pay)
+    q2 = vol2.mesh()
+    faces, area2 = _expand(q2)
+    assert area2 == len(faces) == vol2.count_exposed_faces()
+    lvl0 = q2[(q2["w1"] >> 19) & 1 == 0]
+    # the full brick below shows 63 of its 64 top faces at the voxel level; the lone voxel has 5 exposed faces
+    below = lvl0[(lvl0["w1"] & 0xFFFF) == 4 * 8 + 7]
+    assert (((below["w1"] >> 24) & 0xFF).astype(np.int64) * below["w2"]).sum() == 63
+    assert len(lvl0) - len(below) == 5
 
 
 def test_carve_sphere_removes_exactly_the_voxels_inside(orc):
