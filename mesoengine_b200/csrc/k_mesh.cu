@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
 }
 
 // ---- pass C: brick level -------------------------------------------------------------------------------------------------------
-// One warp per chunk.  Chunks without bricks, without full bricks, or wholly full with six wholly full neighbours (the bulk of a
-// solid's interior; one bit per chunk each) are dismissed first.  Otherwise, per axis, the lanes form the chunk's 4096-bit images
+// One warp per (chunk, axis).  Chunks without bricks, without full bricks, or wholly full with six wholly full neighbours (the bulk of a
+// solid's interior; one bit per chunk each) are dismissed first.  Otherwise the lanes form the chunk's 4096-bit images
 // "full brick whose neighbour on the minus / plus side is absent" in the native word layout (two words per lane, the neighbour's
 // occupancy moved onto the brick's bit: in-chunk words from shared memory, the facing words of the adjacent chunk only where a
 // full brick touches the border) and leave them in shared memory; then lane = (side, brick layer) gathers its 16 rows x 16 bits
@@ -422,8 +422,9 @@ __global__ void __launch_bounds__(CF_WARPS * 32) mesh_chunk_faces_kernel(DVolume
   const int64_t n_chunks = (int64_t)*chunk_count_ptr;
   if (lane == 0) s_n[warp] = 0;
   __syncwarp();
-  for (int64_t item = (int64_t)blockIdx.x * CF_WARPS + warp; item < n_chunks; item += (int64_t)gridDim.x * CF_WARPS) {
-    const int64_t c = (int64_t)chunk_list[item];
+  for (int64_t item = (int64_t)blockIdx.x * CF_WARPS + warp; item < n_chunks * 3; item += (int64_t)gridDim.x * CF_WARPS) {
+    const int64_t c = (int64_t)chunk_list[item / 3];
+    const int axis = (int)(item % 3);
     if (shard_world > 1 && !chunk_may_have_faces(v, c, true, shard_rank, shard_world)) continue;
     int cx, cy, cz;
     chunk_coords(v, c, cx, cy, cz);
@@ -432,8 +433,7 @@ __global__ void __launch_bounds__(CF_WARPS * 32) mesh_chunk_faces_kernel(DVolume
     __syncwarp();
     s_o[warp][lane] = P0.x; s_o[warp][lane + 32] = P1.x;
     __syncwarp();
-#pragma unroll 1
-    for (int axis = 0; axis < 3; axis++) {
+    {
       uint64_t any = 0;
 #pragma unroll
       for (int k = 0; k < 2; k++) {
@@ -537,13 +537,12 @@ __global__ void clear_chunk_marks_kernel(const uint32_t* __restrict__ chunk_list
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, const MeshScratch& ms,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count) {
-  cudaMemsetAsync(ms.work_count, 0, sizeof(uint32_t), lc.stream);
-  cudaMemsetAsync(ms.chunk_count, 0, sizeof(uint32_t), lc.stream);
+  cudaMemsetAsync(ms.work_count, 0, 2 * sizeof(uint32_t), lc.stream);   // work_count and chunk_count are adjacent words
   if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   const int64_t n = v.nchunks * MESO_WORDS;
   mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, ms.work, ms.work_count, ms.chunk_list, ms.chunk_count);
   mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, ms.work, ms.work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
-  const int64_t groups = (v.nchunks + CF_WARPS - 1) / CF_WARPS;
+  const int64_t groups = (v.nchunks * 3 + CF_WARPS - 1) / CF_WARPS;
   mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, groups), CF_WARPS * 32, 0, lc.stream>>>(v, ms.chunk_list, ms.chunk_count, 0, 1, d_quads, cap, d_quad_count);
   (*lc.launches) += 3;
 }
@@ -559,7 +558,7 @@ void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_k
   cudaMemsetAsync(ms.chunk_count, 0, sizeof(uint32_t), lc.stream);
   mark_chunks_kernel<<<(n_keys + 255) / 256, 256, 0, lc.stream>>>(d_keys, n_keys, ms.chunk_mark, ms.chunk_list, ms.chunk_count);
   const int64_t bound = min((int64_t)n_keys, v.nchunks);      // the list cannot be longer than either
-  mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, (bound + CF_WARPS - 1) / CF_WARPS), CF_WARPS * 32, 0, lc.stream>>>(
+  mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, (bound * 3 + CF_WARPS - 1) / CF_WARPS), CF_WARPS * 32, 0, lc.stream>>>(
       v, ms.chunk_list, ms.chunk_count, rank, world, d_quads, cap, d_quad_count);
   clear_chunk_marks_kernel<<<(unsigned)((bound + 255) / 256), 256, 0, lc.stream>>>(ms.chunk_list, ms.chunk_count, ms.chunk_mark);
   (*lc.launches) += 4;

@@ -89,7 +89,7 @@ static void free_scene(MesoCtx* c) {
   cudaFree(c->d_frame); cudaFree(c->d_stats); cudaFree(c->d_touch_chunk); cudaFree(c->d_touch_brick);
   cudaFree(c->d_work); cudaFree(c->d_work_count); cudaFree(c->d_quad_count); cudaFree(c->d_quads);
   cudaFree(c->d_dirty); cudaFree(c->d_dirty_count); cudaFree(c->d_keys); cudaFree(c->d_keys_count); cudaFree(c->d_mark);
-  cudaFree(c->d_chunk_mark); cudaFree(c->d_chunk_list); cudaFree(c->d_chunk_count); c->d_chunk_mark = nullptr; c->d_chunk_list = nullptr; c->d_chunk_count = nullptr;
+  cudaFree(c->d_chunk_mark); cudaFree(c->d_chunk_list); c->d_chunk_mark = nullptr; c->d_chunk_list = nullptr; c->d_chunk_count = nullptr;
   cudaFree(c->d_loaded); cudaFree(c->d_stream_list); cudaFree(c->d_stream_stats);
   cudaFree(c->d_cube_cell); cudaFree(c->d_cube_cellp); cudaFree(c->d_cube_brick); cudaFree(c->d_cube_cell2);
   c->d_cube_cell = nullptr; c->d_cube_cellp = nullptr; c->d_cube_brick = nullptr; c->d_cube_cell2 = nullptr; c->cubes = CubeTables{}; c->cubes_valid = false;
@@ -211,14 +211,15 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   CK(cudaMalloc(&c->d_block_totals, 1024 * 4));
   CK(cudaMalloc(&c->d_stats, sizeof(RayStatsDev)));
   CK(cudaMalloc(&c->d_touch_chunk, nc)); CK(cudaMalloc(&c->d_touch_brick, max_bricks));
-  CK(cudaMalloc(&c->d_work_count, 4)); CK(cudaMalloc(&c->d_quad_count, 8));
+  CK(cudaMalloc(&c->d_work_count, 8)); c->d_chunk_count = c->d_work_count + 1;   // adjacent: one memset clears both
+  CK(cudaMalloc(&c->d_quad_count, 8));
   c->cap_dirty = 1u << 22;
   CK(cudaMalloc(&c->d_dirty, (size_t)c->cap_dirty * 8)); CK(cudaMalloc(&c->d_dirty_count, 4));
   CK(cudaMalloc(&c->d_keys, (size_t)c->cap_dirty * 8)); CK(cudaMalloc(&c->d_keys_count, 4));
   const size_t mark_words = (nc * MESO_BLOCKS + 31) / 32;
   CK(cudaMalloc(&c->d_mark, mark_words * 4)); CK(cudaMemsetAsync(c->d_mark, 0, mark_words * 4, c->stream));
   CK(cudaMalloc(&c->d_chunk_mark, ((nc + 31) / 32) * 4)); CK(cudaMemsetAsync(c->d_chunk_mark, 0, ((nc + 31) / 32) * 4, c->stream));
-  CK(cudaMalloc(&c->d_chunk_list, nc * 4)); CK(cudaMalloc(&c->d_chunk_count, 4));
+  CK(cudaMalloc(&c->d_chunk_list, nc * 4));
   c->cap_inst = 0; c->n_inst = 0; c->n_dirty = 0;
   c->has_scene = true;
   CK(cudaStreamSynchronize(c->stream));

@@ -106,7 +106,7 @@ void launch_pack_rgba8(const LaunchCtx& lc, const MesoHitRecord* d_records, size
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
 // scratch of the mesh passes: brick work list (room for every brick of the rank's chunks) + its counter; chunk list (nchunks
-// entries) + its counter; one bit per chunk, all-zero between calls (re-mesh: chunks that hold a listed brick)
+// entries) + its counter (the word after work_count); one bit per chunk, all-zero between calls (re-mesh: chunks that hold a listed brick)
 struct MeshScratch { uint64_t* work; uint32_t* work_count; uint32_t* chunk_list; uint32_t* chunk_count; uint32_t* chunk_mark; };
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, const MeshScratch& ms,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count = true);
