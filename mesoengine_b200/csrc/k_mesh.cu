@@ -386,15 +386,54 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     __syncwarp();
+    // Phase 2: ONE QUAD PER LANE PER ITERATION of a converged loop.  A lane whose image is used up takes the next queued one
+    // (indices handed out with a ballot: the loop is converged, no atomics), so the lanes stay busy until the queue runs dry
+    // whatever the quad counts of their images; the greedy step itself is branch-free on the 64-bit image -- the lowest set
+    // bit is (first non-empty row v, lowest u0) = the quad the fixed merge order takes next; its run length w from the row; its
+    // height h = index of the first following row that misses a bit of the run (rows past the image shift in as zeros, which
+    // bounds h by itself); the h rows of the run are cleared in one go.  Slots of the staging area come from the same ballot.
     const int ni = min(s_in[warp], MI_CAP);
-    for (int i = lane; i < ni; i += 32) {
-      const ulonglong2 e = s_img[warp][i];
-      greedy_stage(e.x, (int)((e.y >> 48) & 7), (int)((e.y >> 52) & 7), (int)(e.y & 0xFFFF), (int)((e.y >> 16) & 0xFFFF), (int)((e.y >> 32) & 0xFFFF),
-                   s_q[warp], &s_n[warp], quads, cap, quad_count);
+    int n_staged = min(s_n[warp], MQ_CAP);     // phase 1 stages quads itself only when the image queue overflows
+    const unsigned lt = (1u << lane) - 1u;
+    uint64_t img = 0ull, meta = 0ull;
+    int next = 0;
+    for (;;) {
+      const unsigned need = __ballot_sync(0xffffffffu, img == 0ull);
+      if (need != 0u && next < ni) {
+        const int i = next + __popc(need & lt);
+        if (img == 0ull && i < ni) { const ulonglong2 e = s_img[warp][i]; img = e.x; meta = e.y; }
+        next += __popc(need);
+      }
+      const unsigned has = __ballot_sync(0xffffffffu, img != 0ull);
+      if (has == 0u) break;
+      if (n_staged + 32 > MQ_CAP) { flush(n_staged); n_staged = 0; }
+      if (img != 0ull) {
+        const int p = __ffsll((long long)img) - 1;
+        const int vv = p >> 3, u0 = p & 7, sh = p & ~7;
+        const uint64_t t = img >> sh;                       // rows v, v+1, ... in bytes 0, 1, ...
+        const uint32_t row = (uint32_t)t & 0xFFu;
+        const int w = __ffs((int)~(row >> u0)) - 1;
+        const uint32_t m = ((1u << w) - 1u) << u0;
+        const uint32_t m4 = m * 0x01010101u;
+        const uint64_t mrep = ((uint64_t)m4 << 32) | m4;    // the run in every row
+        const uint64_t miss = ~t & mrep;
+        const int h = miss ? ((__ffsll((long long)miss) - 1) >> 3) : 8;
+        const uint64_t clr = h == 8 ? mrep : (mrep & ((1ull << (8 * h)) - 1ull));
+        img &= ~(clr << sh);
+        const uint32_t layer = (uint32_t)(meta >> 52) & 7u;
+        const uint32_t qx = axis == 0 ? layer : (uint32_t)u0;
+        const uint32_t qy = axis == 0 ? (uint32_t)u0 : (axis == 1 ? layer : (uint32_t)vv);
+        const uint32_t qz = axis == 2 ? layer : (uint32_t)vv;
+        // meta = x0 | y0 << 16 | z0 << 32 | dir << 48 | layer << 52 (voxel origin of the brick: the sums cannot carry)
+        const uint4 q = make_uint4((uint32_t)meta + (qx | (qy << 16)), (((uint32_t)(meta >> 32) & 0x0007FFFFu) + qz) | ((uint32_t)w << 24), (uint32_t)h, 0u);
+        s_q[warp][n_staged + __popc(has & lt)] = q;
+      }
+      n_staged += __popc(has);
     }
     __syncwarp();
-    if (lane == 0) s_in[warp] = 0;
-    if (s_n[warp] >= MQ_FLUSH) flush(min(s_n[warp], MQ_CAP));
+    if (lane == 0) { s_in[warp] = 0; s_n[warp] = n_staged; }
+    __syncwarp();
+    if (n_staged >= MQ_FLUSH) flush(n_staged);
     __syncwarp();
   }
   __syncwarp();
