@@ -68,31 +68,40 @@ __device__ __forceinline__ bool chunk_may_have_faces(const DVolume& v, int64_t c
            chunk_wholly_full(v, cx, cy + 1, cz) && chunk_wholly_full(v, cx, cy, cz - 1) && chunk_wholly_full(v, cx, cy, cz + 1));
 }
 
-// Pass A, one thread per 64-brick word: a full brick has voxel-level faces only towards PARTIAL neighbours (towards a full one
-// the face is hidden, towards an absent one it belongs to the brick level).  Survivors are appended to the work list (warp
-// prefix + one atomic per warp).
+// Pass A, one WARP per chunk of this rank (c = rank + world * i), two 64-brick words per lane.  The chunk is dismissed first by
+// its chunk bits, looked up by eight lanes at once (no brick; or wholly full inside six wholly full neighbours).  A full brick
+// has voxel-level faces only towards PARTIAL neighbours (towards a full one the face is hidden, towards an absent one it belongs
+// to the brick level).  Survivors are appended to the work list (warp prefix + one atomic per warp); the chunks that get this far
+// form pass C's list.
 __global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank, int world, uint64_t* work, uint32_t* work_count, uint32_t* chunk_list,
                                                             uint32_t* chunk_count) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t todo = 0;
-  int64_t c = 0; int w = 0;
-  if (t < v.nchunks * MESO_WORDS) {
-    c = t >> 6; w = (int)(t & 63);
-    if (chunk_may_have_faces(v, c, false, rank, world)) {    // whole chunks are dismissed by their chunk bits before a word is read
-      if (w == 0) chunk_list[atomicAdd(chunk_count, 1u)] = (uint32_t)c;     // pass C's work list: the chunks that get this far
-      const ulonglong2 P = __ldg(&v.of[t]);
-      if (P.x) {
-        todo = P.x & ~P.y;
-        if (P.y) {
-          uint64_t pn[6];
-          neighbour_words(v, c, w, [](const ulonglong2 p) { return partial_of(p); }, pn);
-          todo |= P.y & (pn[0] | pn[1] | pn[2] | pn[3] | pn[4] | pn[5]);
-        }
-      }
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)rank + (int64_t)world * ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  if (c >= v.nchunks) return;
+  int cx, cy, cz;
+  chunk_coords(v, c, cx, cy, cz);
+  bool flag = false;
+  if (lane == 0) flag = (__ldg(&v.chunk_any[c >> 5]) >> (c & 31)) & 1u;
+  else if (lane < 8) {
+    const int k = lane - 2;   // lane 1: the chunk itself; lanes 2..7: its neighbours -x +x -y +y -z +z
+    flag = chunk_wholly_full(v, cx + (k == 0 ? -1 : k == 1 ? 1 : 0), cy + (k == 2 ? -1 : k == 3 ? 1 : 0), cz + (k == 4 ? -1 : k == 5 ? 1 : 0));
+  }
+  const unsigned bits = __ballot_sync(0xffffffffu, flag);
+  if (!(bits & 1u) || (bits & 0xFEu) == 0xFEu) return;
+  if (lane == 0) chunk_list[atomicAdd(chunk_count, 1u)] = (uint32_t)c;
+  uint64_t todo[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int w = lane + 32 * k;
+    const ulonglong2 P = __ldg(&v.of[c * 64 + w]);
+    todo[k] = P.x & ~P.y;
+    if (P.y) {
+      uint64_t pn[6];
+      neighbour_words(v, c, w, [](const ulonglong2 p) { return partial_of(p); }, pn);
+      todo[k] |= P.y & (pn[0] | pn[1] | pn[2] | pn[3] | pn[4] | pn[5]);
     }
   }
-  const int lane = threadIdx.x & 31;
-  const uint32_t n = (uint32_t)__popcll(todo);
+  const uint32_t n = (uint32_t)(__popcll(todo[0]) + __popcll(todo[1]));
   uint32_t incl = n;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
@@ -101,10 +110,14 @@ __global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank,
   uint32_t base = 0;
   if (lane == 0) base = atomicAdd(work_count, total);
   base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
-  while (todo) {
-    const int bit = __ffsll((long long)todo) - 1;
-    todo &= todo - 1;
-    work[base++] = (uint64_t)c * MESO_BLOCKS + (uint64_t)(w * 64 + bit);
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    uint64_t t = todo[k];
+    while (t) {
+      const int bit = __ffsll((long long)t) - 1;
+      t &= t - 1;
+      work[base++] = (uint64_t)c * MESO_BLOCKS + (uint64_t)((lane + 32 * k) * 64 + bit);
+    }
   }
 }
 
@@ -145,6 +158,34 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
     }
     if (vv == 7 || (img >> (8 * (vv + 1))) == 0ull) break;   // nothing left in the rows below
   }
+}
+
+#ifndef MB_QUADS_PER_ITER
+#define MB_QUADS_PER_ITER 1
+#endif
+// One step of the greedy merge on a 64-bit image (row v = byte v, bit u), branch-free: the lowest set bit is (first non-empty
+// row v, lowest u0) = the quad the fixed merge order takes next; its run length w from the row; its height h = index of the
+// first following row that misses a bit of the run (rows past the image shift in as zeros, which bounds h by itself); the h rows
+// of the run are cleared in one go.  meta = x0 | y0 << 16 | z0 << 32 | dir << 48 | layer << 52 (voxel origin of the brick: the
+// sums cannot carry).  `axis` is uniform over the warp pass.
+__device__ __forceinline__ uint4 take_quad(uint64_t& img, uint64_t meta, int axis) {
+  const int p = __ffsll((long long)img) - 1;
+  const int vv = p >> 3, u0 = p & 7, sh = p & ~7;
+  const uint64_t t = img >> sh;                       // rows v, v+1, ... in bytes 0, 1, ...
+  const uint32_t row = (uint32_t)t & 0xFFu;
+  const int w = __ffs((int)~(row >> u0)) - 1;
+  const uint32_t m = ((1u << w) - 1u) << u0;
+  const uint32_t m4 = m * 0x01010101u;
+  const uint64_t mrep = ((uint64_t)m4 << 32) | m4;    // the run in every row
+  const uint64_t miss = ~t & mrep;
+  const int h = miss ? ((__ffsll((long long)miss) - 1) >> 3) : 8;
+  const uint64_t clr = h == 8 ? mrep : (mrep & ((1ull << (8 * h)) - 1ull));
+  img &= ~(clr << sh);
+  const uint32_t layer = (uint32_t)(meta >> 52) & 7u;
+  const uint32_t qx = axis == 0 ? layer : (uint32_t)u0;
+  const uint32_t qy = axis == 0 ? (uint32_t)u0 : (axis == 1 ? layer : (uint32_t)vv);
+  const uint32_t qz = axis == 2 ? layer : (uint32_t)vv;
+  return make_uint4((uint32_t)meta + (qx | (qy << 16)), (((uint32_t)(meta >> 32) & 0x0007FFFFu) + qz) | ((uint32_t)w << 24), (uint32_t)h, 0u);
 }
 
 // state of a brick: 0 absent / outside the grid, 1 full, 2 partial (slot = its payload)
@@ -228,7 +269,9 @@ __device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, in
   return axis_plane<AXIS>(s, layer);
 }
 
+#ifndef MB_THREADS
 #define MB_THREADS 128   // 4 warps per CTA: 20 KB of staged quads + 16 KB of queued images in static shared memory
+#endif
 #define MB_WARPS (MB_THREADS / 32)
 #ifndef MI_CAP
 #define MI_CAP 256       // (direction, layer) images a warp can queue per pass (32 bricks x one axis: typically 100-200 non-empty)
@@ -386,12 +429,9 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     __syncwarp();
-    // Phase 2: ONE QUAD PER LANE PER ITERATION of a converged loop.  A lane whose image is used up takes the next queued one
-    // (indices handed out with a ballot: the loop is converged, no atomics), so the lanes stay busy until the queue runs dry
-    // whatever the quad counts of their images; the greedy step itself is branch-free on the 64-bit image -- the lowest set
-    // bit is (first non-empty row v, lowest u0) = the quad the fixed merge order takes next; its run length w from the row; its
-    // height h = index of the first following row that misses a bit of the run (rows past the image shift in as zeros, which
-    // bounds h by itself); the h rows of the run are cleared in one go.  Slots of the staging area come from the same ballot.
+    // Phase 2: ONE QUAD PER LANE PER ITERATION of a converged loop (take_quad).  A lane whose image is used up takes the next
+    // queued one (indices handed out with a ballot: the loop is converged, no atomics), so the lanes stay busy until the queue
+    // runs dry whatever the quad counts of their images.  Slots of the staging area come from the same kind of ballot.
     const int ni = min(s_in[warp], MI_CAP);
     int n_staged = min(s_n[warp], MQ_CAP);     // phase 1 stages quads itself only when the image queue overflows
     const unsigned lt = (1u << lane) - 1u;
@@ -406,29 +446,17 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
       }
       const unsigned has = __ballot_sync(0xffffffffu, img != 0ull);
       if (has == 0u) break;
-      if (n_staged + 32 > MQ_CAP) { flush(n_staged); n_staged = 0; }
-      if (img != 0ull) {
-        const int p = __ffsll((long long)img) - 1;
-        const int vv = p >> 3, u0 = p & 7, sh = p & ~7;
-        const uint64_t t = img >> sh;                       // rows v, v+1, ... in bytes 0, 1, ...
-        const uint32_t row = (uint32_t)t & 0xFFu;
-        const int w = __ffs((int)~(row >> u0)) - 1;
-        const uint32_t m = ((1u << w) - 1u) << u0;
-        const uint32_t m4 = m * 0x01010101u;
-        const uint64_t mrep = ((uint64_t)m4 << 32) | m4;    // the run in every row
-        const uint64_t miss = ~t & mrep;
-        const int h = miss ? ((__ffsll((long long)miss) - 1) >> 3) : 8;
-        const uint64_t clr = h == 8 ? mrep : (mrep & ((1ull << (8 * h)) - 1ull));
-        img &= ~(clr << sh);
-        const uint32_t layer = (uint32_t)(meta >> 52) & 7u;
-        const uint32_t qx = axis == 0 ? layer : (uint32_t)u0;
-        const uint32_t qy = axis == 0 ? (uint32_t)u0 : (axis == 1 ? layer : (uint32_t)vv);
-        const uint32_t qz = axis == 2 ? layer : (uint32_t)vv;
-        // meta = x0 | y0 << 16 | z0 << 32 | dir << 48 | layer << 52 (voxel origin of the brick: the sums cannot carry)
-        const uint4 q = make_uint4((uint32_t)meta + (qx | (qy << 16)), (((uint32_t)(meta >> 32) & 0x0007FFFFu) + qz) | ((uint32_t)w << 24), (uint32_t)h, 0u);
-        s_q[warp][n_staged + __popc(has & lt)] = q;
-      }
+      if (n_staged + 32 * MB_QUADS_PER_ITER > MQ_CAP) { flush(n_staged); n_staged = 0; }
+      if (img != 0ull) s_q[warp][n_staged + __popc(has & lt)] = take_quad(img, meta, axis);
       n_staged += __popc(has);
+#if MB_QUADS_PER_ITER > 1
+#pragma unroll
+      for (int k = 1; k < MB_QUADS_PER_ITER; k++) {     // further quads of the same image before the loop's bookkeeping is paid again
+        const unsigned more = __ballot_sync(0xffffffffu, img != 0ull);
+        if (img != 0ull) s_q[warp][n_staged + __popc(more & lt)] = take_quad(img, meta, axis);
+        n_staged += __popc(more);
+      }
+#endif
     }
     __syncwarp();
     if (lane == 0) { s_in[warp] = 0; s_n[warp] = n_staged; }
@@ -578,8 +606,8 @@ void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, con
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count) {
   cudaMemsetAsync(ms.work_count, 0, 2 * sizeof(uint32_t), lc.stream);   // work_count and chunk_count are adjacent words
   if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
-  const int64_t n = v.nchunks * MESO_WORDS;
-  mesh_worklist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(v, rank, world, ms.work, ms.work_count, ms.chunk_list, ms.chunk_count);
+  const int64_t mine = (v.nchunks - rank + world - 1) / world;     // chunks rank, rank + world, ...: one warp each
+  mesh_worklist_kernel<<<(unsigned)((mine + 7) / 8), 256, 0, lc.stream>>>(v, rank, world, ms.work, ms.work_count, ms.chunk_list, ms.chunk_count);
   mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, ms.work, ms.work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
   const int64_t groups = (v.nchunks * 3 + CF_WARPS - 1) / CF_WARPS;
   mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, groups), CF_WARPS * 32, 0, lc.stream>>>(v, ms.chunk_list, ms.chunk_count, 0, 1, d_quads, cap, d_quad_count);
