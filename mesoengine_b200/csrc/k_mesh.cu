@@ -167,8 +167,9 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
 // row v, lowest u0) = the quad the fixed merge order takes next; its run length w from the row; its height h = index of the
 // first following row that misses a bit of the run (rows past the image shift in as zeros, which bounds h by itself); the h rows
 // of the run are cleared in one go.  meta = x0 | y0 << 16 | z0 << 32 | dir << 48 | layer << 52 (voxel origin of the brick: the
-// sums cannot carry).  `axis` is uniform over the warp pass.
-__device__ __forceinline__ uint4 take_quad(uint64_t& img, uint64_t meta, int axis) {
+// sums cannot carry).
+__device__ __forceinline__ uint4 take_quad(uint64_t& img, uint64_t meta) {
+  const uint32_t axis = (uint32_t)(meta >> 49) & 3u;
   const int p = __ffsll((long long)img) - 1;
   const int vv = p >> 3, u0 = p & 7, sh = p & ~7;
   const uint64_t t = img >> sh;                       // rows v, v+1, ... in bytes 0, 1, ...
@@ -414,6 +415,43 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     if (lane == 0) s_n[warp] = 0;
     __syncwarp();
   };
+  // Phase 2: ONE QUAD PER LANE PER ITERATION of a converged loop (take_quad).  A lane whose image is used up takes the next
+  // queued one (indices handed out with a ballot: the loop is converged, no atomics).  The loop stops as soon as a lane would
+  // idle -- the queue has run dry -- and the lanes KEEP the images they are working on across passes: phase 1 of the next pass
+  // refills the queue, so the merge runs with (nearly) all lanes busy whatever the quad counts of the images; only the last
+  // call drains.  Slots of the staging area come from the same kind of ballot.
+  const unsigned lt = (1u << lane) - 1u;
+  uint64_t img = 0ull, meta = 0ull;
+  auto merge = [&](int ni, bool drain) {
+    int n_staged = min(s_n[warp], MQ_CAP);     // phase 1 stages quads itself only when the image queue overflows
+    int next = 0;
+    for (;;) {
+      const unsigned need = __ballot_sync(0xffffffffu, img == 0ull);
+      if (need != 0u && next < ni) {
+        const int i = next + __popc(need & lt);
+        if (img == 0ull && i < ni) { const ulonglong2 e = s_img[warp][i]; img = e.x; meta = e.y; }
+        next += __popc(need);
+      }
+      const unsigned has = __ballot_sync(0xffffffffu, img != 0ull);
+      if (has == 0u || (!drain && has != 0xffffffffu && next >= ni)) break;
+      if (n_staged + 32 * MB_QUADS_PER_ITER > MQ_CAP) { flush(n_staged); n_staged = 0; }
+      if (img != 0ull) s_q[warp][n_staged + __popc(has & lt)] = take_quad(img, meta);
+      n_staged += __popc(has);
+#if MB_QUADS_PER_ITER > 1
+#pragma unroll
+      for (int k = 1; k < MB_QUADS_PER_ITER; k++) {     // further quads of the same image before the loop's bookkeeping is paid again
+        const unsigned more = __ballot_sync(0xffffffffu, img != 0ull);
+        if (img != 0ull) s_q[warp][n_staged + __popc(more & lt)] = take_quad(img, meta);
+        n_staged += __popc(more);
+      }
+#endif
+    }
+    __syncwarp();
+    if (lane == 0) { s_in[warp] = 0; s_n[warp] = n_staged; }
+    __syncwarp();
+    if (n_staged >= MQ_FLUSH) flush(n_staged);
+    __syncwarp();
+  };
   for (int64_t grp = (int64_t)blockIdx.x * MB_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * MB_WARPS) {
     const int axis = (int)(grp % 3);
     const int64_t item = (grp / 3) * 32 + lane;
@@ -429,41 +467,9 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
     __syncwarp();
-    // Phase 2: ONE QUAD PER LANE PER ITERATION of a converged loop (take_quad).  A lane whose image is used up takes the next
-    // queued one (indices handed out with a ballot: the loop is converged, no atomics), so the lanes stay busy until the queue
-    // runs dry whatever the quad counts of their images.  Slots of the staging area come from the same kind of ballot.
-    const int ni = min(s_in[warp], MI_CAP);
-    int n_staged = min(s_n[warp], MQ_CAP);     // phase 1 stages quads itself only when the image queue overflows
-    const unsigned lt = (1u << lane) - 1u;
-    uint64_t img = 0ull, meta = 0ull;
-    int next = 0;
-    for (;;) {
-      const unsigned need = __ballot_sync(0xffffffffu, img == 0ull);
-      if (need != 0u && next < ni) {
-        const int i = next + __popc(need & lt);
-        if (img == 0ull && i < ni) { const ulonglong2 e = s_img[warp][i]; img = e.x; meta = e.y; }
-        next += __popc(need);
-      }
-      const unsigned has = __ballot_sync(0xffffffffu, img != 0ull);
-      if (has == 0u) break;
-      if (n_staged + 32 * MB_QUADS_PER_ITER > MQ_CAP) { flush(n_staged); n_staged = 0; }
-      if (img != 0ull) s_q[warp][n_staged + __popc(has & lt)] = take_quad(img, meta, axis);
-      n_staged += __popc(has);
-#if MB_QUADS_PER_ITER > 1
-#pragma unroll
-      for (int k = 1; k < MB_QUADS_PER_ITER; k++) {     // further quads of the same image before the loop's bookkeeping is paid again
-        const unsigned more = __ballot_sync(0xffffffffu, img != 0ull);
-        if (img != 0ull) s_q[warp][n_staged + __popc(more & lt)] = take_quad(img, meta, axis);
-        n_staged += __popc(more);
-      }
-#endif
-    }
-    __syncwarp();
-    if (lane == 0) { s_in[warp] = 0; s_n[warp] = n_staged; }
-    __syncwarp();
-    if (n_staged >= MQ_FLUSH) flush(n_staged);
-    __syncwarp();
+    merge(min(s_in[warp], MI_CAP), /*drain=*/false);
   }
+  merge(0, /*drain=*/true);      // the images the lanes still hold
   __syncwarp();
   flush(min(s_n[warp], MQ_CAP));
 }
