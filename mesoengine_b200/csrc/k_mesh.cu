@@ -10,11 +10,13 @@
 // per chunk, direction and brick layer over 16x16-brick images (pass C) -- the block-granular scenes of the reference consist of
 // nothing else, and a flat chunk face is one quad instead of 256.
 //
-// Pass A (worklist): one thread per 64-brick occupancy word; partial bricks, and full bricks with at least one PARTIAL
-// neighbour (decided with word-wide shifts), are compacted with a warp prefix sum + one atomic per warp.
-// Pass B (mesh): one THREAD per (brick, axis), 32 bricks and one axis per warp pass: the brick's eight z-slices in registers, the eight planes
-// along the axis formed from them, the facing plane of the two neighbours, sixteen (direction, layer) 8x8 images merged
-// greedily; quads staged per warp in shared memory and written behind one reservation per batch.
+// Pass A (worklist): one warp per chunk of the rank; partial bricks, and full bricks with at least one PARTIAL neighbour (decided
+// with word-wide shifts), are compacted with a warp prefix sum + one atomic per warp.
+// Pass B (mesh): a warp pass = 32 bricks x one axis.  Phase 1, one THREAD per brick: its eight z-slices in registers, the eight
+// planes along the axis formed from them, the facing plane of the two neighbours, sixteen (direction, layer) 8x8 images, the
+// non-empty ones queued in shared memory.  Phase 2, a converged loop: every lane takes ONE quad off its current image per
+// iteration with a branch-free greedy step and fetches the next queued image when its own is used up; quads staged per warp in
+// shared memory and written behind one reservation per batch as one bulk asynchronous store.
 // HBM-bound integer work on paper: 64 B per populated brick + 16 B per quad (+ neighbour slices, mostly L1 / L2 hits).
 #include "meso_internal.cuh"
 
@@ -160,9 +162,6 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
   }
 }
 
-#ifndef MB_QUADS_PER_ITER
-#define MB_QUADS_PER_ITER 1
-#endif
 // One step of the greedy merge on a 64-bit image (row v = byte v, bit u), branch-free: the lowest set bit is (first non-empty
 // row v, lowest u0) = the quad the fixed merge order takes next; its run length w from the row; its height h = index of the
 // first following row that misses a bit of the run (rows past the image shift in as zeros, which bounds h by itself); the h rows
@@ -170,7 +169,7 @@ __device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, i
 // sums cannot carry).
 __device__ __forceinline__ uint4 take_quad(uint64_t& img, uint64_t meta) {
   const uint32_t axis = (uint32_t)(meta >> 49) & 3u;
-  const int p = __ffsll((long long)img) - 1;
+  const int p = (__ffsll((long long)img) - 1) & 63;    // (& 63: an exhausted image, img == 0, stays well-defined and 0)
   const int vv = p >> 3, u0 = p & 7, sh = p & ~7;
   const uint64_t t = img >> sh;                       // rows v, v+1, ... in bytes 0, 1, ...
   const uint32_t row = (uint32_t)t & 0xFFu;
@@ -356,12 +355,13 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
 // Persistent, grid-stride over the work list (count read from device memory: no host round trip between the passes).
 // A warp pass = 32 bricks x one axis.  Phase 1, one THREAD per brick: the brick's eight z-slices in registers, the eight
 // planes along the axis formed from them (the slices themselves for z, byte / column gathers for y / x), the facing plane of
-// the two neighbours, sixteen exposed-face images; the non-empty ones are queued in shared memory.  Phase 2: the lanes take the
-// queued images round-robin and merge them greedily -- the merge loops run over a dense queue instead of every lane waiting
-// for the lane with the busiest (direction, layer).  Quads are staged per warp and leave in batches behind one reservation.
-// (Round 1's warp-per-two-bricks form spent 55 % of its instructions building slices and images cooperatively and ran the
-// greedy loops at 2-6 active lanes, profiles/r2_mesh_bricks_sass_hot.txt; one thread per (brick, axis) WITHOUT the queue ran
-// them at 4.)
+// the two neighbours, sixteen exposed-face images; the non-empty ones are queued in shared memory.  Phase 2 (`merge` below): a
+// converged loop in which every lane takes one quad off its image per iteration and the next queued image when that is used up.
+// Quads are staged per warp and leave in batches behind one reservation.
+// History (profiles/README.md): round 1's warp-per-two-bricks form spent 55 % of its instructions building slices and images
+// cooperatively and ran the greedy loops at 2-6 active lanes; one thread per (brick, axis) without the queue ran them at 4;
+// the queue with a data-dependent greedy loop per image (lanes round-robin over the images) at 8; the converged one-quad-per-
+// iteration loop runs at 26 (0.58 -> 0.41 ms), and letting the lanes keep their images across passes removes its tail (0.385 ms).
 __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
                                                                     uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
                                                                     int shard_rank, int shard_world) {
@@ -434,17 +434,9 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
       }
       const unsigned has = __ballot_sync(0xffffffffu, img != 0ull);
       if (has == 0u || (!drain && has != 0xffffffffu && next >= ni)) break;
-      if (n_staged + 32 * MB_QUADS_PER_ITER > MQ_CAP) { flush(n_staged); n_staged = 0; }
+      if (n_staged + 32 > MQ_CAP) { flush(n_staged); n_staged = 0; }
       if (img != 0ull) s_q[warp][n_staged + __popc(has & lt)] = take_quad(img, meta);
       n_staged += __popc(has);
-#if MB_QUADS_PER_ITER > 1
-#pragma unroll
-      for (int k = 1; k < MB_QUADS_PER_ITER; k++) {     // further quads of the same image before the loop's bookkeeping is paid again
-        const unsigned more = __ballot_sync(0xffffffffu, img != 0ull);
-        if (img != 0ull) s_q[warp][n_staged + __popc(more & lt)] = take_quad(img, meta);
-        n_staged += __popc(more);
-      }
-#endif
     }
     __syncwarp();
     if (lane == 0) { s_in[warp] = 0; s_n[warp] = n_staged; }
