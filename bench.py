@@ -256,7 +256,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_code": reference_code_timings(nthreads),
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -884,7 +884,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     ctx.close()
     return 0
 
@@ -1490,6 +1490,26 @@ def cpu_baseline(ctx, capi, scene, cams, width, height, args):
             "thread_scaling_mrays_s": scaling, "parity_mismatches": mism}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner with printf when
+    NCCL_DEBUG is set on the box), so file descriptor 1 is pointed at stderr for the rest of the process and the line goes out
+    through a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1509,9 +1529,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not (world == 1 and args.gpus > 1 and args.impl == "ours"):    # (the torchrun re-launch below passes stdout through)
+        claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus:
         if args.gpus == 1 and world == 1:
             pass
