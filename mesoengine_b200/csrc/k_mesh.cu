@@ -75,8 +75,8 @@ __device__ __forceinline__ bool chunk_may_have_faces(const DVolume& v, int64_t c
 // has voxel-level faces only towards PARTIAL neighbours (towards a full one the face is hidden, towards an absent one it belongs
 // to the brick level).  Survivors are appended to the work list (warp prefix + one atomic per warp); the chunks that get this far
 // form pass C's list.
-__global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank, int world, uint64_t* work, uint32_t* work_count, uint32_t* chunk_list,
-                                                            uint32_t* chunk_count) {
+__global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank, int world, uint64_t* work, int64_t work_cap, uint32_t* work_count,
+                                                            uint32_t* full_count, uint32_t* chunk_list, uint32_t* chunk_count) {
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t)rank + (int64_t)world * ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   if (c >= v.nchunks) return;
@@ -91,27 +91,34 @@ __global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank,
   const unsigned bits = __ballot_sync(0xffffffffu, flag);
   if (!(bits & 1u) || (bits & 0xFEu) == 0xFEu) return;
   if (lane == 0) chunk_list[atomicAdd(chunk_count, 1u)] = (uint32_t)c;
-  uint64_t todo[2];
+  uint64_t todo[2], todo_full[2];
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     const int w = lane + 32 * k;
     const ulonglong2 P = __ldg(&v.of[c * 64 + w]);
     todo[k] = P.x & ~P.y;
+    todo_full[k] = 0ull;
     if (P.y) {
       uint64_t pn[6];
       neighbour_words(v, c, w, [](const ulonglong2 p) { return partial_of(p); }, pn);
-      todo[k] |= P.y & (pn[0] | pn[1] | pn[2] | pn[3] | pn[4] | pn[5]);
+      todo_full[k] = P.y & (pn[0] | pn[1] | pn[2] | pn[3] | pn[4] | pn[5]);
     }
   }
-  const uint32_t n = (uint32_t)(__popcll(todo[0]) + __popcll(todo[1]));
-  uint32_t incl = n;
+  // two lists in one buffer: partial bricks from the front, full bricks from the back -- pass B's warp passes are then uniform
+  // (a full brick costs two neighbour planes, a partial one sixteen images: mixed in one pass the full lanes would idle)
+  const uint32_t n = (uint32_t)(__popcll(todo[0]) + __popcll(todo[1])), nf = (uint32_t)(__popcll(todo_full[0]) + __popcll(todo_full[1]));
+  uint32_t incl = n | (nf << 16);                    // both prefix sums in one word (at most 128 bricks per lane, 4096 per warp)
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   if (total == 0) return;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(work_count, total);
-  base = __shfl_sync(0xffffffffu, base, 0) + incl - n;
+  uint32_t base = 0, base_f = 0;
+  if (lane == 0) {
+    if (total & 0xFFFFu) base = atomicAdd(work_count, total & 0xFFFFu);
+    if (total >> 16) base_f = atomicAdd(full_count, total >> 16);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0) + (incl & 0xFFFFu) - n;
+  base_f = __shfl_sync(0xffffffffu, base_f, 0) + (incl >> 16) - nf;
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     uint64_t t = todo[k];
@@ -119,6 +126,12 @@ __global__ void __launch_bounds__(256) mesh_worklist_kernel(DVolume v, int rank,
       const int bit = __ffsll((long long)t) - 1;
       t &= t - 1;
       work[base++] = (uint64_t)c * MESO_BLOCKS + (uint64_t)((lane + 32 * k) * 64 + bit);
+    }
+    t = todo_full[k];
+    while (t) {
+      const int bit = __ffsll((long long)t) - 1;
+      t &= t - 1;
+      work[work_cap - 1 - (int64_t)(base_f++)] = (uint64_t)c * MESO_BLOCKS + (uint64_t)((lane + 32 * k) * 64 + bit);
     }
   }
 }
@@ -204,38 +217,14 @@ __device__ __forceinline__ void load_slices(const DVolume& v, uint32_t slot, uin
 #pragma unroll
   for (int i = 0; i < 4; i++) { const ulonglong2 q = __ldg(p + i); s[2 * i] = q.x; s[2 * i + 1] = q.y; }
 }
-// ---- bulk asynchronous copy (TMA engine, non-tensor form) of brick payloads into shared memory, completion on an mbarrier ----
-// MEASURED AND OFF (MB_BULK = 1 builds it; tools/build_variant.sh): staging the 64-byte payloads of a pass with one
-// cp.async.bulk per lane + an mbarrier wait + LDS reads is correct (parity green) and slower than four LDG.128 per lane --
-// 0.79 vs 0.57 ms at 4096^3 (8 KB more shared memory per CTA = 5 instead of 6 CTAs per SM, a 4-way bank conflict on the
-// read-back, and nothing to hide: the merge loops bound the kernel, not the payload latency).  profiles/README.md.
-#ifndef MB_BULK
-#define MB_BULK 0
-#endif
+// (Staging the 64-byte payloads of a pass in shared memory with one cp.async.bulk per lane + an mbarrier wait + LDS reads was
+// built and measured: correct, and slower than four LDG.128 per lane -- 0.79 vs 0.57 ms at 4096^3 with the kernel of that
+// time: 8 KB more shared memory per CTA, a 4-way bank conflict on the read-back, and nothing to hide.  profiles/README.md.
+// The bulk-copy engine is used where it pays: the staged quad batches leave shared memory as one bulk store each.)
 #ifndef MB_BULK_STORE
 #define MB_BULK_STORE 1
 #endif
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra WAIT_%=;\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 64 bytes (one brick payload) global -> shared, counted against the mbarrier's transaction bytes
-__device__ __forceinline__ void bulk_load_64(void* dst_smem, const void* src_gmem, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(smem_u32(bar)) : "memory");
-}
 
 // plane `l` of the brick along `axis`, as the 8x8 image the oracle defines for that axis:
 //   axis 0 (x = l): row z, bit y;   axis 1 (y = l): row z, bit x;   axis 2 (z = l): row y, bit x (the slice itself)
@@ -284,70 +273,35 @@ __device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, in
 // into the warp's queue as {image, origin | direction | layer} (a full queue merges the image on the spot).
 template <int AXIS>
 __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, int bx, int by, int bz, ulonglong2* queue, int* qn, uint4* stage, int* count,
-                                                  MesoQuad* quads, int64_t cap, unsigned long long* quad_count, uint64_t* pay, uint64_t* bar, uint32_t& phase) {
+                                                  MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
   uint32_t slot = 0;
   const int st = valid ? brick_state(v, bx, by, bz, slot) : 0;
-#if MB_BULK
-  // The payloads of the pass's partial bricks travel global -> shared as bulk asynchronous copies (64 B each, the TMA engine's
-  // non-tensor form) while the lanes resolve their neighbours; one mbarrier per warp counts the bytes.
-  const unsigned partial = __ballot_sync(0xffffffffu, st == 2);
-  if (partial) {
-    if ((threadIdx.x & 31) == 0) mbar_expect_tx(bar, 64u * (uint32_t)__popc(partial));
-    __syncwarp();
-    if (st == 2) bulk_load_64(pay + (threadIdx.x & 31) * 8, v.pool + (size_t)slot * 8, bar);
-  }
-  uint64_t nbm = 0, nbp = 0;
-  if (st != 0) {
-    nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, st == 1 ? ~0ull : 0ull);
-    nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, st == 1 ? ~0ull : 0ull);
-  }
-  uint64_t s[8];
-  if (partial) {
-    mbar_wait(bar, phase & 1u);
-    phase++;
-  }
-  if (st == 2) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(pay + (threadIdx.x & 31) * 8);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { const ulonglong2 q = p[i]; s[2 * i] = q.x; s[2 * i + 1] = q.y; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = ~0ull;
-  }
-  __syncwarp();     // every lane has its slices in registers: the staging area may be overwritten by the next pass
   if (st == 0) return;
-#else
-  if (st == 0) return;
-  uint64_t s[8];
-  if (st == 2) load_slices(v, slot, s);
-  else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = ~0ull;
-  }
-  const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, st == 1 ? ~0ull : 0ull);
-  const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, st == 1 ? ~0ull : 0ull);
-#endif
   const uint64_t org = (uint64_t)(uint32_t)(bx * 8) | ((uint64_t)(uint32_t)(by * 8) << 16) | ((uint64_t)(uint32_t)(bz * 8) << 32);
-  uint64_t prev = nbm, cur = s[0];
-  if (AXIS != 2 && st == 2) cur = axis_plane<AXIS>(s, 0);
+  auto enqueue = [&](uint64_t img, int dir, int l) {
+    if (img) {
+      const int idx = atomicAdd(qn, 1);
+      if (idx < MI_CAP) queue[idx] = make_ulonglong2(img, org | ((uint64_t)dir << 48) | ((uint64_t)l << 52));
+      else greedy_stage(img, dir, l, bx * 8, by * 8, bz * 8, stage, count, quads, cap, quad_count);
+    }
+  };
+  if (st == 1) {
+    // a full brick shows voxel faces only on its two outer layers, where the neighbour is a partial brick (an absent
+    // neighbour counts as covered: that face belongs to the brick level)
+    enqueue(~neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, ~0ull), 2 * AXIS, 0);
+    enqueue(~neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, ~0ull), 2 * AXIS + 1, 7);
+    return;
+  }
+  uint64_t s[8];
+  load_slices(v, slot, s);
+  const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, 0ull);
+  const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, 0ull);
+  uint64_t prev = nbm, cur = axis_plane<AXIS>(s, 0);
 #pragma unroll 1
   for (int l = 0; l < 8; l++) {
-    uint64_t next = nbp;
-    if (l < 7) {
-      next = AXIS == 2 ? axis_plane<2>(s, l + 1) : cur;      // full bricks: every plane equals the first
-      if (AXIS != 2 && st == 2) next = axis_plane<AXIS>(s, l + 1);
-    }
-    const uint64_t em = cur & ~prev, ep = cur & ~next;
-#pragma unroll 1
-    for (int side = 0; side < 2; side++) {
-      const uint64_t img = side ? ep : em;
-      if (img) {
-        const int dir = 2 * AXIS + side;
-        const int idx = atomicAdd(qn, 1);
-        if (idx < MI_CAP) queue[idx] = make_ulonglong2(img, org | ((uint64_t)dir << 48) | ((uint64_t)l << 52));
-        else greedy_stage(img, dir, l, bx * 8, by * 8, bz * 8, stage, count, quads, cap, quad_count);
-      }
-    }
+    const uint64_t next = l < 7 ? axis_plane<AXIS>(s, l + 1) : nbp;
+    enqueue(cur & ~prev, 2 * AXIS, l);
+    enqueue(cur & ~next, 2 * AXIS + 1, l);
     prev = cur; cur = next;
   }
 }
@@ -362,26 +316,21 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
 // cooperatively and ran the greedy loops at 2-6 active lanes; one thread per (brick, axis) without the queue ran them at 4;
 // the queue with a data-dependent greedy loop per image (lanes round-robin over the images) at 8; the converged one-quad-per-
 // iteration loop runs at 26 (0.58 -> 0.41 ms), and letting the lanes keep their images across passes removes its tail (0.385 ms).
-__global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, const uint32_t* __restrict__ work_count_ptr,
-                                                                    uint32_t work_count_imm, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
+// Work: either pass A's two lists (counts read from device memory: partial bricks work[0 .. np), full bricks with a partial
+// neighbour work[work_cap - 1 - i], i < nf) or one list of n_list keys of any state (re-mesh).
+__global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolume v, const uint64_t* __restrict__ work, int64_t work_cap,
+                                                                    const uint32_t* __restrict__ partial_count_ptr, const uint32_t* __restrict__ full_count_ptr,
+                                                                    uint32_t n_list, MesoQuad* quads, int64_t cap, unsigned long long* quad_count,
                                                                     int shard_rank, int shard_world) {
   __shared__ __align__(128) uint4 s_q[MB_WARPS][MQ_CAP];
   __shared__ ulonglong2 s_img[MB_WARPS][MI_CAP];
   __shared__ int s_n[MB_WARPS], s_in[MB_WARPS];
-#if MB_BULK
-  __shared__ __align__(16) uint64_t s_pay[MB_WARPS][32 * 8];   // one pass's brick payloads, 64 B per lane (bulk-copy destination)
-  __shared__ __align__(8) uint64_t s_bar[MB_WARPS];            // one mbarrier per warp
-#else
-  uint64_t (*s_pay)[1] = nullptr; uint64_t* s_bar = nullptr;   // unused
-#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_work = work_count_ptr ? *work_count_ptr : work_count_imm;
-  const int64_t n_groups = (((int64_t)n_work + 31) / 32) * 3;     // (32 bricks, axis)
-  uint32_t phase = 0;
+  const uint32_t n_work = partial_count_ptr ? *partial_count_ptr : n_list;
+  const uint32_t n_full = full_count_ptr ? *full_count_ptr : 0u;
+  const int64_t g_axis = (((int64_t)n_work + 31) / 32) * 3;       // (32 bricks, axis) passes over the first list ...
+  const int64_t n_groups = g_axis + ((int64_t)n_full + 31) / 32;  // ... and 32-brick passes, all three axes at once, over the full bricks
   if (lane == 0) { s_n[warp] = 0; s_in[warp] = 0; }
-#if MB_BULK
-  if (lane == 0) mbar_init(&s_bar[warp], 1u);
-#endif
   __syncwarp();
   // write the first `count` staged quads behind one reservation and empty the staging area
   auto flush = [&](int count) {
@@ -445,19 +394,21 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     __syncwarp();
   };
   for (int64_t grp = (int64_t)blockIdx.x * MB_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * MB_WARPS) {
-    const int axis = (int)(grp % 3);
-    const int64_t item = (grp / 3) * 32 + lane;
-    bool valid = item < (int64_t)n_work;
-    const uint64_t key = valid ? work[item] : 0ull;
+    const bool full_pass = grp >= g_axis;
+    const int axis = full_pass ? 3 : (int)(grp % 3);
+    const int64_t item = (full_pass ? grp - g_axis : grp / 3) * 32 + lane;
+    bool valid = item < (int64_t)(full_pass ? n_full : n_work);
+    const uint64_t key = valid ? work[full_pass ? work_cap - 1 - item : item] : 0ull;
     // key lists (dirty re-mesh) are sharded over the ranks by a hash of the key: the list order is scheduling-dependent and
     // differs between the replicas, the key set does not
     if (shard_world > 1 && (int)(((key * 0x9E3779B97F4A7C15ull) >> 40) % (unsigned)shard_world) != shard_rank) valid = false;
-    const int64_t c = (int64_t)(key >> 12); const int b = (int)(key & 4095);
-    const int cx = (int)(c % v.dims[0]), cy = (int)((c / v.dims[0]) % v.dims[1]), cz = (int)(c / ((int64_t)v.dims[0] * v.dims[1]));
+    const int b = (int)(key & 4095);
+    int cx, cy, cz;
+    chunk_coords(v, (int64_t)(key >> 12), cx, cy, cz);
     const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
-    if (axis == 0) queue_axis_images<0>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
-    else if (axis == 1) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
-    else queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count, MB_BULK ? (uint64_t*)s_pay[warp] : nullptr, MB_BULK ? &s_bar[warp] : nullptr, phase);
+    if (axis == 0 || full_pass) queue_axis_images<0>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    if (axis == 1 || full_pass) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    if (axis == 2 || full_pass) queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
     __syncwarp();
     merge(min(s_in[warp], MI_CAP), /*drain=*/false);
   }
@@ -602,11 +553,11 @@ __global__ void clear_chunk_marks_kernel(const uint32_t* __restrict__ chunk_list
 
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, const MeshScratch& ms,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count) {
-  cudaMemsetAsync(ms.work_count, 0, 2 * sizeof(uint32_t), lc.stream);   // work_count and chunk_count are adjacent words
+  cudaMemsetAsync(ms.work_count, 0, 3 * sizeof(uint32_t), lc.stream);   // work_count, chunk_count and full_count are adjacent words
   if (reset_count) cudaMemsetAsync(d_quad_count, 0, sizeof(unsigned long long), lc.stream);
   const int64_t mine = (v.nchunks - rank + world - 1) / world;     // chunks rank, rank + world, ...: one warp each
-  mesh_worklist_kernel<<<(unsigned)((mine + 7) / 8), 256, 0, lc.stream>>>(v, rank, world, ms.work, ms.work_count, ms.chunk_list, ms.chunk_count);
-  mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, ms.work, ms.work_count, 0u, d_quads, cap, d_quad_count, 0, 1);
+  mesh_worklist_kernel<<<(unsigned)((mine + 7) / 8), 256, 0, lc.stream>>>(v, rank, world, ms.work, ms.work_cap, ms.work_count, ms.full_count, ms.chunk_list, ms.chunk_count);
+  mesh_bricks_kernel<<<lc.sm_count * 12, MB_THREADS, 0, lc.stream>>>(v, ms.work, ms.work_cap, ms.work_count, ms.full_count, 0u, d_quads, cap, d_quad_count, 0, 1);
   const int64_t groups = (v.nchunks * 3 + CF_WARPS - 1) / CF_WARPS;
   mesh_chunk_faces_kernel<<<(unsigned)min((int64_t)lc.sm_count * 16, groups), CF_WARPS * 32, 0, lc.stream>>>(v, ms.chunk_list, ms.chunk_count, 0, 1, d_quads, cap, d_quad_count);
   (*lc.launches) += 3;
@@ -618,7 +569,7 @@ void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_k
   if (n_keys == 0) return;
   const int64_t passes = (((int64_t)n_keys + 31) / 32) * 3;
   const unsigned grid = (unsigned)min((int64_t)lc.sm_count * 12, (passes + MB_WARPS - 1) / MB_WARPS);
-  mesh_bricks_kernel<<<grid, MB_THREADS, 0, lc.stream>>>(v, d_keys, nullptr, n_keys, d_quads, cap, d_quad_count, rank, world);
+  mesh_bricks_kernel<<<grid, MB_THREADS, 0, lc.stream>>>(v, d_keys, 0, nullptr, nullptr, n_keys, d_quads, cap, d_quad_count, rank, world);
   // the brick-level quads of every chunk that holds a listed brick
   cudaMemsetAsync(ms.chunk_count, 0, sizeof(uint32_t), lc.stream);
   mark_chunks_kernel<<<(n_keys + 255) / 256, 256, 0, lc.stream>>>(d_keys, n_keys, ms.chunk_mark, ms.chunk_list, ms.chunk_count);

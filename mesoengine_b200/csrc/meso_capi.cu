@@ -211,7 +211,7 @@ static int scene_alloc(MesoCtx* c, const MesoGPUUniformSceneConfig* cfg, const i
   CK(cudaMalloc(&c->d_block_totals, 1024 * 4));
   CK(cudaMalloc(&c->d_stats, sizeof(RayStatsDev)));
   CK(cudaMalloc(&c->d_touch_chunk, nc)); CK(cudaMalloc(&c->d_touch_brick, max_bricks));
-  CK(cudaMalloc(&c->d_work_count, 8)); c->d_chunk_count = c->d_work_count + 1;   // adjacent: one memset clears both
+  CK(cudaMalloc(&c->d_work_count, 16)); c->d_chunk_count = c->d_work_count + 1;   // work, chunk and full-brick counters are adjacent: one memset clears them
   CK(cudaMalloc(&c->d_quad_count, 8));
   c->cap_dirty = 1u << 22;
   CK(cudaMalloc(&c->d_dirty, (size_t)c->cap_dirty * 8)); CK(cudaMalloc(&c->d_dirty_count, 4));

@@ -62,7 +62,7 @@ struct MesoCtx {
   uint32_t* d_chunk_mark = nullptr;    // one bit per chunk, all-zero between calls (re-mesh: chunks that hold a listed brick)
   uint32_t* d_chunk_list = nullptr;    // nchunks entries
   uint32_t* d_chunk_count = nullptr;
-  MeshScratch mesh_scratch() const { return MeshScratch{d_work, d_work_count, d_chunk_list, d_chunk_count, d_chunk_mark}; }
+  MeshScratch mesh_scratch() const { return MeshScratch{d_work, cap_work, d_work_count, d_chunk_list, d_chunk_count, d_work_count + 2, d_chunk_mark}; }
   int* d_overflow = nullptr;
   // K6
   uint64_t* d_sel_keys = nullptr;         // candidate keys (scratch), sel_cap entries

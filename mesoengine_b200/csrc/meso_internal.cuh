@@ -105,9 +105,11 @@ void launch_build_cubes(const LaunchCtx& lc, const DVolume& v, uint8_t* d_cell, 
 void launch_pack_rgba8(const LaunchCtx& lc, const MesoHitRecord* d_records, size_t n, uint32_t* d_out);
 void launch_compose_tiles(const LaunchCtx& lc, const MesoHitRecord* d_tiles, int world, int width, int height, MesoHitRecord* d_frame);
 
-// scratch of the mesh passes: brick work list (room for every brick of the rank's chunks) + its counter; chunk list (nchunks
-// entries) + its counter (the word after work_count); one bit per chunk, all-zero between calls (re-mesh: chunks that hold a listed brick)
-struct MeshScratch { uint64_t* work; uint32_t* work_count; uint32_t* chunk_list; uint32_t* chunk_count; uint32_t* chunk_mark; };
+// scratch of the mesh passes: brick work list (work_cap entries = every brick of the rank's chunks; partial bricks from the
+// front, full bricks with a partial neighbour from the back) + its two counters; chunk list (nchunks entries) + its counter
+// (counters: three adjacent words work_count, chunk_count, full_count); one bit per chunk, all-zero between calls (re-mesh:
+// chunks that hold a listed brick)
+struct MeshScratch { uint64_t* work; int64_t work_cap; uint32_t* work_count; uint32_t* chunk_list; uint32_t* chunk_count; uint32_t* full_count; uint32_t* chunk_mark; };
 void launch_mesh(const LaunchCtx& lc, const DVolume& v, int rank, int world, const MeshScratch& ms,
                  MesoQuad* d_quads, int64_t cap, unsigned long long* d_quad_count, bool reset_count = true);
 void launch_mesh_list(const LaunchCtx& lc, const DVolume& v, const uint64_t* d_keys, uint32_t n_keys, MesoQuad* d_quads,
