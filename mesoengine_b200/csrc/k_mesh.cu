@@ -269,13 +269,12 @@ __device__ __forceinline__ uint64_t neighbour_plane(const DVolume& v, int bx, in
 #define MB_MINB 6
 #endif
 
-// Phase 1 of a warp pass: the sixteen (direction, layer) exposed-face images of one brick along AXIS; the non-empty ones go
-// into the warp's queue as {image, origin | direction | layer} (a full queue merges the image on the spot).
+// Phase 1 of a warp pass: the sixteen (direction, layer) exposed-face images of one brick (state st: 0 nothing, 1 full, 2 partial
+// with its eight z-slices in s) along AXIS; the non-empty ones go into the warp's queue as {image, origin | direction | layer}
+// (a full queue merges the image on the spot).
 template <int AXIS>
-__device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, int bx, int by, int bz, ulonglong2* queue, int* qn, uint4* stage, int* count,
+__device__ __forceinline__ void queue_axis_images(const DVolume& v, int st, const uint64_t s[8], int bx, int by, int bz, ulonglong2* queue, int* qn, uint4* stage, int* count,
                                                   MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
-  uint32_t slot = 0;
-  const int st = valid ? brick_state(v, bx, by, bz, slot) : 0;
   if (st == 0) return;
   const uint64_t org = (uint64_t)(uint32_t)(bx * 8) | ((uint64_t)(uint32_t)(by * 8) << 16) | ((uint64_t)(uint32_t)(bz * 8) << 32);
   auto enqueue = [&](uint64_t img, int dir, int l) {
@@ -292,8 +291,6 @@ __device__ __forceinline__ void queue_axis_images(const DVolume& v, bool valid, 
     enqueue(~neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, ~0ull), 2 * AXIS + 1, 7);
     return;
   }
-  uint64_t s[8];
-  load_slices(v, slot, s);
   const uint64_t nbm = neighbour_plane<AXIS>(v, bx - (AXIS == 0), by - (AXIS == 1), bz - (AXIS == 2), 7, 0ull);
   const uint64_t nbp = neighbour_plane<AXIS>(v, bx + (AXIS == 0), by + (AXIS == 1), bz + (AXIS == 2), 0, 0ull);
   uint64_t prev = nbm, cur = axis_plane<AXIS>(s, 0);
@@ -328,8 +325,8 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_work = partial_count_ptr ? *partial_count_ptr : n_list;
   const uint32_t n_full = full_count_ptr ? *full_count_ptr : 0u;
-  const int64_t g_axis = (((int64_t)n_work + 31) / 32) * 3;       // (32 bricks, axis) passes over the first list ...
-  const int64_t n_groups = g_axis + ((int64_t)n_full + 31) / 32;  // ... and 32-brick passes, all three axes at once, over the full bricks
+  const int64_t g_first = (((int64_t)n_work + 31) / 32) * 3;      // (32 bricks, axis) passes over the first list ...
+  const int64_t n_groups = g_first + ((int64_t)n_full + 31) / 32; // ... and 32-brick passes, all three axes at once, over the full bricks
   if (lane == 0) { s_n[warp] = 0; s_in[warp] = 0; }
   __syncwarp();
   // write the first `count` staged quads behind one reservation and empty the staging area
@@ -394,9 +391,9 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     __syncwarp();
   };
   for (int64_t grp = (int64_t)blockIdx.x * MB_WARPS + warp; grp < n_groups; grp += (int64_t)gridDim.x * MB_WARPS) {
-    const bool full_pass = grp >= g_axis;
+    const bool full_pass = grp >= g_first;
     const int axis = full_pass ? 3 : (int)(grp % 3);
-    const int64_t item = (full_pass ? grp - g_axis : grp / 3) * 32 + lane;
+    const int64_t item = (full_pass ? grp - g_first : grp / 3) * 32 + lane;
     bool valid = item < (int64_t)(full_pass ? n_full : n_work);
     const uint64_t key = valid ? work[full_pass ? work_cap - 1 - item : item] : 0ull;
     // key lists (dirty re-mesh) are sharded over the ranks by a hash of the key: the list order is scheduling-dependent and
@@ -406,9 +403,17 @@ __global__ void __launch_bounds__(MB_THREADS, MB_MINB) mesh_bricks_kernel(DVolum
     int cx, cy, cz;
     chunk_coords(v, (int64_t)(key >> 12), cx, cy, cz);
     const int bx = cx * 16 + (b & 15), by = cy * 16 + ((b >> 4) & 15), bz = cz * 16 + (b >> 8);
-    if (axis == 0 || full_pass) queue_axis_images<0>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
-    if (axis == 1 || full_pass) queue_axis_images<1>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
-    if (axis == 2 || full_pass) queue_axis_images<2>(v, valid, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    uint32_t slot = 0;
+    const int st = valid ? brick_state(v, bx, by, bz, slot) : 0;
+    uint64_t s[8];
+    if (st == 2) load_slices(v, slot, s);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = 0ull;    // (unused: a full brick's images come from its neighbours' planes alone)
+    }
+    if (axis == 0 || full_pass) queue_axis_images<0>(v, st, s, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    if (axis == 1 || full_pass) queue_axis_images<1>(v, st, s, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
+    if (axis == 2 || full_pass) queue_axis_images<2>(v, st, s, bx, by, bz, s_img[warp], &s_in[warp], s_q[warp], &s_n[warp], quads, cap, quad_count);
     __syncwarp();
     merge(min(s_in[warp], MI_CAP), /*drain=*/false);
   }
