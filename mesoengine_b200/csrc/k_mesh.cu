@@ -147,7 +147,9 @@ __device__ __forceinline__ uint32_t gather_col(uint64_t e, int x) {  // bits (x 
 
 // Greedy merge of one 8x8 image, quads staged in shared memory (slot = shared atomic); what does not fit goes straight to
 // the global list (rare: a warp's ten bricks yield more than MQ_CAP quads between two flushes).
-__device__ __forceinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count,
+// (not inlined: it has twelve call sites in the kernel -- inlined they were a third of its 4 500 instructions and the kernel
+// stalled 11 % of the time on instruction fetch)
+__device__ __noinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count,
                                              MesoQuad* quads, int64_t cap, unsigned long long* quad_count) {
   const int ax = dir >> 1;
 #pragma unroll 1
