@@ -1433,7 +1433,8 @@ def bench_mesh(ctx, capi, scenes, torch, stream, args, dev, n_work=1024):
         q1 = quads[:nq, 1]
         lvl = ((q1 >> 19) & 1) == 1
         brick_faces = int((((q1[lvl] >> 27) & 0x1F).to(torch.int64) * (quads[:nq, 2][lvl] >> 3).to(torch.int64)).sum().item())
-        out[name] = {"meshed_voxels_per_s": n ** 3 / (ms * 1e-3), "ms": ms, "quads": int(nq), "populated_bricks": populated,
+        out[name] = {"meshed_voxels_per_s": n ** 3 / (ms * 1e-3), "populated_voxels_per_s": populated * 512 / (ms * 1e-3),
+                     "quads_per_s": int(nq) / (ms * 1e-3), "ms": ms, "quads": int(nq), "populated_bricks": populated,
                      "partial_bricks": int(len(keys)), "algorithmic_bytes": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
                      "brick_level": {"quads": int(lvl.sum().item()), "brick_faces_covered": brick_faces}}
         if name == "terrain_1024_blocks" and not args.no_cpu:
