@@ -150,3 +150,47 @@ def test_carve_sphere_removes_exactly_the_voxels_inside(orc):
     assert vol.count_voxels() == int(after.sum())
     # idempotent: carving the same sphere again changes nothing
     assert len(vol.carve_sphere(center, radius)) == 0
+
+
+def _expand_dirty(dirty, dims):
+    """Dirty bricks + their six neighbours inside the grid (what meso_remesh_dirty re-meshes), as sorted keys."""
+    out = set()
+    nb = (dims[0] * 16, dims[1] * 16, dims[2] * 16)
+    for key in dirty.tolist():
+        c, b = key >> 12, key & 4095
+        cx, cy, cz = c % dims[0], (c // dims[0]) % dims[1], c // (dims[0] * dims[1])
+        bx, by, bz = cx * 16 + (b & 15), cy * 16 + ((b >> 4) & 15), cz * 16 + (b >> 8)
+        for dx, dy, dz in ((0, 0, 0), (-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)):
+            x, y, z = bx + dx, by + dy, bz + dz
+            if 0 <= x < nb[0] and 0 <= y < nb[1] and 0 <= z < nb[2]:
+                cc = (x >> 4) + dims[0] * ((y >> 4) + dims[1] * (z >> 4))
+                out.add(cc * 4096 + (x & 15) + 16 * (y & 15) + 256 * (z & 15))
+    return np.array(sorted(out), dtype=np.uint64)
+
+
+@pytest.mark.parametrize("case", ["voxel_sphere", "block_terrain"])
+def test_remesh_replacement_rule_keeps_the_list_current(orc, case):
+    """The contract of the dirty re-mesh: drop the voxel-level quads whose corner lies in a re-meshed brick and the brick-level
+    quads whose corner lies in a chunk that holds one, add what the re-mesh returns -- the result is the full mesh of the edited
+    volume (no quad outside that set changes)."""
+    if case == "voxel_sphere":
+        origin, dims, params = scenes.sphere_scene(256)
+        vol = orc.Volume(origin, dims).voxelize(orc.SDF_SPHERE, params, granularity=orc.GRAN_VOXEL)
+        carves = [((128 - 90, 128, 128), 24), ((128, 228, 138), 40), ((128, 128, 128), 30)]
+    else:
+        origin, dims = (0, -1, 0), (2, 2, 2)
+        vol = orc.Volume(origin, dims).voxelize(orc.SDF_TERRAIN, None, granularity=orc.GRAN_BLOCK)
+        carves = [((100, 128, 100), 37), ((128, 120, 128), 60), ((10, 140, 250), 25)]
+    current = vol.mesh()
+    for center, radius in carves:
+        dirty = vol.carve_sphere(center, radius)
+        assert len(dirty) > 0
+        keys = _expand_dirty(dirty, dims)
+        fresh = vol.remesh(keys)
+        x = (current["w0"] & 0xFFFF).astype(np.int64); y = (current["w0"] >> 16).astype(np.int64); z = (current["w1"] & 0xFFFF).astype(np.int64)
+        level = (current["w1"] >> 19) & 1
+        chunk = (x >> 7) + dims[0] * ((y >> 7) + dims[1] * (z >> 7))
+        brick = chunk * 4096 + ((x >> 3) & 15) + 16 * ((y >> 3) & 15) + 256 * ((z >> 3) & 15)
+        stale = np.where(level == 1, np.isin(chunk, np.unique(keys >> np.uint64(12)).astype(np.int64)), np.isin(brick, keys.astype(np.int64)))
+        current = np.concatenate([current[~stale], fresh])
+        assert orc.sort_quads(current.copy()).tobytes() == orc.sort_quads(vol.mesh()).tobytes()
