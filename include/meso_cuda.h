@@ -425,6 +425,10 @@ MESO_API int meso_group_mesh(MesoGroup* g, MesoQuad* host_quads, int64_t cap, in
  * entries); compact != 0 closes the gaps with device-local copies: one contiguous list of *n_quads records. */
 MESO_API int meso_group_mesh_device(MesoGroup* g, void* d_quads_on_member0, int64_t cap, int64_t* n_quads, int64_t* segment_counts,
                                     int compact);
+/* meso_remesh_dirty over the group after meso_group_carve_sphere: the members share the work by a hash of the brick / chunk key,
+ * host_quads = their lists concatenated.  The carve is replicated, so the re-meshed bricks are the same on every member: take the
+ * keys from any one of them (meso_remesh_dirty(meso_group_ctx(g, 0), NULL, 0, &n, keys, cap_keys, &n_keys) returns member 0's
+ * share of the quads and ALL the keys). */
 MESO_API int meso_group_remesh_dirty(MesoGroup* g, MesoQuad* host_quads, int64_t cap, int64_t* n_quads);
 
 /* ---- utilities -------------------------------------------------------------------------------------------- */
