@@ -40,7 +40,7 @@ cap = 1 << 25
 quads = torch.empty((cap, 4), dtype=torch.int32, device="cuda")
 nq = ctx.mesh_device(quads.data_ptr(), cap)
 t = timed(lambda: ctx.mesh_device(quads.data_ptr(), cap, want_count=False), reps=5)
-out["K3 mesh (worklist + bricks)"] = (t, 64.0 * npart + 1024.0 * nch + 16.0 * nq + 4)
+out["K3 mesh (passes A + B + C)   "] = (t, 64.0 * npart + 1024.0 * nch + 16.0 * nq + 4)
 c = [int(v) for v in (np.array(dims) * 64)]
 c[0] -= int(0.39 * N)  # on the sphere surface facing -x
 r = 96
