@@ -10,7 +10,7 @@ def _dense(vol, n):
     occ, full = vol.occ(), vol.full()
     keys, payload = vol.export_partial()
     dims = vol.dims
-    d = np.zeros((n, n, n), dtype=bool)
+    d = np.zeros((n, n, n) if np.isscalar(n) else tuple(n), dtype=bool)
     pay = {int(k): p for k, p in zip(keys, payload)}
     for c in range(vol.nchunks):
         cx, cy, cz = c % dims[0], (c // dims[0]) % dims[1], c // (dims[0] * dims[1])
@@ -194,3 +194,23 @@ def test_remesh_replacement_rule_keeps_the_list_current(orc, case):
         stale = np.where(level == 1, np.isin(chunk, np.unique(keys >> np.uint64(12)).astype(np.int64)), np.isin(brick, keys.astype(np.int64)))
         current = np.concatenate([current[~stale], fresh])
         assert orc.sort_quads(current.copy()).tobytes() == orc.sort_quads(vol.mesh()).tobytes()
+
+
+def test_brick_level_across_chunk_and_grid_borders(orc):
+    """Block-granular terrain over 2 x 2 x 1 chunks: every quad is brick-level, none crosses a chunk border, and together they
+    cover exactly the exposed faces computed independently from the dense volume (grid border = empty outside)."""
+    origin, dims = (0, -1, 0), (2, 2, 1)
+    vol = orc.Volume(origin, dims).voxelize(orc.SDF_TERRAIN, None, granularity=orc.GRAN_BLOCK)
+    quads = vol.mesh()
+    assert len(quads) > 0 and np.all((quads["w1"] >> 19) & 1 == 1)
+    faces, area = _expand(quads)
+    exp = _exposed_faces(_dense(vol, (256, 256, 128)))
+    assert area == len(faces) and faces == exp and vol.count_exposed_faces() == len(exp)
+    x = (quads["w0"] & 0xFFFF).astype(np.int64); y = (quads["w0"] >> 16).astype(np.int64); z = (quads["w1"] & 0xFFFF).astype(np.int64)
+    f = (quads["w1"] >> 16) & 7; w = ((quads["w1"] >> 24) & 0xFF).astype(np.int64); h = quads["w2"].astype(np.int64)
+    ax = f >> 1
+    u0 = np.where(ax == 0, y, x); v0 = np.where(ax == 2, y, z)
+    assert np.all((u0 >> 7) == ((u0 + w - 1) >> 7)) and np.all((v0 >> 7) == ((v0 + h - 1) >> 7))     # inside one chunk
+    assert np.all(u0 % 8 == 0) and np.all(v0 % 8 == 0) and np.all(w % 8 == 0) and np.all(h % 8 == 0)
+    # far fewer quads than brick faces
+    assert len(quads) * 2 < (w // 8 * (h // 8)).sum()
