@@ -214,3 +214,59 @@ def test_brick_level_across_chunk_and_grid_borders(orc):
     assert np.all(u0 % 8 == 0) and np.all(v0 % 8 == 0) and np.all(w % 8 == 0) and np.all(h % 8 == 0)
     # far fewer quads than brick faces
     assert len(quads) * 2 < (w // 8 * (h // 8)).sum()
+
+
+def _greedy_loop(rows):
+    """The definition (oracle/orc_mesh.c): rows ascending, lowest set bit first, run length, then as many following rows as hold
+    the whole run."""
+    r = list(rows)
+    out = []
+    for v in range(8):
+        while r[v]:
+            u0 = (r[v] & -r[v]).bit_length() - 1
+            w = 0
+            while u0 + w < 8 and (r[v] >> (u0 + w)) & 1:
+                w += 1
+            m = ((1 << w) - 1) << u0
+            h = 1
+            while v + h < 8 and (r[v + h] & m) == m:
+                r[v + h] &= ~m
+                h += 1
+            r[v] &= ~m
+            out.append((u0, v, w, h))
+    return out
+
+
+def _greedy_branch_free(img):
+    """The step the mesh kernel runs once per lane and loop iteration (k_mesh.cu:take_quad), restated on a 64-bit integer: lowest
+    set bit = corner; run length from its row; height = index of the first following row that misses a bit of the run (rows past
+    the image shift in as zeros); the covered rows cleared in one go."""
+    M64 = (1 << 64) - 1
+    out = []
+    while img:
+        p = (img & -img).bit_length() - 1
+        v, u0, sh = p >> 3, p & 7, p & ~7
+        t = img >> sh
+        row = t & 0xFF
+        inv = (~(row >> u0)) & 0xFFFFFFFF
+        w = (inv & -inv).bit_length() - 1
+        m = ((1 << w) - 1) << u0
+        mrep = (m * 0x0101010101010101) & M64
+        miss = ~t & mrep & M64
+        h = ((miss & -miss).bit_length() - 1) >> 3 if miss else 8
+        clr = mrep if h == 8 else mrep & ((1 << (8 * h)) - 1)
+        img &= ~(clr << sh) & M64
+        out.append((u0, v, w, h))
+    return out
+
+
+def test_branch_free_greedy_step_equals_the_definition():
+    rng = np.random.default_rng(3)
+    images = [0xFFFFFFFFFFFFFFFF, 0x0000001818000000, 0xAA55AA55AA55AA55, 0x8000000000000001, 0x00FF00FF00FF00FF, 0xFF818181818181FF]
+    images += [int(x) for x in rng.integers(0, 2 ** 63, size=3000, dtype=np.int64).astype(np.uint64)]
+    # dense and sparse images exercise long runs / tall quads and isolated faces
+    images += [int(a | b) for a, b in zip(rng.integers(0, 2 ** 63, size=1500, dtype=np.int64).astype(np.uint64), rng.integers(0, 2 ** 63, size=1500, dtype=np.int64).astype(np.uint64))]
+    images += [int(a & b & c) for a, b, c in zip(*(rng.integers(0, 2 ** 63, size=1500, dtype=np.int64).astype(np.uint64) for _ in range(3)))]
+    for img in images:
+        rows = [(img >> (8 * v)) & 0xFF for v in range(8)]
+        assert _greedy_branch_free(img) == _greedy_loop(rows), hex(img)
