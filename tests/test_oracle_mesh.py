@@ -270,3 +270,47 @@ def test_branch_free_greedy_step_equals_the_definition():
     for img in images:
         rows = [(img >> (8 * v)) & 0xFF for v in range(8)]
         assert _greedy_branch_free(img) == _greedy_loop(rows), hex(img)
+
+
+def test_word_shift_form_of_the_brick_level_exposure():
+    """Pass C of the mesh (k_mesh.cu:mesh_chunk_faces_kernel) forms "full brick whose neighbour on the minus / plus side is absent"
+    on whole 64-brick words (word = z*4 + y/4, four 16-bit x-rows) by shifting the neighbour's occupancy onto the brick's bit.
+    The same arithmetic restated on Python integers against the per-brick definition, on random 3 x 3 x 3 chunk neighbourhoods."""
+    M64 = (1 << 64) - 1
+    X0, X15 = 0x0001000100010001, 0x8000800080008000
+    rng = np.random.default_rng(9)
+    for trial in range(6):
+        dims = (3, 3, 3)
+        occ = rng.integers(0, 2, size=(48, 48, 48)).astype(bool) if trial else np.ones((48, 48, 48), bool)
+        if trial == 2:
+            occ = rng.random((48, 48, 48)) < 0.9
+        full = occ & (rng.random((48, 48, 48)) < 0.7)
+
+        def word(a, cx, cy, cz, w):        # 64-brick word w of chunk (cx, cy, cz) of bit volume a, zero outside the grid
+            if not (0 <= cx < 3 and 0 <= cy < 3 and 0 <= cz < 3):
+                return 0
+            z, yq = w >> 2, w & 3
+            v = 0
+            for j in range(4):
+                for x in range(16):
+                    if a[cx * 16 + x, cy * 16 + yq * 4 + j, cz * 16 + z]:
+                        v |= 1 << (16 * j + x)
+            return v
+
+        cx = cy = cz = 1
+        for w in rng.choice(64, size=12, replace=False).tolist() + [0, 3, 60, 63]:
+            z, yq = w >> 2, w & 3
+            F, me = word(full, cx, cy, cz, w), word(occ, cx, cy, cz, w)
+            om = [((me << 1) & ~X0 & M64) | ((word(occ, cx - 1, cy, cz, w) >> 15) & X0),
+                  ((me >> 1) & ~X15) | ((word(occ, cx + 1, cy, cz, w) << 15) & X15),
+                  ((me << 16) & M64) | ((word(occ, cx, cy, cz, w - 1) if yq > 0 else word(occ, cx, cy - 1, cz, z * 4 + 3)) >> 48),
+                  (me >> 16) | (((word(occ, cx, cy, cz, w + 1) if yq < 3 else word(occ, cx, cy + 1, cz, z * 4 + 0)) << 48) & M64),
+                  word(occ, cx, cy, cz, w - 4) if z > 0 else word(occ, cx, cy, cz - 1, 15 * 4 + yq),
+                  word(occ, cx, cy, cz, w + 4) if z < 15 else word(occ, cx, cy, cz + 1, 0 * 4 + yq)]
+            for d, (dx, dy, dz) in enumerate(((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1))):
+                e = F & ~om[d] & M64
+                for j in range(4):
+                    for x in range(16):
+                        bx, by, bz = 16 + x, 16 + yq * 4 + j, 16 + z
+                        nb = occ[bx + dx, by + dy, bz + dz]      # (the centre chunk's neighbours are inside the 3^3 grid)
+                        assert bool((e >> (16 * j + x)) & 1) == bool(full[bx, by, bz] and not nb), (trial, w, d, x, j)
