@@ -145,8 +145,9 @@ __device__ __forceinline__ uint32_t gather_col(uint64_t e, int x) {  // bits (x 
 #endif
 #define MQ_FLUSH (MQ_CAP / 2)  // staged quads are written out once this many have accumulated (and at the end of the warp's work)
 
-// Greedy merge of one 8x8 image, quads staged in shared memory (slot = shared atomic); what does not fit goes straight to
-// the global list (rare: a warp's ten bricks yield more than MQ_CAP quads between two flushes).
+// The loop form of the greedy merge of one 8x8 image, as the oracle writes it.  Only the FALLBACK of phase 1 when the warp's
+// image queue is full (more than MI_CAP non-empty images in one pass: checkerboard bricks): the image is merged on the spot, quads
+// staged in shared memory (slot = shared atomic), and what does not fit the staging area goes straight to the global list.
 // (not inlined: it has twelve call sites in the kernel -- inlined they were a third of its 4 500 instructions and the kernel
 // stalled 11 % of the time on instruction fetch)
 __device__ __noinline__ void greedy_stage(uint64_t img, int dir, int layer, int ox, int oy, int oz, uint4* stage, int* count,
